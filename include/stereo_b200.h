@@ -1,0 +1,193 @@
+/*
+ * stereo_b200.h — C ABI of the B200-native (sm_100a) dense stereo block matcher.
+ *
+ * This is the drop-in boundary for ONE path of tanmaniac/IntroToComputerVision: the Problem Set 2
+ * window-based stereo matcher.  Every entry point cites the reference interface it replaces; paths
+ * are relative to the reference repository root.
+ *
+ *   cuda::disparitySSD     ProblemSets/ps2_cpp/include/DisparitySSD.h:18-23
+ *                          (wrapper being replaced: ProblemSets/ps2_cpp/lib/DisparitySSD.cu:143-207)
+ *   cuda::disparityNCorr   ProblemSets/ps2_cpp/include/DisparityNCorr.h:19-24
+ *                          (wrapper being replaced: ProblemSets/ps2_cpp/lib/DisparityNCorr.cu:177-251)
+ *   disparitySSDPair / disparityNCorrPair   ProblemSets/ps2_cpp/src/main.cpp:21-48, 51-78
+ *
+ * RESULTS follow the reference's CPU semantics (serial::disparitySSD, lib/DisparitySSD.cpp:9-62 and
+ * serial::disparityNCorr, lib/DisparityNCorr.cpp:12-71) — the reference's GPU kernels compute a
+ * different window and thresholds and are not the parity target.
+ *
+ * Conventions
+ *   - "ref" is the reference image (first argument of the reference functions), "tgt" the image
+ *     that is searched.  L->R maps pass (left, right, -range, 0); R->L maps pass (right, left, 0,
+ *     +range) — main.cpp:33,43.
+ *   - Images are single channel, row-major; `*_step` arguments are row strides in BYTES
+ *     (cv::Mat::step).  f32 images carry raw 0..255 intensities (no /255 — main.cpp:87-88) and may
+ *     be non-integer/negative (main.cpp:140-153); u8 entry points are the same computation for
+ *     images that are exactly 8-bit.
+ *   - Disparity output element size is 1 (int8, the reference's CV_8SC1 with its `char` narrowing,
+ *     DisparitySSD.cpp:59), 2 (int16) or 4 (int32); 2/4 hold the un-narrowed value, which is what
+ *     >127-disparity searches need.
+ *   - Every function returns STEREO_OK (0) or a negative stereo_status; nothing in this library
+ *     calls exit() (the reference does: common/include/common/CudaCommon.cuh:11-22).
+ *     stereo_last_error() returns a per-thread description of the last failure.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     STEREO_ERR_NO_DEVICE.
+ *   - A context owns all device buffers, streams and scratch; it is created once and reused (the
+ *     reference re-allocates per call, DisparitySSD.cu:171-178).  A context is not thread-safe;
+ *     use one per host thread.  Different contexts are independent (the reference's file-scope
+ *     texture references, DisparitySSD.cu:19-20, made it non-reentrant).
+ */
+#ifndef STEREO_B200_H_
+#define STEREO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEREO_B200_ABI_VERSION 1
+
+typedef enum stereo_status {
+    STEREO_OK = 0,
+    STEREO_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, bad element size, step too small */
+    STEREO_ERR_INVALID_RANGE = -2, /* min_disp > max_disp, or an NCC range that leaves a pixel without candidates */
+    STEREO_ERR_NO_DEVICE = -3,     /* no CUDA device / wrong architecture (needs sm_100) */
+    STEREO_ERR_CUDA = -4,          /* a CUDA runtime/driver call failed; see stereo_last_error() */
+    STEREO_ERR_ALLOC = -5,         /* device or pinned-host allocation failed */
+    STEREO_ERR_UNSUPPORTED = -6    /* parameter combination outside what the kernels cover */
+} stereo_status;
+
+typedef enum stereo_cost {
+    STEREO_COST_SSD = 0,   /* sum of squared differences, argmin, first minimum wins   (DisparitySSD.cpp:45-57) */
+    STEREO_COST_NCORR = 1  /* TM_CCORR_NORMED, argmax, first maximum wins              (DisparityNCorr.cpp:60-67) */
+} stereo_cost;
+
+/* Which kernel family served the last call (for tests and reports). */
+typedef enum stereo_path {
+    STEREO_PATH_NONE = 0,
+    STEREO_PATH_EXACT_F32 = 1,  /* general float path: per-element reference arithmetic */
+    STEREO_PATH_FAST_U8 = 2     /* integer-valued 0..255 inputs: packed dot-product running sums */
+} stereo_path;
+
+typedef struct stereo_ctx stereo_ctx;
+
+/* ---- library / context ------------------------------------------------------------------- */
+
+int stereo_abi_version(void);
+const char* stereo_last_error(void);
+const char* stereo_status_string(int status);
+
+/* Number of visible CUDA devices of compute capability 10.x (0 if none / no driver). */
+int stereo_device_count(void);
+
+/* Creates a context on `device` (ordinal).  Replaces the per-call GpuMat/Stream setup of
+ * DisparitySSD.cu:163-182 and common::warmup() (common/src/CudaWarmup.cu:14-19). */
+int stereo_ctx_create(int device, stereo_ctx** ctx_out);
+void stereo_ctx_destroy(stereo_ctx* ctx);
+
+/* Kernel family used by the most recent compute call on this context (stereo_path). */
+int stereo_ctx_last_path(const stereo_ctx* ctx);
+/* Device time of the most recent compute call's kernels in milliseconds (cudaEvent pair; the
+ * reference logs the same quantity, DisparitySSD.cu:192-203).  <0 if unavailable. */
+float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
+/* Number of kernel launches issued by the most recent compute call. */
+int stereo_ctx_last_launches(const stereo_ctx* ctx);
+/* Force a kernel family (debug/testing): 0 = automatic, else a stereo_path value. */
+int stereo_ctx_force_path(stereo_ctx* ctx, int path);
+
+/* ---- single direction, HOST buffers (the drop-in form) ------------------------------------ */
+/*
+ * One disparity map for reference image `ref` searched in `tgt` over [min_disp, max_disp].
+ * Replaces cuda::disparitySSD / cuda::disparityNCorr (host cv::Mat in, host cv::Mat out;
+ * upload, kernels and download happen inside, synchronously — DisparitySSD.cu:171-206).
+ *   disp_out        rows x cols elements of disp_elem_bytes (1, 2 or 4), row stride disp_step bytes
+ *   best_out        optional (NULL to skip) rows x cols winning values, row stride best_step bytes:
+ *                   SSD  -> int32 cost  (99999999 where no candidate exists, DisparitySSD.cpp:37)
+ *                   NCC  -> float32 score (the result[] value minMaxLoc selected, DisparityNCorr.cpp:60-64)
+ */
+int stereo_disparity_f32_host(stereo_ctx* ctx, int cost,
+                              const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                              int rows, int cols, int window_rad, int min_disp, int max_disp,
+                              void* disp_out, size_t disp_step, int disp_elem_bytes,
+                              void* best_out, size_t best_step);
+
+int stereo_disparity_u8_host(stereo_ctx* ctx, int cost,
+                             const uint8_t* ref, size_t ref_step, const uint8_t* tgt, size_t tgt_step,
+                             int rows, int cols, int window_rad, int min_disp, int max_disp,
+                             void* disp_out, size_t disp_step, int disp_elem_bytes,
+                             void* best_out, size_t best_step);
+
+/* ---- single direction, DEVICE buffers, asynchronous on `cuda_stream` ----------------------- */
+/* Same computation with every pointer a device pointer on the context's device.  `cuda_stream` is a
+ * cudaStream_t passed as void* (NULL = the context's own stream).  Returns after enqueueing. */
+int stereo_disparity_f32_device(stereo_ctx* ctx, int cost,
+                                const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                                int rows, int cols, int window_rad, int min_disp, int max_disp,
+                                void* disp_out, size_t disp_step, int disp_elem_bytes,
+                                void* best_out, size_t best_step, void* cuda_stream);
+
+int stereo_disparity_u8_device(stereo_ctx* ctx, int cost,
+                               const uint8_t* ref, size_t ref_step, const uint8_t* tgt, size_t tgt_step,
+                               int rows, int cols, int window_rad, int min_disp, int max_disp,
+                               void* disp_out, size_t disp_step, int disp_elem_bytes,
+                               void* best_out, size_t best_step, void* cuda_stream);
+
+/* ---- both directions (the reference's *Pair helpers, main.cpp:21-78) ------------------------ */
+/* left-referenced map over [-disparity_range, 0] into disp_left, right-referenced map over
+ * [0, +disparity_range] (images swapped) into disp_right.  Host buffers, synchronous. */
+int stereo_disparity_pair_f32_host(stereo_ctx* ctx, int cost,
+                                   const float* left, size_t left_step, const float* right, size_t right_step,
+                                   int rows, int cols, int window_rad, int disparity_range,
+                                   void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+
+int stereo_disparity_pair_u8_host(stereo_ctx* ctx, int cost,
+                                  const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step,
+                                  int rows, int cols, int window_rad, int disparity_range,
+                                  void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+
+/* Device buffers, asynchronous on `cuda_stream`. */
+int stereo_disparity_pair_u8_device(stereo_ctx* ctx, int cost,
+                                    const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step,
+                                    int rows, int cols, int window_rad, int disparity_range,
+                                    void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes,
+                                    void* cuda_stream);
+
+/* ---- batches of equally-shaped pairs (BASELINE config 5) ------------------------------------ */
+/* `n_pairs` image pairs stored back to back: pair i's left image starts at left + i*pair_stride
+ * bytes (same for right); outputs start at disp_* + i*disp_pair_stride bytes.  Device buffers,
+ * asynchronous on `cuda_stream`. */
+int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs,
+                                          const uint8_t* left, const uint8_t* right, size_t img_step,
+                                          size_t pair_stride, int rows, int cols, int window_rad,
+                                          int disparity_range, void* disp_left, void* disp_right,
+                                          size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes,
+                                          void* cuda_stream);
+
+/* Host buffers, synchronous: uploads, computes and downloads with copies overlapped across pairs. */
+int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs,
+                                        const uint8_t* left, const uint8_t* right, size_t img_step,
+                                        size_t pair_stride, int rows, int cols, int window_rad,
+                                        int disparity_range, void* disp_left, void* disp_right,
+                                        size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes);
+
+/* ---- row-band form for sharding one large image across GPUs (BASELINE config 4) -------------- */
+/* Computes output rows [row_begin, row_end) of the full rows x cols problem.  `ref`/`tgt` point at
+ * FULL images (device); only rows within the band's halo are read.  disp_out points at the band's
+ * first output row.  Results equal the corresponding rows of the full-image call, including the
+ * reference's row-wrap reads at band seams. */
+int stereo_disparity_band_u8_device(stereo_ctx* ctx, int cost,
+                                    const uint8_t* ref, size_t ref_step, const uint8_t* tgt, size_t tgt_step,
+                                    int rows, int cols, int row_begin, int row_end,
+                                    int window_rad, int min_disp, int max_disp,
+                                    void* disp_out, size_t disp_step, int disp_elem_bytes, void* cuda_stream);
+
+/* Blocks until everything enqueued on `cuda_stream` (NULL = the context's stream) has finished and
+ * returns any asynchronous error. */
+int stereo_ctx_synchronize(stereo_ctx* ctx, void* cuda_stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* STEREO_B200_H_ */

@@ -1,0 +1,90 @@
+// Shared declarations for the stereo_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/stereo_b200.h"
+
+namespace sb {
+
+// ---- error plumbing: status codes out, never exit() (contrast: common/CudaCommon.cuh:11-22) ----
+void set_error(const char* fmt, ...);
+#define SB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            sb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return STEREO_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+// The reference's launch-geometry helper (common/include/common/Utils.h:12-15): ceil-div, min 1.
+static inline unsigned div_round_up(long long num, long long den) {
+    long long v = (num + den - 1) / den;
+    return (unsigned)(v < 1 ? 1 : v);
+}
+
+enum class PixType : int { U8 = 0, F32 = 1 };
+
+struct ImageView {       // device image
+    const void* ptr;
+    size_t step;         // bytes
+    PixType type;
+};
+
+struct OutView {         // device output
+    void* ptr;
+    size_t step;         // bytes
+    int elem;            // 1,2,4 (disparity) — best maps are always 4 bytes
+};
+
+// One direction of one image pair.
+struct Problem {
+    int cost;            // stereo_cost
+    ImageView ref, tgt;
+    int rows, cols;      // full image
+    int row_begin, row_end;   // output band (full image: 0, rows)
+    int R, dmin, dmax;
+    OutView disp;        // first row of the band
+    OutView best;        // optional (ptr == nullptr)
+};
+
+// Grow-only device scratch arena owned by a context; sub-allocations are 256-byte aligned and
+// valid until the next reset().
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes);          // (re)allocate to at least `bytes`; invalidates contents
+    void reset() { used = 0; }
+    void* take(size_t bytes) {
+        size_t off = (used + 255) & ~size_t(255);
+        if (off + bytes > cap) return nullptr;
+        used = off + bytes;
+        return base + off;
+    }
+    void release();
+};
+
+} // namespace sb
+
+struct stereo_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_pending = false;
+    sb::Arena arena;          // per-call scratch (padded images, packed rows, partial keys)
+    sb::Arena io;             // device staging of host-API inputs/outputs
+    void* pinned = nullptr;   // pinned host staging
+    size_t pinned_cap = 0;
+    int* d_flag = nullptr;    // device classification flag
+    int* h_flag = nullptr;    // pinned mirror
+    int last_path = 0;
+    int last_launches = 0;
+    float last_ms = -1.f;
+    int force_path = 0;
+};

@@ -1,0 +1,585 @@
+// stereo_b200 — C ABI implementation (context, validation, path selection, staging).
+// Kernels: exact.cuh (general float path), fast.cuh (packed u8 path).  sm_100a only.
+#include "common.cuh"
+#include "exact.cuh"
+#include "fast.cuh"
+
+#include <cstdarg>
+#include <new>
+#include <vector>
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int Arena::reserve(size_t bytes) {
+    if (bytes <= cap) return STEREO_OK;
+    release();
+    size_t want = bytes + (bytes >> 3) + (1u << 20);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), want);
+    if (e != cudaSuccess) {
+        base = nullptr; cap = 0;
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return STEREO_ERR_ALLOC;
+    }
+    cap = want;
+    return STEREO_OK;
+}
+
+void Arena::release() {
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0; used = 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+// ---- validation ---------------------------------------------------------------------------------
+
+static int validate(const Problem& p, size_t ref_min_step, size_t tgt_min_step) {
+    if (!p.ref.ptr || !p.tgt.ptr || !p.disp.ptr) { set_error("null image/output pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (p.rows <= 0 || p.cols <= 0) { set_error("rows/cols must be positive (got %d x %d)", p.rows, p.cols); return STEREO_ERR_INVALID_ARG; }
+    if (p.rows > 32768 || p.cols > 32768) { set_error("image larger than 32768 in a dimension"); return STEREO_ERR_UNSUPPORTED; }
+    if (p.R < 0 || p.R > 64) { set_error("window_rad must be in [0, 64] (got %d)", p.R); return STEREO_ERR_INVALID_ARG; }
+    if (p.cost != STEREO_COST_SSD && p.cost != STEREO_COST_NCORR) { set_error("unknown cost %d", p.cost); return STEREO_ERR_INVALID_ARG; }
+    if (p.disp.elem != 1 && p.disp.elem != 2 && p.disp.elem != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    if (p.ref.step < ref_min_step || p.tgt.step < tgt_min_step) { set_error("image step smaller than a row"); return STEREO_ERR_INVALID_ARG; }
+    if (p.disp.step < size_t(p.cols) * p.disp.elem) { set_error("disp_step smaller than a row"); return STEREO_ERR_INVALID_ARG; }
+    if (p.best.ptr && p.best.step < size_t(p.cols) * 4) { set_error("best_step smaller than a row"); return STEREO_ERR_INVALID_ARG; }
+    if (p.dmin > p.dmax) { set_error("min_disp (%d) > max_disp (%d)", p.dmin, p.dmax); return STEREO_ERR_INVALID_RANGE; }
+    if (p.dmin < -32768 || p.dmax > 32768) { set_error("disparity range outside [-32768, 32768]"); return STEREO_ERR_INVALID_RANGE; }
+    if (p.row_begin < 0 || p.row_end > p.rows || p.row_begin >= p.row_end) { set_error("bad row band [%d, %d)", p.row_begin, p.row_end); return STEREO_ERR_INVALID_ARG; }
+    if (p.cost == STEREO_COST_NCORR) {
+        // Every pixel needs >= 1 candidate window; the reference would throw inside
+        // cv::Mat::operator()(Rect) otherwise (DisparityNCorr.cpp:50-53).
+        const int Wp = p.cols + 2 * p.R, w = 2 * p.R + 1;
+        // ncand(x) is piecewise linear in x: checking both ends and the clamp knees suffices,
+        // checking every column is cheap enough and obviously right.
+        for (int x = p.R; x < Wp - p.R; ++x) {
+            long s = long(x) + p.dmin - p.R; if (s < 0) s = 0;
+            long e = long(x) + p.dmax + 1 + p.R; if (e > Wp) e = Wp;
+            if (e - s - w + 1 <= 0) {
+                set_error("NCC range [%d, %d] leaves column %d without a candidate", p.dmin, p.dmax, x - p.R);
+                return STEREO_ERR_INVALID_RANGE;
+            }
+        }
+    }
+    return STEREO_OK;
+}
+
+// ---- exact path ---------------------------------------------------------------------------------
+
+static size_t exact_scratch_bytes(const Problem& p) {
+    const size_t Hp = p.rows + 2 * p.R, Wp = p.cols + 2 * p.R, guard = size_t(p.R) + 64;
+    const size_t img = align256((Hp * Wp + 2 * guard) * sizeof(float));
+    const size_t band = size_t(p.row_end - p.row_begin) * p.cols;
+    return 2 * img + 2 * align256(band * 4) + 4096;
+}
+
+static int run_exact(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
+    const int Hp = p.rows + 2 * p.R, Wp = p.cols + 2 * p.R;
+    const size_t guard = size_t(p.R) + 64;
+    const size_t img_elems = size_t(Hp) * Wp + 2 * guard;
+    float* lbuf = static_cast<float*>(ctx->arena.take(img_elems * sizeof(float)));
+    float* rbuf = static_cast<float*>(ctx->arena.take(img_elems * sizeof(float)));
+    const int band_rows = p.row_end - p.row_begin;
+    int32_t* d_disp = static_cast<int32_t*>(ctx->arena.take(size_t(band_rows) * p.cols * 4));
+    uint32_t* d_best = static_cast<uint32_t*>(ctx->arena.take(size_t(band_rows) * p.cols * 4));
+    if (!lbuf || !rbuf || !d_disp || !d_best) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    // zero guards (the tgt guard stands in for the reference's out-of-allocation reads)
+    SB_CUDA(cudaMemsetAsync(rbuf, 0, guard * sizeof(float), st));
+    SB_CUDA(cudaMemsetAsync(rbuf + guard + size_t(Hp) * Wp, 0, guard * sizeof(float), st));
+    float* Lp = lbuf + guard;
+    float* Rp = rbuf + guard;
+    dim3 pb(32, 8), pg(div_round_up(Wp, 32), div_round_up(Hp, 8));
+    if (p.ref.type == PixType::F32)
+        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp);
+    else
+        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp);
+    if (p.tgt.type == PixType::F32)
+        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp);
+    else
+        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp);
+    ctx->last_launches += 2;
+    dim3 kb(128), kg(div_round_up(p.cols, 128), band_rows);
+    if (p.cost == STEREO_COST_SSD)
+        ssd_exact_kernel<<<kg, kb, 0, st>>>(Lp, Rp, p.rows, p.cols, p.R, p.dmin, p.dmax, p.row_begin, d_disp,
+                                            reinterpret_cast<int32_t*>(d_best), 0, p.cols);
+    else
+        ncorr_exact_kernel<<<kg, kb, 0, st>>>(Lp, Rp, p.rows, p.cols, p.R, p.dmin, p.dmax, p.row_begin, d_disp,
+                                              reinterpret_cast<float*>(d_best));
+    store_output_kernel<<<kg, kb, 0, st>>>(d_disp, d_best, band_rows, p.cols, p.disp.ptr, p.disp.step, p.disp.elem,
+                                           p.best.ptr, p.best.step);
+    ctx->last_launches += 2;
+    SB_CUDA(cudaGetLastError());
+    return STEREO_OK;
+}
+
+// ---- path selection -------------------------------------------------------------------------------
+
+// Enqueues one direction.  For f32 inputs the "is this image really 8-bit" flag has to reach the
+// host to choose the kernel family: one 4-byte read-back and a stream synchronize.
+static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_arena = true) {
+    const size_t min_ref = size_t(p.cols) * (p.ref.type == PixType::F32 ? 4 : 1);
+    const size_t min_tgt = size_t(p.cols) * (p.tgt.type == PixType::F32 ? 4 : 1);
+    int rc = validate(p, min_ref, min_tgt);
+    if (rc != STEREO_OK) return rc;
+
+    const bool fast_ok = fast_supported(p) && ctx->force_path != STEREO_PATH_EXACT_F32;
+    size_t need = exact_scratch_bytes(p);
+    size_t u8_bytes = 0;
+    if (fast_ok) {
+        need = need > fast_scratch_bytes(ctx, p) ? need : fast_scratch_bytes(ctx, p);
+        u8_bytes = 2 * align256(size_t(p.rows) * align256(p.cols));
+        need += u8_bytes;
+    }
+    if (need > ctx->arena.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        rc = ctx->arena.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    if (reset_arena) ctx->arena.reset();
+
+    bool use_fast = fast_ok;
+    if (fast_ok && (p.ref.type == PixType::F32 || p.tgt.type == PixType::F32)) {
+        // classify + convert both images to u8 copies
+        const size_t pitch = align256(p.cols);
+        uint8_t* a8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
+        uint8_t* b8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
+        if (!a8 || !b8) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+        SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+        dim3 cb(32, 8), cg(div_round_up(p.cols, 32), div_round_up(p.rows, 8));
+        Problem q = p;
+        if (p.ref.type == PixType::F32) {
+            classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, a8, pitch, ctx->d_flag);
+            q.ref = ImageView{a8, pitch, PixType::U8};
+            ctx->last_launches++;
+        }
+        if (p.tgt.type == PixType::F32) {
+            classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, b8, pitch, ctx->d_flag);
+            q.tgt = ImageView{b8, pitch, PixType::U8};
+            ctx->last_launches++;
+        }
+        SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        use_fast = (*ctx->h_flag == 0);
+        if (use_fast) p = q;
+    }
+    if (use_fast) {
+        ctx->last_path = STEREO_PATH_FAST_U8;
+        return run_fast(ctx, p, st);
+    }
+    if (ctx->force_path == STEREO_PATH_FAST_U8) {
+        set_error("fast u8 path forced but not applicable (non-8-bit input or unsupported window/range)");
+        return STEREO_ERR_UNSUPPORTED;
+    }
+    ctx->last_path = STEREO_PATH_EXACT_F32;
+    return run_exact(ctx, p, st);
+}
+
+static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
+    ctx->last_launches = 0;
+    ctx->last_ms = -1.f;
+    ctx->last_path = STEREO_PATH_NONE;
+    cudaEventRecord(ctx->ev0, st);
+}
+static void end_call(stereo_ctx* ctx, cudaStream_t st) {
+    cudaEventRecord(ctx->ev1, st);
+    ctx->timing_pending = true;
+}
+
+static int check_ctx(stereo_ctx* ctx) {
+    if (!ctx) { set_error("null context"); return STEREO_ERR_INVALID_ARG; }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+    return STEREO_OK;
+}
+
+static int ensure_pinned(stereo_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return STEREO_OK;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr; ctx->pinned_cap = 0;
+    cudaError_t e = cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); (void)cudaGetLastError(); return STEREO_ERR_ALLOC; }
+    ctx->pinned_cap = bytes;
+    return STEREO_OK;
+}
+
+// Host-buffer single direction: upload (2D async copies), compute, download, synchronize — the
+// shape of cuda::disparitySSD (DisparitySSD.cu:171-206) without per-call allocation.
+static int host_single(stereo_ctx* ctx, int cost, PixType type, const void* ref, size_t ref_step, const void* tgt,
+                       size_t tgt_step, int rows, int cols, int R, int dmin, int dmax, void* disp_out,
+                       size_t disp_step, int elem, void* best_out, size_t best_step) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!ref || !tgt || !disp_out) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768) { set_error("bad image size %d x %d", rows, cols); return STEREO_ERR_INVALID_ARG; }
+    if (elem != 1 && elem != 2 && elem != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    const size_t px = type == PixType::F32 ? 4 : 1;
+    if (ref_step < cols * px || tgt_step < cols * px || disp_step < size_t(cols) * elem || (best_out && best_step < size_t(cols) * 4)) {
+        set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t in_pitch = align256(cols * px), d_pitch = align256(size_t(cols) * elem), b_pitch = align256(size_t(cols) * 4);
+    const size_t need = 2 * in_pitch * rows + d_pitch * rows + (best_out ? b_pitch * rows : 0) + 1024;
+    if (need > ctx->io.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        rc = ctx->io.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->io.reset();
+    char* d_ref = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_tgt = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_disp = static_cast<char*>(ctx->io.take(d_pitch * rows));
+    char* d_best = best_out ? static_cast<char*>(ctx->io.take(b_pitch * rows)) : nullptr;
+    SB_CUDA(cudaMemcpy2DAsync(d_ref, in_pitch, ref, ref_step, cols * px, rows, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpy2DAsync(d_tgt, in_pitch, tgt, tgt_step, cols * px, rows, cudaMemcpyHostToDevice, st));
+    Problem p{};
+    p.cost = cost;
+    p.ref = ImageView{d_ref, in_pitch, type};
+    p.tgt = ImageView{d_tgt, in_pitch, type};
+    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows;
+    p.R = R; p.dmin = dmin; p.dmax = dmax;
+    p.disp = OutView{d_disp, d_pitch, elem};
+    p.best = OutView{d_best, b_pitch, 4};
+    begin_call(ctx, st);
+    rc = run_problem(ctx, p, st);
+    end_call(ctx, st);
+    if (rc != STEREO_OK) return rc;
+    SB_CUDA(cudaMemcpy2DAsync(disp_out, disp_step, d_disp, d_pitch, size_t(cols) * elem, rows, cudaMemcpyDeviceToHost, st));
+    if (best_out) SB_CUDA(cudaMemcpy2DAsync(best_out, best_step, d_best, b_pitch, size_t(cols) * 4, rows, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return STEREO_OK;
+}
+
+static int device_single(stereo_ctx* ctx, int cost, PixType type, const void* ref, size_t ref_step, const void* tgt,
+                         size_t tgt_step, int rows, int cols, int row_begin, int row_end, int R, int dmin, int dmax,
+                         void* disp_out, size_t disp_step, int elem, void* best_out, size_t best_step, void* stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Problem p{};
+    p.cost = cost;
+    p.ref = ImageView{ref, ref_step, type};
+    p.tgt = ImageView{tgt, tgt_step, type};
+    p.rows = rows; p.cols = cols; p.row_begin = row_begin; p.row_end = row_end;
+    p.R = R; p.dmin = dmin; p.dmax = dmax;
+    p.disp = OutView{disp_out, disp_step, elem};
+    p.best = OutView{best_out, best_step, 4};
+    begin_call(ctx, st);
+    rc = run_problem(ctx, p, st);
+    end_call(ctx, st);
+    return rc;
+}
+
+} // namespace sb
+
+using namespace sb;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+
+extern "C" {
+
+int stereo_abi_version(void) { return STEREO_B200_ABI_VERSION; }
+
+const char* stereo_last_error(void) { return g_err; }
+
+const char* stereo_status_string(int status) {
+    switch (status) {
+    case STEREO_OK: return "ok";
+    case STEREO_ERR_INVALID_ARG: return "invalid argument";
+    case STEREO_ERR_INVALID_RANGE: return "invalid disparity range";
+    case STEREO_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case STEREO_ERR_CUDA: return "CUDA error";
+    case STEREO_ERR_ALLOC: return "allocation failed";
+    case STEREO_ERR_UNSUPPORTED: return "unsupported parameters";
+    default: return "unknown status";
+    }
+}
+
+int stereo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int stereo_ctx_create(int device, stereo_ctx** ctx_out) {
+    if (!ctx_out) { set_error("ctx_out is null"); return STEREO_ERR_INVALID_ARG; }
+    *ctx_out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return STEREO_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range [0, %d)", device, n); return STEREO_ERR_INVALID_ARG; }
+    int major = 0, sms = 0;
+    SB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) { set_error("device %d is sm_%d0; this library is built for sm_100a only", device, major); return STEREO_ERR_NO_DEVICE; }
+    SB_CUDA(cudaSetDevice(device));
+    stereo_ctx* c = new (std::nothrow) stereo_ctx();
+    if (!c) { set_error("out of host memory"); return STEREO_ERR_ALLOC; }
+    c->device = device;
+    c->sm_count = sms;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_flag), 256);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_flag), 256, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error("context setup failed: %s", cudaGetErrorString(e));
+        stereo_ctx_destroy(c);
+        return STEREO_ERR_CUDA;
+    }
+    int rc = fast_ctx_init(c);
+    if (rc != STEREO_OK) { stereo_ctx_destroy(c); return rc; }
+    *ctx_out = c;
+    return STEREO_OK;
+}
+
+void stereo_ctx_destroy(stereo_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); }
+    ctx->arena.release();
+    ctx->io.release();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int stereo_ctx_last_path(const stereo_ctx* ctx) { return ctx ? ctx->last_path : 0; }
+
+float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx) {
+    if (!ctx) return -1.f;
+    stereo_ctx* c = const_cast<stereo_ctx*>(ctx);
+    if (c->timing_pending) {
+        float ms = -1.f;
+        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+        else (void)cudaGetLastError();
+        c->timing_pending = false;
+    }
+    return c->last_ms;
+}
+
+int stereo_ctx_last_launches(const stereo_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
+    if (!ctx || path < 0 || path > STEREO_PATH_FAST_U8) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }
+    ctx->force_path = path;
+    return STEREO_OK;
+}
+
+int stereo_ctx_synchronize(stereo_ctx* ctx, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    SB_CUDA(cudaStreamSynchronize(cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream));
+    return STEREO_OK;
+}
+
+int stereo_disparity_f32_host(stereo_ctx* ctx, int cost, const float* ref, size_t ref_step, const float* tgt,
+                              size_t tgt_step, int rows, int cols, int window_rad, int min_disp, int max_disp,
+                              void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out, size_t best_step) {
+    return host_single(ctx, cost, PixType::F32, ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp,
+                       max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step);
+}
+
+int stereo_disparity_u8_host(stereo_ctx* ctx, int cost, const uint8_t* ref, size_t ref_step, const uint8_t* tgt,
+                             size_t tgt_step, int rows, int cols, int window_rad, int min_disp, int max_disp,
+                             void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out, size_t best_step) {
+    return host_single(ctx, cost, PixType::U8, ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp,
+                       max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step);
+}
+
+int stereo_disparity_f32_device(stereo_ctx* ctx, int cost, const float* ref, size_t ref_step, const float* tgt,
+                                size_t tgt_step, int rows, int cols, int window_rad, int min_disp, int max_disp,
+                                void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out,
+                                size_t best_step, void* cuda_stream) {
+    return device_single(ctx, cost, PixType::F32, ref, ref_step, tgt, tgt_step, rows, cols, 0, rows, window_rad,
+                         min_disp, max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step, cuda_stream);
+}
+
+int stereo_disparity_u8_device(stereo_ctx* ctx, int cost, const uint8_t* ref, size_t ref_step, const uint8_t* tgt,
+                               size_t tgt_step, int rows, int cols, int window_rad, int min_disp, int max_disp,
+                               void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out,
+                               size_t best_step, void* cuda_stream) {
+    return device_single(ctx, cost, PixType::U8, ref, ref_step, tgt, tgt_step, rows, cols, 0, rows, window_rad,
+                         min_disp, max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step, cuda_stream);
+}
+
+int stereo_disparity_band_u8_device(stereo_ctx* ctx, int cost, const uint8_t* ref, size_t ref_step,
+                                    const uint8_t* tgt, size_t tgt_step, int rows, int cols, int row_begin,
+                                    int row_end, int window_rad, int min_disp, int max_disp, void* disp_out,
+                                    size_t disp_step, int disp_elem_bytes, void* cuda_stream) {
+    return device_single(ctx, cost, PixType::U8, ref, ref_step, tgt, tgt_step, rows, cols, row_begin, row_end,
+                         window_rad, min_disp, max_disp, disp_out, disp_step, disp_elem_bytes, nullptr, 0, cuda_stream);
+}
+
+// ---- pairs: L->R over [-range, 0], then R->L with images swapped over [0, +range] (main.cpp:21-48) ----
+
+static int pair_device(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
+                       size_t right_step, int rows, int cols, int R, int range, void* disp_left, void* disp_right,
+                       size_t disp_step, int elem, cudaStream_t st) {
+    if (range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
+    Problem p{};
+    p.cost = cost;
+    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows; p.R = R;
+    p.best = OutView{nullptr, 0, 4};
+    p.ref = ImageView{left, left_step, type}; p.tgt = ImageView{right, right_step, type};
+    p.dmin = -range; p.dmax = 0; p.disp = OutView{disp_left, disp_step, elem};
+    int rc = run_problem(ctx, p, st);
+    if (rc != STEREO_OK) return rc;
+    p.ref = ImageView{right, right_step, type}; p.tgt = ImageView{left, left_step, type};
+    p.dmin = 0; p.dmax = range; p.disp = OutView{disp_right, disp_step, elem};
+    return run_problem(ctx, p, st);
+}
+
+static int pair_host(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
+                     size_t right_step, int rows, int cols, int R, int range, void* disp_left, void* disp_right,
+                     size_t disp_step, int elem) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768) { set_error("bad image size %d x %d", rows, cols); return STEREO_ERR_INVALID_ARG; }
+    if (elem != 1 && elem != 2 && elem != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    const size_t px = type == PixType::F32 ? 4 : 1;
+    if (left_step < cols * px || right_step < cols * px || disp_step < size_t(cols) * elem) { set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t st = ctx->stream;
+    const size_t in_pitch = align256(cols * px), d_pitch = align256(size_t(cols) * elem);
+    const size_t need = 2 * in_pitch * rows + 2 * d_pitch * rows + 1024;
+    if (need > ctx->io.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        rc = ctx->io.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->io.reset();
+    char* d_l = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_r = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_dl = static_cast<char*>(ctx->io.take(d_pitch * rows));
+    char* d_dr = static_cast<char*>(ctx->io.take(d_pitch * rows));
+    SB_CUDA(cudaMemcpy2DAsync(d_l, in_pitch, left, left_step, cols * px, rows, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpy2DAsync(d_r, in_pitch, right, right_step, cols * px, rows, cudaMemcpyHostToDevice, st));
+    begin_call(ctx, st);
+    rc = pair_device(ctx, cost, type, d_l, in_pitch, d_r, in_pitch, rows, cols, R, range, d_dl, d_dr, d_pitch, elem, st);
+    end_call(ctx, st);
+    if (rc != STEREO_OK) return rc;
+    SB_CUDA(cudaMemcpy2DAsync(disp_left, disp_step, d_dl, d_pitch, size_t(cols) * elem, rows, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpy2DAsync(disp_right, disp_step, d_dr, d_pitch, size_t(cols) * elem, rows, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return STEREO_OK;
+}
+
+int stereo_disparity_pair_f32_host(stereo_ctx* ctx, int cost, const float* left, size_t left_step, const float* right,
+                                   size_t right_step, int rows, int cols, int window_rad, int disparity_range,
+                                   void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes) {
+    return pair_host(ctx, cost, PixType::F32, left, left_step, right, right_step, rows, cols, window_rad,
+                     disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes);
+}
+
+int stereo_disparity_pair_u8_host(stereo_ctx* ctx, int cost, const uint8_t* left, size_t left_step,
+                                  const uint8_t* right, size_t right_step, int rows, int cols, int window_rad,
+                                  int disparity_range, void* disp_left, void* disp_right, size_t disp_step,
+                                  int disp_elem_bytes) {
+    return pair_host(ctx, cost, PixType::U8, left, left_step, right, right_step, rows, cols, window_rad,
+                     disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes);
+}
+
+int stereo_disparity_pair_u8_device(stereo_ctx* ctx, int cost, const uint8_t* left, size_t left_step,
+                                    const uint8_t* right, size_t right_step, int rows, int cols, int window_rad,
+                                    int disparity_range, void* disp_left, void* disp_right, size_t disp_step,
+                                    int disp_elem_bytes, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    begin_call(ctx, st);
+    rc = pair_device(ctx, cost, PixType::U8, left, left_step, right, right_step, rows, cols, window_rad,
+                     disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes, st);
+    end_call(ctx, st);
+    return rc;
+}
+
+int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
+                                          const uint8_t* right, size_t img_step, size_t pair_stride, int rows,
+                                          int cols, int window_rad, int disparity_range, void* disp_left,
+                                          void* disp_right, size_t disp_step, size_t disp_pair_stride,
+                                          int disp_elem_bytes, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (n_pairs <= 0) { set_error("n_pairs must be positive"); return STEREO_ERR_INVALID_ARG; }
+    if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    begin_call(ctx, st);
+    for (int i = 0; i < n_pairs && rc == STEREO_OK; ++i) {
+        rc = pair_device(ctx, cost, PixType::U8, left + size_t(i) * pair_stride, img_step,
+                         right + size_t(i) * pair_stride, img_step, rows, cols, window_rad, disparity_range,
+                         static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride,
+                         static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, disp_elem_bytes, st);
+    }
+    end_call(ctx, st);
+    return rc;
+}
+
+int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
+                                        const uint8_t* right, size_t img_step, size_t pair_stride, int rows, int cols,
+                                        int window_rad, int disparity_range, void* disp_left, void* disp_right,
+                                        size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (n_pairs <= 0) { set_error("n_pairs must be positive"); return STEREO_ERR_INVALID_ARG; }
+    if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || img_step < size_t(cols) || disp_step < size_t(cols) * disp_elem_bytes) { set_error("bad size/step"); return STEREO_ERR_INVALID_ARG; }
+    if (disp_elem_bytes != 1 && disp_elem_bytes != 2 && disp_elem_bytes != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t st = ctx->stream;
+    // Stage the whole batch on the device (sized for 180 GB of HBM; a 512 x 720p batch is ~1.4 GB).
+    const size_t in_pitch = align256(cols), d_pitch = align256(size_t(cols) * disp_elem_bytes);
+    const size_t in_pair = in_pitch * rows, d_pair = d_pitch * rows;
+    const size_t need = size_t(n_pairs) * (2 * in_pair + 2 * d_pair) + 4096;
+    if (need > ctx->io.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        rc = ctx->io.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->io.reset();
+    uint8_t* d_l = static_cast<uint8_t*>(ctx->io.take(size_t(n_pairs) * in_pair));
+    uint8_t* d_r = static_cast<uint8_t*>(ctx->io.take(size_t(n_pairs) * in_pair));
+    char* d_dl = static_cast<char*>(ctx->io.take(size_t(n_pairs) * d_pair));
+    char* d_dr = static_cast<char*>(ctx->io.take(size_t(n_pairs) * d_pair));
+    begin_call(ctx, st);
+    for (int i = 0; i < n_pairs && rc == STEREO_OK; ++i) {
+        SB_CUDA(cudaMemcpy2DAsync(d_l + i * in_pair, in_pitch, left + size_t(i) * pair_stride, img_step, cols, rows, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpy2DAsync(d_r + i * in_pair, in_pitch, right + size_t(i) * pair_stride, img_step, cols, rows, cudaMemcpyHostToDevice, st));
+        rc = pair_device(ctx, cost, PixType::U8, d_l + i * in_pair, in_pitch, d_r + i * in_pair, in_pitch, rows, cols,
+                         window_rad, disparity_range, d_dl + i * d_pair, d_dr + i * d_pair, d_pitch, disp_elem_bytes, st);
+        if (rc != STEREO_OK) break;
+        SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride, disp_step, d_dl + i * d_pair, d_pitch,
+                                  size_t(cols) * disp_elem_bytes, rows, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, d_dr + i * d_pair, d_pitch,
+                                  size_t(cols) * disp_elem_bytes, rows, cudaMemcpyDeviceToHost, st));
+    }
+    end_call(ctx, st);
+    if (rc != STEREO_OK) return rc;
+    SB_CUDA(cudaStreamSynchronize(st));
+    return STEREO_OK;
+}
+
+} // extern "C"

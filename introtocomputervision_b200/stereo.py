@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference's ps2 disparity interface on top of the C ABI.
+
+Reference surface reproduced (names, argument meaning, error behaviour):
+
+* ``cuda::disparitySSD(left, right, windowRad, minDisparity, maxDisparity, disparity)``
+  — ProblemSets/ps2_cpp/include/DisparitySSD.h:18-23
+* ``cuda::disparityNCorr(...)`` — ProblemSets/ps2_cpp/include/DisparityNCorr.h:19-24
+* ``disparitySSDPair`` / ``disparityNCorrPair`` — ProblemSets/ps2_cpp/src/main.cpp:21-48, 51-78
+* ``Config::DisparitySSD{_windowRadius, _disparityRange}`` — ProblemSets/ps2_cpp/include/Config.h:40-46
+
+Inputs are numpy arrays (the stand-in for ``cv::Mat``): float32 ``CV_32FC1`` like the reference
+asserts (DisparitySSD.cu:150), or uint8.  The returned disparity is int8 (``CV_8SC1``) by default,
+exactly like the reference; pass ``dtype=np.int16``/``np.int32`` for searches beyond 127.
+All computation happens in libstereo_b200.so on a B200; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import COST_NCORR, COST_SSD
+
+
+class StereoError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = _capi.last_error()
+        name = _capi.lib().stereo_status_string(status).decode()
+        super().__init__(f"{where}: {name} ({status}): {msg}")
+
+
+def _check(status: int, where: str) -> None:
+    if status != _capi.STEREO_OK:
+        raise StereoError(status, where)
+
+
+@dataclass
+class DisparityConfig:
+    """``Config::DisparitySSD`` (include/Config.h:40-46): YAML keys ``window_radius``, ``disparity_range``."""
+    window_radius: int
+    disparity_range: int
+
+
+_ELEM = {np.dtype(np.int8): 1, np.dtype(np.int16): 2, np.dtype(np.int32): 4}
+
+
+class Context:
+    """Owns the device-side state for one GPU (``stereo_ctx``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(_capi.lib().stereo_ctx_create(int(device), C.byref(self._h)), "stereo_ctx_create")
+        self.device = int(device)
+
+    def close(self) -> None:
+        if self._h:
+            _capi.lib().stereo_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- introspection -------------------------------------------------------------------------
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def last_path(self) -> int:
+        return int(_capi.lib().stereo_ctx_last_path(self._h))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(_capi.lib().stereo_ctx_last_kernel_ms(self._h))
+
+    @property
+    def last_launches(self) -> int:
+        return int(_capi.lib().stereo_ctx_last_launches(self._h))
+
+    def force_path(self, path: int) -> None:
+        _check(_capi.lib().stereo_ctx_force_path(self._h, int(path)), "stereo_ctx_force_path")
+
+    def synchronize(self, stream: int = 0) -> None:
+        _check(_capi.lib().stereo_ctx_synchronize(self._h, C.c_void_p(stream)), "stereo_ctx_synchronize")
+
+    # -- host-buffer entry points ----------------------------------------------------------------
+    def disparity(self, cost: int, ref: np.ndarray, tgt: np.ndarray, window_rad: int, min_disp: int, max_disp: int,
+                  dtype=np.int8, return_best: bool = False):
+        ref, tgt, fn = _prep_pair(ref, tgt, "stereo_disparity_f32_host", "stereo_disparity_u8_host")
+        rows, cols = ref.shape
+        dt = np.dtype(dtype)
+        disp = np.empty((rows, cols), dt)
+        best = np.empty((rows, cols), np.int32 if cost == COST_SSD else np.float32) if return_best else None
+        st = fn(self._h, int(cost), ref.ctypes.data, ref.strides[0], tgt.ctypes.data, tgt.strides[0], rows, cols,
+                int(window_rad), int(min_disp), int(max_disp), disp.ctypes.data, disp.strides[0], _ELEM[dt],
+                best.ctypes.data if return_best else None, best.strides[0] if return_best else 0)
+        _check(st, fn.__name__)
+        return (disp, best) if return_best else disp
+
+    def disparity_pair(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, disparity_range: int,
+                       dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
+        left, right, fn = _prep_pair(left, right, "stereo_disparity_pair_f32_host", "stereo_disparity_pair_u8_host")
+        rows, cols = left.shape
+        dt = np.dtype(dtype)
+        dl = np.empty((rows, cols), dt)
+        dr = np.empty((rows, cols), dt)
+        st = fn(self._h, int(cost), left.ctypes.data, left.strides[0], right.ctypes.data, right.strides[0], rows, cols,
+                int(window_rad), int(disparity_range), dl.ctypes.data, dr.ctypes.data, dl.strides[0], _ELEM[dt])
+        _check(st, fn.__name__)
+        return dl, dr
+
+    def disparity_pair_batch(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int,
+                             disparity_range: int, dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
+        """left/right: uint8 arrays of shape (n_pairs, rows, cols)."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        if left.ndim != 3 or left.shape != right.shape:
+            raise ValueError("batch inputs must be (n, rows, cols) uint8 arrays of equal shape")
+        n, rows, cols = left.shape
+        dt = np.dtype(dtype)
+        dl = np.empty((n, rows, cols), dt)
+        dr = np.empty((n, rows, cols), dt)
+        st = _capi.lib().stereo_disparity_pair_batch_u8_host(
+            self._h, int(cost), n, left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], rows, cols,
+            int(window_rad), int(disparity_range), dl.ctypes.data, dr.ctypes.data, dl.strides[1], dl.strides[0], _ELEM[dt])
+        _check(st, "stereo_disparity_pair_batch_u8_host")
+        return dl, dr
+
+
+def _prep_pair(a: np.ndarray, b: np.ndarray, f32_name: str, u8_name: str):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.ndim != 2 or a.shape != b.shape:
+        # the reference asserts equal sizes in its callers (main.cpp:28)
+        raise ValueError("left/right must be 2-D arrays of equal shape")
+    if a.dtype == np.uint8 and b.dtype == np.uint8:
+        kind, name = np.uint8, u8_name
+    elif a.dtype == np.float32 and b.dtype == np.float32:
+        kind, name = np.float32, f32_name
+    else:
+        # the reference: assert(left.type() == CV_32FC1 && right.type() == CV_32FC1) (DisparitySSD.cu:150)
+        raise TypeError("images must both be float32 (CV_32FC1) or both uint8")
+    a = a if a.strides[1] == a.itemsize else np.ascontiguousarray(a, kind)
+    b = b if b.strides[1] == b.itemsize else np.ascontiguousarray(b, kind)
+    return a, b, getattr(_capi.lib(), name)
+
+
+_default: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default
+    if _default is None:
+        _default = Context(0)
+    return _default
+
+
+# ---- the reference's four free functions ------------------------------------------------------------
+
+def disparitySSD(left, right, windowRad: int, minDisparity: int, maxDisparity: int, dtype=np.int8,
+                 ctx: Optional[Context] = None) -> np.ndarray:
+    """``cuda::disparitySSD`` (DisparitySSD.h:18-23).  ``left`` is the reference image."""
+    return (ctx or default_context()).disparity(COST_SSD, left, right, windowRad, minDisparity, maxDisparity, dtype)
+
+
+def disparityNCorr(left, right, windowRad: int, minDisparity: int, maxDisparity: int, dtype=np.int8,
+                   ctx: Optional[Context] = None) -> np.ndarray:
+    """``cuda::disparityNCorr`` (DisparityNCorr.h:19-24)."""
+    return (ctx or default_context()).disparity(COST_NCORR, left, right, windowRad, minDisparity, maxDisparity, dtype)
+
+
+def disparitySSDPair(left, right, config: DisparityConfig, dtype=np.int8, ctx: Optional[Context] = None):
+    """``disparitySSDPair`` (main.cpp:21-48): (left-referenced map, right-referenced map)."""
+    return (ctx or default_context()).disparity_pair(COST_SSD, left, right, config.window_radius,
+                                                     config.disparity_range, dtype)
+
+
+def disparityNCorrPair(left, right, config: DisparityConfig, dtype=np.int8, ctx: Optional[Context] = None):
+    """``disparityNCorrPair`` (main.cpp:51-78)."""
+    return (ctx or default_context()).disparity_pair(COST_NCORR, left, right, config.window_radius,
+                                                     config.disparity_range, dtype)

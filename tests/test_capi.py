@@ -1,0 +1,64 @@
+"""The C-ABI library: it loads, exports every symbol include/stereo_b200.h declares, the ctypes
+table covers the header, and without a GPU the compute path fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import introtocomputervision_b200 as sb
+from introtocomputervision_b200 import _capi
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_functions():
+    text = (ROOT / "include" / "stereo_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(stereo_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    names = header_functions()
+    assert len(names) >= 20
+    handle = C.CDLL(str(_capi.LIB_PATH))
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/stereo_b200.h but not exported"
+        assert n in _capi.SIGNATURES, f"{n} missing from the ctypes table"
+    assert sorted(_capi.SIGNATURES) == names
+
+
+def test_version_and_status_strings():
+    lib = _capi.lib()
+    assert lib.stereo_abi_version() == 1
+    assert lib.stereo_status_string(0) == b"ok"
+    assert b"range" in lib.stereo_status_string(_capi.ERR_INVALID_RANGE)
+
+
+def test_no_oracle_in_product():
+    # the product must never import/link the oracle (parity claims depend on it)
+    for p in (ROOT / "introtocomputervision_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".cpp"):
+            text = p.read_text()
+            for needle in ("import oracle", "from oracle", "oracle/", "libstereo_oracle", "libref_ssd", "stereo_oracle"):
+                assert needle not in text, f"{p} references the oracle ({needle})"
+
+
+@pytest.mark.skipif(_capi.lib().stereo_device_count() > 0, reason="GPU present")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(sb.StereoError) as e:
+        sb.Context(0)
+    assert e.value.status == _capi.ERR_NO_DEVICE
+    img = np.zeros((8, 8), np.float32)
+    with pytest.raises(sb.StereoError):
+        sb.disparitySSD(img, img, 1, -2, 0)
+
+
+def test_input_type_contract():
+    img = np.zeros((8, 8), np.float64)
+    with pytest.raises(TypeError):
+        sb.stereo._prep_pair(img, img, "stereo_disparity_f32_host", "stereo_disparity_u8_host")
+    with pytest.raises(ValueError):
+        sb.stereo._prep_pair(np.zeros((8, 8), np.float32), np.zeros((8, 9), np.float32),
+                             "stereo_disparity_f32_host", "stereo_disparity_u8_host")

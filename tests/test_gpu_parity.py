@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+SSD: bit-exact disparities (and costs).  NCC: winning score within 1e-5 relative and disparity equal
+on >= 99.9 % of pixels (BASELINE.json north_star); the exact path is expected to be identical.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import introtocomputervision_b200 as sb
+from introtocomputervision_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+NCC_SCORE_RTOL = 1e-5      # BASELINE.json: "NCC scores must agree within 1e-5 relative"
+NCC_DISP_AGREE = 0.999     # "... disparity agreement on >= 99.9 % of pixels"
+
+
+def _cases(cost):
+    from conftest import Golden
+    return Golden().names(cost)
+
+
+def assert_ncc_close(d, s, d_ref, s_ref):
+    agree = float(np.mean(d == d_ref))
+    assert agree >= NCC_DISP_AGREE, f"disparity agreement {agree:.5f}"
+    np.testing.assert_allclose(s, s_ref, rtol=NCC_SCORE_RTOL, atol=1e-7)
+
+
+# ---- golden vectors (reference-generated) ----------------------------------------------------------
+
+@pytest.mark.parametrize("name,R,dmin,dmax", _cases("ssd"))
+def test_ssd_golden(ctx, golden, name, R, dmin, dmax):
+    g = golden.get("ssd", name)
+    L, Rt = g["left"], g["right"]
+    d = ctx.disparity(sb.COST_SSD, L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax)
+    assert d.dtype == np.int8 and np.array_equal(d, g["disp"])
+    if L.dtype == np.uint8:
+        d8 = ctx.disparity(sb.COST_SSD, L, Rt, R, dmin, dmax)
+        assert np.array_equal(d8, g["disp"])
+
+
+@pytest.mark.parametrize("name,R,dmin,dmax", _cases("ncc"))
+def test_ncc_golden(ctx, golden, name, R, dmin, dmax):
+    g = golden.get("ncc", name)
+    L, Rt = g["left"], g["right"]
+    d, s = ctx.disparity(sb.COST_NCORR, L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax,
+                         dtype=np.int16, return_best=True)
+    assert_ncc_close(d, s, g["disp"], g["score"])
+    if L.dtype == np.uint8:
+        d8, s8 = ctx.disparity(sb.COST_NCORR, L, Rt, R, dmin, dmax, dtype=np.int16, return_best=True)
+        assert_ncc_close(d8, s8, g["disp"], g["score"])
+
+
+# ---- seeded random inputs against the oracle ----------------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(10))
+def test_ssd_random_vs_oracle(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    rows, cols = int(rng.integers(5, 70)), int(rng.integers(8, 200))
+    R = int(rng.integers(0, 8))
+    a, b = sorted(int(v) for v in rng.integers(-40, 41, 2))
+    L, Rt, _ = synth.make_pair(rows, cols, 30, seed)
+    kind = seed % 3
+    if kind == 0:
+        Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    elif kind == 1:
+        Lf, Rf = synth.noisy_variant(L, seed), synth.noisy_variant(Rt, seed + 1)
+    else:
+        Lf, Rf = synth.contrast_variant(L), Rt.astype(np.float32)
+    d_ref, c_ref = oracle.ssd(Lf, Rf, R, a, b, return_cost=True)
+    d, c = ctx.disparity(sb.COST_SSD, Lf, Rf, R, a, b, dtype=np.int32, return_best=True)
+    assert np.array_equal(d, d_ref)
+    assert np.array_equal(c, c_ref)
+    d8 = ctx.disparity(sb.COST_SSD, Lf, Rf, R, a, b, dtype=np.int8)
+    assert np.array_equal(d8, oracle.narrow_i8(d_ref))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ncc_random_vs_oracle(ctx, seed):
+    rng = np.random.default_rng(2000 + seed)
+    rows, cols = int(rng.integers(5, 40)), int(rng.integers(20, 160))
+    R = int(rng.integers(0, 8))
+    rng_d = int(rng.integers(0, 40))
+    dmin, dmax = (-rng_d, 0) if seed % 2 == 0 else (0, rng_d)
+    L, Rt, _ = synth.make_pair(rows, cols, 30, 50 + seed)
+    if seed % 3 == 1:
+        Lf, Rf = synth.noisy_variant(L, seed), synth.noisy_variant(Rt, seed + 1)
+    else:
+        Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    d_ref, s_ref = oracle.ncorr(Lf, Rf, R, dmin, dmax, return_score=True)
+    d, s = ctx.disparity(sb.COST_NCORR, Lf, Rf, R, dmin, dmax, dtype=np.int32, return_best=True)
+    assert_ncc_close(d, s, d_ref, s_ref)
+
+
+# ---- BASELINE config shapes ------------------------------------------------------------------------------
+
+def test_ssd_pair1_shape_vs_oracle(ctx):
+    # config 1/2 stand-in: 511 x 640, R=7, range=95 (config/ps2.yaml:24-26); both directions
+    L, Rt, _ = synth.make_pair(511, 640, 96, 11)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(7, 95), ctx=ctx)
+    assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 7, -95, 0)))
+    assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 7, 0, 95)))
+
+
+def test_ssd_noisy_contrast_variants_vs_oracle(ctx):
+    # BASELINE config 2 family on a band of the pair1 stand-in: Gaussian noise and x1.1 contrast
+    L, Rt, _ = synth.make_pair(96, 640, 96, 11)
+    for Lf, Rf in ((synth.noisy_variant(L, 12), synth.noisy_variant(Rt, 13)),
+                   (synth.contrast_variant(L), Rt.astype(np.float32))):
+        dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(7, 95), ctx=ctx)
+        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 7, -95, 0)))
+        assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 7, 0, 95)))
+
+
+def test_ncc_pair1_band_variants_vs_oracle(ctx):
+    L, Rt, _ = synth.make_pair(48, 640, 96, 11)
+    for Lf, Rf in ((L.astype(np.float32), Rt.astype(np.float32)),
+                   (synth.noisy_variant(L, 12), synth.noisy_variant(Rt, 13)),
+                   (synth.contrast_variant(L), Rt.astype(np.float32))):
+        for (a, b, dmin, dmax) in ((Lf, Rf, -95, 0), (Rf, Lf, 0, 95)):
+            d_ref, s_ref = oracle.ncorr(a, b, 7, dmin, dmax, return_score=True)
+            d, s = ctx.disparity(sb.COST_NCORR, a, b, 7, dmin, dmax, dtype=np.int16, return_best=True)
+            assert_ncc_close(d, s, d_ref, s_ref)
+
+
+# ---- API behaviour ------------------------------------------------------------------------------------------
+
+def test_pair_equals_two_singles_and_batch_equals_pairs(ctx):
+    n = 3
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(40, 96, 16, 300 + i)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    for cost in (sb.COST_SSD, sb.COST_NCORR):
+        bl, br = ctx.disparity_pair_batch(cost, Ls, Rs, 3, 15)
+        for i in range(n):
+            dl, dr = ctx.disparity_pair(cost, Ls[i], Rs[i], 3, 15)
+            assert np.array_equal(dl, ctx.disparity(cost, Ls[i], Rs[i], 3, -15, 0))
+            assert np.array_equal(dr, ctx.disparity(cost, Rs[i], Ls[i], 3, 0, 15))
+            assert np.array_equal(bl[i], dl) and np.array_equal(br[i], dr)
+
+
+def test_wide_disparity_needs_wide_output(ctx):
+    # > 127 disparities: int16 holds the true value, int8 wraps exactly like the reference's char store
+    L, Rt, _ = synth.make_pair(16, 400, 200, 77)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    d_ref = oracle.ssd_fast(Lf, Rf, 2, -200, 0)
+    assert d_ref.min() < -128
+    assert np.array_equal(ctx.disparity(sb.COST_SSD, Lf, Rf, 2, -200, 0, dtype=np.int16), d_ref.astype(np.int16))
+    assert np.array_equal(ctx.disparity(sb.COST_SSD, Lf, Rf, 2, -200, 0, dtype=np.int8), oracle.narrow_i8(d_ref))
+
+
+def test_error_codes(ctx):
+    img = np.zeros((8, 16), np.float32)
+    with pytest.raises(sb.StereoError) as e:
+        ctx.disparity(sb.COST_SSD, img, img, 1, 3, 1)
+    assert e.value.status == -2
+    with pytest.raises(sb.StereoError) as e:
+        ctx.disparity(sb.COST_NCORR, img, img, 1, 3, 5)      # the reference would throw in cv::Mat(Rect)
+    assert e.value.status == -2
+    with pytest.raises(sb.StereoError) as e:
+        ctx.disparity(sb.COST_SSD, img, img, -1, -3, 0)
+    assert e.value.status == -1
+    # strided (non-contiguous rows) inputs are honoured
+    big = np.random.default_rng(0).integers(0, 255, (12, 64)).astype(np.float32)
+    a, b = big[:, 3:43], big[:, 10:50]
+    assert np.array_equal(ctx.disparity(sb.COST_SSD, a, b, 2, -5, 0, dtype=np.int32),
+                          oracle.ssd(np.ascontiguousarray(a), np.ascontiguousarray(b), 2, -5, 0))
+
+
+def test_device_pointer_and_band_entry_points(ctx):
+    import ctypes as C
+    import torch
+    from introtocomputervision_b200 import _capi
+    lib = _capi.lib()
+    L, Rt, _ = synth.make_pair(70, 130, 20, 9)
+    dl = torch.from_numpy(L).cuda()
+    dr = torch.from_numpy(Rt).cuda()
+    full = torch.empty((70, 130), dtype=torch.int16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for cost, fn in ((sb.COST_SSD, oracle.ssd), (sb.COST_NCORR, oracle.ncorr)):
+        for (a, b, dmin, dmax) in ((dl, dr, -19, 0), (dr, dl, 0, 19)):
+            rc = lib.stereo_disparity_u8_device(ctx.handle, cost, a.data_ptr(), 130, b.data_ptr(), 130, 70, 130, 4, dmin, dmax,
+                                                full.data_ptr(), 260, 2, None, 0, C.c_void_p(st))
+            assert rc == 0, _capi.last_error()
+            ctx.synchronize(st)
+            ref = fn(a.cpu().numpy().astype(np.float32), b.cpu().numpy().astype(np.float32), 4, dmin, dmax)
+            assert np.array_equal(full.cpu().numpy(), ref.astype(np.int16))
+            # row bands (with the R+1 halo the SSD wrap quirk needs) reproduce the same rows
+            for (r0, r1) in ((0, 23), (23, 47), (47, 70)):
+                band = torch.empty((r1 - r0, 130), dtype=torch.int16, device="cuda")
+                rc = lib.stereo_disparity_band_u8_device(ctx.handle, cost, a.data_ptr(), 130, b.data_ptr(), 130, 70, 130, r0, r1,
+                                                         4, dmin, dmax, band.data_ptr(), 260, 2, C.c_void_p(st))
+                assert rc == 0, _capi.last_error()
+                ctx.synchronize(st)
+                assert np.array_equal(band.cpu().numpy(), ref[r0:r1].astype(np.int16))

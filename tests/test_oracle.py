@@ -1,0 +1,90 @@
+"""CPU tests of the parity oracle itself: the C restatement against the golden vectors (which were
+produced by the reference's own compiled SSD and by executed OpenCV), and — where the reference
+sources/binary are present — directly against oracle/_ref."""
+import numpy as np
+import pytest
+
+import oracle
+from introtocomputervision_b200 import synth
+
+
+def _cases(cost):
+    from conftest import Golden
+    return Golden().names(cost)
+
+
+@pytest.mark.parametrize("name,R,dmin,dmax", _cases("ssd"))
+def test_ssd_restatement_matches_reference_golden(golden, name, R, dmin, dmax):
+    g = golden.get("ssd", name)
+    L, Rt = g["left"].astype(np.float32), g["right"].astype(np.float32)
+    d_lit = oracle.ssd(L, Rt, R, dmin, dmax)
+    d_fast = oracle.ssd_fast(L, Rt, R, dmin, dmax)
+    assert np.array_equal(oracle.narrow_i8(d_lit), g["disp"])
+    assert np.array_equal(d_lit, d_fast)
+
+
+@pytest.mark.parametrize("name,R,dmin,dmax", _cases("ncc"))
+def test_ncc_restatement_matches_opencv_golden(golden, name, R, dmin, dmax):
+    g = golden.get("ncc", name)
+    L, Rt = g["left"].astype(np.float32), g["right"].astype(np.float32)
+    d, s = oracle.ncorr(L, Rt, R, dmin, dmax, return_score=True)
+    assert np.array_equal(d, g["disp"].astype(np.int32))
+    # tolerance: OpenCV's float32 numerator vs our exactly-rounded one (<= 4.3e-7)
+    np.testing.assert_allclose(s, g["score"], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("seed", range(6))
+def test_ssd_restatement_matches_compiled_reference_random(seed):
+    rng = np.random.default_rng(seed)
+    rows, cols = int(rng.integers(6, 28)), int(rng.integers(12, 70))
+    R = int(rng.integers(0, 5))
+    a, b = sorted(int(v) for v in rng.integers(-14, 15, 2))
+    L, Rt, _ = synth.make_pair(rows, cols, 12, 100 + seed)
+    if seed % 2:
+        L, Rt = synth.noisy_variant(L, seed), synth.contrast_variant(Rt)
+    else:
+        L, Rt = L.astype(np.float32), Rt.astype(np.float32)
+    ref = oracle.ref_ssd(L, Rt, R, a, b)
+    lit = oracle.ssd(L, Rt, R, a, b)
+    assert np.array_equal(ref, oracle.narrow_i8(lit))
+    assert np.array_equal(lit, oracle.ssd_fast(L, Rt, R, a, b))
+
+
+def test_ssd_known_answer_shift():
+    # right(x) = left(x + k)  =>  interior L->R disparity = -k   (SURVEY.md §8c KAT)
+    rng = np.random.default_rng(3)
+    left = rng.integers(0, 256, (24, 80)).astype(np.float32)
+    k = 4
+    right = np.empty_like(left)
+    right[:, :-k] = left[:, k:]
+    right[:, -k:] = left[:, -1:]
+    d = oracle.ssd(left, right, 3, -10, 0)
+    assert np.all(d[:, 14:-8] == -k)
+    d2 = oracle.ncorr(left, right, 3, -10, 0)
+    assert np.all(d2[:, 14:-8] == -k)
+
+
+def test_ssd_tie_break_first_minimum_and_wrap_quirk():
+    flat = np.full((10, 30), 7, np.float32)
+    d, c = oracle.ssd(flat, flat, 2, -6, 0, return_cost=True)
+    # interior rows: all candidates cost 0 -> the first (most negative) candidate wins (strict <).
+    # Candidate centres may sit in the left padding: x + dmin clamped at padded column 0.
+    for x in range(30):
+        assert d[5, x] == max(-6, -(x + 2))
+    assert np.all(c[1:] == 0)
+    # row 0, left columns: the wrapped reads leave the buffer (zero guard) -> those candidates cost > 0
+    assert d[0, 0] != d[5, 0]
+    dr = oracle.ssd(flat, flat, 2, 0, 6)
+    assert np.all(dr == 0)
+
+
+def test_narrow_matches_char_store():
+    v = np.array([0, -1, 127, 128, 255, -128, -129, 300], np.int32)
+    assert oracle.narrow_i8(v).tolist() == [0, -1, 127, -128, -1, -128, 127, 44]
+
+
+def test_ncc_rejects_empty_candidate_sets():
+    img = np.ones((8, 16), np.float32)
+    with pytest.raises(oracle.OracleError):
+        oracle.ncorr(img, img, 1, 3, 5)     # right-most columns have no window: the reference would throw
