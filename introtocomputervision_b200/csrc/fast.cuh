@@ -1,10 +1,577 @@
-// Packed u8 path (placeholder until the kernels land): reports "not supported" so that every call
-// takes the exact path.
+// Packed u8 path: the hot kernels of the library (sm_100a).
+//
+// For images that are exactly 8-bit the window cost is an integer and
+//     SSD(x,d) = EL(x) + ER(x+d) - 2*C(x,d),   C = sum over the window of l*r,
+//     NCC(x,d) = C(x,d) / sqrt(EL(x) * ER(x+d)),
+// so the per-disparity work is ONE box-filtered cross term C; the energies are box sums computed
+// once per image, not per disparity (north-star item (b)).  The kernel computes C with separable
+// running sums held entirely in registers:
+//
+//   * vertical:   col[m][c] += l_new*r_new - l_old*r_old      ONE IDP.2A (dp2a, s16 x u8) per unit
+//                 (the new and the leaving row are packed into one operand pair by the prep kernels)
+//   * horizontal: s[m] += col[m][c+2R+1] - col[m][c]          ONE IADD3 per unit
+//   * WTA:        key = E2[pos] + 256*s (cost*128 + position) ONE IMAD/LEA, then VIMNMX3 in-thread
+//                 and REDUX.MIN across the 32 lanes of the warp (lanes = disparities)
+//
+// The cost volume never exists in memory: a thread owns K=24 pixels x M=4 disparities, a warp
+// 24 pixels x 128 disparities, and only the winning key per pixel and 128-disparity group leaves
+// the SM.  Operand rows are staged in shared memory with TMA bulk copies (cp.async.bulk, SASS
+// UBLKCP) through a 4-stage mbarrier ring; all warps of a CTA share the staged rows.
+//
+// Reference semantics reproduced: replicate padding, the clamped candidate
+// range in padded coordinates, the flat-index row wrap of the SSD target reads (realised by building
+// the target operand rows from an "extended" image whose out-of-row columns come from the
+// neighbouring padded row / zero guard), first-minimum (SSD) and first-maximum (NCC) tie-breaks.
 #pragma once
 #include "common.cuh"
+#include "exact.cuh"
+#include <climits>
+
 namespace sb {
-static inline bool fast_supported(const Problem&) { return false; }
-static inline size_t fast_scratch_bytes(stereo_ctx*, const Problem&) { return 0; }
-static inline int fast_ctx_init(stereo_ctx*) { return STEREO_OK; }
-static inline int run_fast(stereo_ctx*, const Problem&, cudaStream_t) { set_error("fast path not built"); return STEREO_ERR_UNSUPPORTED; }
+
+constexpr int FK = 24;          // pixels per thread (strip width)
+constexpr int FM = 4;           // disparities per thread
+constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
+constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
+constexpr int FRPS = 8;         // operand rows per pipeline stage
+constexpr int FNST = 4;         // pipeline stages
+constexpr int FWARPS = 8;       // warps per CTA
+constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
+constexpr int KEY_INVALID = INT_MAX;
+
+// ---------------------------------------------------------------------------------------------------
+// Geometry shared by host and device
+// ---------------------------------------------------------------------------------------------------
+struct FastGeom {
+    // problem
+    int rows, cols, R, dmin, dmax, cost;
+    int rb, re;            // output band
+    // derived
+    int G;                 // number of 128-disparity groups
+    int gc;                // groups per CTA (1 or 2)
+    int spc;               // strips per CTA = FWARPS / gc
+    int nstrips;           // ceil(cols / FK)
+    int tilesX;            // ceil(nstrips / spc)
+    int gblocks;           // ceil(G / gc)
+    int base_y;            // step row of operand row 0 (multiple of FRPS, <= rb - (2R+1))
+    int J;                 // operand rows (multiple of FRPS)
+    int qoff, eoff;        // column offsets of the RQ / E2 arrays
+    int lp_pitch, rq_pitch, e2_pitch;   // words
+    int lpw, rqw, e2w;     // tile widths in words (multiples of 4)
+    int wpart;             // partial-key map width (= tilesX*spc*FK)
+    int nrows;             // re - rb
+    int ctas;              // grid size
+    long long total;       // tile-rows
+    long long L;           // tile-rows per CTA
+    // valid centre columns (unpadded coordinates)
+    int cmin, cmax;
+};
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+
+struct FastArrays {
+    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
+    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
+    int32_t* E2;       // [J][e2_pitch]   128*ER + position, or KEY_INVALID
+    int32_t* H;        // horizontal energy sums of the extended target image
+    int32_t* PART;     // [G][nrows][wpart] winning keys
+    float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c) {
+    int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
+__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c) {
+    int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ int4 lds128(const int* p) { return *reinterpret_cast<const int4*>(p); }
+
+// The target image the reference actually reads: padded row i+R of the
+// replicate-padded image, extended by R columns either side that alias the neighbouring padded row
+// through the flat index of the unchecked cv::Mat::at (DisparitySSD.cpp:50).  `i` is the unpadded row
+// index (may lie outside [0,rows)), `e` = unpadded column + 2R.  Reads outside the padded buffer
+// (row -1 / row Hp) return 0 (the oracle's zero guard).
+__device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, int rows, int cols, int R, int i, int e) {
+    const int Wp = cols + 2 * R;
+    const int c = e - R;                 // padded column, may be < 0 or >= Wp
+    int src_row = i, src_col;
+    if (c < 0) {                         // previous padded row, right padding
+        if (i + R - 1 < 0) return 0;
+        src_row = i - 1; src_col = cols - 1;
+    } else if (c >= Wp) {                // next padded row, left padding
+        if (i + R + 1 > rows + 2 * R - 1) return 0;
+        src_row = i + 1; src_col = 0;
+    } else {
+        src_col = clampi(c - R, 0, cols - 1);
+    }
+    src_row = clampi(src_row, 0, rows - 1);
+    return B[size_t(src_row) * step + src_col];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Prep kernels: operand rows in the layout the hot loop consumes
+// ---------------------------------------------------------------------------------------------------
+__global__ void prep_lp_kernel(const uint8_t* __restrict__ A, size_t step, FastGeom g, int32_t* __restrict__ LP) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (p >= g.lp_pitch) return;
+    const int y = g.base_y + j;
+    const int col = clampi(p - g.R, 0, g.cols - 1);
+    const int lnew = A[size_t(clampi(y + g.R, 0, g.rows - 1)) * step + col];
+    const int lold = A[size_t(clampi(y - g.R - 1, 0, g.rows - 1)) * step + col];
+    LP[size_t(j) * g.lp_pitch + p] = int(uint32_t(uint16_t(int16_t(-lnew))) | (uint32_t(uint16_t(lold)) << 16));
+}
+
+__global__ void prep_rq_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, uint32_t* __restrict__ RQ) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jp = blockIdx.y;
+    if (q >= g.rq_pitch) return;
+    const int ye = g.base_y + 2 * jp;
+    const int e = q - g.qoff;
+    const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e);
+    const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e);
+    const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e);
+    const uint32_t b3 = bext(B, step, g.rows, g.cols, g.R, ye - g.R, e);
+    RQ[size_t(jp) * g.rq_pitch + q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+// H[hi][q2] = sum_{t=-R..R} bext(i, e_c + t)^2 for unpadded row i = rb - R + hi and centre column
+// u_c = q2 - eoff (e_c = u_c + 2R).
+__global__ void prep_h_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, int32_t* __restrict__ H) {
+    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hi = blockIdx.y;
+    if (q2 >= g.e2_pitch) return;
+    const int i = g.rb - g.R + hi;
+    const int ec = q2 - g.eoff + 2 * g.R;
+    int s = 0;
+    for (int t = -g.R; t <= g.R; ++t) { const int v = bext(B, step, g.rows, g.cols, g.R, i, ec + t); s += v * v; }
+    H[size_t(hi) * g.e2_pitch + q2] = s;
+}
+
+// E2[j][q2] = 128*ER + q2 for valid centres, KEY_INVALID otherwise; RS (NCC) = 1/sqrt(ER) (0 if ER==0).
+__global__ void prep_e2_kernel(const int32_t* __restrict__ H, FastGeom g, int32_t* __restrict__ E2, float* __restrict__ RS) {
+    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;                 // output row index within the band
+    if (q2 >= g.e2_pitch) return;
+    const int y = g.rb + yy;
+    const int j = y - g.base_y;
+    int er = 0;
+    for (int t = 0; t <= 2 * g.R; ++t) er += H[size_t(yy + t) * g.e2_pitch + q2];
+    const int uc = q2 - g.eoff;
+    const bool valid = uc >= g.cmin && uc <= g.cmax;
+    if (g.cost == STEREO_COST_SSD) {
+        E2[size_t(j) * g.e2_pitch + q2] = valid ? (er << FKEY_BITS) + q2 : KEY_INVALID;
+    } else {
+        E2[size_t(j) * g.e2_pitch + q2] = valid ? er : -1;
+        RS[size_t(j) * g.e2_pitch + q2] = (valid && er > 0) ? rsqrtf(float(er)) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The hot kernel
+// ---------------------------------------------------------------------------------------------------
+struct FastKernelParams {
+    FastGeom g;
+    const int32_t* LP;
+    const uint32_t* RQ;
+    const int32_t* E2;
+    int32_t* PART;
+};
+
+template <int R>
+struct RowShape {
+    static constexpr int NC = FK + 2 * R;              // columns whose sums a thread keeps
+    static constexpr int NC4 = (NC + 3) / 4 * 4;
+    static constexpr int NQ = NC + FM - 1;             // target positions a thread touches
+    static constexpr int NQ4 = (NQ + 3) / 4 * 4;
+    static constexpr int NE = FK + FM - 1;             // centre positions
+    static constexpr int NE4 = (NE + 3) / 4 * 4;
+};
+
+// One operand row for one warp.  MODE 0: warm-up (add the entering row only, no output);
+// MODE 1: regular row; MODE 2: regular row with candidate masking.  PAR selects the byte pair.
+template <int R, int PAR, int MODE>
+__device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const int* __restrict__ lp_row,
+                                         const int* __restrict__ rq_row, const int* __restrict__ e2_row,
+                                         int32_t* __restrict__ out_row, int mmax, int lane) {
+    using S = RowShape<R>;
+    int lpv[S::NC4];
+    int rqv[S::NQ4];
+#pragma unroll
+    for (int i = 0; i < S::NC4 / 4; ++i) {
+        const int4 v = lds128(lp_row + 4 * i);
+        lpv[4 * i] = v.x; lpv[4 * i + 1] = v.y; lpv[4 * i + 2] = v.z; lpv[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < S::NQ4 / 4; ++i) {
+        const int4 v = lds128(rq_row + 4 * i);
+        rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < S::NC; ++c) {
+        const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];
+#pragma unroll
+        for (int m = 0; m < FM; ++m) {
+            col[m][c] = PAR ? dp2a_hi(a, unsigned(rqv[c + m]), col[m][c]) : dp2a_lo(a, unsigned(rqv[c + m]), col[m][c]);
+        }
+    }
+    if (MODE == 0) return;
+
+    int e2v[S::NE4];
+#pragma unroll
+    for (int i = 0; i < S::NE4 / 4; ++i) {
+        const int4 v = lds128(e2_row + 4 * i);
+        e2v[4 * i] = v.x; e2v[4 * i + 1] = v.y; e2v[4 * i + 2] = v.z; e2v[4 * i + 3] = v.w;
+    }
+    int s[FM];
+#pragma unroll
+    for (int m = 0; m < FM; ++m) {
+        int acc = 0;
+#pragma unroll
+        for (int c = 0; c < 2 * R; ++c) acc += col[m][c];
+        s[m] = acc;
+    }
+    int res[4];
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+        int key[FM];
+#pragma unroll
+        for (int m = 0; m < FM; ++m) {
+            s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
+            // s = -C (the packed operand carries -l): key = 128*(ER - 2C) + position
+            int kv = int(unsigned(e2v[k + m]) + unsigned(s[m]) * unsigned(2 << FKEY_BITS));
+            if (MODE == 2) kv = (e2v[k + m] == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
+            key[m] = kv;
+        }
+        int best = min(min(key[0], key[1]), min(key[2], key[3]));
+        res[k & 3] = __reduce_min_sync(0xffffffffu, best);
+        if ((k & 3) == 3 && lane == 0)
+            *reinterpret_cast<int4*>(out_row + k - 3) = make_int4(res[0], res[1], res[2], res[3]);
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKernelParams P) {
+    using S = RowShape<R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const FastGeom& g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
+    const int stage_words = lp_stage + rq_stage + e2_stage;
+    int* smem = reinterpret_cast<int*>(smem_raw);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(FNST) * stage_words * 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST);
+
+    if (tid == 0) {
+        for (int i = 0; i < FNST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, FWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- this CTA's share of the (tile, row) space -------------------------------------------------
+    const long long lin_begin = (long long)blockIdx.x * g.L;
+    long long lin_end = lin_begin + g.L;
+    if (lin_end > g.total) lin_end = g.total;
+    if (lin_begin >= lin_end) return;
+    const int w = 2 * R + 1;
+
+    // producer state (thread 0 only): iterates the same stage sequence, FNST-2 stages ahead
+    long long p_lin = lin_begin;   // start of the producer's current segment
+    int p_sj = 0, p_sj_end = -1;   // stage range of the producer's segment
+    int p_tile = 0;
+    int pn = 0;                    // loads issued
+    auto producer_open_segment = [&]() {
+        p_tile = int(p_lin / g.nrows);
+        const int r0 = int(p_lin % g.nrows);
+        long long rem = lin_end - p_lin;
+        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
+        const int js = g.rb + r0 - w - g.base_y, je = g.rb + r1 - g.base_y;
+        p_sj = js / FRPS; p_sj_end = (je - 1) / FRPS;
+        p_lin += r1 - r0;
+    };
+    auto producer_issue = [&]() -> bool {     // returns false when nothing is left
+        if (p_sj > p_sj_end) {
+            if (p_lin >= lin_end) return false;
+            producer_open_segment();
+        }
+        const int slot = pn % FNST;
+        if (pn >= FNST) mbar_wait(empty0 + 8 * slot, ((pn / FNST) - 1) & 1);
+        const int xt = p_tile % g.tilesX, gb = p_tile / g.tilesX;
+        const int p0 = xt * g.spc * FK;
+        const int q0 = p0 + g.dmin + FGROUP * gb * g.gc + g.R + g.qoff;
+        const int q20 = p0 + g.dmin + FGROUP * gb * g.gc + g.eoff;
+        const uint32_t bar = full0 + 8 * slot;
+        int* st = smem + size_t(slot) * stage_words;
+        mbar_expect_tx(bar, uint32_t(stage_words) * 4u);
+        const int j0 = p_sj * FRPS;
+#pragma unroll 1
+        for (int r = 0; r < FRPS; ++r)
+            tma_load_1d(smem_u32(st + r * g.lpw), P.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
+#pragma unroll 1
+        for (int r = 0; r < FRPS / 2; ++r)
+            tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), P.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+#pragma unroll 1
+        for (int r = 0; r < FRPS; ++r)
+            tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), P.E2 + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
+        ++pn; ++p_sj;
+        return true;
+    };
+    if (tid == 0) {
+        for (int i = 0; i < FNST - 2; ++i) if (!producer_issue()) break;
+    }
+
+    // ---- consumers -----------------------------------------------------------------------------------
+    int n = 0;                      // stages consumed
+    long long lin = lin_begin;
+    int col[FM][S::NC];
+    while (lin < lin_end) {
+        const int tile = int(lin / g.nrows);
+        const int r0 = int(lin % g.nrows);
+        const long long rem = lin_end - lin;
+        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
+        lin += r1 - r0;
+        const int xt = tile % g.tilesX, gb = tile / g.tilesX;
+        const int strip = xt * g.spc + warp / g.gc;
+        const int grp = gb * g.gc + warp % g.gc;
+        const int x0 = strip * FK;
+        const bool active = (x0 < g.cols) && (grp < g.G);
+        const int y0 = g.rb + r0, y1 = g.rb + r1;
+        const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
+        // candidate masking is needed if any (pixel, disparity) of this warp's block is invalid
+        const int dlo = g.dmin + FGROUP * grp;                         // first disparity of the group
+        const bool need_mask = (x0 + dlo < g.cmin) || (x0 + FK - 1 + dlo + FGROUP - 1 > g.cmax) || (dlo + FGROUP - 1 > g.dmax);
+        const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
+        const int lp_off = (warp / g.gc) * FK;
+        const int rq_off = (warp / g.gc) * FK + FGROUP * (warp % g.gc) + FM * lane;
+        int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
+#pragma unroll
+        for (int m = 0; m < FM; ++m)
+#pragma unroll
+            for (int c = 0; c < S::NC; ++c) col[m][c] = 0;
+
+        for (int sj = js / FRPS; sj <= (je - 1) / FRPS; ++sj, ++n) {
+            if (tid == 0) producer_issue();
+            const int slot = n % FNST;
+            mbar_wait(full0 + 8 * slot, (n / FNST) & 1);
+            if (active) {
+                const int* st = smem + size_t(slot) * stage_words;
+                const int jlo = max(js, sj * FRPS), jhi = min(je, sj * FRPS + FRPS);
+                for (int j = jlo; j < jhi; ++j) {
+                    const int r = j - sj * FRPS;
+                    const int* lp_row = st + r * g.lpw + lp_off;
+                    const int* rq_row = st + lp_stage + (r >> 1) * g.rqw + rq_off;
+                    const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
+                    int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
+                    const int par = j & 1;
+                    if (j < jreg) {
+                        if (par) fast_row<R, 1, 0>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                        else     fast_row<R, 0, 0>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                    } else if (!need_mask) {
+                        if (par) fast_row<R, 1, 1>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                        else     fast_row<R, 0, 1>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                    } else {
+                        if (par) fast_row<R, 1, 2>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                        else     fast_row<R, 0, 2>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Merge: winning key per group -> disparity (+ cost), in the caller's layout
+// ---------------------------------------------------------------------------------------------------
+__global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom g, const uint8_t* __restrict__ A,
+                                      size_t a_step, void* disp_out, size_t disp_step, int elem, void* best_out,
+                                      size_t best_step) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (x >= g.cols) return;
+    int bestc = INT_MAX, bestd = 0;
+    bool found = false;
+    for (int grp = 0; grp < g.G; ++grp) {
+        const int key = PART[(size_t(grp) * g.nrows + yy) * g.wpart + x];
+        if (key == KEY_INVALID) continue;
+        const int qlo = x + g.dmin + FGROUP * grp + g.eoff;        // position of the group's first candidate
+        const int q2 = qlo + ((key - qlo) & (FGROUP - 1));
+        const int c = (key - q2) >> FKEY_BITS;                     // ER - 2C (exact: multiple of 128)
+        if (!found || c < bestc) { bestc = c; bestd = q2 - g.eoff - x; found = true; }
+    }
+    int cost = 99999999;                                           // DisparitySSD.cpp:37
+    if (found) {
+        // EL(x): window energy of the reference image (replicate padding) — only needed to report
+        // the cost and to honour the 99999999 threshold.
+        int el = 0;
+        const int y = g.rb + yy;
+        for (int wy = -g.R; wy <= g.R; ++wy) {
+            const uint8_t* row = A + size_t(clampi(y + wy, 0, g.rows - 1)) * a_step;
+            for (int wx = -g.R; wx <= g.R; ++wx) { const int v = row[clampi(x + wx, 0, g.cols - 1)]; el += v * v; }
+        }
+        const int sum = bestc + el;
+        if (sum < 99999999) cost = sum; else bestd = 0;
+    }
+    char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
+    if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(bestd) & 0xFFu));
+    else if (elem == 2) reinterpret_cast<int16_t*>(drow)[x] = int16_t(bestd);
+    else reinterpret_cast<int32_t*>(drow)[x] = bestd;
+    if (best_out) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = cost;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+static inline bool fast_supported(const Problem& p) {
+    if (p.cost != STEREO_COST_SSD) return false;           // NCC: exact path for now
+    if (p.R > FMAXR) return false;
+    if (p.cols < 1 || p.rows < 1) return false;
+    if (p.dmax - p.dmin + 1 > 4096) return false;
+    // positions must fit the key arithmetic comfortably
+    if (p.cols + 2 * (p.dmax - p.dmin) + 1024 > (1 << 20)) return false;
+    return true;
+}
+
+static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGeom& g) {
+    g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.dmin = p.dmin; g.dmax = p.dmax; g.cost = p.cost;
+    g.rb = p.row_begin; g.re = p.row_end; g.nrows = g.re - g.rb;
+    const int D = p.dmax - p.dmin + 1;
+    g.G = (D + FGROUP - 1) / FGROUP;
+    g.gc = (g.G % 2 == 0) ? 2 : 1;
+    g.spc = FWARPS / g.gc;
+    g.nstrips = (p.cols + FK - 1) / FK;
+    g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
+    g.gblocks = g.G / g.gc;
+    const int w = 2 * p.R + 1;
+    g.base_y = floor_div(g.rb - w, FRPS) * FRPS;
+    g.J = round_up(g.re - g.base_y, FRPS);
+    if (p.cost == STEREO_COST_SSD) { g.cmin = -p.R; g.cmax = p.cols - 1 + p.R; }
+    else { g.cmin = 0; g.cmax = p.cols - 1; }
+    // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
+    int qo = -(p.dmin + p.R); if (qo < 0) qo = 0;
+    while (((p.dmin + p.R + qo) & 3) != 0) ++qo;
+    g.qoff = qo;
+    int eo = -p.dmin; if (eo < 0) eo = 0;
+    while (((p.dmin + eo) & 3) != 0) ++eo;
+    g.eoff = eo;
+    const int tile_px = g.spc * FK;
+    g.lpw = round_up(tile_px + 2 * p.R, 4);
+    g.rqw = round_up(tile_px + 2 * p.R + FGROUP * g.gc + FM, 4);
+    g.e2w = round_up(tile_px + FGROUP * g.gc + FM, 4);
+    g.wpart = g.tilesX * tile_px;
+    g.lp_pitch = round_up((g.tilesX - 1) * tile_px + g.lpw, 64);
+    const int last_p0 = (g.tilesX - 1) * tile_px;
+    const int gmax = FGROUP * (g.gblocks - 1) * g.gc;
+    g.rq_pitch = round_up(last_p0 + p.dmin + gmax + p.R + g.qoff + g.rqw, 64);
+    g.e2_pitch = round_up(last_p0 + p.dmin + gmax + g.eoff + g.e2w, 64);
+    g.total = (long long)g.tilesX * g.gblocks * g.nrows;
+    // grid: one CTA per SM, but keep segments long enough that the (2R+1)-row warm-up stays small
+    long long min_rows = 4LL * w; if (min_rows < 32) min_rows = 32;
+    long long ctas = g.total / min_rows; if (ctas < 1) ctas = 1;
+    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
+    g.L = (g.total + ctas - 1) / ctas;
+    g.ctas = int((g.total + g.L - 1) / g.L);
+}
+
+static inline size_t fast_smem_bytes(const FastGeom& g) {
+    const size_t stage_words = size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w;
+    return size_t(FNST) * stage_words * 4 + 2 * FNST * 8 + 16;
+}
+
+static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
+    FastGeom g; fast_geometry(ctx, p, g);
+    size_t b = 0;
+    auto add = [&](size_t bytes) { b += ((bytes + 255) & ~size_t(255)); };
+    add(size_t(g.J) * g.lp_pitch * 4);
+    add(size_t(g.J / 2) * g.rq_pitch * 4);
+    add(size_t(g.J) * g.e2_pitch * 4);
+    add(size_t(g.nrows + 2 * g.R) * g.e2_pitch * 4);
+    add(size_t(g.G) * g.nrows * g.wpart * 4);
+    if (p.cost == STEREO_COST_NCORR) add(size_t(g.J) * g.e2_pitch * 4);
+    return b + 4096;
+}
+
+typedef void (*fast_kernel_fn)(const FastKernelParams);
+static inline fast_kernel_fn fast_pick_ssd(int R) {
+    switch (R) {
+    case 0: return fast_ssd_kernel<0>;
+    case 1: return fast_ssd_kernel<1>;
+    case 2: return fast_ssd_kernel<2>;
+    case 3: return fast_ssd_kernel<3>;
+    case 4: return fast_ssd_kernel<4>;
+    case 5: return fast_ssd_kernel<5>;
+    case 6: return fast_ssd_kernel<6>;
+    case 7: return fast_ssd_kernel<7>;
+    }
+    return nullptr;
+}
+
+static inline int fast_ctx_init(stereo_ctx*) {
+    for (int R = 0; R <= FMAXR; ++R) {
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fast_pick_ssd(R)),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+    }
+    return STEREO_OK;
+}
+
+static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
+    FastGeom g; fast_geometry(ctx, p, g);
+    FastArrays a{};
+    a.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
+    a.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
+    a.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+    a.H = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows + 2 * g.R) * g.e2_pitch * 4));
+    a.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
+    if (!a.LP || !a.RQ || !a.E2 || !a.H || !a.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    const uint8_t* A = static_cast<const uint8_t*>(p.ref.ptr);
+    const uint8_t* B = static_cast<const uint8_t*>(p.tgt.ptr);
+    const dim3 tb(256);
+    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch, 256), g.J), tb, 0, st>>>(A, p.ref.step, g, a.LP);
+    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch, 256), g.J / 2), tb, 0, st>>>(B, p.tgt.step, g, a.RQ);
+    prep_h_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows + 2 * g.R), tb, 0, st>>>(B, p.tgt.step, g, a.H);
+    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows), tb, 0, st>>>(a.H, g, a.E2, a.RS);
+    FastKernelParams kp{g, a.LP, a.RQ, a.E2, a.PART};
+    fast_pick_ssd(p.R)<<<g.ctas, FWARPS * 32, fast_smem_bytes(g), st>>>(kp);
+    fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
+        a.PART, g, A, p.ref.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
+    ctx->last_launches += 6;
+    SB_CUDA(cudaGetLastError());
+    return STEREO_OK;
+}
+
+} // namespace sb

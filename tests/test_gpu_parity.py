@@ -198,3 +198,68 @@ def test_device_pointer_and_band_entry_points(ctx):
                 assert rc == 0, _capi.last_error()
                 ctx.synchronize(st)
                 assert np.array_equal(band.cpu().numpy(), ref[r0:r1].astype(np.int16))
+
+
+# ---- the packed u8 kernels ------------------------------------------------------------------------------------
+
+FAST_SHAPES = [
+    # rows, cols, R, dmin, dmax
+    (40, 100, 2, -10, 0),
+    (40, 100, 2, 0, 10),
+    (64, 200, 5, -63, 0),
+    (64, 200, 5, 0, 63),
+    (37, 333, 4, -127, 0),      # exactly one 128-disparity group
+    (37, 333, 4, 0, 127),
+    (50, 300, 3, -255, 0),      # two groups
+    (50, 300, 3, 0, 255),
+    (33, 500, 7, -95, 0),       # ps2.yaml problem 2 parameters
+    (33, 500, 6, 0, 3),         # ps2.yaml problem 1 parameters
+    (45, 260, 1, -80, 0),       # 81 candidates: not a multiple of 4
+    (45, 260, 0, -17, 9),       # 1x1 window, mixed-sign range
+    (21, 50, 5, -300, 300),     # range far wider than the image
+    (150, 97, 2, -30, 0),       # tall and narrow: several row segments
+    (9, 24, 3, 5, 11),          # positive-only range
+    (300, 700, 5, -130, 0),     # 131 candidates: 2 groups, second almost empty
+]
+
+
+@pytest.mark.parametrize("rows,cols,R,dmin,dmax", FAST_SHAPES)
+def test_ssd_fast_u8_vs_oracle(ctx, rows, cols, R, dmin, dmax):
+    L, Rt, _ = synth.make_pair(rows, cols, max(2, min(64, max(abs(dmin), abs(dmax)))), rows * 1000 + cols)
+    d_ref, c_ref = oracle.ssd_fast(L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax, return_cost=True)
+    d, c = ctx.disparity(sb.COST_SSD, L, Rt, R, dmin, dmax, dtype=np.int32, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    bad = np.argwhere(d != d_ref)
+    assert bad.size == 0, f"{len(bad)} mismatching pixels, first {bad[:5].tolist()}"
+    assert np.array_equal(c, c_ref)
+    # float images holding 8-bit values take the same kernels
+    d2 = ctx.disparity(sb.COST_SSD, L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax, dtype=np.int32)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert np.array_equal(d2, d_ref)
+
+
+def test_ssd_fast_flat_and_saturated_images(ctx):
+    # ties everywhere (first minimum must win), extreme intensities (largest keys)
+    for val in (0, 7, 255):
+        img = np.full((40, 90), val, np.uint8)
+        for (dmin, dmax) in ((-20, 0), (0, 20)):
+            d_ref = oracle.ssd_fast(img.astype(np.float32), img.astype(np.float32), 7, dmin, dmax)
+            assert np.array_equal(ctx.disparity(sb.COST_SSD, img, img, 7, dmin, dmax, dtype=np.int32), d_ref)
+    a = np.zeros((30, 120), np.uint8)
+    b = np.full((30, 120), 255, np.uint8)
+    d_ref, c_ref = oracle.ssd_fast(a.astype(np.float32), b.astype(np.float32), 7, -100, 0, return_cost=True)
+    d, c = ctx.disparity(sb.COST_SSD, a, b, 7, -100, 0, dtype=np.int32, return_best=True)
+    assert np.array_equal(d, d_ref) and np.array_equal(c, c_ref)
+
+
+def test_ssd_fast_equals_exact_path(ctx):
+    L, Rt, _ = synth.make_pair(120, 400, 100, 4242)
+    try:
+        ctx.force_path(sb.PATH_EXACT_F32)
+        d_exact = ctx.disparity(sb.COST_SSD, L, Rt, 5, -140, 0, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_EXACT_F32
+    finally:
+        ctx.force_path(0)
+    d_fast = ctx.disparity(sb.COST_SSD, L, Rt, 5, -140, 0, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert np.array_equal(d_fast, d_exact)
