@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — disparity Mpix x disparities / s of the ps2 stereo block matcher on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU implementation, host cores
+
+A step = one pass of the hot path over one batch of synthetic stereo pairs (both directions per
+pair, like the reference's disparitySSDPair, main.cpp:21-48).  Workload at every N: per GPU a batch
+of B synthetic 3840x2160 pairs, 256 disparities, 11x11 window, SSD (BASELINE config 4's shape and
+the config the north-star target is quoted on), pairs sharded by rank (weak scaling); for N > 1 the
+per-rank disparity maps are all-gathered over NCCL inside the timed step (BASELINE config 5's
+"sharded by pair ... with NCCL gather").
+
+`value`   : whole-job Mpix x disp / s with inputs resident in HBM, CUDA events on the launching stream,
+            L2 flushed between steps, max over ranks.
+`e2e`     : the same metric through the reference-facing C-ABI call with HOST float32 (CV_32FC1)
+            buffers — H2D and D2H copies inside the timed region, wall clock, max over ranks.
+`roofline`: the hot kernel (fast_ssd_kernel) against the FP32/INT32 issue roofline of SURVEY.md §8d
+            (8 algorithmic lane-ops per pixel x disparity; peak = SMs x 128 lanes x max SM clock), plus
+            the HBM view (algorithmic bytes / kernel time vs the measured copy bandwidth).
+`cpu_baseline`: the reference's own serial::disparitySSD (compiled in place into oracle/_ref) on a
+            bounded sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "disparity Mpix x disparities/s"
+UNIT = "Mpix*disp/s"
+OPS_PER_UNIT = {"ssd": 8, "ncc": 9}          # SURVEY.md §8d algorithmic lane-ops per pixel x disparity
+
+WORKLOADS = {
+    # name: rows, cols, n_disp, window_rad, seed
+    "4k_d256_w11": dict(rows=2160, cols=3840, ndisp=256, R=5, seed=1002),
+    "1080p_d128_w9": dict(rows=1080, cols=1920, ndisp=128, R=4, seed=1001),
+    "720p_d64_w9": dict(rows=720, cols=1280, ndisp=64, R=4, seed=2000),
+}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU implementation on host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, rows_per_thread: int, threads: int):
+    """Times the reference's serial::disparitySSD (oracle/_ref; falls back to the C port when the
+    compiled reference is absent) on `threads` disjoint full-width row bands of the workload's
+    left->right problem.  Returns (Mpix*disp/s, description dict)."""
+    import oracle
+    from introtocomputervision_b200 import synth
+
+    R, nd = wl["R"], wl["ndisp"]
+    band = max(1, rows_per_thread)
+    L, Rt, _ = synth.make_pair(band * threads, wl["cols"], nd, wl["seed"])
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    kind = "reference" if oracle.have_ref() else "port"
+    oracle.set_num_threads(1)
+
+    def work(i):
+        a = np.ascontiguousarray(Lf[i * band:(i + 1) * band])
+        b = np.ascontiguousarray(Rf[i * band:(i + 1) * band])
+        if kind == "reference":
+            oracle.ref_ssd(a, b, R, -(nd - 1), 0)
+        else:
+            oracle.ssd(a, b, R, -(nd - 1), 0)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    units = threads * band * wl["cols"] * nd          # every row of every band is computed
+    desc = {"kind": kind, "cores": threads,
+            "sample": f"{threads} threads x {band}-row full-width bands ({wl['cols']} cols, {nd} disparities, "
+                      f"{2 * R + 1}x{2 * R + 1} window), L->R SSD, "
+                      + ("reference serial::disparitySSD compiled -O2 from /root/reference (oracle/_ref)"
+                         if kind == "reference" else "C port of serial::disparitySSD (oracle/stereo_oracle.c)")}
+    return units / dt / 1e6, dt, desc
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_sample(wl, 1, threads)
+    vals, times = [], []
+    for _ in range(args.steps):
+        v, dt, desc = cpu_reference_sample(wl, args.ref_rows, threads)
+        vals.append(v), times.append(dt)
+    total_units = sum(v * t for v, t in zip(vals, times))
+    value = total_units / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->int32", "data": "synthetic",
+        "config": {"workload": args.workload + "_ssd", **{k: wl[k] for k in ("rows", "cols", "ndisp")},
+                   "window": 2 * wl["R"] + 1, "sample_rows_per_thread": args.ref_rows},
+        "cpu_baseline": {**desc, "value": round(value, 3), "unit": UNIT},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import introtocomputervision_b200 as sb
+    from introtocomputervision_b200 import _capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.lib()
+    ctx = sb.Context(local)
+    cost = sb.COST_SSD
+    rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
+    B = args.pairs
+    elem_dtype, elem = (torch.int8, 1) if nd <= 128 else (torch.int16, 2)
+
+    # synthetic pairs of this rank (pair-sharded batch: rank r owns pairs r*B .. r*B+B-1)
+    Ls, Rs = [], []
+    for i in range(B):
+        L, Rt, _ = synth.make_pair(rows, cols, nd, wl["seed"] + rank * B + i)
+        Ls.append(L), Rs.append(Rt)
+    h_left = torch.from_numpy(np.stack(Ls))
+    h_right = torch.from_numpy(np.stack(Rs))
+    d_left, d_right = h_left.to(dev), h_right.to(dev)
+    d_dl = torch.empty((B, rows, cols), dtype=elem_dtype, device=dev)
+    d_dr = torch.empty_like(d_dl)
+    gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev) if world > 1 else None
+    mine = torch.empty((2, B, rows, cols), dtype=elem_dtype, device=dev) if world > 1 else None
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    stream = torch.cuda.Stream(device=dev)              # a real (non-default) stream: the library enqueues on it
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step_device():
+        rc = lib.stereo_disparity_pair_batch_u8_device(
+            ctx.handle, cost, B, d_left.data_ptr(), d_right.data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
+            d_dl.data_ptr(), d_dr.data_ptr(), cols * elem, rows * cols * elem, elem, sp)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+        if world > 1:       # the batch config's exchange step: gather every rank's maps
+            mine[0].copy_(d_dl), mine[1].copy_(d_dr)
+            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    units_rank = B * 2 * rows * cols * nd
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    hot_ms, hot_n, launches = 0.0, 0, 0
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()                                     # L2 flush, outside the per-step event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        evs.append((e0, e1))
+        launches += ctx.last_launches
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # hot-kernel time of the last step (events recorded by the library on the same stream)
+    ms, nmeas = ctx.last_hot_kernel_ms()
+    if nmeas > 0:
+        hot_ms, hot_n = ms, nmeas
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * units_rank * args.steps / (dev_ms * 1e-3) / 1e6
+
+    # ---- e2e: reference-facing host call, float32 (CV_32FC1) host buffers, copies inside the timed region
+    hf_left = h_left.to(torch.float32).pin_memory()
+    hf_right = h_right.to(torch.float32).pin_memory()
+    h_dl = torch.empty((B, rows, cols), dtype=elem_dtype).pin_memory()
+    h_dr = torch.empty((B, rows, cols), dtype=elem_dtype).pin_memory()
+
+    def step_host():
+        for i in range(B):
+            rc = lib.stereo_disparity_pair_f32_host(
+                ctx.handle, cost, hf_left[i].data_ptr(), cols * 4, hf_right[i].data_ptr(), cols * 4, rows, cols, R, nd - 1,
+                h_dl[i].data_ptr(), h_dr[i].data_ptr(), cols * elem, elem)
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * units_rank * e2e_steps / e2e_s / 1e6
+    e2e_launches = ctx.last_launches * B * e2e_steps
+
+    # u8 host entry (same computation for callers that hold 8-bit images)
+    hu_l, hu_r = h_left.pin_memory(), h_right.pin_memory()
+
+    def step_host_u8():
+        rc = lib.stereo_disparity_pair_batch_u8_host(
+            ctx.handle, cost, B, hu_l.data_ptr(), hu_r.data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
+            h_dl.data_ptr(), h_dr.data_ptr(), cols * elem, rows * cols * elem, elem)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+
+    step_host_u8()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host_u8()
+    barrier()
+    e2e8_s = time.perf_counter() - t0
+    t = torch.tensor([e2e8_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e8_value = world * units_rank * e2e_steps / float(t.item()) / 1e6
+
+    if rank == 0:
+        peaks = measured_peaks()
+        props = torch.cuda.get_device_properties(dev)
+        sms = props.multi_processor_count
+        peak_lane_ops = sms * 128 * peaks["sm_max_mhz"] * 1e6               # lane-ops / s
+        roof = None
+        if hot_n > 0:
+            units_hot = hot_n * rows * cols * nd                            # one direction per hot launch
+            t_hot = hot_ms * 1e-3
+            achieved = OPS_PER_UNIT["ssd"] * units_hot / t_hot
+            b_in, b_out = 1, elem
+            alg_bytes = rows * cols * (2 * b_in + b_out)                    # per launch
+            roof = {
+                "bound": "alu", "kernel": "fast_ssd_kernel",
+                "achieved": round(achieved / 1e12, 3), "peak": round(peak_lane_ops / 1e12, 3), "unit": "Tlane-op/s",
+                "frac": round(achieved / peak_lane_ops, 4),
+                "ops_per_unit": OPS_PER_UNIT["ssd"], "units_per_launch": rows * cols * nd,
+                "launch_ms": round(hot_ms / hot_n, 4), "launches_timed": hot_n,
+                "peak_def": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
+                "traffic": None,
+                "hbm": {"achieved": round(alg_bytes / (hot_ms / hot_n * 1e-3) / 1e9, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(alg_bytes / (hot_ms / hot_n * 1e-3) / 1e9 / peaks["hbm_gbs"], 5),
+                        "algorithmic_bytes_per_launch": alg_bytes, "of": peaks["source"]},
+            }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, dt, desc = cpu_reference_sample(wl, args.ref_rows, os.cpu_count() or 1)
+            cpu = {**desc, "value": round(v, 3), "unit": UNIT, "seconds": round(dt, 2)}
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 (int32 accumulate)", "data": "synthetic",
+            "config": {"workload": args.workload + "_ssd_pair", "rows": rows, "cols": cols, "ndisp": nd,
+                       "window": 2 * R + 1, "pairs_per_gpu_per_step": B, "directions": 2,
+                       "sharding": "by pair" + (", NCCL all_gather of maps inside the step" if world > 1 else ""),
+                       "l2": "flushed between steps (512 MiB memset outside the per-step event pair)",
+                       "out_dtype": str(elem_dtype).replace("torch.", "")},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * 2 * rows * cols * 4,
+                    "d2h_bytes_per_step": B * 2 * rows * cols * elem, "steps": e2e_steps,
+                    "api": "stereo_disparity_pair_f32_host (CV_32FC1 host images, pinned)",
+                    "u8_host_api_value": round(e2e8_value, 1)},
+            "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k_d256_w11", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=2, help="stereo pairs per GPU per step")
+    ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,4 +87,9 @@ struct stereo_ctx {
     int last_launches = 0;
     float last_ms = -1.f;
     int force_path = 0;
+    // device time of the hot kernels only (fast_*_kernel), per direction, for the roofline report
+    static constexpr int HOT_EVENTS = 16;
+    cudaEvent_t hot0[HOT_EVENTS] = {}, hot1[HOT_EVENTS] = {};
+    int hot_used = 0;          // event pairs recorded by the last call
+    int hot_total = 0;         // hot-kernel launches of the last call (may exceed HOT_EVENTS)
 };

@@ -37,7 +37,18 @@ constexpr int FRPS = 8;         // operand rows per pipeline stage
 constexpr int FNST = 4;         // pipeline stages
 constexpr int FWARPS = 8;       // warps per CTA
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
-constexpr int KEY_INVALID = INT_MAX;
+constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
+constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone
+
+// Keys are unsigned:  key = BIAS + 128*(ER - 2C) + position,  BIAS = 128*Emax, Emax = (2R+1)^2*255^2,
+// so valid keys lie in [0, 256*Emax + position].  A candidate whose centre is not a legal search
+// position carries E2 = KEY_INVALID; its key KEY_INVALID - 256*C stays above every valid key as long
+// as 512*Emax < 2^32 (R <= 5), i.e. border masking costs no instruction there.
+__host__ __device__ static inline uint32_t key_emax(int R) { return uint32_t((2 * R + 1) * (2 * R + 1)) * 65025u; }
+__host__ __device__ static inline uint32_t key_bias(int R) { return key_emax(R) << FKEY_BITS; }
+__host__ __device__ static inline uint32_t key_invalid_threshold(int R) {
+    return R <= FFREE_MASK_R ? KEY_INVALID - (key_emax(R) << (FKEY_BITS + 1)) : KEY_INVALID;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Geometry shared by host and device
@@ -73,7 +84,7 @@ static inline int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && (
 struct FastArrays {
     int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
     uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
-    int32_t* E2;       // [J][e2_pitch]   128*ER + position, or KEY_INVALID
+    int32_t* E2;       // [J][e2_pitch]   BIAS + 128*ER + position, or KEY_INVALID
     int32_t* H;        // horizontal energy sums of the extended target image
     int32_t* PART;     // [G][nrows][wpart] winning keys
     float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
@@ -180,7 +191,7 @@ __global__ void prep_h_kernel(const uint8_t* __restrict__ B, size_t step, FastGe
     H[size_t(hi) * g.e2_pitch + q2] = s;
 }
 
-// E2[j][q2] = 128*ER + q2 for valid centres, KEY_INVALID otherwise; RS (NCC) = 1/sqrt(ER) (0 if ER==0).
+// E2[j][q2] = BIAS + 128*ER + q2 for valid centres, KEY_INVALID otherwise; RS (NCC) = 1/sqrt(ER) (0 if ER==0).
 __global__ void prep_e2_kernel(const int32_t* __restrict__ H, FastGeom g, int32_t* __restrict__ E2, float* __restrict__ RS) {
     const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y;                 // output row index within the band
@@ -192,7 +203,7 @@ __global__ void prep_e2_kernel(const int32_t* __restrict__ H, FastGeom g, int32_
     const int uc = q2 - g.eoff;
     const bool valid = uc >= g.cmin && uc <= g.cmax;
     if (g.cost == STEREO_COST_SSD) {
-        E2[size_t(j) * g.e2_pitch + q2] = valid ? (er << FKEY_BITS) + q2 : KEY_INVALID;
+        E2[size_t(j) * g.e2_pitch + q2] = int(valid ? key_bias(g.R) + (uint32_t(er) << FKEY_BITS) + uint32_t(q2) : KEY_INVALID);
     } else {
         E2[size_t(j) * g.e2_pitch + q2] = valid ? er : -1;
         RS[size_t(j) * g.e2_pitch + q2] = (valid && er > 0) ? rsqrtf(float(er)) : 0.f;
@@ -208,6 +219,7 @@ struct FastKernelParams {
     const uint32_t* RQ;
     const int32_t* E2;
     int32_t* PART;
+    int kmul;          // 2 << FKEY_BITS, passed at run time so that ptxas keeps an IMAD for these keys
 };
 
 template <int R>
@@ -220,12 +232,18 @@ struct RowShape {
     static constexpr int NE4 = (NE + 3) / 4 * 4;
 };
 
-// One operand row for one warp.  MODE 0: warm-up (add the entering row only, no output);
-// MODE 1: regular row; MODE 2: regular row with candidate masking.  PAR selects the byte pair.
+// One operand row for one warp.
+//   MODE 0: warm-up (add the entering row only, no output)
+//   MODE 1: regular row; invalid search positions lose through their E2 entry alone (R <= 5)
+//   MODE 2: MODE 1 + whole lanes beyond max_disp are excluded (one LOP3 per pixel)
+//   MODE 3: explicit per-candidate selects (partially valid lanes, or border positions with R >= 6)
+// PAR selects the byte pair of the RQ words (even/odd step row).
+// The column updates (IDP.2A, FMA-heavy pipe) are interleaved with the horizontal slide / WTA of the
+// same row (IADD3, VIMNMX on the ALU pipe) so that a single warp keeps both half-rate pipes busy.
 template <int R, int PAR, int MODE>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
-                                         int32_t* __restrict__ out_row, int mmax, int lane) {
+                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int kmul) {
     using S = RowShape<R>;
     int lpv[S::NC4];
     int rqv[S::NQ4];
@@ -239,16 +257,17 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const 
         const int4 v = lds128(rq_row + 4 * i);
         rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
     }
-#pragma unroll
-    for (int c = 0; c < S::NC; ++c) {
+    auto update = [&](int c) {
         const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];
 #pragma unroll
-        for (int m = 0; m < FM; ++m) {
+        for (int m = 0; m < FM; ++m)
             col[m][c] = PAR ? dp2a_hi(a, unsigned(rqv[c + m]), col[m][c]) : dp2a_lo(a, unsigned(rqv[c + m]), col[m][c]);
-        }
+    };
+    if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < S::NC; ++c) update(c);
+        return;
     }
-    if (MODE == 0) return;
-
     int e2v[S::NE4];
 #pragma unroll
     for (int i = 0; i < S::NE4 / 4; ++i) {
@@ -257,28 +276,34 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const 
     }
     int s[FM];
 #pragma unroll
-    for (int m = 0; m < FM; ++m) {
-        int acc = 0;
+    for (int m = 0; m < FM; ++m) s[m] = 0;
 #pragma unroll
-        for (int c = 0; c < 2 * R; ++c) acc += col[m][c];
-        s[m] = acc;
+    for (int c = 0; c < 2 * R; ++c) {
+        update(c);
+#pragma unroll
+        for (int m = 0; m < FM; ++m) s[m] += col[m][c];
     }
-    int res[4];
+    uint32_t res[4];
 #pragma unroll
     for (int k = 0; k < FK; ++k) {
-        int key[FM];
+        update(k + 2 * R);
+        uint32_t key[FM];
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
-            // s = -C (the packed operand carries -l): key = 128*(ER - 2C) + position
-            int kv = int(unsigned(e2v[k + m]) + unsigned(s[m]) * unsigned(2 << FKEY_BITS));
-            if (MODE == 2) kv = (e2v[k + m] == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
+            // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
+            // Half of the keys use a register multiplier (IMAD, FMA-heavy pipe), half a literal shift
+            // (LEA, ALU pipe) to balance the two half-rate integer pipes.
+            uint32_t kv = ((k + m) & 1) ? uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(kmul)
+                                        : uint32_t(e2v[k + m]) + (uint32_t(s[m]) << (FKEY_BITS + 1));
+            if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
             key[m] = kv;
         }
-        int best = min(min(key[0], key[1]), min(key[2], key[3]));
+        uint32_t best = min(min(key[0], key[1]), min(key[2], key[3]));
+        if (MODE == 2) best |= lane_or;
         res[k & 3] = __reduce_min_sync(0xffffffffu, best);
         if ((k & 3) == 3 && lane == 0)
-            *reinterpret_cast<int4*>(out_row + k - 3) = make_int4(res[0], res[1], res[2], res[3]);
+            *reinterpret_cast<uint4*>(out_row + k - 3) = make_uint4(res[0], res[1], res[2], res[3]);
     }
 }
 
@@ -370,10 +395,14 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
         const bool active = (x0 < g.cols) && (grp < g.G);
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
-        // candidate masking is needed if any (pixel, disparity) of this warp's block is invalid
+        // which flavour of candidate masking this warp's (24 pixels x 128 disparities) block needs
         const int dlo = g.dmin + FGROUP * grp;                         // first disparity of the group
-        const bool need_mask = (x0 + dlo < g.cmin) || (x0 + FK - 1 + dlo + FGROUP - 1 > g.cmax) || (dlo + FGROUP - 1 > g.dmax);
+        const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + FK - 1 + dlo + FGROUP - 1 > g.cmax);
+        const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
+        const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
+        const int mode = (partial_lane || (pos_invalid && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
         const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
+        const uint32_t lane_or = mmax < 0 ? KEY_INVALID : 0u;
         const int lp_off = (warp / g.gc) * FK;
         const int rq_off = (warp / g.gc) * FK + FGROUP * (warp % g.gc) + FM * lane;
         int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
@@ -396,16 +425,12 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
                     const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
-                    if (j < jreg) {
-                        if (par) fast_row<R, 1, 0>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                        else     fast_row<R, 0, 0>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                    } else if (!need_mask) {
-                        if (par) fast_row<R, 1, 1>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                        else     fast_row<R, 0, 1>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                    } else {
-                        if (par) fast_row<R, 1, 2>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                        else     fast_row<R, 0, 2>(col, lp_row, rq_row, e2_row, out_row, mmax, lane);
-                    }
+#define SB_ROW(P_, M_) fast_row<R, P_, M_>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, P.kmul)
+                    if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
+                    else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
+                    else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
+                    else                { if (par) SB_ROW(1, 3); else SB_ROW(0, 3); }
+#undef SB_ROW
                 }
             }
             __syncwarp();
@@ -425,26 +450,27 @@ __global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom
     if (x >= g.cols) return;
     int bestc = INT_MAX, bestd = 0;
     bool found = false;
+    const uint32_t thresh = key_invalid_threshold(g.R), bias = key_bias(g.R);
     for (int grp = 0; grp < g.G; ++grp) {
-        const int key = PART[(size_t(grp) * g.nrows + yy) * g.wpart + x];
-        if (key == KEY_INVALID) continue;
-        const int qlo = x + g.dmin + FGROUP * grp + g.eoff;        // position of the group's first candidate
-        const int q2 = qlo + ((key - qlo) & (FGROUP - 1));
-        const int c = (key - q2) >> FKEY_BITS;                     // ER - 2C (exact: multiple of 128)
-        if (!found || c < bestc) { bestc = c; bestd = q2 - g.eoff - x; found = true; }
+        const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
+        if (key >= thresh) continue;                               // no legal candidate in this group
+        const uint32_t qlo = uint32_t(x + g.dmin + FGROUP * grp + g.eoff);   // position of the group's first candidate
+        const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
+        const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
+        if (!found || c < bestc) { bestc = c; bestd = int(q2) - g.eoff - x; found = true; }
     }
     int cost = 99999999;                                           // DisparitySSD.cpp:37
-    if (found) {
-        // EL(x): window energy of the reference image (replicate padding) — only needed to report
-        // the cost and to honour the 99999999 threshold.
+    // EL(x), the window energy of the reference image (replicate padding), is only needed to report
+    // the cost and to honour the 99999999 threshold; with (2R+1)^2 * 255^2 < 99999999 (R <= 19) the
+    // threshold can never bind, so the energy is computed only when the caller asked for costs.
+    if (found && best_out) {
         int el = 0;
         const int y = g.rb + yy;
         for (int wy = -g.R; wy <= g.R; ++wy) {
             const uint8_t* row = A + size_t(clampi(y + wy, 0, g.rows - 1)) * a_step;
             for (int wx = -g.R; wx <= g.R; ++wx) { const int v = row[clampi(x + wx, 0, g.cols - 1)]; el += v * v; }
         }
-        const int sum = bestc + el;
-        if (sum < 99999999) cost = sum; else bestd = 0;
+        cost = bestc + el;
     }
     char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
     if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(bestd) & 0xFFu));
@@ -565,8 +591,12 @@ static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
     prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch, 256), g.J / 2), tb, 0, st>>>(B, p.tgt.step, g, a.RQ);
     prep_h_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows + 2 * g.R), tb, 0, st>>>(B, p.tgt.step, g, a.H);
     prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows), tb, 0, st>>>(a.H, g, a.E2, a.RS);
-    FastKernelParams kp{g, a.LP, a.RQ, a.E2, a.PART};
+    FastKernelParams kp{g, a.LP, a.RQ, a.E2, a.PART, 2 << FKEY_BITS};
+    const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
+    if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
     fast_pick_ssd(p.R)<<<g.ctas, FWARPS * 32, fast_smem_bytes(g), st>>>(kp);
+    if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; }
+    ctx->hot_total++;
     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
         a.PART, g, A, p.ref.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
     ctx->last_launches += 6;

@@ -189,6 +189,8 @@ static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
     ctx->last_launches = 0;
     ctx->last_ms = -1.f;
     ctx->last_path = STEREO_PATH_NONE;
+    ctx->hot_used = 0;
+    ctx->hot_total = 0;
     cudaEventRecord(ctx->ev0, st);
 }
 static void end_call(stereo_ctx* ctx, cudaStream_t st) {
@@ -340,6 +342,10 @@ int stereo_ctx_create(int device, stereo_ctx** ctx_out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    for (int i = 0; i < stereo_ctx::HOT_EVENTS && e == cudaSuccess; ++i) {
+        e = cudaEventCreate(&c->hot0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&c->hot1[i]);
+    }
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->d_flag), 256);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_flag), 256, cudaHostAllocDefault);
     if (e != cudaSuccess) {
@@ -364,6 +370,10 @@ void stereo_ctx_destroy(stereo_ctx* ctx) {
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int i = 0; i < stereo_ctx::HOT_EVENTS; ++i) {
+        if (ctx->hot0[i]) cudaEventDestroy(ctx->hot0[i]);
+        if (ctx->hot1[i]) cudaEventDestroy(ctx->hot1[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -383,6 +393,22 @@ float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx) {
 }
 
 int stereo_ctx_last_launches(const stereo_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measured) {
+    if (launches_measured) *launches_measured = 0;
+    if (!ctx || ctx->hot_used == 0) return -1.f;
+    float total = 0.f;
+    for (int i = 0; i < ctx->hot_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->hot1[i]) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->hot0[i], ctx->hot1[i]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return -1.f;
+        }
+        total += ms;
+    }
+    if (launches_measured) *launches_measured = ctx->hot_used;
+    return total;
+}
 
 int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
     if (!ctx || path < 0 || path > STEREO_PATH_FAST_U8) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }

@@ -90,6 +90,12 @@ class Context:
     def last_launches(self) -> int:
         return int(_capi.lib().stereo_ctx_last_launches(self._h))
 
+    def last_hot_kernel_ms(self):
+        """(milliseconds, launches measured) of the last call's hot kernels; (-1, 0) if none ran."""
+        n = C.c_int(0)
+        ms = float(_capi.lib().stereo_ctx_last_hot_kernel_ms(self._h, C.byref(n)))
+        return ms, int(n.value)
+
     def force_path(self, path: int) -> None:
         _check(_capi.lib().stereo_ctx_force_path(self._h, int(path)), "stereo_ctx_force_path")
 
