@@ -26,16 +26,17 @@
 #include "common.cuh"
 #include "exact.cuh"
 #include <climits>
+#include <cstdlib>
 
 namespace sb {
 
-constexpr int FK = 24;          // pixels per thread (strip width)
+constexpr int FK_DEFAULT = 24;  // pixels per thread (strip width); template parameter K of the kernels
 constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
 constexpr int FRPS = 8;         // operand rows per pipeline stage
-constexpr int FNST = 4;         // pipeline stages
-constexpr int FWARPS = 8;       // warps per CTA
+constexpr int FNST = 8;         // pipeline stages
+constexpr int FWARPS_MAX = 12;   // warps per CTA: 8 (K=24, <=255 regs) or 12 (K=16, <=168 regs)
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone
@@ -57,6 +58,8 @@ struct FastGeom {
     // problem
     int rows, cols, R, dmin, dmax, cost;
     int rb, re;            // output band
+    int K;                 // pixels per thread (strip width): 24 or 16
+    int nw;                // warps per CTA: 8 (K=24) or 12 (K=16)
     // derived
     int G;                 // number of 128-disparity groups
     int gc;                // groups per CTA (1 or 2)
@@ -85,8 +88,8 @@ struct FastArrays {
     int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
     uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
     int32_t* E2;       // [J][e2_pitch]   BIAS + 128*ER + position, or KEY_INVALID
-    int32_t* H;        // horizontal energy sums of the extended target image
     int32_t* PART;     // [G][nrows][wpart] winning keys
+    int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
     float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
 };
 
@@ -154,59 +157,99 @@ __device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, 
 // ---------------------------------------------------------------------------------------------------
 // Prep kernels: operand rows in the layout the hot loop consumes
 // ---------------------------------------------------------------------------------------------------
-__global__ void prep_lp_kernel(const uint8_t* __restrict__ A, size_t step, FastGeom g, int32_t* __restrict__ LP) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+// LP[j][p]: 4 columns per thread, 16-byte stores.
+__global__ void __launch_bounds__(256) prep_lp_kernel(const uint8_t* __restrict__ A, size_t step, FastGeom g, int32_t* __restrict__ LP) {
+    const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int j = blockIdx.y;
-    if (p >= g.lp_pitch) return;
+    if (p4 >= g.lp_pitch) return;
     const int y = g.base_y + j;
-    const int col = clampi(p - g.R, 0, g.cols - 1);
-    const int lnew = A[size_t(clampi(y + g.R, 0, g.rows - 1)) * step + col];
-    const int lold = A[size_t(clampi(y - g.R - 1, 0, g.rows - 1)) * step + col];
-    LP[size_t(j) * g.lp_pitch + p] = int(uint32_t(uint16_t(int16_t(-lnew))) | (uint32_t(uint16_t(lold)) << 16));
+    const uint8_t* rnew = A + size_t(clampi(y + g.R, 0, g.rows - 1)) * step;
+    const uint8_t* rold = A + size_t(clampi(y - g.R - 1, 0, g.rows - 1)) * step;
+    int v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int col = clampi(p4 + t - g.R, 0, g.cols - 1);
+        const int lnew = rnew[col], lold = rold[col];
+        v[t] = int(uint32_t(uint16_t(int16_t(-lnew))) | (uint32_t(uint16_t(lold)) << 16));
+    }
+    *reinterpret_cast<int4*>(LP + size_t(j) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
 }
 
-__global__ void prep_rq_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, uint32_t* __restrict__ RQ) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// RQ[jp][q]: 4 positions per thread, 16-byte stores.
+__global__ void __launch_bounds__(256) prep_rq_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, uint32_t* __restrict__ RQ) {
+    const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int jp = blockIdx.y;
-    if (q >= g.rq_pitch) return;
+    if (q4 >= g.rq_pitch) return;
     const int ye = g.base_y + 2 * jp;
-    const int e = q - g.qoff;
-    const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e);
-    const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e);
-    const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e);
-    const uint32_t b3 = bext(B, step, g.rows, g.cols, g.R, ye - g.R, e);
-    RQ[size_t(jp) * g.rq_pitch + q] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    uint32_t v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int e = q4 + t - g.qoff;
+        const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e);
+        const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e);
+        const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e);
+        const uint32_t b3 = bext(B, step, g.rows, g.cols, g.R, ye - g.R, e);
+        v[t] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    *reinterpret_cast<uint4*>(RQ + size_t(jp) * g.rq_pitch + q4) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 
-// H[hi][q2] = sum_{t=-R..R} bext(i, e_c + t)^2 for unpadded row i = rb - R + hi and centre column
-// u_c = q2 - eoff (e_c = u_c + 2R).
-__global__ void prep_h_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, int32_t* __restrict__ H) {
-    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int hi = blockIdx.y;
-    if (q2 >= g.e2_pitch) return;
-    const int i = g.rb - g.R + hi;
-    const int ec = q2 - g.eoff + 2 * g.R;
-    int s = 0;
-    for (int t = -g.R; t <= g.R; ++t) { const int v = bext(B, step, g.rows, g.cols, g.R, i, ec + t); s += v * v; }
-    H[size_t(hi) * g.e2_pitch + q2] = s;
+// Window energies of the extended target image, separably:
+//   pass 1 (prep_v_kernel): V[yy][x] = sum_{j=-R..R} bext(y+j, e)^2, a running sum down the rows;
+//           one thread per column and PV_ROWS-row chunk, no synchronisation.  Column x <-> e = x + vbase.
+//   pass 2 (prep_e2_kernel): ER = sum_{t=-R..R} V[yy][centre + t] from a shared-memory tile, then
+//           E2[j][q2] = BIAS + 128*ER + q2 for legal centres (KEY_INVALID otherwise); RS (NCC) = 1/sqrt(ER).
+constexpr int PV_ROWS = 32;
+__global__ void __launch_bounds__(128) prep_v_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g,
+                                                    int32_t* __restrict__ V, int vpitch, int vbase) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= vpitch) return;
+    const int e = x + vbase;
+    const int yy0 = blockIdx.y * PV_ROWS, yy1 = min(g.nrows, yy0 + PV_ROWS);
+    const int R = g.R;
+    int v = 0;
+    for (int i = g.rb + yy0 - R; i < g.rb + yy0 + R; ++i) { const int b = bext(B, step, g.rows, g.cols, R, i, e); v += b * b; }
+    for (int yy = yy0; yy < yy1; ++yy) {
+        const int y = g.rb + yy;
+        const int bn = bext(B, step, g.rows, g.cols, R, y + R, e);
+        v += bn * bn;
+        V[size_t(yy) * vpitch + x] = v;
+        const int bo = bext(B, step, g.rows, g.cols, R, y - R, e);
+        v -= bo * bo;
+    }
 }
 
-// E2[j][q2] = BIAS + 128*ER + q2 for valid centres, KEY_INVALID otherwise; RS (NCC) = 1/sqrt(ER) (0 if ER==0).
-__global__ void prep_e2_kernel(const int32_t* __restrict__ H, FastGeom g, int32_t* __restrict__ E2, float* __restrict__ RS) {
-    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yy = blockIdx.y;                 // output row index within the band
+constexpr int PE_COLS = 256;
+constexpr int PE_ROWS = 8;
+__global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const int32_t* __restrict__ V, int vpitch, FastGeom g,
+                                                         int32_t* __restrict__ E2, float* __restrict__ RS) {
+    extern __shared__ int pe_smem[];                       // [PE_ROWS][PE_COLS + 2R]
+    const int R = g.R, tw = PE_COLS + 2 * R;
+    const int tid = threadIdx.x;
+    const int q20 = blockIdx.x * PE_COLS;
+    const int yy0 = blockIdx.y * PE_ROWS;
+    const int nr = min(PE_ROWS, g.nrows - yy0);
+    // V column x <-> ext column e = x + vbase with vbase = -eoff + R, so centre q2 (e_c = q2 - eoff + 2R) is
+    // V column q2 + R and its window is V columns q2 .. q2 + 2R.
+    for (int idx = tid; idx < nr * tw; idx += PE_COLS) {
+        const int r = idx / tw, c = idx - r * tw;
+        pe_smem[idx] = V[size_t(yy0 + r) * vpitch + q20 + c];
+    }
+    __syncthreads();
+    const int q2 = q20 + tid;
     if (q2 >= g.e2_pitch) return;
-    const int y = g.rb + yy;
-    const int j = y - g.base_y;
-    int er = 0;
-    for (int t = 0; t <= 2 * g.R; ++t) er += H[size_t(yy + t) * g.e2_pitch + q2];
     const int uc = q2 - g.eoff;
     const bool valid = uc >= g.cmin && uc <= g.cmax;
-    if (g.cost == STEREO_COST_SSD) {
-        E2[size_t(j) * g.e2_pitch + q2] = int(valid ? key_bias(g.R) + (uint32_t(er) << FKEY_BITS) + uint32_t(q2) : KEY_INVALID);
-    } else {
-        E2[size_t(j) * g.e2_pitch + q2] = valid ? er : -1;
-        RS[size_t(j) * g.e2_pitch + q2] = (valid && er > 0) ? rsqrtf(float(er)) : 0.f;
+    for (int r = 0; r < nr; ++r) {
+        int er = 0;
+        for (int t = 0; t <= 2 * R; ++t) er += pe_smem[r * tw + tid + t];
+        const size_t o = size_t(g.rb + yy0 + r - g.base_y) * g.e2_pitch + q2;
+        if (g.cost == STEREO_COST_SSD) {
+            E2[o] = int(valid ? key_bias(R) + (uint32_t(er) << FKEY_BITS) + uint32_t(q2) : KEY_INVALID);
+        } else {
+            E2[o] = valid ? er : -1;
+            RS[o] = (valid && er > 0) ? rsqrtf(float(er)) : 0.f;
+        }
     }
 }
 
@@ -222,13 +265,13 @@ struct FastKernelParams {
     int kmul;          // 2 << FKEY_BITS, passed at run time so that ptxas keeps an IMAD for these keys
 };
 
-template <int R>
+template <int R, int K>
 struct RowShape {
-    static constexpr int NC = FK + 2 * R;              // columns whose sums a thread keeps
+    static constexpr int NC = K + 2 * R;              // columns whose sums a thread keeps
     static constexpr int NC4 = (NC + 3) / 4 * 4;
     static constexpr int NQ = NC + FM - 1;             // target positions a thread touches
     static constexpr int NQ4 = (NQ + 3) / 4 * 4;
-    static constexpr int NE = FK + FM - 1;             // centre positions
+    static constexpr int NE = K + FM - 1;              // centre positions
     static constexpr int NE4 = (NE + 3) / 4 * 4;
 };
 
@@ -240,11 +283,11 @@ struct RowShape {
 // PAR selects the byte pair of the RQ words (even/odd step row).
 // The column updates (IDP.2A, FMA-heavy pipe) are interleaved with the horizontal slide / WTA of the
 // same row (IADD3, VIMNMX on the ALU pipe) so that a single warp keeps both half-rate pipes busy.
-template <int R, int PAR, int MODE>
-__device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const int* __restrict__ lp_row,
+template <int R, int K, int PAR, int MODE>
+__device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
                                          int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int kmul) {
-    using S = RowShape<R>;
+    using S = RowShape<R, K>;
     int lpv[S::NC4];
     int rqv[S::NQ4];
 #pragma unroll
@@ -285,17 +328,16 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const 
     }
     uint32_t res[4];
 #pragma unroll
-    for (int k = 0; k < FK; ++k) {
+    for (int k = 0; k < K; ++k) {
         update(k + 2 * R);
         uint32_t key[FM];
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
             // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
-            // Half of the keys use a register multiplier (IMAD, FMA-heavy pipe), half a literal shift
-            // (LEA, ALU pipe) to balance the two half-rate integer pipes.
-            uint32_t kv = ((k + m) & 1) ? uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(kmul)
-                                        : uint32_t(e2v[k + m]) + (uint32_t(s[m]) << (FKEY_BITS + 1));
+            // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
+            // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
+            uint32_t kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
             if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
             key[m] = kv;
         }
@@ -307,9 +349,9 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R>::NC], const 
     }
 }
 
-template <int R>
-__global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKernelParams P) {
-    using S = RowShape<R>;
+template <int R, int K, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) fast_ssd_kernel(const FastKernelParams P) {
+    using S = RowShape<R, K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FastGeom& g = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -321,7 +363,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST);
 
     if (tid == 0) {
-        for (int i = 0; i < FNST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, FWARPS); }
+        for (int i = 0; i < FNST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -355,7 +397,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
         const int slot = pn % FNST;
         if (pn >= FNST) mbar_wait(empty0 + 8 * slot, ((pn / FNST) - 1) & 1);
         const int xt = p_tile % g.tilesX, gb = p_tile / g.tilesX;
-        const int p0 = xt * g.spc * FK;
+        const int p0 = xt * g.spc * K;
         const int q0 = p0 + g.dmin + FGROUP * gb * g.gc + g.R + g.qoff;
         const int q20 = p0 + g.dmin + FGROUP * gb * g.gc + g.eoff;
         const uint32_t bar = full0 + 8 * slot;
@@ -374,7 +416,10 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
         ++pn; ++p_sj;
         return true;
     };
-    if (tid == 0) {
+    // The producer is lane 0 of the LAST warp: the SMSP arbiter favours higher warp ids, so that warp
+    // tends to run ahead and operand rows are requested as early as the ring allows.
+    const bool is_producer = (tid == (NW - 1) * 32);
+    if (is_producer) {
         for (int i = 0; i < FNST - 2; ++i) if (!producer_issue()) break;
     }
 
@@ -391,20 +436,20 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
         const int xt = tile % g.tilesX, gb = tile / g.tilesX;
         const int strip = xt * g.spc + warp / g.gc;
         const int grp = gb * g.gc + warp % g.gc;
-        const int x0 = strip * FK;
+        const int x0 = strip * K;
         const bool active = (x0 < g.cols) && (grp < g.G);
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
         // which flavour of candidate masking this warp's (24 pixels x 128 disparities) block needs
         const int dlo = g.dmin + FGROUP * grp;                         // first disparity of the group
-        const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + FK - 1 + dlo + FGROUP - 1 > g.cmax);
+        const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + K - 1 + dlo + FGROUP - 1 > g.cmax);
         const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
         const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
         const int mode = (partial_lane || (pos_invalid && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
         const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
         const uint32_t lane_or = mmax < 0 ? KEY_INVALID : 0u;
-        const int lp_off = (warp / g.gc) * FK;
-        const int rq_off = (warp / g.gc) * FK + FGROUP * (warp % g.gc) + FM * lane;
+        const int lp_off = (warp / g.gc) * K;
+        const int rq_off = (warp / g.gc) * K + FGROUP * (warp % g.gc) + FM * lane;
         int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
 #pragma unroll
         for (int m = 0; m < FM; ++m)
@@ -412,7 +457,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
             for (int c = 0; c < S::NC; ++c) col[m][c] = 0;
 
         for (int sj = js / FRPS; sj <= (je - 1) / FRPS; ++sj, ++n) {
-            if (tid == 0) producer_issue();
+            if (is_producer) producer_issue();
             const int slot = n % FNST;
             mbar_wait(full0 + 8 * slot, (n / FNST) & 1);
             if (active) {
@@ -425,7 +470,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) fast_ssd_kernel(const FastKern
                     const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
-#define SB_ROW(P_, M_) fast_row<R, P_, M_>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, P.kmul)
+#define SB_ROW(P_, M_) fast_row<R, K, P_, M_>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, P.kmul)
                     if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
                     else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
                     else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
@@ -492,14 +537,23 @@ static inline bool fast_supported(const Problem& p) {
     return true;
 }
 
+// Strip width: 24 pixels per thread by default; STEREO_FAST_K=16 selects the narrower variant (debug knob).
+static inline int fast_pick_k(const Problem& p) {
+    static const int forced = [] { const char* e = getenv("STEREO_FAST_K"); return e ? atoi(e) : 0; }();
+    if (forced == 16 && (p.R == 4 || p.R == 5)) return 16;
+    return FK_DEFAULT;
+}
+
 static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGeom& g) {
     g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.dmin = p.dmin; g.dmax = p.dmax; g.cost = p.cost;
     g.rb = p.row_begin; g.re = p.row_end; g.nrows = g.re - g.rb;
     const int D = p.dmax - p.dmin + 1;
+    g.K = fast_pick_k(p);
     g.G = (D + FGROUP - 1) / FGROUP;
     g.gc = (g.G % 2 == 0) ? 2 : 1;
-    g.spc = FWARPS / g.gc;
-    g.nstrips = (p.cols + FK - 1) / FK;
+    g.nw = (g.K == 16) ? 12 : 8;
+    g.spc = g.nw / g.gc;
+    g.nstrips = (p.cols + g.K - 1) / g.K;
     g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
     g.gblocks = g.G / g.gc;
     const int w = 2 * p.R + 1;
@@ -514,7 +568,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGe
     int eo = -p.dmin; if (eo < 0) eo = 0;
     while (((p.dmin + eo) & 3) != 0) ++eo;
     g.eoff = eo;
-    const int tile_px = g.spc * FK;
+    const int tile_px = g.spc * g.K;
     g.lpw = round_up(tile_px + 2 * p.R, 4);
     g.rqw = round_up(tile_px + 2 * p.R + FGROUP * g.gc + FM, 4);
     g.e2w = round_up(tile_px + FGROUP * g.gc + FM, 4);
@@ -545,33 +599,43 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     add(size_t(g.J) * g.lp_pitch * 4);
     add(size_t(g.J / 2) * g.rq_pitch * 4);
     add(size_t(g.J) * g.e2_pitch * 4);
-    add(size_t(g.nrows + 2 * g.R) * g.e2_pitch * 4);
     add(size_t(g.G) * g.nrows * g.wpart * 4);
+    add(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + 256, 64) * 4);
     if (p.cost == STEREO_COST_NCORR) add(size_t(g.J) * g.e2_pitch * 4);
     return b + 4096;
 }
 
 typedef void (*fast_kernel_fn)(const FastKernelParams);
-static inline fast_kernel_fn fast_pick_ssd(int R) {
+static inline fast_kernel_fn fast_pick_ssd(int R, int K) {
+    if (K == 16) {
+        switch (R) {
+        case 4: return fast_ssd_kernel<4, 16, 12>;
+        case 5: return fast_ssd_kernel<5, 16, 12>;
+        }
+        return nullptr;
+    }
     switch (R) {
-    case 0: return fast_ssd_kernel<0>;
-    case 1: return fast_ssd_kernel<1>;
-    case 2: return fast_ssd_kernel<2>;
-    case 3: return fast_ssd_kernel<3>;
-    case 4: return fast_ssd_kernel<4>;
-    case 5: return fast_ssd_kernel<5>;
-    case 6: return fast_ssd_kernel<6>;
-    case 7: return fast_ssd_kernel<7>;
+    case 0: return fast_ssd_kernel<0, 24, 8>;
+    case 1: return fast_ssd_kernel<1, 24, 8>;
+    case 2: return fast_ssd_kernel<2, 24, 8>;
+    case 3: return fast_ssd_kernel<3, 24, 8>;
+    case 4: return fast_ssd_kernel<4, 24, 8>;
+    case 5: return fast_ssd_kernel<5, 24, 8>;
+    case 6: return fast_ssd_kernel<6, 24, 8>;
+    case 7: return fast_ssd_kernel<7, 24, 8>;
     }
     return nullptr;
 }
 
 static inline int fast_ctx_init(stereo_ctx*) {
-    for (int R = 0; R <= FMAXR; ++R) {
-        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fast_pick_ssd(R)),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
-    }
+    for (int K = 16; K <= 24; K += 8)
+        for (int R = 0; R <= FMAXR; ++R) {
+            fast_kernel_fn fn = fast_pick_ssd(R, K);
+            if (!fn) continue;
+            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+        }
     return STEREO_OK;
 }
 
@@ -581,20 +645,24 @@ static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
     a.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
     a.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
     a.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
-    a.H = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows + 2 * g.R) * g.e2_pitch * 4));
     a.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
-    if (!a.LP || !a.RQ || !a.E2 || !a.H || !a.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    a.V = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64) * 4));
+    if (!a.LP || !a.RQ || !a.E2 || !a.PART || !a.V) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
     const uint8_t* A = static_cast<const uint8_t*>(p.ref.ptr);
     const uint8_t* B = static_cast<const uint8_t*>(p.tgt.ptr);
     const dim3 tb(256);
-    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch, 256), g.J), tb, 0, st>>>(A, p.ref.step, g, a.LP);
-    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch, 256), g.J / 2), tb, 0, st>>>(B, p.tgt.step, g, a.RQ);
-    prep_h_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows + 2 * g.R), tb, 0, st>>>(B, p.tgt.step, g, a.H);
-    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, 256), g.nrows), tb, 0, st>>>(a.H, g, a.E2, a.RS);
+    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J), tb, 0, st>>>(A, p.ref.step, g, a.LP);
+    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2), tb, 0, st>>>(B, p.tgt.step, g, a.RQ);
+    const int vpitch = round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64);
+    prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS)), 128, 0, st>>>(
+        B, p.tgt.step, g, a.V, vpitch, -g.eoff + g.R);
+    const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
+    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS)), PE_COLS, pe_smem, st>>>(
+        a.V, vpitch, g, a.E2, a.RS);
     FastKernelParams kp{g, a.LP, a.RQ, a.E2, a.PART, 2 << FKEY_BITS};
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
     if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
-    fast_pick_ssd(p.R)<<<g.ctas, FWARPS * 32, fast_smem_bytes(g), st>>>(kp);
+    fast_pick_ssd(p.R, g.K)<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
     if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; }
     ctx->hot_total++;
     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
