@@ -14,7 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-    "-diag-suppress", "177",
+    "-diag-suppress", "177,128",
 ]
 
 

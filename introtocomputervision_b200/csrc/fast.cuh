@@ -91,6 +91,7 @@ struct FastArrays {
     int32_t* PART;     // [G][nrows][wpart] winning keys
     int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
     float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
+    float* SC;         // NCC: [nstrips][nrows] magic = 2^ceil(log2 sqrt(max EL of the strip row))
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(256) prep_lp_kernel(const uint8_t* __restrict_
     for (int t = 0; t < 4; ++t) {
         const int col = clampi(p4 + t - g.R, 0, g.cols - 1);
         const int lnew = rnew[col], lold = rold[col];
-        v[t] = int(uint32_t(uint16_t(int16_t(-lnew))) | (uint32_t(uint16_t(lold)) << 16));
+        // SSD: (-l_new, +l_old) so the running sums hold -C; NCC: (+l_new, -l_old), sums hold +C
+        const int a_new = g.cost == STEREO_COST_SSD ? -lnew : lnew, a_old = g.cost == STEREO_COST_SSD ? lold : -lold;
+        v[t] = int(uint32_t(uint16_t(int16_t(a_new))) | (uint32_t(uint16_t(int16_t(a_old))) << 16));
     }
     *reinterpret_cast<int4*>(LP + size_t(j) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
 }
@@ -248,9 +251,33 @@ __global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const int32_t* __restr
             E2[o] = int(valid ? key_bias(R) + (uint32_t(er) << FKEY_BITS) + uint32_t(q2) : KEY_INVALID);
         } else {
             E2[o] = valid ? er : -1;
-            RS[o] = (valid && er > 0) ? rsqrtf(float(er)) : 0.f;
+            RS[o] = (valid && er > 0) ? float(1.0 / sqrt(double(er))) : 0.f;
         }
     }
+}
+
+// NCC: per strip (K pixels) and output row, the power of two just above sqrt(max EL) — the binade the
+// fixed-point keys of that strip row live in.  V holds the vertical (2R+1)-sums of squares of the
+// replicate-padded REFERENCE image: V column c = padded column c, so EL(x) = sum V[yy][x .. x+2R].
+__global__ void __launch_bounds__(128) prep_scale_kernel(const int32_t* __restrict__ V, int vpitch, FastGeom g,
+                                                        float* __restrict__ SC) {
+    const int strip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (strip >= g.tilesX * g.spc) return;
+    const int x0 = strip * g.K;
+    float magic = 1.f;
+    if (x0 < g.cols) {
+        const int32_t* v = V + size_t(yy) * vpitch + x0;
+        const int x1 = min(g.K, g.cols - x0);
+        int el = 0, elmax = 0;
+        for (int t = 0; t < 2 * g.R; ++t) el += v[t];
+        for (int x = 0; x < x1; ++x) { el += v[x + 2 * g.R]; elmax = max(elmax, el); el -= v[x]; }
+        // smallest power of two strictly above sqrt(elmax) * (1 + 2^-20)  (C*rs <= sqrt(EL), rounding slack)
+        const float bound = float(sqrt(double(elmax)) * (1.0 + 1.0 / 1048576.0));
+        int e; frexpf(bound, &e);                                       // bound = f * 2^e, f in [0.5, 1)
+        magic = elmax > 0 ? ldexpf(1.f, e) : 1.f;                       // 2^e > bound
+    }
+    SC[size_t(strip) * g.nrows + yy] = magic;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -260,9 +287,9 @@ struct FastKernelParams {
     FastGeom g;
     const int32_t* LP;
     const uint32_t* RQ;
-    const int32_t* E2;
+    const int32_t* E2;   // SSD: key offsets; NCC: the RS array (f32 bit patterns)
     int32_t* PART;
-    int kmul;          // 2 << FKEY_BITS, passed at run time so that ptxas keeps an IMAD for these keys
+    const float* SC;     // NCC: [strip][output row] power-of-two magic (see fast_row)
 };
 
 template <int R, int K>
@@ -277,17 +304,37 @@ struct RowShape {
 
 // One operand row for one warp.
 //   MODE 0: warm-up (add the entering row only, no output)
-//   MODE 1: regular row; invalid search positions lose through their E2 entry alone (R <= 5)
+//   MODE 1: regular row; SSD: invalid search positions lose through their E2 entry alone (R <= 5);
+//           NCC: every candidate of the block is legal
 //   MODE 2: MODE 1 + whole lanes beyond max_disp are excluded (one LOP3 per pixel)
-//   MODE 3: explicit per-candidate selects (partially valid lanes, or border positions with R >= 6)
+//   MODE 3: explicit per-candidate selects (partially valid lanes, border positions)
 // PAR selects the byte pair of the RQ words (even/odd step row).
 // The column updates (IDP.2A, FMA-heavy pipe) are interleaved with the horizontal slide / WTA of the
 // same row (IADD3, VIMNMX on the ALU pipe) so that a single warp keeps both half-rate pipes busy.
-template <int R, int K, int PAR, int MODE>
+//
+// NCC keys.  v = C * RS[pos] (f32, C an exact integer) orders the candidates of one pixel; the oracle's
+// first-maximum rule (cv::minMaxLoc, DisparityNCorr.cpp:62-64) needs the full f32 precision of v AND the
+// position in one 32-bit key, which an f32 bit pattern cannot hold.  So v is turned into a 23-bit
+// fixed-point number first: r = v + magic with magic = the power of two just above sqrt(max EL) of the
+// strip row (C*RS <= sqrt(EL) by Cauchy-Schwarz), i.e. r lies in the binade [magic, 2*magic) and its
+// mantissa IS round(v * 2^23 / magic).  key = (bits(r) << 9) + (reversed position << 2 | 3): 23 value
+// bits, 7 position bits, low bits 11 so that 0 can mean "no legal candidate".  Unsigned max.
+// For (2R+1)^2*255^2 < 2^23 (R <= 5) the running sums carry the float bias 0x4B000000, i.e. they ARE
+// the float 2^23 + C, and v = fma(2^23 + C, rs, -2^23*rs) is the correctly rounded product with no
+// conversion instruction; larger windows convert with I2F and fold the magic add into the FFMA.
+constexpr int NCC_BIAS_MAX_R = 5;
+constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
+constexpr int NCC_KEY_SHIFT = 9;                  // mantissa -> bits 9..31
+constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses every unsigned max)
+
+template <int R, int K, int PAR, int MODE, int COST>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
-                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int kmul) {
+                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int cbase,
+                                         int cols, float magic) {
     using S = RowShape<R, K>;
+    constexpr bool NCC = (COST == STEREO_COST_NCORR);
+    constexpr bool BIASED = NCC && (R <= NCC_BIAS_MAX_R);
     int lpv[S::NC4];
     int rqv[S::NQ4];
 #pragma unroll
@@ -301,7 +348,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
     }
     auto update = [&](int c) {
-        const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];
+        const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];      // warm-up: entering row only
 #pragma unroll
         for (int m = 0; m < FM; ++m)
             col[m][c] = PAR ? dp2a_hi(a, unsigned(rqv[c + m]), col[m][c]) : dp2a_lo(a, unsigned(rqv[c + m]), col[m][c]);
@@ -319,7 +366,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     }
     int s[FM];
 #pragma unroll
-    for (int m = 0; m < FM; ++m) s[m] = 0;
+    for (int m = 0; m < FM; ++m) s[m] = BIASED ? NCC_FLOAT_BIAS : 0;
 #pragma unroll
     for (int c = 0; c < 2 * R; ++c) {
         update(c);
@@ -334,23 +381,41 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
-            // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
-            // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
-            // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
-            uint32_t kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
-            if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
-            key[m] = kv;
+            if (!NCC) {
+                // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
+                // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
+                // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
+                uint32_t kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
+                key[m] = kv;
+            } else {
+                const float rs = __int_as_float(e2v[k + m]);
+                const float r = BIASED ? __fadd_rn(__fmaf_rn(__int_as_float(s[m]), rs, rs * -8388608.0f), magic)
+                                       : __fmaf_rn(__int2float_rn(s[m]), rs, magic);
+                // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
+                uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
+                if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax) ? NCC_KEY_NONE : kv;
+                key[m] = kv;
+            }
         }
-        uint32_t best = min(min(key[0], key[1]), min(key[2], key[3]));
-        if (MODE == 2) best |= lane_or;
-        res[k & 3] = __reduce_min_sync(0xffffffffu, best);
+        uint32_t best;
+        if (!NCC) {
+            best = min(min(key[0], key[1]), min(key[2], key[3]));
+            if (MODE == 2) best |= lane_or;
+            res[k & 3] = __reduce_min_sync(0xffffffffu, best);
+        } else {
+            best = max(max(key[0], key[1]), max(key[2], key[3]));
+            if (MODE == 2) best = mmax < 0 ? NCC_KEY_NONE : best;
+            res[k & 3] = __reduce_max_sync(0xffffffffu, best);
+        }
         if ((k & 3) == 3 && lane == 0)
             *reinterpret_cast<uint4*>(out_row + k - 3) = make_uint4(res[0], res[1], res[2], res[3]);
     }
 }
 
-template <int R, int K, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) fast_ssd_kernel(const FastKernelParams P) {
+template <int R, int K, int NW, int COST>
+__global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelParams P) {
+    constexpr bool NCC = (COST == STEREO_COST_NCORR);
     using S = RowShape<R, K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FastGeom& g = P.g;
@@ -445,9 +510,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_ssd_kernel(const FastKernelPa
         const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + K - 1 + dlo + FGROUP - 1 > g.cmax);
         const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
         const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
-        const int mode = (partial_lane || (pos_invalid && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
+        const int mode = (partial_lane || (pos_invalid && (NCC || R > FFREE_MASK_R))) ? 3 : (lane_invalid ? 2 : 1);
         const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
-        const uint32_t lane_or = mmax < 0 ? KEY_INVALID : 0u;
+        // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
+        const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * lane) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
+        const float* sc_row = NCC ? P.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
+        const int cbase = x0 + dlo + FM * lane;                          // centre column of candidate (k=0, m=0)
         const int lp_off = (warp / g.gc) * K;
         const int rq_off = (warp / g.gc) * K + FGROUP * (warp % g.gc) + FM * lane;
         int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
@@ -470,7 +538,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_ssd_kernel(const FastKernelPa
                     const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
-#define SB_ROW(P_, M_) fast_row<R, K, P_, M_>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, P.kmul)
+                    const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
+#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, cbase, g.cols, magic)
                     if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
                     else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
                     else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
@@ -524,11 +593,56 @@ __global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom
     if (best_out) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = cost;
 }
 
+// NCC: winning key per group -> first maximum over the groups -> disparity with the reference's
+// alignment rule (DisparityNCorr.cpp:67) and, on request, the winning score recomputed exactly with
+// TM_CCORR_NORMED's arithmetic (float32 numerator, double energies; see ncorr_exact_kernel).
+__global__ void fast_merge_ncc_kernel(const int32_t* __restrict__ PART, FastGeom g, const uint8_t* __restrict__ A,
+                                      size_t a_step, const uint8_t* __restrict__ B, size_t b_step, void* disp_out,
+                                      size_t disp_step, int elem, void* best_out, size_t best_step) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (x >= g.cols) return;
+    long long bestv = -1; int bestd = 0;
+    for (int grp = 0; grp < g.G; ++grp) {
+        const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
+        if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
+        const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
+        if (v > bestv) { bestv = v; bestd = g.dmin + FGROUP * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+    }
+    const int centre = x + bestd;                                   // winning window centre (unpadded column)
+    const int startc = max(0, x + g.dmin), endc = min(g.cols - 1, x + g.dmax);
+    const bool right_aligned = (g.dmin <= 0 && g.dmax <= 0);
+    const int disp = (centre - startc) - (right_aligned ? endc - startc : 0);
+    char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
+    if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(disp) & 0xFFu));
+    else if (elem == 2) reinterpret_cast<int16_t*>(drow)[x] = int16_t(disp);
+    else reinterpret_cast<int32_t*>(drow)[x] = disp;
+    if (best_out) {
+        const int y = g.rb + yy;
+        int c = 0, el = 0, er = 0;
+        for (int wy = -g.R; wy <= g.R; ++wy) {
+            const uint8_t* arow = A + size_t(clampi(y + wy, 0, g.rows - 1)) * a_step;
+            const uint8_t* brow = B + size_t(clampi(y + wy, 0, g.rows - 1)) * b_step;
+            for (int wx = -g.R; wx <= g.R; ++wx) {
+                const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre + wx, 0, g.cols - 1)];
+                c += l * r; el += l * l; er += r * r;
+            }
+        }
+        double num = double(float(c));
+        const double wnd = double(er);
+        const double lim = fmin(0.5, 10 * double(FLT_EPSILON) * wnd);
+        const double t = (wnd <= lim) ? 0 : sqrt(wnd) * sqrt(double(el));
+        if (fabs(num) < t) num /= t;
+        else if (fabs(num) < t * 1.125) num = num > 0 ? 1 : -1;
+        else num = 0;
+        reinterpret_cast<float*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = float(num);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
 static inline bool fast_supported(const Problem& p) {
-    if (p.cost != STEREO_COST_SSD) return false;           // NCC: exact path for now
     if (p.R > FMAXR) return false;
     if (p.cols < 1 || p.rows < 1) return false;
     if (p.dmax - p.dmin + 1 > 4096) return false;
@@ -601,41 +715,46 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     add(size_t(g.J) * g.e2_pitch * 4);
     add(size_t(g.G) * g.nrows * g.wpart * 4);
     add(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + 256, 64) * 4);
-    if (p.cost == STEREO_COST_NCORR) add(size_t(g.J) * g.e2_pitch * 4);
+    if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
     return b + 4096;
 }
 
 typedef void (*fast_kernel_fn)(const FastKernelParams);
-static inline fast_kernel_fn fast_pick_ssd(int R, int K) {
+template <int COST>
+static inline fast_kernel_fn fast_pick_cost(int R, int K) {
     if (K == 16) {
         switch (R) {
-        case 4: return fast_ssd_kernel<4, 16, 12>;
-        case 5: return fast_ssd_kernel<5, 16, 12>;
+        case 4: return fast_cost_kernel<4, 16, 12, COST>;
+        case 5: return fast_cost_kernel<5, 16, 12, COST>;
         }
         return nullptr;
     }
     switch (R) {
-    case 0: return fast_ssd_kernel<0, 24, 8>;
-    case 1: return fast_ssd_kernel<1, 24, 8>;
-    case 2: return fast_ssd_kernel<2, 24, 8>;
-    case 3: return fast_ssd_kernel<3, 24, 8>;
-    case 4: return fast_ssd_kernel<4, 24, 8>;
-    case 5: return fast_ssd_kernel<5, 24, 8>;
-    case 6: return fast_ssd_kernel<6, 24, 8>;
-    case 7: return fast_ssd_kernel<7, 24, 8>;
+    case 0: return fast_cost_kernel<0, 24, 8, COST>;
+    case 1: return fast_cost_kernel<1, 24, 8, COST>;
+    case 2: return fast_cost_kernel<2, 24, 8, COST>;
+    case 3: return fast_cost_kernel<3, 24, 8, COST>;
+    case 4: return fast_cost_kernel<4, 24, 8, COST>;
+    case 5: return fast_cost_kernel<5, 24, 8, COST>;
+    case 6: return fast_cost_kernel<6, 24, 8, COST>;
+    case 7: return fast_cost_kernel<7, 24, 8, COST>;
     }
     return nullptr;
 }
+static inline fast_kernel_fn fast_pick(int cost, int R, int K) {
+    return cost == STEREO_COST_SSD ? fast_pick_cost<STEREO_COST_SSD>(R, K) : fast_pick_cost<STEREO_COST_NCORR>(R, K);
+}
 
 static inline int fast_ctx_init(stereo_ctx*) {
-    for (int K = 16; K <= 24; K += 8)
-        for (int R = 0; R <= FMAXR; ++R) {
-            fast_kernel_fn fn = fast_pick_ssd(R, K);
-            if (!fn) continue;
-            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
-        }
+    for (int cost = 0; cost <= 1; ++cost)
+        for (int K = 16; K <= 24; K += 8)
+            for (int R = 0; R <= FMAXR; ++R) {
+                fast_kernel_fn fn = fast_pick(cost, R, K);
+                if (!fn) continue;
+                cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+            }
     return STEREO_OK;
 }
 
@@ -647,7 +766,13 @@ static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
     a.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
     a.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
     a.V = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64) * 4));
-    if (!a.LP || !a.RQ || !a.E2 || !a.PART || !a.V) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    if (p.cost == STEREO_COST_NCORR) {
+        a.RS = static_cast<float*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+        a.SC = static_cast<float*>(ctx->arena.take(size_t(g.tilesX) * g.spc * g.nrows * 4));
+    }
+    if (!a.LP || !a.RQ || !a.E2 || !a.PART || !a.V || (p.cost == STEREO_COST_NCORR && (!a.RS || !a.SC))) {
+        set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC;
+    }
     const uint8_t* A = static_cast<const uint8_t*>(p.ref.ptr);
     const uint8_t* B = static_cast<const uint8_t*>(p.tgt.ptr);
     const dim3 tb(256);
@@ -659,14 +784,25 @@ static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
     const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
     prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS)), PE_COLS, pe_smem, st>>>(
         a.V, vpitch, g, a.E2, a.RS);
-    FastKernelParams kp{g, a.LP, a.RQ, a.E2, a.PART, 2 << FKEY_BITS};
+    const bool ncc = p.cost == STEREO_COST_NCORR;
+    if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
+        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS)), 128, 0, st>>>(
+            A, p.ref.step, g, a.V, vpitch, g.R);
+        prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows), 128, 0, st>>>(a.V, vpitch, g, a.SC);
+        ctx->last_launches += 2;
+    }
+    FastKernelParams kp{g, a.LP, a.RQ, ncc ? reinterpret_cast<const int32_t*>(a.RS) : a.E2, a.PART, a.SC};
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
     if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
-    fast_pick_ssd(p.R, g.K)<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
+    fast_pick(p.cost, p.R, g.K)<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
     if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; }
     ctx->hot_total++;
-    fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
-        a.PART, g, A, p.ref.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
+    if (ncc)
+        fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
+            a.PART, g, A, p.ref.step, B, p.tgt.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
+    else
+        fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
+            a.PART, g, A, p.ref.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
     ctx->last_launches += 6;
     SB_CUDA(cudaGetLastError());
     return STEREO_OK;

@@ -10,6 +10,7 @@ from .oracle import (  # noqa: F401
     have_ref,
     narrow_i8,
     ncorr,
+    ncorr_fast,
     ref_ssd,
     set_num_threads,
     num_threads,

@@ -46,7 +46,7 @@ def _load():
         _lib = C.CDLL(str(_LIB))
         fp, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int32)
         for name, last in (("oracle_disparity_ssd", i32p), ("oracle_disparity_ssd_fast", i32p),
-                           ("oracle_disparity_ncorr", fp)):
+                           ("oracle_disparity_ncorr", fp), ("oracle_disparity_ncorr_fast", fp)):
             fn = getattr(_lib, name)
             fn.restype = C.c_int
             fn.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, last]
@@ -99,6 +99,11 @@ def ssd_fast(ref, tgt, window_rad, min_disp, max_disp, return_cost=False):
 def ncorr(ref, tgt, window_rad, min_disp, max_disp, return_score=False):
     """Restatement of serial::disparityNCorr (DisparityNCorr.cpp:27-68) + TM_CCORR_NORMED."""
     return _run("oracle_disparity_ncorr", ref, tgt, window_rad, min_disp, max_disp, return_score, np.float32)
+
+
+def ncorr_fast(ref, tgt, window_rad, min_disp, max_disp, return_score=False):
+    """Same results as :func:`ncorr` in O(rows*cols*D) for integer-valued images (running sums in double)."""
+    return _run("oracle_disparity_ncorr_fast", ref, tgt, window_rad, min_disp, max_disp, return_score, np.float32)
 
 
 def narrow_i8(disp):

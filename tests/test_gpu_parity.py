@@ -189,7 +189,11 @@ def test_device_pointer_and_band_entry_points(ctx):
             assert rc == 0, _capi.last_error()
             ctx.synchronize(st)
             ref = fn(a.cpu().numpy().astype(np.float32), b.cpu().numpy().astype(np.float32), 4, dmin, dmax)
-            assert np.array_equal(full.cpu().numpy(), ref.astype(np.int16))
+            if cost == sb.COST_SSD:
+                assert np.array_equal(full.cpu().numpy(), ref.astype(np.int16))
+            else:
+                assert float(np.mean(full.cpu().numpy() == ref)) >= NCC_DISP_AGREE
+                ref = full.cpu().numpy().astype(np.int32)        # bands must reproduce the full call exactly
             # row bands (with the R+1 halo the SSD wrap quirk needs) reproduce the same rows
             for (r0, r1) in ((0, 23), (23, 47), (47, 70)):
                 band = torch.empty((r1 - r0, 130), dtype=torch.int16, device="cuda")
@@ -263,3 +267,101 @@ def test_ssd_fast_equals_exact_path(ctx):
     d_fast = ctx.disparity(sb.COST_SSD, L, Rt, 5, -140, 0, dtype=np.int16)
     assert ctx.last_path == sb.PATH_FAST_U8
     assert np.array_equal(d_fast, d_exact)
+
+
+# ---- the packed u8 NCC kernels -------------------------------------------------------------------------
+
+NCC_FAST_SHAPES = [
+    # rows, cols, R, dmin, dmax   (NCC ranges must contain 0 or some border pixel has no candidate)
+    (40, 100, 2, -10, 0),
+    (40, 100, 2, 0, 10),
+    (64, 200, 5, -63, 0),
+    (64, 200, 5, 0, 63),
+    (37, 333, 4, -127, 0),      # exactly one 128-disparity group
+    (37, 333, 4, 0, 127),
+    (50, 300, 3, -255, 0),      # two groups
+    (50, 300, 3, 0, 255),
+    (33, 500, 7, -95, 0),       # ps2.yaml problem 4 parameters (I2F keys: (2R+1)^2*255^2 >= 2^23)
+    (33, 500, 7, 0, 80),        # ps2.yaml problem 5 parameters
+    (33, 200, 6, -40, 0),
+    (45, 260, 1, -80, 0),       # 81 candidates: not a multiple of 4
+    (45, 260, 0, -17, 9),       # 1x1 window, mixed-sign range (left-aligned result index)
+    (21, 50, 5, -300, 300),     # range far wider than the image
+    (150, 97, 2, -30, 0),       # tall and narrow: several row segments
+    (300, 700, 5, -130, 0),     # 131 candidates: 2 groups, second almost empty
+]
+
+
+@pytest.mark.parametrize("rows,cols,R,dmin,dmax", NCC_FAST_SHAPES)
+def test_ncc_fast_u8_vs_oracle(ctx, rows, cols, R, dmin, dmax):
+    L, Rt, _ = synth.make_pair(rows, cols, max(2, min(64, max(abs(dmin), abs(dmax)))), rows * 1000 + cols + 1)
+    d_ref, s_ref = oracle.ncorr_fast(L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax, return_score=True)
+    d, s = ctx.disparity(sb.COST_NCORR, L, Rt, R, dmin, dmax, dtype=np.int32, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert_ncc_close(d, s, d_ref, s_ref)
+    # where the disparity agrees the recomputed score is the oracle's, bit for bit
+    same = d == d_ref
+    assert np.array_equal(s[same], s_ref[same])
+    d2 = ctx.disparity(sb.COST_NCORR, L.astype(np.float32), Rt.astype(np.float32), R, dmin, dmax, dtype=np.int32)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert np.array_equal(d2, d)
+
+
+def test_ncc_fast_flat_dark_and_saturated_images(ctx):
+    # exact ties (first maximum must win), zero-energy windows (score 0), extreme intensities
+    for val in (0, 1, 255):
+        img = np.full((40, 90), val, np.uint8)
+        for (dmin, dmax) in ((-20, 0), (0, 20)):
+            for R in (2, 7):
+                d_ref, s_ref = oracle.ncorr(img.astype(np.float32), img.astype(np.float32), R, dmin, dmax, return_score=True)
+                d, s = ctx.disparity(sb.COST_NCORR, img, img, R, dmin, dmax, dtype=np.int32, return_best=True)
+                assert ctx.last_path == sb.PATH_FAST_U8
+                assert np.array_equal(d, d_ref) and np.array_equal(s, s_ref)
+    # half black / half textured: zero-energy candidates next to real ones
+    L, Rt, _ = synth.make_pair(30, 160, 16, 5)
+    L[:, :60] = 0
+    Rt[:, 40:90] = 0
+    for (a, b, dmin, dmax) in ((L, Rt, -30, 0), (Rt, L, 0, 30)):
+        d_ref, s_ref = oracle.ncorr(a.astype(np.float32), b.astype(np.float32), 3, dmin, dmax, return_score=True)
+        d, s = ctx.disparity(sb.COST_NCORR, a, b, 3, dmin, dmax, dtype=np.int32, return_best=True)
+        assert_ncc_close(d, s, d_ref, s_ref)
+
+
+def test_ncc_fast_smooth_low_texture(ctx):
+    # smooth gradients + weak texture: many near-ties, the hardest case for the 17-bit keys
+    yy, xx = np.mgrid[0:60, 0:400]
+    rng = np.random.default_rng(5)
+    L = np.clip(60 + 0.3 * xx + 0.2 * yy + rng.integers(-3, 4, xx.shape), 0, 255).astype(np.uint8)
+    Rt = np.clip(60 + 0.3 * (xx + 7) + 0.2 * yy + rng.integers(-3, 4, xx.shape), 0, 255).astype(np.uint8)
+    d_ref, s_ref = oracle.ncorr_fast(L.astype(np.float32), Rt.astype(np.float32), 4, -40, 0, return_score=True)
+    d, s = ctx.disparity(sb.COST_NCORR, L, Rt, 4, -40, 0, dtype=np.int32, return_best=True)
+    np.testing.assert_allclose(s, s_ref, rtol=NCC_SCORE_RTOL, atol=1e-7)
+    agree = float(np.mean(d == d_ref))
+    assert agree >= 0.99, f"low-texture agreement {agree:.4f}"   # near-ties within ~2^-22 relative may resolve differently
+
+
+def test_ncc_fast_equals_exact_path(ctx):
+    L, Rt, _ = synth.make_pair(60, 300, 100, 4243)
+    try:
+        ctx.force_path(sb.PATH_EXACT_F32)
+        d_exact, s_exact = ctx.disparity(sb.COST_NCORR, L, Rt, 5, -140, 0, dtype=np.int16, return_best=True)
+        assert ctx.last_path == sb.PATH_EXACT_F32
+    finally:
+        ctx.force_path(0)
+    d_fast, s_fast = ctx.disparity(sb.COST_NCORR, L, Rt, 5, -140, 0, dtype=np.int16, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert_ncc_close(d_fast, s_fast, d_exact, s_exact)
+
+
+# ---- BASELINE config 3 at full size: 1920x1080, 128 disparities, 9x9, SSD and NCC ------------------------
+
+def test_config3_full_size_ssd_and_ncc(ctx):
+    L, Rt, _ = synth.make_pair(1080, 1920, 128, 1001)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    dl, dr = ctx.disparity_pair(sb.COST_SSD, L, Rt, 4, 127)
+    assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 4, -127, 0)))
+    assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 4, 0, 127)))
+    d_ref, s_ref = oracle.ncorr_fast(Lf, Rf, 4, -127, 0, return_score=True)
+    d, s = ctx.disparity(sb.COST_NCORR, L, Rt, 4, -127, 0, dtype=np.int16, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert_ncc_close(d, s, d_ref, s_ref)

@@ -88,3 +88,13 @@ def test_ncc_rejects_empty_candidate_sets():
     img = np.ones((8, 16), np.float32)
     with pytest.raises(oracle.OracleError):
         oracle.ncorr(img, img, 1, 3, 5)     # right-most columns have no window: the reference would throw
+
+
+@pytest.mark.parametrize("rows,cols,R,dmin,dmax", [(30, 90, 3, -20, 0), (30, 90, 3, 0, 20), (25, 70, 5, -7, 9),
+                                                   (18, 60, 0, -5, 0), (24, 120, 7, -95, 0)])
+def test_ncc_fast_restatement_equals_literal(rows, cols, R, dmin, dmax):
+    L, Rt, _ = synth.make_pair(rows, cols, 16, rows + cols)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    d1, s1 = oracle.ncorr(Lf, Rf, R, dmin, dmax, return_score=True)
+    d2, s2 = oracle.ncorr_fast(Lf, Rf, R, dmin, dmax, return_score=True)
+    assert np.array_equal(d1, d2) and np.array_equal(s1, s2)

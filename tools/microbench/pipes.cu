@@ -28,8 +28,8 @@ constexpr int CH = 8;       // independent chains
 #define A_LOP(i)   asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(ia), "r"(ib));
 #define A_SHL(i)   asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(ia), "r"(ib));
 #define A_PRMT(i)  asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(ia), "r"(ib));
-#define A_I2F(i)   asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(f[i]) : "r"(x[i]));
-#define A_F2I(i)   asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(x[i]) : "f"(f[i]));
+#define A_I2F(i)   asm volatile("{.reg .f32 t; cvt.rn.f32.s32 t, %0; mov.b32 %0, t;}" : "+r"(x[i]));
+#define A_F2I(i)   asm volatile("{.reg .s32 t; cvt.rzi.s32.f32 t, %0; mov.b32 %0, t;}" : "+f"(f[i]));
 #define A_SHFL(i)  asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(x[i]));
 #define A_REDUX(i) asm volatile("redux.sync.min.s32 %0, %0, 0xffffffff;" : "+r"(x[i]));
 #define A_LDS32(i) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x[i]) : "r"(saddr + (i)*128));
@@ -54,6 +54,12 @@ constexpr int CH = 8;       // independent chains
 #define MIX_IMAD_IADD    REP8(A_IMAD) REP8(A_IADD3)
 #define MIX_FFMA3_IADD   REP8(A_FFMA) REP8(A_FFMA) REP8(A_FFMA) REP8(A_IADD3)
 #define MIX_NCC          REP8(A_DP2A) REP8(A_IADD3) REP8(A_FFMA) REP8(A_FSEL)
+#define A_FFMA3(i) asm volatile("fma.rn.f32 %0, %1, %2, %3;" : "=f"(g[i]) : "f"(f[i]), "f"(fa), "f"(fb));
+#define A_KEYLOP(i) asm volatile("lop3.b32 %0, %1, 0xffffff80, %2, 0xf8;" : "=r"(y[i]) : "r"(x[i]), "r"(ia));
+#define MIX_NCC5      REP8(A_DP2A) REP8(A_IADD3) REP8(A_FFMA) REP8(A_KEYLOP) REP8(A_MIN)
+#define MIX_NCC7      REP8(A_DP2A) REP8(A_IADD3) REP8(A_I2F) REP8(A_FMUL) REP8(A_KEYLOP) REP8(A_MIN)
+#define MIX_I2F_DP    REP8(A_I2F) REP8(A_DP2A)
+#define MIX_I2F_ADD3  REP8(A_I2F) REP8(A_IADD3)
 #define MIX_DP_LDS       REP8(A_DP2A) REP8(A_DP2A) REP8(A_DP2A) REP8(A_DP2A) A_LDS128(0)
 
 template<int TEST> __global__ void __launch_bounds__(1024,1) kern(int* out, long long* cyc, int ia, int ib, float fa, float fb)
@@ -110,6 +116,10 @@ template<int TEST> __global__ void __launch_bounds__(1024,1) kern(int* out, long
       if (TEST == 39) { MIX_FFMA3_IADD }
       if (TEST == 40) { MIX_NCC }
       if (TEST == 41) { MIX_DP_LDS }
+      if (TEST == 42) { MIX_NCC5 }
+      if (TEST == 43) { MIX_NCC7 }
+      if (TEST == 44) { MIX_I2F_DP }
+      if (TEST == 45) { MIX_I2F_ADD3 }
     }
   }
   long long t1 = clock64();
@@ -127,7 +137,7 @@ static const Test tests[] = {
   {14,"LDS.32",8},{15,"LDS.64",8},{16,"LDS.128",8},{17,"LDS.128 bcast",8},{18,"FSETP+2SEL (3 instr)",24},{19,"FMNMX",8},
   {30,"mix DP2A:IADD3 1:1",16},{31,"mix DP2A:IADD3:IMAD:MIN",32},{32,"mix DP2A:IADD3:LEA:MIN",32},{33,"mix 3DP:3ADD3:2IMAD:2MIN",80},
   {34,"mix 2FFMA:IADD3:IMAD:MIN",40},{35,"mix FFMA:IADD3",16},{36,"mix FFMA:IMAD",16},{37,"mix FFMA:DP2A",16},{38,"mix IMAD:IADD3",16},{39,"mix 3FFMA:IADD3",32},
-  {40,"mix DP2A:IADD3:FFMA:FSEL3",48},{41,"mix 32DP2A:1LDS128",33},
+  {40,"mix DP2A:IADD3:FFMA:FSEL3",48},{41,"mix 32DP2A:1LDS128",33},{42,"mix NCC R<=5 DP:ADD3:FFMA:LOP:MIN3",36},{43,"mix NCC R>=6 DP:ADD3:I2F:FMUL:LOP:MIN3",44},{44,"mix I2F:DP2A",16},{45,"mix I2F:IADD3",16},
 };
 
 template<int T> void launch(int grid, int block, int* out, long long* cyc, cudaStream_t s) { kern<T><<<grid, block, 0, s>>>(out, cyc, 3, 5, 1.0001f, 0.5f); }
@@ -136,7 +146,7 @@ static LaunchFn fn(int id) {
   switch(id){
 #define C(n) case n: return launch<n>;
   C(0)C(1)C(2)C(3)C(4)C(5)C(6)C(7)C(8)C(9)C(10)C(11)C(12)C(13)C(14)C(15)C(16)C(17)C(18)C(19)C(20)C(21)C(22)C(23)
-  C(30)C(31)C(32)C(33)C(34)C(35)C(36)C(37)C(38)C(39)C(40)C(41)
+  C(30)C(31)C(32)C(33)C(34)C(35)C(36)C(37)C(38)C(39)C(40)C(41)C(42)C(43)C(44)C(45)
   }
   return nullptr;
 }
