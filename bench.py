@@ -197,8 +197,10 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
     ctx = sb.Context(local)
-    cost = sb.COST_SSD
+    cost = sb.COST_SSD if args.cost == "ssd" else sb.COST_NCORR
     rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
+    if args.mode == "bands":
+        return run_bands(args, wl, lib, ctx, cost, dev, rank, world, local)
     B = args.pairs
     elem_dtype, elem = (torch.int8, 1) if nd <= 128 else (torch.int16, 2)
 
@@ -326,14 +328,14 @@ def run_ours(args, wl):
         if hot_n > 0:
             units_hot = hot_n * rows * cols * nd                            # one direction per hot launch
             t_hot = hot_ms * 1e-3
-            achieved = OPS_PER_UNIT["ssd"] * units_hot / t_hot
+            achieved = OPS_PER_UNIT[args.cost] * units_hot / t_hot
             b_in, b_out = 1, elem
             alg_bytes = rows * cols * (2 * b_in + b_out)                    # per launch
             roof = {
-                "bound": "alu", "kernel": "fast_ssd_kernel",
+                "bound": "alu", "kernel": f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>",
                 "achieved": round(achieved / 1e12, 3), "peak": round(peak_lane_ops / 1e12, 3), "unit": "Tlane-op/s",
                 "frac": round(achieved / peak_lane_ops, 4),
-                "ops_per_unit": OPS_PER_UNIT["ssd"], "units_per_launch": rows * cols * nd,
+                "ops_per_unit": OPS_PER_UNIT[args.cost], "units_per_launch": rows * cols * nd,
                 "launch_ms": round(hot_ms / hot_n, 4), "launches_timed": hot_n,
                 "peak_def": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                 "traffic": None,
@@ -349,7 +351,7 @@ def run_ours(args, wl):
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (int32 accumulate)", "data": "synthetic",
-            "config": {"workload": args.workload + "_ssd_pair", "rows": rows, "cols": cols, "ndisp": nd,
+            "config": {"workload": args.workload + f"_{args.cost}_pair", "rows": rows, "cols": cols, "ndisp": nd,
                        "window": 2 * R + 1, "pairs_per_gpu_per_step": B, "directions": 2,
                        "sharding": "by pair" + (", NCCL all_gather of maps inside the step" if world > 1 else ""),
                        "l2": "flushed between steps (512 MiB memset outside the per-step event pair)",
@@ -367,6 +369,78 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
+    """BASELINE config 4: one synthetic pair, output rows sharded over the ranks (R+1 halo rows from the
+    rank's own slab, no neighbour exchange), maps all-gathered over NCCL inside the timed step."""
+    import torch
+    import torch.distributed as dist
+    from introtocomputervision_b200 import _capi, sharding, synth
+
+    rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
+    elem_dtype, elem = (torch.int8, 1) if nd <= 128 else (torch.int16, 2)
+    L, Rt, _ = synth.make_pair(rows, cols, nd, wl["seed"])
+    r0, r1 = sharding.band_shard(rows, world, rank)
+    h0, h1 = sharding.band_halo(rows, r0, r1, R)
+    band = -(-rows // world)
+    d_l, d_r = torch.from_numpy(L[h0:h1].copy()).to(dev), torch.from_numpy(Rt[h0:h1].copy()).to(dev)   # this rank's slab only
+    mine = torch.zeros((2, band, cols), dtype=elem_dtype, device=dev)
+    gathered = torch.empty((world, 2, band, cols), dtype=elem_dtype, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        for k, (a, b, dmin, dmax) in enumerate(((d_l, d_r, -(nd - 1), 0), (d_r, d_l, 0, nd - 1))):
+            rc = lib.stereo_disparity_band_halo_u8_device(ctx.handle, cost, a.data_ptr(), cols, b.data_ptr(), cols, rows, cols,
+                                                          r0, r1, h0, h1, R, dmin, dmax, mine[k].data_ptr(), cols * elem, elem, sp)
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    if rank == 0:
+        units = 2 * rows * cols * nd * args.steps                       # the WHOLE image pair, all ranks together
+        line = {"metric": METRIC, "value": round(units / (dev_ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 4),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 (int32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": args.workload + f"_{args.cost}_pair_bands", "rows": rows, "cols": cols, "ndisp": nd,
+                           "window": 2 * R + 1, "band_rows": band, "halo_rows": R + 1, "directions": 2,
+                           "sharding": "by row band, slab with halo resident per rank"
+                                       + (", NCCL all_gather of the bands inside the step" if world > 1 else ""),
+                           "l2": "flushed between steps"},
+                "gpu_launches": ctx.last_launches * 2 * args.steps, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,6 +451,10 @@ def main():
     ap.add_argument("--pairs", type=int, default=2, help="stereo pairs per GPU per step")
     ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cost", default="ssd", choices=["ssd", "ncc"], help="window cost (the headline line is ssd)")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
+                    help="pairs: batch sharded by pair, weak scaling (default, the driver's line); "
+                         "bands: ONE image sharded by row band with halo, strong scaling (BASELINE config 4)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

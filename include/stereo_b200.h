@@ -187,6 +187,21 @@ int stereo_disparity_band_u8_device(stereo_ctx* ctx, int cost,
                                     int window_rad, int min_disp, int max_disp,
                                     void* disp_out, size_t disp_step, int disp_elem_bytes, void* cuda_stream);
 
+/* Same, for callers that hold only a slab of the images (one rank of a row-band sharded job): `ref_halo`/
+ * `tgt_halo` point at image row `halo_begin`; rows [halo_begin, halo_end) are present.  The slab must
+ * contain the rows stereo_band_halo_rows() reports for the band — window_rad rows above and below plus
+ * one more for the reference's row-wrap reads, clamped to the image — then the result equals the
+ * corresponding rows of the full-image call bit for bit. */
+int stereo_disparity_band_halo_u8_device(stereo_ctx* ctx, int cost,
+                                         const uint8_t* ref_halo, size_t ref_step, const uint8_t* tgt_halo, size_t tgt_step,
+                                         int rows, int cols, int row_begin, int row_end, int halo_begin, int halo_end,
+                                         int window_rad, int min_disp, int max_disp,
+                                         void* disp_out, size_t disp_step, int disp_elem_bytes, void* cuda_stream);
+
+/* Input rows [*halo_begin, *halo_end) a band [row_begin, row_end) of a rows-high image needs (pure host
+ * arithmetic, no device). */
+int stereo_band_halo_rows(int rows, int row_begin, int row_end, int window_rad, int* halo_begin, int* halo_end);
+
 /* Blocks until everything enqueued on `cuda_stream` (NULL = the context's stream) has finished and
  * returns any asynchronous error. */
 int stereo_ctx_synchronize(stereo_ctx* ctx, void* cuda_stream);

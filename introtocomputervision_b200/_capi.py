@@ -5,7 +5,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libstereo_b200.so"
+import os
+
+# STEREO_B200_LIB overrides the library file (kernel-variant experiments); the default is the in-tree build.
+LIB_PATH = Path(os.environ.get("STEREO_B200_LIB") or (Path(__file__).resolve().parent / "libstereo_b200.so"))
 
 STEREO_OK = 0
 ERR_INVALID_ARG, ERR_INVALID_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
@@ -40,6 +43,8 @@ SIGNATURES = {
     "stereo_disparity_pair_u8_device": (_i, _PAIR_HOST + [_vp]),
     "stereo_disparity_pair_batch_u8_device": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i, _vp]),
     "stereo_disparity_pair_batch_u8_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
+    "stereo_disparity_band_halo_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "stereo_band_halo_rows": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "stereo_disparity_band_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
 }
 

@@ -48,6 +48,7 @@ struct Problem {
     ImageView ref, tgt;
     int rows, cols;      // full image
     int row_begin, row_end;   // output band (full image: 0, rows)
+    int avail_begin, avail_end;   // image rows the buffers actually hold (pointers are full-image origins)
     int R, dmin, dmax;
     OutView disp;        // first row of the band
     OutView best;        // optional (ptr == nullptr)

@@ -15,11 +15,11 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // cv::copyMakeBorder(..., BORDER_REPLICATE) (DisparitySSD.cpp:20-23) into a contiguous float image.
 template <typename T>
 __global__ void pad_replicate_kernel(const T* __restrict__ img, size_t step, int rows, int cols, int R,
-                                     float* __restrict__ out, int Hp, int Wp) {
+                                     float* __restrict__ out, int Hp, int Wp, int ar0, int ar1) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= Wp || y >= Hp) return;
-    const T* row = reinterpret_cast<const T*>(reinterpret_cast<const char*>(img) + size_t(clampi(y - R, 0, rows - 1)) * step);
+    const T* row = reinterpret_cast<const T*>(reinterpret_cast<const char*>(img) + size_t(clampi(clampi(y - R, 0, rows - 1), ar0, ar1 - 1)) * step);
     out[size_t(y) * Wp + x] = float(row[clampi(x - R, 0, cols - 1)]);
 }
 

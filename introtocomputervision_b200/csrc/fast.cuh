@@ -58,6 +58,7 @@ struct FastGeom {
     // problem
     int rows, cols, R, dmin, dmax, cost;
     int rb, re;            // output band
+    int ar0, ar1;          // image rows present in the caller's buffers (full image: 0, rows); reads clamp into it
     int K;                 // pixels per thread (strip width): 24 or 16
     int nw;                // warps per CTA: 8 (K=24) or 12 (K=16)
     // derived
@@ -138,7 +139,8 @@ __device__ __forceinline__ int4 lds128(const int* p) { return *reinterpret_cast<
 // through the flat index of the unchecked cv::Mat::at (DisparitySSD.cpp:50).  `i` is the unpadded row
 // index (may lie outside [0,rows)), `e` = unpadded column + 2R.  Reads outside the padded buffer
 // (row -1 / row Hp) return 0 (the oracle's zero guard).
-__device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, int rows, int cols, int R, int i, int e) {
+__device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, int rows, int cols, int R, int i, int e,
+                                    int ar0, int ar1) {
     const int Wp = cols + 2 * R;
     const int c = e - R;                 // padded column, may be < 0 or >= Wp
     int src_row = i, src_col;
@@ -151,7 +153,7 @@ __device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, 
     } else {
         src_col = clampi(c - R, 0, cols - 1);
     }
-    src_row = clampi(src_row, 0, rows - 1);
+    src_row = clampi(clampi(src_row, 0, rows - 1), ar0, ar1 - 1);
     return B[size_t(src_row) * step + src_col];
 }
 
@@ -164,8 +166,8 @@ __global__ void __launch_bounds__(256) prep_lp_kernel(const uint8_t* __restrict_
     const int j = blockIdx.y;
     if (p4 >= g.lp_pitch) return;
     const int y = g.base_y + j;
-    const uint8_t* rnew = A + size_t(clampi(y + g.R, 0, g.rows - 1)) * step;
-    const uint8_t* rold = A + size_t(clampi(y - g.R - 1, 0, g.rows - 1)) * step;
+    const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+    const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
     int v[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -188,10 +190,10 @@ __global__ void __launch_bounds__(256) prep_rq_kernel(const uint8_t* __restrict_
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int e = q4 + t - g.qoff;
-        const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e);
-        const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e);
-        const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e);
-        const uint32_t b3 = bext(B, step, g.rows, g.cols, g.R, ye - g.R, e);
+        const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e, g.ar0, g.ar1);
+        const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e, g.ar0, g.ar1);
+        const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e, g.ar0, g.ar1);
+        const uint32_t b3 = bext(B, step, g.rows, g.cols, g.R, ye - g.R, e, g.ar0, g.ar1);
         v[t] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
     *reinterpret_cast<uint4*>(RQ + size_t(jp) * g.rq_pitch + q4) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -211,13 +213,13 @@ __global__ void __launch_bounds__(128) prep_v_kernel(const uint8_t* __restrict__
     const int yy0 = blockIdx.y * PV_ROWS, yy1 = min(g.nrows, yy0 + PV_ROWS);
     const int R = g.R;
     int v = 0;
-    for (int i = g.rb + yy0 - R; i < g.rb + yy0 + R; ++i) { const int b = bext(B, step, g.rows, g.cols, R, i, e); v += b * b; }
+    for (int i = g.rb + yy0 - R; i < g.rb + yy0 + R; ++i) { const int b = bext(B, step, g.rows, g.cols, R, i, e, g.ar0, g.ar1); v += b * b; }
     for (int yy = yy0; yy < yy1; ++yy) {
         const int y = g.rb + yy;
-        const int bn = bext(B, step, g.rows, g.cols, R, y + R, e);
+        const int bn = bext(B, step, g.rows, g.cols, R, y + R, e, g.ar0, g.ar1);
         v += bn * bn;
         V[size_t(yy) * vpitch + x] = v;
-        const int bo = bext(B, step, g.rows, g.cols, R, y - R, e);
+        const int bo = bext(B, step, g.rows, g.cols, R, y - R, e, g.ar0, g.ar1);
         v -= bo * bo;
     }
 }
@@ -322,6 +324,9 @@ struct RowShape {
 // For (2R+1)^2*255^2 < 2^23 (R <= 5) the running sums carry the float bias 0x4B000000, i.e. they ARE
 // the float 2^23 + C, and v = fma(2^23 + C, rs, -2^23*rs) is the correctly rounded product with no
 // conversion instruction; larger windows convert with I2F and fold the magic add into the FFMA.
+#ifndef SB_KEY_LEA_MASK
+#define SB_KEY_LEA_MASK 0
+#endif
 constexpr int NCC_BIAS_MAX_R = 5;
 constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
 constexpr int NCC_KEY_SHIFT = 9;                  // mantissa -> bits 9..31
@@ -385,7 +390,12 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
                 // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
                 // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
-                uint32_t kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                uint32_t kv;
+                if (SB_KEY_LEA_MASK & (1 << m)) {      // shift-add on the ALU pipe
+                    asm("{.reg .b32 t; shl.b32 t, %1, 8; add.s32 %0, t, %2;}" : "=r"(kv) : "r"(s[m]), "r"(e2v[k + m]));
+                } else {                                // IMAD (immediate) on the FMA-heavy pipe
+                    kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                }
                 if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
                 key[m] = kv;
             } else {
@@ -581,7 +591,7 @@ __global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom
         int el = 0;
         const int y = g.rb + yy;
         for (int wy = -g.R; wy <= g.R; ++wy) {
-            const uint8_t* row = A + size_t(clampi(y + wy, 0, g.rows - 1)) * a_step;
+            const uint8_t* row = A + size_t(clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * a_step;
             for (int wx = -g.R; wx <= g.R; ++wx) { const int v = row[clampi(x + wx, 0, g.cols - 1)]; el += v * v; }
         }
         cost = bestc + el;
@@ -621,8 +631,9 @@ __global__ void fast_merge_ncc_kernel(const int32_t* __restrict__ PART, FastGeom
         const int y = g.rb + yy;
         int c = 0, el = 0, er = 0;
         for (int wy = -g.R; wy <= g.R; ++wy) {
-            const uint8_t* arow = A + size_t(clampi(y + wy, 0, g.rows - 1)) * a_step;
-            const uint8_t* brow = B + size_t(clampi(y + wy, 0, g.rows - 1)) * b_step;
+            const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+            const uint8_t* arow = A + size_t(wr) * a_step;
+            const uint8_t* brow = B + size_t(wr) * b_step;
             for (int wx = -g.R; wx <= g.R; ++wx) {
                 const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre + wx, 0, g.cols - 1)];
                 c += l * r; el += l * l; er += r * r;
@@ -661,6 +672,7 @@ static inline int fast_pick_k(const Problem& p) {
 static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGeom& g) {
     g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.dmin = p.dmin; g.dmax = p.dmax; g.cost = p.cost;
     g.rb = p.row_begin; g.re = p.row_end; g.nrows = g.re - g.rb;
+    g.ar0 = p.avail_begin; g.ar1 = p.avail_end;
     const int D = p.dmax - p.dmin + 1;
     g.K = fast_pick_k(p);
     g.G = (D + FGROUP - 1) / FGROUP;

@@ -56,6 +56,10 @@ static int validate(const Problem& p, size_t ref_min_step, size_t tgt_min_step) 
     if (p.dmin > p.dmax) { set_error("min_disp (%d) > max_disp (%d)", p.dmin, p.dmax); return STEREO_ERR_INVALID_RANGE; }
     if (p.dmin < -32768 || p.dmax > 32768) { set_error("disparity range outside [-32768, 32768]"); return STEREO_ERR_INVALID_RANGE; }
     if (p.row_begin < 0 || p.row_end > p.rows || p.row_begin >= p.row_end) { set_error("bad row band [%d, %d)", p.row_begin, p.row_end); return STEREO_ERR_INVALID_ARG; }
+    if (p.avail_begin < 0 || p.avail_end > p.rows || p.avail_begin > p.row_begin || p.avail_end < p.row_end) {
+        set_error("available rows [%d, %d) do not cover the band [%d, %d)", p.avail_begin, p.avail_end, p.row_begin, p.row_end);
+        return STEREO_ERR_INVALID_ARG;
+    }
     if (p.cost == STEREO_COST_NCORR) {
         // Every pixel needs >= 1 candidate window; the reference would throw inside
         // cv::Mat::operator()(Rect) otherwise (DisparityNCorr.cpp:50-53).
@@ -100,13 +104,13 @@ static int run_exact(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
     float* Rp = rbuf + guard;
     dim3 pb(32, 8), pg(div_round_up(Wp, 32), div_round_up(Hp, 8));
     if (p.ref.type == PixType::F32)
-        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp);
+        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp, p.avail_begin, p.avail_end);
     else
-        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp);
+        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.ref.ptr), p.ref.step, p.rows, p.cols, p.R, Lp, Hp, Wp, p.avail_begin, p.avail_end);
     if (p.tgt.type == PixType::F32)
-        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp);
+        pad_replicate_kernel<float><<<pg, pb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp, p.avail_begin, p.avail_end);
     else
-        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp);
+        pad_replicate_kernel<uint8_t><<<pg, pb, 0, st>>>(static_cast<const uint8_t*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, p.R, Rp, Hp, Wp, p.avail_begin, p.avail_end);
     ctx->last_launches += 2;
     dim3 kb(128), kg(div_round_up(p.cols, 128), band_rows);
     if (p.cost == STEREO_COST_SSD)
@@ -248,7 +252,7 @@ static int host_single(stereo_ctx* ctx, int cost, PixType type, const void* ref,
     p.cost = cost;
     p.ref = ImageView{d_ref, in_pitch, type};
     p.tgt = ImageView{d_tgt, in_pitch, type};
-    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows;
+    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows; p.avail_begin = 0; p.avail_end = rows;
     p.R = R; p.dmin = dmin; p.dmax = dmax;
     p.disp = OutView{d_disp, d_pitch, elem};
     p.best = OutView{d_best, b_pitch, 4};
@@ -264,7 +268,8 @@ static int host_single(stereo_ctx* ctx, int cost, PixType type, const void* ref,
 
 static int device_single(stereo_ctx* ctx, int cost, PixType type, const void* ref, size_t ref_step, const void* tgt,
                          size_t tgt_step, int rows, int cols, int row_begin, int row_end, int R, int dmin, int dmax,
-                         void* disp_out, size_t disp_step, int elem, void* best_out, size_t best_step, void* stream) {
+                         void* disp_out, size_t disp_step, int elem, void* best_out, size_t best_step, void* stream,
+                         int avail_begin = 0, int avail_end = -1) {
     int rc = check_ctx(ctx);
     if (rc != STEREO_OK) return rc;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
@@ -273,6 +278,7 @@ static int device_single(stereo_ctx* ctx, int cost, PixType type, const void* re
     p.ref = ImageView{ref, ref_step, type};
     p.tgt = ImageView{tgt, tgt_step, type};
     p.rows = rows; p.cols = cols; p.row_begin = row_begin; p.row_end = row_end;
+    p.avail_begin = avail_begin; p.avail_end = avail_end < 0 ? rows : avail_end;
     p.R = R; p.dmin = dmin; p.dmax = dmax;
     p.disp = OutView{disp_out, disp_step, elem};
     p.best = OutView{best_out, best_step, 4};
@@ -461,6 +467,34 @@ int stereo_disparity_band_u8_device(stereo_ctx* ctx, int cost, const uint8_t* re
                          window_rad, min_disp, max_disp, disp_out, disp_step, disp_elem_bytes, nullptr, 0, cuda_stream);
 }
 
+int stereo_disparity_band_halo_u8_device(stereo_ctx* ctx, int cost, const uint8_t* ref_halo, size_t ref_step,
+                                         const uint8_t* tgt_halo, size_t tgt_step, int rows, int cols, int row_begin,
+                                         int row_end, int halo_begin, int halo_end, int window_rad, int min_disp,
+                                         int max_disp, void* disp_out, size_t disp_step, int disp_elem_bytes,
+                                         void* cuda_stream) {
+    if (!ref_halo || !tgt_halo) { set_error("null image pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (halo_begin < 0 || halo_end > rows || halo_begin >= halo_end) { set_error("bad halo rows [%d, %d)", halo_begin, halo_end); return STEREO_ERR_INVALID_ARG; }
+    // Full-image origins that are never dereferenced outside [halo_begin, halo_end): every row index is clamped
+    // into the available range, which changes nothing when the halo covers what the band needs.
+    const uint8_t* ref0 = ref_halo - size_t(halo_begin) * ref_step;
+    const uint8_t* tgt0 = tgt_halo - size_t(halo_begin) * tgt_step;
+    return device_single(ctx, cost, PixType::U8, ref0, ref_step, tgt0, tgt_step, rows, cols, row_begin, row_end,
+                         window_rad, min_disp, max_disp, disp_out, disp_step, disp_elem_bytes, nullptr, 0, cuda_stream,
+                         halo_begin, halo_end);
+}
+
+int stereo_band_halo_rows(int rows, int row_begin, int row_end, int window_rad, int* halo_begin, int* halo_end) {
+    if (!halo_begin || !halo_end || rows <= 0 || row_begin < 0 || row_end > rows || row_begin >= row_end || window_rad < 0) {
+        set_error("bad arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    // R rows of window above and below, +1 for the neighbouring padded row the reference's SSD reads
+    // through its flat index; clamped to the image (replicate padding).
+    int b = row_begin - window_rad - 1, e = row_end + window_rad + 1;
+    *halo_begin = b < 0 ? 0 : b;
+    *halo_end = e > rows ? rows : e;
+    return STEREO_OK;
+}
+
 // ---- pairs: L->R over [-range, 0], then R->L with images swapped over [0, +range] (main.cpp:21-48) ----
 
 static int pair_device(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
@@ -469,7 +503,7 @@ static int pair_device(stereo_ctx* ctx, int cost, PixType type, const void* left
     if (range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
     Problem p{};
     p.cost = cost;
-    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows; p.R = R;
+    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows; p.avail_begin = 0; p.avail_end = rows; p.R = R;
     p.best = OutView{nullptr, 0, 4};
     p.ref = ImageView{left, left_step, type}; p.tgt = ImageView{right, right_step, type};
     p.dmin = -range; p.dmax = 0; p.disp = OutView{disp_left, disp_step, elem};

@@ -1,0 +1,148 @@
+"""Multi-GPU sharding of the stereo matcher: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The path has no exchange step inside the computation — every output pixel depends on a
+(2R+1)-row neighbourhood of the two inputs — so it shards two ways, neither of which the reference has
+(it is single-GPU, single-stream: ProblemSets/ps2_cpp/lib/DisparitySSD.cu:143-207):
+
+* **by stereo pair** for batches (BASELINE config 5): rank r owns a contiguous block of pairs;
+* **by row band with a halo** for one large image (BASELINE config 4): rank r owns output rows
+  [r0, r1) and reads input rows [r0-R-1, r1+R+1) clamped to the image — R rows of window plus one more
+  for the neighbouring padded row the reference's SSD reads through its flat index.
+
+The only collective is the gather of the per-rank results (``all_gather_into_tensor``; NCCL over NVLink
+on GPUs, gloo in the CPU tests).  The compute itself is a call into libstereo_b200.so per rank; a
+``compute`` object can be injected so that the partition/gather logic is testable without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+
+
+def pair_shard(n_pairs: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [begin, end) of pair indices owned by `rank`; block sizes differ by at most one."""
+    if n_pairs < 0 or world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad pair_shard arguments")
+    base, extra = divmod(n_pairs, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def band_shard(rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Output rows [r0, r1) of `rank`: equal bands of ceil(rows / world) rows, the last one(s) shorter or empty."""
+    if rows <= 0 or world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad band_shard arguments")
+    band = -(-rows // world)
+    r0 = min(rows, rank * band)
+    return r0, min(rows, r0 + band)
+
+
+def band_halo(rows: int, r0: int, r1: int, window_rad: int) -> Tuple[int, int]:
+    """Input rows [h0, h1) the band [r0, r1) needs (``stereo_band_halo_rows``: host arithmetic, no device)."""
+    h0, h1 = C.c_int(0), C.c_int(0)
+    st = _capi.lib().stereo_band_halo_rows(int(rows), int(r0), int(r1), int(window_rad), C.byref(h0), C.byref(h1))
+    if st != _capi.STEREO_OK:
+        raise ValueError(_capi.last_error())
+    return int(h0.value), int(h1.value)
+
+
+class GpuCompute:
+    """Per-rank compute on this rank's B200 through the C ABI (device buffers are torch tensors)."""
+
+    def __init__(self, ctx, device):
+        import torch
+        self.torch, self.ctx, self.device = torch, ctx, device
+        self._elem = {torch.int8: 1, torch.int16: 2, torch.int32: 4}
+
+    def band(self, cost, left_slab, right_slab, rows, cols, r0, r1, h0, h1, window_rad, min_disp, max_disp, dtype):
+        torch = self.torch
+        dl = torch.as_tensor(np.ascontiguousarray(left_slab)).to(self.device, non_blocking=True)
+        dr = torch.as_tensor(np.ascontiguousarray(right_slab)).to(self.device, non_blocking=True)
+        out = torch.empty((r1 - r0, cols), dtype=dtype, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        st = _capi.lib().stereo_disparity_band_halo_u8_device(
+            self.ctx.handle, int(cost), dl.data_ptr(), cols, dr.data_ptr(), cols, rows, cols, r0, r1, h0, h1,
+            int(window_rad), int(min_disp), int(max_disp), out.data_ptr(), cols * self._elem[dtype], self._elem[dtype],
+            C.c_void_p(stream))
+        if st != _capi.STEREO_OK:
+            raise RuntimeError(_capi.last_error())
+        return out
+
+    def pair_batch(self, cost, lefts, rights, window_rad, disparity_range, dtype):
+        torch = self.torch
+        n, rows, cols = lefts.shape
+        dl = torch.as_tensor(np.ascontiguousarray(lefts)).to(self.device, non_blocking=True)
+        dr = torch.as_tensor(np.ascontiguousarray(rights)).to(self.device, non_blocking=True)
+        out = torch.empty((2, n, rows, cols), dtype=dtype, device=self.device)
+        e = self._elem[dtype]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if n:
+            st = _capi.lib().stereo_disparity_pair_batch_u8_device(
+                self.ctx.handle, int(cost), n, dl.data_ptr(), dr.data_ptr(), cols, rows * cols, rows, cols,
+                int(window_rad), int(disparity_range), out[0].data_ptr(), out[1].data_ptr(), cols * e, rows * cols * e, e,
+                C.c_void_p(stream))
+            if st != _capi.STEREO_OK:
+                raise RuntimeError(_capi.last_error())
+        return out
+
+
+class ShardedStereo:
+    """Row-band and pair sharding over the ranks of a ``torch.distributed`` process group."""
+
+    def __init__(self, compute, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.compute, self.group = compute, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def _gather(self, mine):
+        if self.world == 1:
+            return mine.unsqueeze(0)
+        # output = the ranks' tensors concatenated along dim 0 (the layout both NCCL and gloo accept)
+        # gathered as raw bytes: the maps are int8/int16/int32 and gloo has no int16 collectives
+        mine = mine.contiguous()
+        flat = mine.view(self.torch.uint8).reshape(-1)
+        out = self.torch.empty(self.world * flat.numel(), dtype=self.torch.uint8, device=mine.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view(mine.dtype).view((self.world,) + tuple(mine.shape))
+
+    # -- one large image, row bands with halo (BASELINE config 4) -----------------------------------
+    def disparity_bands(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, min_disp: int,
+                        max_disp: int, dtype=None):
+        """Full rows x cols disparity map on every rank.  `left`/`right` are uint8 host images; each rank
+        touches only its slab of them."""
+        torch = self.torch
+        dtype = dtype or torch.int16
+        rows, cols = left.shape
+        band = -(-rows // self.world)
+        r0, r1 = band_shard(rows, self.world, self.rank)
+        mine = torch.zeros((band, cols), dtype=dtype, device=getattr(self.compute, "device", "cpu"))
+        if r1 > r0:
+            h0, h1 = band_halo(rows, r0, r1, window_rad)
+            mine[:r1 - r0] = self.compute.band(cost, left[h0:h1], right[h0:h1], rows, cols, r0, r1, h0, h1,
+                                               window_rad, min_disp, max_disp, dtype)
+        return self._gather(mine).reshape(self.world * band, cols)[:rows]
+
+    # -- batches, sharded by pair (BASELINE config 5) ---------------------------------------------------
+    def disparity_pair_batch(self, cost: int, lefts: np.ndarray, rights: np.ndarray, window_rad: int,
+                             disparity_range: int, dtype=None):
+        """(left maps, right maps), each n x rows x cols, on every rank; rank r computes pairs pair_shard(n, world, r)."""
+        torch = self.torch
+        dtype = dtype or torch.int8
+        n, rows, cols = lefts.shape
+        per = -(-n // self.world)
+        b, e = pair_shard(n, self.world, self.rank)
+        mine = torch.zeros((2, per, rows, cols), dtype=dtype, device=getattr(self.compute, "device", "cpu"))
+        if e > b:
+            mine[:, :e - b] = self.compute.pair_batch(cost, lefts[b:e], rights[b:e], window_rad, disparity_range, dtype)
+        g = self._gather(mine)                                        # world x 2 x per x rows x cols
+        counts = [pair_shard(n, self.world, r) for r in range(self.world)]
+        dl = torch.cat([g[r, 0, :c1 - c0] for r, (c0, c1) in enumerate(counts)])
+        dr = torch.cat([g[r, 1, :c1 - c0] for r, (c0, c1) in enumerate(counts)])
+        return dl, dr
