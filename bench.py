@@ -229,7 +229,7 @@ def run_ours(args, wl):
             raise RuntimeError(_capi.last_error())
         if world > 1:       # the batch config's exchange step: gather every rank's maps
             mine[0].copy_(d_dl), mine[1].copy_(d_dr)
-            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))   # bytes: NCCL has no int16
 
     def barrier():
         if world > 1:
@@ -397,7 +397,7 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
             if rc != 0:
                 raise RuntimeError(_capi.last_error())
         if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))
+            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))
 
     def barrier():
         if world > 1:

@@ -125,7 +125,8 @@ int stereo_disparity_u8_host(stereo_ctx* ctx, int cost,
 
 /* ---- single direction, DEVICE buffers, asynchronous on `cuda_stream` ----------------------- */
 /* Same computation with every pointer a device pointer on the context's device.  `cuda_stream` is a
- * cudaStream_t passed as void* (NULL = the context's own stream).  Returns after enqueueing. */
+ * cudaStream_t passed as void* (NULL = the context's own stream; pass cudaStreamLegacy, (void*)1, for the
+ * CUDA legacy default stream).  Returns after enqueueing. */
 int stereo_disparity_f32_device(stereo_ctx* ctx, int cost,
                                 const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
                                 int rows, int cols, int window_rad, int min_disp, int max_disp,

@@ -50,8 +50,12 @@ def band_halo(rows: int, r0: int, r1: int, window_rad: int) -> Tuple[int, int]:
     return int(h0.value), int(h1.value)
 
 
+CUDA_STREAM_LEGACY = 1   # cudaStreamLegacy: torch reports its default stream as handle 0, which the C ABI reads as "context stream"
+
+
 class GpuCompute:
-    """Per-rank compute on this rank's B200 through the C ABI (device buffers are torch tensors)."""
+    """Per-rank compute on this rank's B200 through the C ABI (device buffers are torch tensors).  Work is
+    enqueued on torch's current stream, so it is ordered with the surrounding torch ops and collectives."""
 
     def __init__(self, ctx, device):
         import torch
@@ -63,7 +67,7 @@ class GpuCompute:
         dl = torch.as_tensor(np.ascontiguousarray(left_slab)).to(self.device, non_blocking=True)
         dr = torch.as_tensor(np.ascontiguousarray(right_slab)).to(self.device, non_blocking=True)
         out = torch.empty((r1 - r0, cols), dtype=dtype, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = torch.cuda.current_stream(self.device).cuda_stream or CUDA_STREAM_LEGACY
         st = _capi.lib().stereo_disparity_band_halo_u8_device(
             self.ctx.handle, int(cost), dl.data_ptr(), cols, dr.data_ptr(), cols, rows, cols, r0, r1, h0, h1,
             int(window_rad), int(min_disp), int(max_disp), out.data_ptr(), cols * self._elem[dtype], self._elem[dtype],
@@ -79,7 +83,7 @@ class GpuCompute:
         dr = torch.as_tensor(np.ascontiguousarray(rights)).to(self.device, non_blocking=True)
         out = torch.empty((2, n, rows, cols), dtype=dtype, device=self.device)
         e = self._elem[dtype]
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = torch.cuda.current_stream(self.device).cuda_stream or CUDA_STREAM_LEGACY
         if n:
             st = _capi.lib().stereo_disparity_pair_batch_u8_device(
                 self.ctx.handle, int(cost), n, dl.data_ptr(), dr.data_ptr(), cols, rows * cols, rows, cols,
