@@ -100,6 +100,12 @@ float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measure
 int stereo_ctx_last_launches(const stereo_ctx* ctx);
 /* Force a kernel family (debug/testing): 0 = automatic, else a stereo_path value. */
 int stereo_ctx_force_path(stereo_ctx* ctx, int path);
+/* Host entry points overlap upload, compute and download by cutting each image pair into row bands
+ * (with the window halo) that flow through three streams.  bands = 0 (default) picks the band count
+ * from the image size and the number of pairs; bands >= 1 forces it (1 = whole images).  Results do not
+ * depend on it.  The reference uploads, computes and downloads one after the other
+ * (DisparitySSD.cu:171-206). */
+int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands);
 
 /* ---- single direction, HOST buffers (the drop-in form) ------------------------------------ */
 /*

@@ -33,6 +33,7 @@ SIGNATURES = {
     "stereo_ctx_last_launches": (_i, [_vp]),
     "stereo_ctx_last_hot_kernel_ms": (C.c_float, [_vp, C.POINTER(_i)]),
     "stereo_ctx_force_path": (_i, [_vp, _i]),
+    "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),
     "stereo_disparity_f32_host": (_i, _SINGLE_HOST),
     "stereo_disparity_u8_host": (_i, _SINGLE_HOST),

@@ -1,19 +1,26 @@
-"""In-tree build of the CUDA library (sm_100a only; nvcc cross-compiles without a GPU)."""
+"""In-tree build of the CUDA library (sm_100a only; nvcc cross-compiles without a GPU).
+
+The hot-kernel instantiations (csrc/fast_inst.cu, one translation unit per SB_PART) and the host/C-ABI
+unit (csrc/stereo_b200.cu) compile in parallel into csrc/_build/*.o and are linked into
+libstereo_b200.so next to this file."""
 from __future__ import annotations
 
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
+OBJ = CSRC / "_build"
 LIB = PKG / "libstereo_b200.so"
+FAST_PARTS = 8
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-diag-suppress", "177,128",
 ]
 
@@ -23,6 +30,13 @@ def _nvcc() -> str:
         if cand and Path(cand).exists():
             return cand
     raise RuntimeError("nvcc not found (needed to build libstereo_b200.so for sm_100a)")
+
+
+def units():
+    """(object name, source, extra flags) of every translation unit."""
+    u = [("stereo_b200.o", CSRC / "stereo_b200.cu", [])]
+    u += [(f"fast_inst_{i}.o", CSRC / "fast_inst.cu", [f"-DSB_PART={i}"]) for i in range(FAST_PARTS)]
+    return u
 
 
 def sources():
@@ -41,14 +55,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into libstereo_b200.so next to this file."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, sources())]
+    nvcc = _nvcc()
+    OBJ.mkdir(exist_ok=True)
+
+    def compile_one(unit):
+        name, src, extra = unit
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", str(OBJ / name), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name} {extra}:\n" + res.stdout + res.stderr)
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(units()), os.cpu_count() or 1)) as ex:
+        logs = list(ex.map(compile_one, units()))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+        print("\n".join(logs))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *(str(OBJ / n) for n, _, _ in units())]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -28,6 +28,8 @@ static inline unsigned div_round_up(long long num, long long den) {
     return (unsigned)(v < 1 ? 1 : v);
 }
 
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
 enum class PixType : int { U8 = 0, F32 = 1 };
 
 struct ImageView {       // device image
@@ -76,6 +78,9 @@ struct stereo_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host entry points
+    cudaEvent_t* pipe_ev = nullptr;                 // pool of timing-free events for the pipeline
+    int pipe_ev_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
     sb::Arena arena;          // per-call scratch (padded images, packed rows, partial keys)
@@ -88,6 +93,7 @@ struct stereo_ctx {
     int last_launches = 0;
     float last_ms = -1.f;
     int force_path = 0;
+    int pipe_bands = 0;       // 0 = automatic
     // device time of the hot kernels only (fast_*_kernel), per direction, for the roofline report
     static constexpr int HOT_EVENTS = 16;
     cudaEvent_t hot0[HOT_EVENTS] = {}, hot1[HOT_EVENTS] = {};

@@ -10,7 +10,6 @@
 
 namespace sb {
 
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // cv::copyMakeBorder(..., BORDER_REPLICATE) (DisparitySSD.cpp:20-23) into a contiguous float image.
 template <typename T>

@@ -1,138 +1,11 @@
-// Packed u8 path: the hot kernels of the library (sm_100a).
-//
-// For images that are exactly 8-bit the window cost is an integer and
-//     SSD(x,d) = EL(x) + ER(x+d) - 2*C(x,d),   C = sum over the window of l*r,
-//     NCC(x,d) = C(x,d) / sqrt(EL(x) * ER(x+d)),
-// so the per-disparity work is ONE box-filtered cross term C; the energies are box sums computed
-// once per image, not per disparity (north-star item (b)).  The kernel computes C with separable
-// running sums held entirely in registers:
-//
-//   * vertical:   col[m][c] += l_new*r_new - l_old*r_old      ONE IDP.2A (dp2a, s16 x u8) per unit
-//                 (the new and the leaving row are packed into one operand pair by the prep kernels)
-//   * horizontal: s[m] += col[m][c+2R+1] - col[m][c]          ONE IADD3 per unit
-//   * WTA:        key = E2[pos] + 256*s (cost*128 + position) ONE IMAD/LEA, then VIMNMX3 in-thread
-//                 and REDUX.MIN across the 32 lanes of the warp (lanes = disparities)
-//
-// The cost volume never exists in memory: a thread owns K=24 pixels x M=4 disparities, a warp
-// 24 pixels x 128 disparities, and only the winning key per pixel and 128-disparity group leaves
-// the SM.  Operand rows are staged in shared memory with TMA bulk copies (cp.async.bulk, SASS
-// UBLKCP) through a 4-stage mbarrier ring; all warps of a CTA share the staged rows.
-//
-// Reference semantics reproduced: replicate padding, the clamped candidate
-// range in padded coordinates, the flat-index row wrap of the SSD target reads (realised by building
-// the target operand rows from an "extended" image whose out-of-row columns come from the
-// neighbouring padded row / zero guard), first-minimum (SSD) and first-maximum (NCC) tie-breaks.
+// Packed u8 path, host side + the streaming kernels around the hot kernel: operand preparation (prep_*),
+// merge of the per-group winners, geometry and launch.  The hot kernel itself is in fast_kernel.cuh and is
+// instantiated in fast_inst.cu.
 #pragma once
-#include "common.cuh"
+#include "fast_kernel.cuh"
 #include "exact.cuh"
-#include <climits>
-#include <cstdlib>
 
 namespace sb {
-
-constexpr int FK_DEFAULT = 24;  // pixels per thread (strip width); template parameter K of the kernels
-constexpr int FM = 4;           // disparities per thread
-constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
-constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
-constexpr int FRPS = 8;         // operand rows per pipeline stage
-constexpr int FNST = 8;         // pipeline stages
-constexpr int FWARPS_MAX = 12;   // warps per CTA: 8 (K=24, <=255 regs) or 12 (K=16, <=168 regs)
-constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
-constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
-constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone
-
-// Keys are unsigned:  key = BIAS + 128*(ER - 2C) + position,  BIAS = 128*Emax, Emax = (2R+1)^2*255^2,
-// so valid keys lie in [0, 256*Emax + position].  A candidate whose centre is not a legal search
-// position carries E2 = KEY_INVALID; its key KEY_INVALID - 256*C stays above every valid key as long
-// as 512*Emax < 2^32 (R <= 5), i.e. border masking costs no instruction there.
-__host__ __device__ static inline uint32_t key_emax(int R) { return uint32_t((2 * R + 1) * (2 * R + 1)) * 65025u; }
-__host__ __device__ static inline uint32_t key_bias(int R) { return key_emax(R) << FKEY_BITS; }
-__host__ __device__ static inline uint32_t key_invalid_threshold(int R) {
-    return R <= FFREE_MASK_R ? KEY_INVALID - (key_emax(R) << (FKEY_BITS + 1)) : KEY_INVALID;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Geometry shared by host and device
-// ---------------------------------------------------------------------------------------------------
-struct FastGeom {
-    // problem
-    int rows, cols, R, dmin, dmax, cost;
-    int rb, re;            // output band
-    int ar0, ar1;          // image rows present in the caller's buffers (full image: 0, rows); reads clamp into it
-    int K;                 // pixels per thread (strip width): 24 or 16
-    int nw;                // warps per CTA: 8 (K=24) or 12 (K=16)
-    // derived
-    int G;                 // number of 128-disparity groups
-    int gc;                // groups per CTA (1 or 2)
-    int spc;               // strips per CTA = FWARPS / gc
-    int nstrips;           // ceil(cols / FK)
-    int tilesX;            // ceil(nstrips / spc)
-    int gblocks;           // ceil(G / gc)
-    int base_y;            // step row of operand row 0 (multiple of FRPS, <= rb - (2R+1))
-    int J;                 // operand rows (multiple of FRPS)
-    int qoff, eoff;        // column offsets of the RQ / E2 arrays
-    int lp_pitch, rq_pitch, e2_pitch;   // words
-    int lpw, rqw, e2w;     // tile widths in words (multiples of 4)
-    int wpart;             // partial-key map width (= tilesX*spc*FK)
-    int nrows;             // re - rb
-    int ctas;              // grid size
-    long long total;       // tile-rows
-    long long L;           // tile-rows per CTA
-    // valid centre columns (unpadded coordinates)
-    int cmin, cmax;
-};
-
-static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-static inline int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
-
-struct FastArrays {
-    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
-    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
-    int32_t* E2;       // [J][e2_pitch]   BIAS + 128*ER + position, or KEY_INVALID
-    int32_t* PART;     // [G][nrows][wpart] winning keys
-    int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
-    float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
-    float* SC;         // NCC: [nstrips][nrows] magic = 2^ceil(log2 sqrt(max EL of the strip row))
-};
-
-// ---------------------------------------------------------------------------------------------------
-// Device helpers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int dp2a_lo(int a, unsigned b, int c) {
-    int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
-}
-__device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c) {
-    int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ int4 lds128(const int* p) { return *reinterpret_cast<const int4*>(p); }
 
 // The target image the reference actually reads: padded row i+R of the
 // replicate-padded image, extended by R columns either side that alias the neighbouring padded row
@@ -280,287 +153,6 @@ __global__ void __launch_bounds__(128) prep_scale_kernel(const int32_t* __restri
         magic = elmax > 0 ? ldexpf(1.f, e) : 1.f;                       // 2^e > bound
     }
     SC[size_t(strip) * g.nrows + yy] = magic;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// The hot kernel
-// ---------------------------------------------------------------------------------------------------
-struct FastKernelParams {
-    FastGeom g;
-    const int32_t* LP;
-    const uint32_t* RQ;
-    const int32_t* E2;   // SSD: key offsets; NCC: the RS array (f32 bit patterns)
-    int32_t* PART;
-    const float* SC;     // NCC: [strip][output row] power-of-two magic (see fast_row)
-};
-
-template <int R, int K>
-struct RowShape {
-    static constexpr int NC = K + 2 * R;              // columns whose sums a thread keeps
-    static constexpr int NC4 = (NC + 3) / 4 * 4;
-    static constexpr int NQ = NC + FM - 1;             // target positions a thread touches
-    static constexpr int NQ4 = (NQ + 3) / 4 * 4;
-    static constexpr int NE = K + FM - 1;              // centre positions
-    static constexpr int NE4 = (NE + 3) / 4 * 4;
-};
-
-// One operand row for one warp.
-//   MODE 0: warm-up (add the entering row only, no output)
-//   MODE 1: regular row; SSD: invalid search positions lose through their E2 entry alone (R <= 5);
-//           NCC: every candidate of the block is legal
-//   MODE 2: MODE 1 + whole lanes beyond max_disp are excluded (one LOP3 per pixel)
-//   MODE 3: explicit per-candidate selects (partially valid lanes, border positions)
-// PAR selects the byte pair of the RQ words (even/odd step row).
-// The column updates (IDP.2A, FMA-heavy pipe) are interleaved with the horizontal slide / WTA of the
-// same row (IADD3, VIMNMX on the ALU pipe) so that a single warp keeps both half-rate pipes busy.
-//
-// NCC keys.  v = C * RS[pos] (f32, C an exact integer) orders the candidates of one pixel; the oracle's
-// first-maximum rule (cv::minMaxLoc, DisparityNCorr.cpp:62-64) needs the full f32 precision of v AND the
-// position in one 32-bit key, which an f32 bit pattern cannot hold.  So v is turned into a 23-bit
-// fixed-point number first: r = v + magic with magic = the power of two just above sqrt(max EL) of the
-// strip row (C*RS <= sqrt(EL) by Cauchy-Schwarz), i.e. r lies in the binade [magic, 2*magic) and its
-// mantissa IS round(v * 2^23 / magic).  key = (bits(r) << 9) + (reversed position << 2 | 3): 23 value
-// bits, 7 position bits, low bits 11 so that 0 can mean "no legal candidate".  Unsigned max.
-// For (2R+1)^2*255^2 < 2^23 (R <= 5) the running sums carry the float bias 0x4B000000, i.e. they ARE
-// the float 2^23 + C, and v = fma(2^23 + C, rs, -2^23*rs) is the correctly rounded product with no
-// conversion instruction; larger windows convert with I2F and fold the magic add into the FFMA.
-#ifndef SB_KEY_LEA_MASK
-#define SB_KEY_LEA_MASK 0
-#endif
-constexpr int NCC_BIAS_MAX_R = 5;
-constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
-constexpr int NCC_KEY_SHIFT = 9;                  // mantissa -> bits 9..31
-constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses every unsigned max)
-
-template <int R, int K, int PAR, int MODE, int COST>
-__device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
-                                         const int* __restrict__ rq_row, const int* __restrict__ e2_row,
-                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int cbase,
-                                         int cols, float magic) {
-    using S = RowShape<R, K>;
-    constexpr bool NCC = (COST == STEREO_COST_NCORR);
-    constexpr bool BIASED = NCC && (R <= NCC_BIAS_MAX_R);
-    int lpv[S::NC4];
-    int rqv[S::NQ4];
-#pragma unroll
-    for (int i = 0; i < S::NC4 / 4; ++i) {
-        const int4 v = lds128(lp_row + 4 * i);
-        lpv[4 * i] = v.x; lpv[4 * i + 1] = v.y; lpv[4 * i + 2] = v.z; lpv[4 * i + 3] = v.w;
-    }
-#pragma unroll
-    for (int i = 0; i < S::NQ4 / 4; ++i) {
-        const int4 v = lds128(rq_row + 4 * i);
-        rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
-    }
-    auto update = [&](int c) {
-        const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];      // warm-up: entering row only
-#pragma unroll
-        for (int m = 0; m < FM; ++m)
-            col[m][c] = PAR ? dp2a_hi(a, unsigned(rqv[c + m]), col[m][c]) : dp2a_lo(a, unsigned(rqv[c + m]), col[m][c]);
-    };
-    if (MODE == 0) {
-#pragma unroll
-        for (int c = 0; c < S::NC; ++c) update(c);
-        return;
-    }
-    int e2v[S::NE4];
-#pragma unroll
-    for (int i = 0; i < S::NE4 / 4; ++i) {
-        const int4 v = lds128(e2_row + 4 * i);
-        e2v[4 * i] = v.x; e2v[4 * i + 1] = v.y; e2v[4 * i + 2] = v.z; e2v[4 * i + 3] = v.w;
-    }
-    int s[FM];
-#pragma unroll
-    for (int m = 0; m < FM; ++m) s[m] = BIASED ? NCC_FLOAT_BIAS : 0;
-#pragma unroll
-    for (int c = 0; c < 2 * R; ++c) {
-        update(c);
-#pragma unroll
-        for (int m = 0; m < FM; ++m) s[m] += col[m][c];
-    }
-    uint32_t res[4];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        update(k + 2 * R);
-        uint32_t key[FM];
-#pragma unroll
-        for (int m = 0; m < FM; ++m) {
-            s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
-            if (!NCC) {
-                // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
-                // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
-                // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
-                uint32_t kv;
-                if (SB_KEY_LEA_MASK & (1 << m)) {      // shift-add on the ALU pipe
-                    asm("{.reg .b32 t; shl.b32 t, %1, 8; add.s32 %0, t, %2;}" : "=r"(kv) : "r"(s[m]), "r"(e2v[k + m]));
-                } else {                                // IMAD (immediate) on the FMA-heavy pipe
-                    kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
-                }
-                if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
-                key[m] = kv;
-            } else {
-                const float rs = __int_as_float(e2v[k + m]);
-                const float r = BIASED ? __fadd_rn(__fmaf_rn(__int_as_float(s[m]), rs, rs * -8388608.0f), magic)
-                                       : __fmaf_rn(__int2float_rn(s[m]), rs, magic);
-                // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
-                uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
-                if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax) ? NCC_KEY_NONE : kv;
-                key[m] = kv;
-            }
-        }
-        uint32_t best;
-        if (!NCC) {
-            best = min(min(key[0], key[1]), min(key[2], key[3]));
-            if (MODE == 2) best |= lane_or;
-            res[k & 3] = __reduce_min_sync(0xffffffffu, best);
-        } else {
-            best = max(max(key[0], key[1]), max(key[2], key[3]));
-            if (MODE == 2) best = mmax < 0 ? NCC_KEY_NONE : best;
-            res[k & 3] = __reduce_max_sync(0xffffffffu, best);
-        }
-        if ((k & 3) == 3 && lane == 0)
-            *reinterpret_cast<uint4*>(out_row + k - 3) = make_uint4(res[0], res[1], res[2], res[3]);
-    }
-}
-
-template <int R, int K, int NW, int COST>
-__global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelParams P) {
-    constexpr bool NCC = (COST == STEREO_COST_NCORR);
-    using S = RowShape<R, K>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const FastGeom& g = P.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
-    const int stage_words = lp_stage + rq_stage + e2_stage;
-    int* smem = reinterpret_cast<int*>(smem_raw);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(FNST) * stage_words * 4);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST);
-
-    if (tid == 0) {
-        for (int i = 0; i < FNST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, NW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // ---- this CTA's share of the (tile, row) space -------------------------------------------------
-    const long long lin_begin = (long long)blockIdx.x * g.L;
-    long long lin_end = lin_begin + g.L;
-    if (lin_end > g.total) lin_end = g.total;
-    if (lin_begin >= lin_end) return;
-    const int w = 2 * R + 1;
-
-    // producer state (thread 0 only): iterates the same stage sequence, FNST-2 stages ahead
-    long long p_lin = lin_begin;   // start of the producer's current segment
-    int p_sj = 0, p_sj_end = -1;   // stage range of the producer's segment
-    int p_tile = 0;
-    int pn = 0;                    // loads issued
-    auto producer_open_segment = [&]() {
-        p_tile = int(p_lin / g.nrows);
-        const int r0 = int(p_lin % g.nrows);
-        long long rem = lin_end - p_lin;
-        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
-        const int js = g.rb + r0 - w - g.base_y, je = g.rb + r1 - g.base_y;
-        p_sj = js / FRPS; p_sj_end = (je - 1) / FRPS;
-        p_lin += r1 - r0;
-    };
-    auto producer_issue = [&]() -> bool {     // returns false when nothing is left
-        if (p_sj > p_sj_end) {
-            if (p_lin >= lin_end) return false;
-            producer_open_segment();
-        }
-        const int slot = pn % FNST;
-        if (pn >= FNST) mbar_wait(empty0 + 8 * slot, ((pn / FNST) - 1) & 1);
-        const int xt = p_tile % g.tilesX, gb = p_tile / g.tilesX;
-        const int p0 = xt * g.spc * K;
-        const int q0 = p0 + g.dmin + FGROUP * gb * g.gc + g.R + g.qoff;
-        const int q20 = p0 + g.dmin + FGROUP * gb * g.gc + g.eoff;
-        const uint32_t bar = full0 + 8 * slot;
-        int* st = smem + size_t(slot) * stage_words;
-        mbar_expect_tx(bar, uint32_t(stage_words) * 4u);
-        const int j0 = p_sj * FRPS;
-#pragma unroll 1
-        for (int r = 0; r < FRPS; ++r)
-            tma_load_1d(smem_u32(st + r * g.lpw), P.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
-#pragma unroll 1
-        for (int r = 0; r < FRPS / 2; ++r)
-            tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), P.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
-#pragma unroll 1
-        for (int r = 0; r < FRPS; ++r)
-            tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), P.E2 + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
-        ++pn; ++p_sj;
-        return true;
-    };
-    // The producer is lane 0 of the LAST warp: the SMSP arbiter favours higher warp ids, so that warp
-    // tends to run ahead and operand rows are requested as early as the ring allows.
-    const bool is_producer = (tid == (NW - 1) * 32);
-    if (is_producer) {
-        for (int i = 0; i < FNST - 2; ++i) if (!producer_issue()) break;
-    }
-
-    // ---- consumers -----------------------------------------------------------------------------------
-    int n = 0;                      // stages consumed
-    long long lin = lin_begin;
-    int col[FM][S::NC];
-    while (lin < lin_end) {
-        const int tile = int(lin / g.nrows);
-        const int r0 = int(lin % g.nrows);
-        const long long rem = lin_end - lin;
-        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
-        lin += r1 - r0;
-        const int xt = tile % g.tilesX, gb = tile / g.tilesX;
-        const int strip = xt * g.spc + warp / g.gc;
-        const int grp = gb * g.gc + warp % g.gc;
-        const int x0 = strip * K;
-        const bool active = (x0 < g.cols) && (grp < g.G);
-        const int y0 = g.rb + r0, y1 = g.rb + r1;
-        const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
-        // which flavour of candidate masking this warp's (24 pixels x 128 disparities) block needs
-        const int dlo = g.dmin + FGROUP * grp;                         // first disparity of the group
-        const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + K - 1 + dlo + FGROUP - 1 > g.cmax);
-        const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
-        const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
-        const int mode = (partial_lane || (pos_invalid && (NCC || R > FFREE_MASK_R))) ? 3 : (lane_invalid ? 2 : 1);
-        const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
-        // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
-        const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * lane) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
-        const float* sc_row = NCC ? P.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
-        const int cbase = x0 + dlo + FM * lane;                          // centre column of candidate (k=0, m=0)
-        const int lp_off = (warp / g.gc) * K;
-        const int rq_off = (warp / g.gc) * K + FGROUP * (warp % g.gc) + FM * lane;
-        int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
-#pragma unroll
-        for (int m = 0; m < FM; ++m)
-#pragma unroll
-            for (int c = 0; c < S::NC; ++c) col[m][c] = 0;
-
-        for (int sj = js / FRPS; sj <= (je - 1) / FRPS; ++sj, ++n) {
-            if (is_producer) producer_issue();
-            const int slot = n % FNST;
-            mbar_wait(full0 + 8 * slot, (n / FNST) & 1);
-            if (active) {
-                const int* st = smem + size_t(slot) * stage_words;
-                const int jlo = max(js, sj * FRPS), jhi = min(je, sj * FRPS + FRPS);
-                for (int j = jlo; j < jhi; ++j) {
-                    const int r = j - sj * FRPS;
-                    const int* lp_row = st + r * g.lpw + lp_off;
-                    const int* rq_row = st + lp_stage + (r >> 1) * g.rqw + rq_off;
-                    const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
-                    int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
-                    const int par = j & 1;
-                    const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
-#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, cbase, g.cols, magic)
-                    if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
-                    else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
-                    else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
-                    else                { if (par) SB_ROW(1, 3); else SB_ROW(0, 3); }
-#undef SB_ROW
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -729,32 +321,6 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     add(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + 256, 64) * 4);
     if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
     return b + 4096;
-}
-
-typedef void (*fast_kernel_fn)(const FastKernelParams);
-template <int COST>
-static inline fast_kernel_fn fast_pick_cost(int R, int K) {
-    if (K == 16) {
-        switch (R) {
-        case 4: return fast_cost_kernel<4, 16, 12, COST>;
-        case 5: return fast_cost_kernel<5, 16, 12, COST>;
-        }
-        return nullptr;
-    }
-    switch (R) {
-    case 0: return fast_cost_kernel<0, 24, 8, COST>;
-    case 1: return fast_cost_kernel<1, 24, 8, COST>;
-    case 2: return fast_cost_kernel<2, 24, 8, COST>;
-    case 3: return fast_cost_kernel<3, 24, 8, COST>;
-    case 4: return fast_cost_kernel<4, 24, 8, COST>;
-    case 5: return fast_cost_kernel<5, 24, 8, COST>;
-    case 6: return fast_cost_kernel<6, 24, 8, COST>;
-    case 7: return fast_cost_kernel<7, 24, 8, COST>;
-    }
-    return nullptr;
-}
-static inline fast_kernel_fn fast_pick(int cost, int R, int K) {
-    return cost == STEREO_COST_SSD ? fast_pick_cost<STEREO_COST_SSD>(R, K) : fast_pick_cost<STEREO_COST_NCORR>(R, K);
 }
 
 static inline int fast_ctx_init(stereo_ctx*) {

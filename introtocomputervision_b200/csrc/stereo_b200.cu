@@ -219,6 +219,178 @@ static int ensure_pinned(stereo_ctx* ctx, size_t bytes) {
     return STEREO_OK;
 }
 
+// ---- pipelined host entry points --------------------------------------------------------------------
+// The reference wrapper uploads, computes and downloads strictly one after the other on pageable
+// memory (DisparitySSD.cu:171-206).  Here a host call is cut into (pair, row band) work items that flow
+// through three streams — H2D of band b+1, compute of band b (both directions) and D2H of band b-1 run
+// concurrently — so a call costs about max(upload, compute, download) instead of their sum.  Bands are
+// the same R(+1)-row-halo bands the multi-GPU sharding uses: bit-identical results.
+// f32 images are converted to u8 band by band while the "is it really 8-bit" flag accumulates; it is
+// read once at the end, and a non-8-bit image makes the caller redo the call on the exact path.
+
+struct HostDir {          // one direction of a host pair job
+    bool swap;            // false: ref = left, tgt = right; true: ref = right, tgt = left
+    int dmin, dmax;
+    void* const* out;     // per pair: host output pointer
+};
+struct HostPairIn { const void* left; size_t left_step; const void* right; size_t right_step; };
+
+enum { PIPE_NOT_APPLICABLE = 1, PIPE_NOT_8BIT = 2 };
+
+static int ensure_pipe(stereo_ctx* ctx, int events) {
+    if (!ctx->s_in) SB_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) SB_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    if (events > ctx->pipe_ev_cap) {
+        const int cap = events + 64;
+        cudaEvent_t* ev = new (std::nothrow) cudaEvent_t[cap]();
+        if (!ev) { set_error("out of host memory"); return STEREO_ERR_ALLOC; }
+        for (int i = 0; i < ctx->pipe_ev_cap; ++i) ev[i] = ctx->pipe_ev[i];
+        for (int i = ctx->pipe_ev_cap; i < cap; ++i) {
+            cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) {
+                for (int k = ctx->pipe_ev_cap; k < i; ++k) cudaEventDestroy(ev[k]);
+                delete[] ev;
+                set_error("cudaEventCreate: %s", cudaGetErrorString(e));
+                return STEREO_ERR_CUDA;
+            }
+        }
+        delete[] ctx->pipe_ev;
+        ctx->pipe_ev = ev;
+        ctx->pipe_ev_cap = cap;
+    }
+    return STEREO_OK;
+}
+
+static int pipe_bands(const stereo_ctx* ctx, int n_pairs, int rows) {
+    if (ctx->pipe_bands > 0) return ctx->pipe_bands < rows ? ctx->pipe_bands : rows;
+    if (n_pairs >= 4 || rows < 512) return 1;           // enough pairs in flight / too small to be worth cutting
+    int nb = (rows + 255) / 512;                        // ~512-row bands: the (2R+1)-row warm-up stays < 3 %
+    return nb < 1 ? 1 : (nb > 8 ? 8 : nb);
+}
+
+static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
+                                const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
+    if (ctx->force_path == STEREO_PATH_EXACT_F32) return PIPE_NOT_APPLICABLE;
+    const size_t px = type == PixType::F32 ? 4 : 1;
+    const size_t in_pitch = align256(cols * px), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
+    // validate each direction on a full-image problem (pointers only need to be non-null here)
+    Problem full{};
+    full.cost = cost; full.rows = rows; full.cols = cols; full.row_begin = 0; full.row_end = rows;
+    full.avail_begin = 0; full.avail_end = rows; full.R = R;
+    full.ref = ImageView{in, u8_pitch, PixType::U8}; full.tgt = full.ref;
+    full.disp = OutView{ctx, d_pitch, elem}; full.best = OutView{nullptr, 0, 4};
+    const int nb = pipe_bands(ctx, n_pairs, rows);
+    const int band_rows = (rows + nb - 1) / nb;
+    size_t scratch = 0;
+    for (int d = 0; d < n_dirs; ++d) {
+        full.dmin = dirs[d].dmin; full.dmax = dirs[d].dmax;
+        int rc = validate(full, u8_pitch, u8_pitch);
+        if (rc != STEREO_OK) return rc;
+        if (!fast_supported(full)) return PIPE_NOT_APPLICABLE;
+        Problem band = full; band.row_end = band_rows < rows ? band_rows : rows;
+        const size_t need = fast_scratch_bytes(ctx, band);
+        scratch = need > scratch ? need : scratch;
+    }
+    int rc = ensure_pipe(ctx, 3 * n_pairs * nb + 4);
+    if (rc != STEREO_OK) return rc;
+    cudaStream_t s_in = ctx->s_in, s_cmp = ctx->stream, s_out = ctx->s_out;
+
+    const int S = n_pairs < 3 ? n_pairs : 3;            // device slots (ring)
+    const size_t slot_bytes = 2 * align256(in_pitch * rows) + (type == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
+                              + size_t(n_dirs) * align256(d_pitch * rows);
+    if (size_t(S) * slot_bytes + 1024 > ctx->io.cap || scratch > ctx->arena.cap) {
+        SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
+        if (size_t(S) * slot_bytes + 1024 > ctx->io.cap) { rc = ctx->io.reserve(size_t(S) * slot_bytes + 1024); if (rc != STEREO_OK) return rc; }
+        if (scratch > ctx->arena.cap) { rc = ctx->arena.reserve(scratch); if (rc != STEREO_OK) return rc; }
+    }
+    ctx->io.reset();
+    struct Slot { char* l; char* r; uint8_t* l8; uint8_t* r8; char* out[2]; } slot[3] = {};
+    for (int k = 0; k < S; ++k) {
+        slot[k].l = static_cast<char*>(ctx->io.take(in_pitch * rows));
+        slot[k].r = static_cast<char*>(ctx->io.take(in_pitch * rows));
+        if (type == PixType::F32) {
+            slot[k].l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+            slot[k].r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+        } else {
+            slot[k].l8 = reinterpret_cast<uint8_t*>(slot[k].l);
+            slot[k].r8 = reinterpret_cast<uint8_t*>(slot[k].r);
+        }
+        for (int d = 0; d < n_dirs; ++d) slot[k].out[d] = static_cast<char*>(ctx->io.take(d_pitch * rows));
+        if (!slot[k].l || !slot[k].r || !slot[k].l8 || !slot[k].r8 || !slot[k].out[n_dirs - 1]) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    }
+    auto ev = [&](int pair, int band, int kind) { return ctx->pipe_ev[3 * (pair * nb + band) + kind + 1]; };   // kind: 0 in, 1 cmp, 2 out
+
+    begin_call(ctx, s_cmp);
+    // copy streams start after whatever the context's stream was doing with these buffers
+    SB_CUDA(cudaEventRecord(ctx->pipe_ev[0], s_cmp));
+    SB_CUDA(cudaStreamWaitEvent(s_in, ctx->pipe_ev[0], 0));
+    SB_CUDA(cudaStreamWaitEvent(s_out, ctx->pipe_ev[0], 0));
+    if (type == PixType::F32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s_cmp));
+    ctx->last_path = STEREO_PATH_FAST_U8;
+
+    for (int i = 0; i < n_pairs; ++i) {
+        const Slot& sl = slot[i % S];
+        int uploaded = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int rb = b * band_rows, re = (rb + band_rows < rows) ? rb + band_rows : rows;
+            if (rb >= re) {           // (rows not divisible: trailing empty band) keep the event chain intact
+                SB_CUDA(cudaEventRecord(ev(i, b, 0), s_in)); SB_CUDA(cudaEventRecord(ev(i, b, 1), s_cmp)); SB_CUDA(cudaEventRecord(ev(i, b, 2), s_out));
+                continue;
+            }
+            // ---- upload the rows this band adds: window halo R, the +1 row of the SSD flat-index wrap, and the
+            //      operand rows the FRPS-row pipeline stages round up to
+            const int up_hi = (b == nb - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
+            if (b == 0 && i >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(i - S, nb - 1, 1), 0));   // slot inputs free again
+            if (up_hi > uploaded) {
+                const int nr = up_hi - uploaded;
+                SB_CUDA(cudaMemcpy2DAsync(sl.l + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(in[i].left) + size_t(uploaded) * in[i].left_step,
+                                          in[i].left_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
+                SB_CUDA(cudaMemcpy2DAsync(sl.r + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(in[i].right) + size_t(uploaded) * in[i].right_step,
+                                          in[i].right_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
+            }
+            SB_CUDA(cudaEventRecord(ev(i, b, 0), s_in));
+            // ---- compute
+            SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(i, b, 0), 0));
+            if (b == 0 && i >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(i - S, nb - 1, 2), 0));  // slot outputs downloaded
+            if (type == PixType::F32 && up_hi > uploaded) {
+                const int nr = up_hi - uploaded;
+                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8));
+                classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl.l + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
+                                                             sl.l8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
+                classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl.r + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
+                                                             sl.r8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
+                ctx->last_launches += 2;
+            }
+            if (up_hi > uploaded) uploaded = up_hi;
+            for (int d = 0; d < n_dirs; ++d) {
+                Problem p = full;
+                p.row_begin = rb; p.row_end = re;
+                p.dmin = dirs[d].dmin; p.dmax = dirs[d].dmax;
+                p.ref = ImageView{dirs[d].swap ? sl.r8 : sl.l8, u8_pitch, PixType::U8};
+                p.tgt = ImageView{dirs[d].swap ? sl.l8 : sl.r8, u8_pitch, PixType::U8};
+                p.disp = OutView{sl.out[d] + size_t(rb) * d_pitch, d_pitch, elem};
+                ctx->arena.reset();
+                rc = run_fast(ctx, p, s_cmp);
+                if (rc != STEREO_OK) return rc;
+            }
+            SB_CUDA(cudaEventRecord(ev(i, b, 1), s_cmp));
+            // ---- download
+            SB_CUDA(cudaStreamWaitEvent(s_out, ev(i, b, 1), 0));
+            for (int d = 0; d < n_dirs; ++d)
+                SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(dirs[d].out[i]) + size_t(rb) * disp_step, disp_step, sl.out[d] + size_t(rb) * d_pitch, d_pitch,
+                                          size_t(cols) * elem, re - rb, cudaMemcpyDeviceToHost, s_out));
+            SB_CUDA(cudaEventRecord(ev(i, b, 2), s_out));
+        }
+    }
+    if (type == PixType::F32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
+    end_call(ctx, s_cmp);
+    SB_CUDA(cudaStreamSynchronize(s_cmp));
+    SB_CUDA(cudaStreamSynchronize(s_out));
+    SB_CUDA(cudaStreamSynchronize(s_in));
+    if (type == PixType::F32 && *ctx->h_flag != 0) return PIPE_NOT_8BIT;
+    return STEREO_OK;
+}
+
 // Host-buffer single direction: upload (2D async copies), compute, download, synchronize — the
 // shape of cuda::disparitySSD (DisparitySSD.cu:171-206) without per-call allocation.
 static int host_single(stereo_ctx* ctx, int cost, PixType type, const void* ref, size_t ref_step, const void* tgt,
@@ -232,6 +404,13 @@ static int host_single(stereo_ctx* ctx, int cost, PixType type, const void* ref,
     const size_t px = type == PixType::F32 ? 4 : 1;
     if (ref_step < cols * px || tgt_step < cols * px || disp_step < size_t(cols) * elem || (best_out && best_step < size_t(cols) * 4)) {
         set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG;
+    }
+    if (!best_out) {      // pipelined band-by-band; falls through to the sequential path when the packed kernels do not apply
+        const HostPairIn in{ref, ref_step, tgt, tgt_step};
+        void* outs[1] = {disp_out};
+        const HostDir dir{false, dmin, dmax, outs};
+        rc = pairs_host_pipelined(ctx, cost, type, 1, &in, &dir, 1, rows, cols, R, disp_step, elem);
+        if (rc <= STEREO_OK) return rc;
     }
     cudaStream_t st = ctx->stream;
     const size_t in_pitch = align256(cols * px), d_pitch = align256(size_t(cols) * elem), b_pitch = align256(size_t(cols) * 4);
@@ -380,6 +559,10 @@ void stereo_ctx_destroy(stereo_ctx* ctx) {
         if (ctx->hot0[i]) cudaEventDestroy(ctx->hot0[i]);
         if (ctx->hot1[i]) cudaEventDestroy(ctx->hot1[i]);
     }
+    for (int i = 0; i < ctx->pipe_ev_cap; ++i) cudaEventDestroy(ctx->pipe_ev[i]);
+    delete[] ctx->pipe_ev;
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -419,6 +602,12 @@ float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measure
 int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
     if (!ctx || path < 0 || path > STEREO_PATH_FAST_U8) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->force_path = path;
+    return STEREO_OK;
+}
+
+int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands) {
+    if (!ctx || bands < 0 || bands > 4096) { set_error("bad pipe_bands argument"); return STEREO_ERR_INVALID_ARG; }
+    ctx->pipe_bands = bands;
     return STEREO_OK;
 }
 
@@ -524,6 +713,15 @@ static int pair_host(stereo_ctx* ctx, int cost, PixType type, const void* left, 
     if (elem != 1 && elem != 2 && elem != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
     const size_t px = type == PixType::F32 ? 4 : 1;
     if (left_step < cols * px || right_step < cols * px || disp_step < size_t(cols) * elem) { set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG; }
+    if (range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
+    {
+        const HostPairIn in{left, left_step, right, right_step};
+        void* outs_l[1] = {disp_left};
+        void* outs_r[1] = {disp_right};
+        const HostDir dirs[2] = {{false, -range, 0, outs_l}, {true, 0, range, outs_r}};
+        rc = pairs_host_pipelined(ctx, cost, type, 1, &in, dirs, 2, rows, cols, R, disp_step, elem);
+        if (rc <= STEREO_OK) return rc;
+    }
     cudaStream_t st = ctx->stream;
     const size_t in_pitch = align256(cols * px), d_pitch = align256(size_t(cols) * elem);
     const size_t need = 2 * in_pitch * rows + 2 * d_pitch * rows + 1024;
@@ -609,8 +807,21 @@ int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs, 
     if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
     if (rows <= 0 || cols <= 0 || img_step < size_t(cols) || disp_step < size_t(cols) * disp_elem_bytes) { set_error("bad size/step"); return STEREO_ERR_INVALID_ARG; }
     if (disp_elem_bytes != 1 && disp_elem_bytes != 2 && disp_elem_bytes != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    if (disparity_range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
+    {   // pipelined: pair i+1 uploads while pair i computes and pair i-1 downloads (3 device slots)
+        std::vector<HostPairIn> in(n_pairs);
+        std::vector<void*> outs_l(n_pairs), outs_r(n_pairs);
+        for (int i = 0; i < n_pairs; ++i) {
+            in[i] = HostPairIn{left + size_t(i) * pair_stride, img_step, right + size_t(i) * pair_stride, img_step};
+            outs_l[i] = static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride;
+            outs_r[i] = static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride;
+        }
+        const HostDir dirs[2] = {{false, -disparity_range, 0, outs_l.data()}, {true, 0, disparity_range, outs_r.data()}};
+        rc = pairs_host_pipelined(ctx, cost, PixType::U8, n_pairs, in.data(), dirs, 2, rows, cols, window_rad, disp_step, disp_elem_bytes);
+        if (rc <= STEREO_OK) return rc;
+    }
     cudaStream_t st = ctx->stream;
-    // Stage the whole batch on the device (sized for 180 GB of HBM; a 512 x 720p batch is ~1.4 GB).
+    // Sequential fallback (parameters the packed kernels do not cover): stage the whole batch on the device.
     const size_t in_pitch = align256(cols), d_pitch = align256(size_t(cols) * disp_elem_bytes);
     const size_t in_pair = in_pitch * rows, d_pair = d_pitch * rows;
     const size_t need = size_t(n_pairs) * (2 * in_pair + 2 * d_pair) + 4096;

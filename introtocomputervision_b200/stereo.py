@@ -99,6 +99,10 @@ class Context:
     def force_path(self, path: int) -> None:
         _check(_capi.lib().stereo_ctx_force_path(self._h, int(path)), "stereo_ctx_force_path")
 
+    def set_pipe_bands(self, bands: int) -> None:
+        """Row bands per image pair in the pipelined host entry points (0 = automatic)."""
+        _check(_capi.lib().stereo_ctx_set_pipe_bands(self._h, int(bands)), "stereo_ctx_set_pipe_bands")
+
     def synchronize(self, stream: int = 0) -> None:
         _check(_capi.lib().stereo_ctx_synchronize(self._h, C.c_void_p(stream)), "stereo_ctx_synchronize")
 

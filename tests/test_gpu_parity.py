@@ -204,6 +204,71 @@ def test_device_pointer_and_band_entry_points(ctx):
                 assert np.array_equal(band.cpu().numpy(), ref[r0:r1].astype(np.int16))
 
 
+# ---- pipelined host entry points (row bands through upload / compute / download streams) --------------
+
+@pytest.mark.parametrize("bands", [1, 2, 3, 7])
+def test_pipelined_host_bands_vs_oracle(ctx, bands):
+    L, Rt, _ = synth.make_pair(101, 300, 40, 900 + bands)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l = oracle.ssd_fast(Lf, Rf, 5, -39, 0)
+    ref_r = oracle.ssd_fast(Rf, Lf, 5, 0, 39)
+    try:
+        ctx.set_pipe_bands(bands)
+        for a, b in ((Lf, Rf), (L, Rt)):                       # CV_32FC1 like the reference, and u8
+            dl, dr = ctx.disparity_pair(sb.COST_SSD, a, b, 5, 39, dtype=np.int16)
+            assert ctx.last_path == sb.PATH_FAST_U8
+            assert np.array_equal(dl, ref_l) and np.array_equal(dr, ref_r)
+        # single direction, R->L (the SSD row wrap reads the NEXT row there: band seams need the +1 halo row)
+        assert np.array_equal(ctx.disparity(sb.COST_SSD, Rf, Lf, 5, 0, 39, dtype=np.int16), ref_r)
+        # NCC: banded result == whole-image result, and close to the oracle
+        dn = ctx.disparity(sb.COST_NCORR, Lf, Rf, 5, -39, 0, dtype=np.int16)
+        ctx.set_pipe_bands(1)
+        assert np.array_equal(dn, ctx.disparity(sb.COST_NCORR, Lf, Rf, 5, -39, 0, dtype=np.int16))
+        assert float(np.mean(dn == oracle.ncorr_fast(Lf, Rf, 5, -39, 0))) >= NCC_DISP_AGREE
+    finally:
+        ctx.set_pipe_bands(0)
+
+
+@pytest.mark.parametrize("bands", [0, 2])
+def test_pipelined_batch_reuses_device_slots(ctx, bands):
+    # 7 pairs through 3 device slots: every slot is overwritten at least once while its predecessor downloads
+    n = 7
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(45, 150, 24, 700 + i)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    try:
+        ctx.set_pipe_bands(bands)
+        bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, 23, dtype=np.int8)
+    finally:
+        ctx.set_pipe_bands(0)
+    for i in range(n):
+        Lf, Rf = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+        assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 4, -23, 0))), i
+        assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 4, 0, 23))), i
+
+
+def test_pipelined_host_non_8bit_falls_back_to_exact(ctx):
+    # the 8-bit flag is only known after the pipelined pass: a noisy image must be redone on the exact path
+    L, Rt, _ = synth.make_pair(60, 200, 30, 31)
+    Lf, Rf = synth.noisy_variant(L, 1), synth.noisy_variant(Rt, 2)
+    Lf[-1, -1] += 0.25                                          # ... even when only the very last pixel is non-integer
+    try:
+        ctx.set_pipe_bands(3)
+        dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(3, 29), ctx=ctx)
+        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 3, -29, 0)))
+        assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 3, 0, 29)))
+        Li = L.astype(np.float32)
+        Li[-1, -1] += 0.5
+        d = ctx.disparity(sb.COST_SSD, Li, Rt.astype(np.float32), 3, -29, 0, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert np.array_equal(d, oracle.ssd_fast(Li, Rt.astype(np.float32), 3, -29, 0))
+    finally:
+        ctx.set_pipe_bands(0)
+
+
 # ---- the packed u8 kernels ------------------------------------------------------------------------------------
 
 FAST_SHAPES = [
