@@ -197,6 +197,8 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
     ctx = sb.Context(local)
+    if args.pipe_bands:
+        ctx.set_pipe_bands(args.pipe_bands)
     cost = sb.COST_SSD if args.cost == "ssd" else sb.COST_NCORR
     rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
     if args.mode == "bands":
@@ -451,6 +453,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=2, help="stereo pairs per GPU per step")
     ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipe-bands", type=int, default=0, help="row bands per pair in the pipelined host entry points (0 = automatic)")
     ap.add_argument("--cost", default="ssd", choices=["ssd", "ncc"], help="window cost (the headline line is ssd)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
                     help="pairs: batch sharded by pair, weak scaling (default, the driver's line); "

@@ -211,8 +211,12 @@ __global__ void fast_merge_ncc_kernel(const int32_t* __restrict__ PART, FastGeom
         const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
         if (v > bestv) { bestv = v; bestd = g.dmin + FGROUP * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
     }
-    const int centre = x + bestd;                                   // winning window centre (unpadded column)
     const int startc = max(0, x + g.dmin), endc = min(g.cols - 1, x + g.dmax);
+    int centre = x + bestd;                                         // winning window centre (unpadded column)
+    // Illegal positions (centre outside the image) carry the score-0 key of their position (RS = 0).  One of
+    // them winning means every legal candidate scored exactly 0 (a non-zero C*rs never quantises to 0:
+    // rs >= 1/sqrt(Emax) > magic * 2^-24), and the first maximum of an all-zero result row is its first entry.
+    if (centre < startc || centre > endc) centre = startc;
     const bool right_aligned = (g.dmin <= 0 && g.dmax <= 0);
     const int disp = (centre - startc) - (right_aligned ? endc - startc : 0);
     char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;

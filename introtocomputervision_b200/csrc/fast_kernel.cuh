@@ -389,7 +389,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
         const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + K - 1 + dlo + FGROUP - 1 > g.cmax);
         const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
         const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
-        const int mode = (partial_lane || (pos_invalid && (NCC || R > FFREE_MASK_R))) ? 3 : (lane_invalid ? 2 : 1);
+        // NCC: an illegal search position carries RS = 0, i.e. the score-0 key of its position; it can only win
+        // when every legal candidate scores exactly 0 too, which the merge recognises (winner outside the image
+        // -> first legal candidate, cv::minMaxLoc's first maximum).  So NCC never needs the explicit selects
+        // for border positions, and SSD only for R > 5.
+        const int mode = (partial_lane || (pos_invalid && !NCC && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
         const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
         // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
         const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * lane) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
