@@ -261,6 +261,7 @@ def run_ours(args, wl):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     # hot-kernel time of the last step (events recorded by the library on the same stream)
     ms, nmeas = ctx.last_hot_kernel_ms()
+    hot_jobs = ctx.last_hot_jobs
     if nmeas > 0:
         hot_ms, hot_n = ms, nmeas
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -328,16 +329,18 @@ def run_ours(args, wl):
         peak_lane_ops = sms * 128 * peaks["sm_max_mhz"] * 1e6               # lane-ops / s
         roof = None
         if hot_n > 0:
-            units_hot = hot_n * rows * cols * nd                            # one direction per hot launch
+            jobs_per_launch = hot_jobs / hot_n                              # directions one hot launch covers
+            units_hot = hot_jobs * rows * cols * nd
             t_hot = hot_ms * 1e-3
             achieved = OPS_PER_UNIT[args.cost] * units_hot / t_hot
             b_in, b_out = 1, elem
-            alg_bytes = rows * cols * (2 * b_in + b_out)                    # per launch
+            alg_bytes = int(jobs_per_launch * rows * cols * (2 * b_in + b_out))   # per launch
             roof = {
                 "bound": "alu", "kernel": f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>",
                 "achieved": round(achieved / 1e12, 3), "peak": round(peak_lane_ops / 1e12, 3), "unit": "Tlane-op/s",
                 "frac": round(achieved / peak_lane_ops, 4),
-                "ops_per_unit": OPS_PER_UNIT[args.cost], "units_per_launch": rows * cols * nd,
+                "ops_per_unit": OPS_PER_UNIT[args.cost], "units_per_launch": int(jobs_per_launch * rows * cols * nd),
+                "directions_per_launch": jobs_per_launch,
                 "launch_ms": round(hot_ms / hot_n, 4), "launches_timed": hot_n,
                 "peak_def": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                 "traffic": None,

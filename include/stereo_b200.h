@@ -91,11 +91,13 @@ int stereo_ctx_last_path(const stereo_ctx* ctx);
 /* Device time of the most recent compute call's kernels in milliseconds (cudaEvent pair; the
  * reference logs the same quantity, DisparitySSD.cu:192-203).  <0 if unavailable. */
 float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
-/* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels, one per
- * direction), summed over the launches that were measured (at most 16 per call); *launches_measured
- * (nullable) receives how many that was.  <0 if the call used no hot kernel.  This is the number the
- * roofline report divides by. */
+/* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels; one launch
+ * covers up to 8 directions of equally shaped problems), summed over the launches that were measured
+ * (at most 16 per call); *launches_measured (nullable) receives how many that was.  <0 if the call used
+ * no hot kernel.  This is the number the roofline report divides by. */
 float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measured);
+/* Directions (disparity maps) the measured hot launches of the most recent call computed. */
+int stereo_ctx_last_hot_jobs(const stereo_ctx* ctx);
 /* Number of kernel launches issued by the most recent compute call. */
 int stereo_ctx_last_launches(const stereo_ctx* ctx);
 /* Force a kernel family (debug/testing): 0 = automatic, else a stereo_path value. */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "stereo_ctx_last_kernel_ms": (C.c_float, [_vp]),
     "stereo_ctx_last_launches": (_i, [_vp]),
     "stereo_ctx_last_hot_kernel_ms": (C.c_float, [_vp, C.POINTER(_i)]),
+    "stereo_ctx_last_hot_jobs": (_i, [_vp]),
     "stereo_ctx_force_path": (_i, [_vp, _i]),
     "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),

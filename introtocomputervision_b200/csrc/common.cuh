@@ -99,4 +99,5 @@ struct stereo_ctx {
     cudaEvent_t hot0[HOT_EVENTS] = {}, hot1[HOT_EVENTS] = {};
     int hot_used = 0;          // event pairs recorded by the last call
     int hot_total = 0;         // hot-kernel launches of the last call (may exceed HOT_EVENTS)
+    int hot_jobs = 0;          // directions (jobs) covered by the measured hot launches
 };

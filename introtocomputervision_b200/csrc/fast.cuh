@@ -34,7 +34,12 @@ __device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, 
 // Prep kernels: operand rows in the layout the hot loop consumes
 // ---------------------------------------------------------------------------------------------------
 // LP[j][p]: 4 columns per thread, 16-byte stores.
-__global__ void __launch_bounds__(256) prep_lp_kernel(const uint8_t* __restrict__ A, size_t step, FastGeom g, int32_t* __restrict__ LP) {
+// Every prep / merge kernel takes the launch's parameter block; blockIdx.z selects the job.
+__global__ void __launch_bounds__(256) prep_lp_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const uint8_t* __restrict__ A = job.A; const size_t step = job.a_step;
+    int32_t* __restrict__ LP = job.LP;
     const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int j = blockIdx.y;
     if (p4 >= g.lp_pitch) return;
@@ -54,7 +59,11 @@ __global__ void __launch_bounds__(256) prep_lp_kernel(const uint8_t* __restrict_
 }
 
 // RQ[jp][q]: 4 positions per thread, 16-byte stores.
-__global__ void __launch_bounds__(256) prep_rq_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g, uint32_t* __restrict__ RQ) {
+__global__ void __launch_bounds__(256) prep_rq_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const uint8_t* __restrict__ B = job.B; const size_t step = job.b_step;
+    uint32_t* __restrict__ RQ = job.RQ;
     const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int jp = blockIdx.y;
     if (q4 >= g.rq_pitch) return;
@@ -62,7 +71,7 @@ __global__ void __launch_bounds__(256) prep_rq_kernel(const uint8_t* __restrict_
     uint32_t v[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        const int e = q4 + t - g.qoff;
+        const int e = q4 + t - job.qoff;
         const uint32_t b0 = bext(B, step, g.rows, g.cols, g.R, ye + g.R, e, g.ar0, g.ar1);
         const uint32_t b1 = bext(B, step, g.rows, g.cols, g.R, ye - g.R - 1, e, g.ar0, g.ar1);
         const uint32_t b2 = bext(B, step, g.rows, g.cols, g.R, ye + 1 + g.R, e, g.ar0, g.ar1);
@@ -78,8 +87,14 @@ __global__ void __launch_bounds__(256) prep_rq_kernel(const uint8_t* __restrict_
 //   pass 2 (prep_e2_kernel): ER = sum_{t=-R..R} V[yy][centre + t] from a shared-memory tile, then
 //           E2[j][q2] = BIAS + 128*ER + q2 for legal centres (KEY_INVALID otherwise); RS (NCC) = 1/sqrt(ER).
 constexpr int PV_ROWS = 32;
-__global__ void __launch_bounds__(128) prep_v_kernel(const uint8_t* __restrict__ B, size_t step, FastGeom g,
-                                                    int32_t* __restrict__ V, int vpitch, int vbase) {
+// of_ref = 0: the job's target image, V column x <-> e = x - eoff + R;  of_ref = 1 (NCC scale pass): the job's
+// reference image, V column x <-> e = x + R (the padded column x).
+__global__ void __launch_bounds__(128) prep_v_kernel(const __grid_constant__ FastKernelParams P, int vpitch, int of_ref) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const uint8_t* __restrict__ B = of_ref ? job.A : job.B; const size_t step = of_ref ? job.a_step : job.b_step;
+    int32_t* __restrict__ V = job.V;
+    const int vbase = of_ref ? g.R : -job.eoff + g.R;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= vpitch) return;
     const int e = x + vbase;
@@ -99,8 +114,11 @@ __global__ void __launch_bounds__(128) prep_v_kernel(const uint8_t* __restrict__
 
 constexpr int PE_COLS = 256;
 constexpr int PE_ROWS = 8;
-__global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const int32_t* __restrict__ V, int vpitch, FastGeom g,
-                                                         int32_t* __restrict__ E2, float* __restrict__ RS) {
+__global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const __grid_constant__ FastKernelParams P, int vpitch) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int32_t* __restrict__ V = job.V;
+    int32_t* __restrict__ E2 = job.E2; float* __restrict__ RS = job.RS;
     extern __shared__ int pe_smem[];                       // [PE_ROWS][PE_COLS + 2R]
     const int R = g.R, tw = PE_COLS + 2 * R;
     const int tid = threadIdx.x;
@@ -116,8 +134,8 @@ __global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const int32_t* __restr
     __syncthreads();
     const int q2 = q20 + tid;
     if (q2 >= g.e2_pitch) return;
-    const int uc = q2 - g.eoff;
-    const bool valid = uc >= g.cmin && uc <= g.cmax;
+    const int uc = q2 - job.eoff;
+    const bool valid = uc >= job.cmin && uc <= job.cmax;
     for (int r = 0; r < nr; ++r) {
         int er = 0;
         for (int t = 0; t <= 2 * R; ++t) er += pe_smem[r * tw + tid + t];
@@ -134,8 +152,11 @@ __global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const int32_t* __restr
 // NCC: per strip (K pixels) and output row, the power of two just above sqrt(max EL) — the binade the
 // fixed-point keys of that strip row live in.  V holds the vertical (2R+1)-sums of squares of the
 // replicate-padded REFERENCE image: V column c = padded column c, so EL(x) = sum V[yy][x .. x+2R].
-__global__ void __launch_bounds__(128) prep_scale_kernel(const int32_t* __restrict__ V, int vpitch, FastGeom g,
-                                                        float* __restrict__ SC) {
+__global__ void __launch_bounds__(128) prep_scale_kernel(const __grid_constant__ FastKernelParams P, int vpitch) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int32_t* __restrict__ V = job.V;
+    float* __restrict__ SC = job.SC;
     const int strip = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y;
     if (strip >= g.tilesX * g.spc) return;
@@ -158,9 +179,13 @@ __global__ void __launch_bounds__(128) prep_scale_kernel(const int32_t* __restri
 // ---------------------------------------------------------------------------------------------------
 // Merge: winning key per group -> disparity (+ cost), in the caller's layout
 // ---------------------------------------------------------------------------------------------------
-__global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom g, const uint8_t* __restrict__ A,
-                                      size_t a_step, void* disp_out, size_t disp_step, int elem, void* best_out,
-                                      size_t best_step) {
+__global__ void fast_merge_ssd_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int32_t* __restrict__ PART = job.PART;
+    const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
+    void* disp_out = job.disp; const size_t disp_step = job.disp_step; const int elem = job.elem;
+    void* best_out = job.best; const size_t best_step = job.best_step;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y;
     if (x >= g.cols) return;
@@ -170,10 +195,10 @@ __global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom
     for (int grp = 0; grp < g.G; ++grp) {
         const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
         if (key >= thresh) continue;                               // no legal candidate in this group
-        const uint32_t qlo = uint32_t(x + g.dmin + FGROUP * grp + g.eoff);   // position of the group's first candidate
+        const uint32_t qlo = uint32_t(x + job.dmin + g.dg * grp + job.eoff);   // position of the group's first candidate
         const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
         const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
-        if (!found || c < bestc) { bestc = c; bestd = int(q2) - g.eoff - x; found = true; }
+        if (!found || c < bestc) { bestc = c; bestd = int(q2) - job.eoff - x; found = true; }
     }
     int cost = 99999999;                                           // DisparitySSD.cpp:37
     // EL(x), the window energy of the reference image (replicate padding), is only needed to report
@@ -198,9 +223,14 @@ __global__ void fast_merge_ssd_kernel(const int32_t* __restrict__ PART, FastGeom
 // NCC: winning key per group -> first maximum over the groups -> disparity with the reference's
 // alignment rule (DisparityNCorr.cpp:67) and, on request, the winning score recomputed exactly with
 // TM_CCORR_NORMED's arithmetic (float32 numerator, double energies; see ncorr_exact_kernel).
-__global__ void fast_merge_ncc_kernel(const int32_t* __restrict__ PART, FastGeom g, const uint8_t* __restrict__ A,
-                                      size_t a_step, const uint8_t* __restrict__ B, size_t b_step, void* disp_out,
-                                      size_t disp_step, int elem, void* best_out, size_t best_step) {
+__global__ void fast_merge_ncc_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int32_t* __restrict__ PART = job.PART;
+    const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
+    const uint8_t* __restrict__ B = job.B; const size_t b_step = job.b_step;
+    void* disp_out = job.disp; const size_t disp_step = job.disp_step; const int elem = job.elem;
+    void* best_out = job.best; const size_t best_step = job.best_step;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y;
     if (x >= g.cols) return;
@@ -209,15 +239,15 @@ __global__ void fast_merge_ncc_kernel(const int32_t* __restrict__ PART, FastGeom
         const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
         if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
         const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
-        if (v > bestv) { bestv = v; bestd = g.dmin + FGROUP * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+        if (v > bestv) { bestv = v; bestd = job.dmin + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
     }
-    const int startc = max(0, x + g.dmin), endc = min(g.cols - 1, x + g.dmax);
+    const int startc = max(0, x + job.dmin), endc = min(g.cols - 1, x + job.dmax);
     int centre = x + bestd;                                         // winning window centre (unpadded column)
     // Illegal positions (centre outside the image) carry the score-0 key of their position (RS = 0).  One of
     // them winning means every legal candidate scored exactly 0 (a non-zero C*rs never quantises to 0:
     // rs >= 1/sqrt(Emax) > magic * 2^-24), and the first maximum of an all-zero result row is its first entry.
     if (centre < startc || centre > endc) centre = startc;
-    const bool right_aligned = (g.dmin <= 0 && g.dmax <= 0);
+    const bool right_aligned = (job.dmin <= 0 && job.dmax <= 0);
     const int disp = (centre - startc) - (right_aligned ? endc - startc : 0);
     char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
     if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(disp) & 0xFFu));
@@ -258,49 +288,83 @@ static inline bool fast_supported(const Problem& p) {
     return true;
 }
 
-// Strip width: 24 pixels per thread by default; STEREO_FAST_K=16 selects the narrower variant (debug knob).
-static inline int fast_pick_k(const Problem& p) {
-    static const int forced = [] { const char* e = getenv("STEREO_FAST_K"); return e ? atoi(e) : 0; }();
-    if (forced == 16 && (p.R == 4 || p.R == 5)) return 16;
-    return FK_DEFAULT;
+// Problems that may share one launch sequence: same images shape, band, window, cost and candidate count.
+static inline bool fast_batchable(const Problem& a, const Problem& b) {
+    return a.cost == b.cost && a.rows == b.rows && a.cols == b.cols && a.R == b.R && a.row_begin == b.row_begin &&
+           a.row_end == b.row_end && a.avail_begin == b.avail_begin && a.avail_end == b.avail_end &&
+           (a.dmax - a.dmin) == (b.dmax - b.dmin) && a.ref.type == PixType::U8 && b.ref.type == PixType::U8 &&
+           a.tgt.type == PixType::U8 && b.tgt.type == PixType::U8;
 }
 
-static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGeom& g) {
-    g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.dmin = p.dmin; g.dmax = p.dmax; g.cost = p.cost;
+// Strips per warp: 2 for searches of at most 64 candidates (a warp then covers 2 x 24 pixels x 64 disparities
+// instead of leaving half its lanes idle).  STEREO_FAST_HS=1 forces the single-strip kernels (debug knob).
+static inline int fast_pick_hs(int D) {
+    static const int forced = [] { const char* e = getenv("STEREO_FAST_HS"); return e ? atoi(e) : 0; }();
+    if (forced == 1) return 1;
+    return D <= 64 ? 2 : 1;
+}
+
+static inline size_t fast_stage_bytes(const FastGeom& g) {
+    return (size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w) * 4;
+}
+
+// Geometry of a launch over `n` batchable problems; fills the per-job offsets of `jobs` (pointers are the
+// caller's business).
+static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs) {
+    const Problem& p = ps[0];
+    g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.cost = p.cost;
+    g.D = p.dmax - p.dmin + 1;
     g.rb = p.row_begin; g.re = p.row_end; g.nrows = g.re - g.rb;
     g.ar0 = p.avail_begin; g.ar1 = p.avail_end;
-    const int D = p.dmax - p.dmin + 1;
-    g.K = fast_pick_k(p);
-    g.G = (D + FGROUP - 1) / FGROUP;
-    g.gc = (g.G % 2 == 0) ? 2 : 1;
-    g.nw = (g.K == 16) ? 12 : 8;
-    g.spc = g.nw / g.gc;
+    g.njobs = n;
+    g.K = FK_DEFAULT;
+    g.nw = FWARPS;
+    g.hs = fast_pick_hs(g.D);
+    const int w = 2 * p.R + 1;
+    for (;;) {
+        g.dg = FGROUP / g.hs;
+        g.G = (g.D + g.dg - 1) / g.dg;
+        g.gc = (g.hs == 1 && g.G % 2 == 0) ? 2 : 1;
+        g.spc = g.nw * g.hs / g.gc;
+        const int tile_px = g.spc * g.K;
+        g.lpw = round_up(tile_px + 2 * p.R, 4);
+        g.rqw = round_up(tile_px + 2 * p.R + g.dg * g.gc + FM, 4);
+        g.e2w = round_up(tile_px + g.dg * g.gc + FM, 4);
+        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16) / fast_stage_bytes(g));
+        if (g.nst > FNST_MAX) g.nst = FNST_MAX;
+        if (g.nst >= 4 || g.hs == 1) break;
+        g.hs = 1;                                  // tile rows too wide for a useful pipeline: single-strip kernels
+    }
+    const int tile_px = g.spc * g.K;
     g.nstrips = (p.cols + g.K - 1) / g.K;
     g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
     g.gblocks = g.G / g.gc;
-    const int w = 2 * p.R + 1;
     g.base_y = floor_div(g.rb - w, FRPS) * FRPS;
     g.J = round_up(g.re - g.base_y, FRPS);
-    if (p.cost == STEREO_COST_SSD) { g.cmin = -p.R; g.cmax = p.cols - 1 + p.R; }
-    else { g.cmin = 0; g.cmax = p.cols - 1; }
-    // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
-    int qo = -(p.dmin + p.R); if (qo < 0) qo = 0;
-    while (((p.dmin + p.R + qo) & 3) != 0) ++qo;
-    g.qoff = qo;
-    int eo = -p.dmin; if (eo < 0) eo = 0;
-    while (((p.dmin + eo) & 3) != 0) ++eo;
-    g.eoff = eo;
-    const int tile_px = g.spc * g.K;
-    g.lpw = round_up(tile_px + 2 * p.R, 4);
-    g.rqw = round_up(tile_px + 2 * p.R + FGROUP * g.gc + FM, 4);
-    g.e2w = round_up(tile_px + FGROUP * g.gc + FM, 4);
     g.wpart = g.tilesX * tile_px;
     g.lp_pitch = round_up((g.tilesX - 1) * tile_px + g.lpw, 64);
     const int last_p0 = (g.tilesX - 1) * tile_px;
-    const int gmax = FGROUP * (g.gblocks - 1) * g.gc;
-    g.rq_pitch = round_up(last_p0 + p.dmin + gmax + p.R + g.qoff + g.rqw, 64);
-    g.e2_pitch = round_up(last_p0 + p.dmin + gmax + g.eoff + g.e2w, 64);
-    g.total = (long long)g.tilesX * g.gblocks * g.nrows;
+    const int gmax = g.dg * (g.gblocks - 1) * g.gc;
+    g.rq_pitch = 0; g.e2_pitch = 0;
+    for (int i = 0; i < n; ++i) {
+        FastJob& jb = jobs[i];
+        const Problem& q = ps[i];
+        jb.dmin = q.dmin; jb.dmax = q.dmax;
+        if (q.cost == STEREO_COST_SSD) { jb.cmin = -q.R; jb.cmax = q.cols - 1 + q.R; }
+        else { jb.cmin = 0; jb.cmax = q.cols - 1; }
+        // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
+        int qo = -(q.dmin + q.R); if (qo < 0) qo = 0;
+        while (((q.dmin + q.R + qo) & 3) != 0) ++qo;
+        jb.qoff = qo;
+        int eo = -q.dmin; if (eo < 0) eo = 0;
+        while (((q.dmin + eo) & 3) != 0) ++eo;
+        jb.eoff = eo;
+        const int rqp = round_up(last_p0 + q.dmin + gmax + q.R + jb.qoff + g.rqw, 64);
+        const int e2p = round_up(last_p0 + q.dmin + gmax + jb.eoff + g.e2w, 64);
+        if (rqp > g.rq_pitch) g.rq_pitch = rqp;
+        if (e2p > g.e2_pitch) g.e2_pitch = e2p;
+    }
+    g.total = (long long)n * g.tilesX * g.gblocks * g.nrows;
     // grid: one CTA per SM, but keep segments long enough that the (2R+1)-row warm-up stays small
     long long min_rows = 4LL * w; if (min_rows < 32) min_rows = 32;
     long long ctas = g.total / min_rows; if (ctas < 1) ctas = 1;
@@ -310,84 +374,94 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem& p, FastGe
 }
 
 static inline size_t fast_smem_bytes(const FastGeom& g) {
-    const size_t stage_words = size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w;
-    return size_t(FNST) * stage_words * 4 + 2 * FNST * 8 + 16;
+    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16;
 }
 
+static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64); }
+
+// Scratch of ONE job of a launch over problems shaped like `p`.
 static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
-    FastGeom g; fast_geometry(ctx, p, g);
+    FastGeom g; FastJob jb{};
+    fast_geometry(ctx, &p, 1, g, &jb);
+    // pitches may grow by one alignment step when jobs with other range signs join the launch
+    g.rq_pitch += 64; g.e2_pitch += 64;
     size_t b = 0;
     auto add = [&](size_t bytes) { b += ((bytes + 255) & ~size_t(255)); };
     add(size_t(g.J) * g.lp_pitch * 4);
     add(size_t(g.J / 2) * g.rq_pitch * 4);
     add(size_t(g.J) * g.e2_pitch * 4);
     add(size_t(g.G) * g.nrows * g.wpart * 4);
-    add(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + 256, 64) * 4);
+    add(size_t(g.nrows) * fast_vpitch(g) * 4);
     if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
     return b + 4096;
 }
 
 static inline int fast_ctx_init(stereo_ctx*) {
     for (int cost = 0; cost <= 1; ++cost)
-        for (int K = 16; K <= 24; K += 8)
+        for (int hs = 1; hs <= 2; ++hs)
             for (int R = 0; R <= FMAXR; ++R) {
-                fast_kernel_fn fn = fast_pick(cost, R, K);
-                if (!fn) continue;
+                fast_kernel_fn fn = fast_pick(cost, R, hs);
+                if (!fn) { set_error("hot kernel (cost %d, R %d, hs %d) missing from the build", cost, R, hs); return STEREO_ERR_UNSUPPORTED; }
                 cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn),
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
             }
     return STEREO_OK;
 }
 
-static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
-    FastGeom g; fast_geometry(ctx, p, g);
-    FastArrays a{};
-    a.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
-    a.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
-    a.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
-    a.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
-    a.V = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows) * round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64) * 4));
-    if (p.cost == STEREO_COST_NCORR) {
-        a.RS = static_cast<float*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
-        a.SC = static_cast<float*>(ctx->arena.take(size_t(g.tilesX) * g.spc * g.nrows * 4));
+// One launch sequence (prep x4-6, hot kernel, merge) over `n` <= FMAXJOBS batchable problems.
+static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st) {
+    if (n < 1 || n > FMAXJOBS) { set_error("bad job count (internal)"); return STEREO_ERR_INVALID_ARG; }
+    FastKernelParams kp{};
+    FastGeom& g = kp.g;
+    fast_geometry(ctx, ps, n, g, kp.job);
+    const bool ncc = ps[0].cost == STEREO_COST_NCORR;
+    const int vpitch = fast_vpitch(g);
+    for (int i = 0; i < n; ++i) {
+        FastJob& jb = kp.job[i];
+        const Problem& p = ps[i];
+        jb.A = static_cast<const uint8_t*>(p.ref.ptr); jb.a_step = p.ref.step;
+        jb.B = static_cast<const uint8_t*>(p.tgt.ptr); jb.b_step = p.tgt.step;
+        jb.disp = p.disp.ptr; jb.disp_step = p.disp.step; jb.elem = p.disp.elem;
+        jb.best = p.best.ptr; jb.best_step = p.best.step;
+        jb.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
+        jb.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
+        jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+        jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
+        jb.V = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows) * vpitch * 4));
+        if (ncc) {
+            jb.RS = static_cast<float*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+            jb.SC = static_cast<float*>(ctx->arena.take(size_t(g.tilesX) * g.spc * g.nrows * 4));
+        }
+        if (!jb.LP || !jb.RQ || !jb.E2 || !jb.PART || !jb.V || (ncc && (!jb.RS || !jb.SC))) {
+            set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC;
+        }
     }
-    if (!a.LP || !a.RQ || !a.E2 || !a.PART || !a.V || (p.cost == STEREO_COST_NCORR && (!a.RS || !a.SC))) {
-        set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC;
-    }
-    const uint8_t* A = static_cast<const uint8_t*>(p.ref.ptr);
-    const uint8_t* B = static_cast<const uint8_t*>(p.tgt.ptr);
-    const dim3 tb(256);
-    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J), tb, 0, st>>>(A, p.ref.step, g, a.LP);
-    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2), tb, 0, st>>>(B, p.tgt.step, g, a.RQ);
-    const int vpitch = round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64);
-    prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS)), 128, 0, st>>>(
-        B, p.tgt.step, g, a.V, vpitch, -g.eoff + g.R);
+    const unsigned nz = unsigned(n);
+    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, nz), 256, 0, st>>>(kp);
+    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
+    prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
     const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
-    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS)), PE_COLS, pe_smem, st>>>(
-        a.V, vpitch, g, a.E2, a.RS);
-    const bool ncc = p.cost == STEREO_COST_NCORR;
+    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
     if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
-        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS)), 128, 0, st>>>(
-            A, p.ref.step, g, a.V, vpitch, g.R);
-        prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows), 128, 0, st>>>(a.V, vpitch, g, a.SC);
+        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 1);
+        prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
         ctx->last_launches += 2;
     }
-    FastKernelParams kp{g, a.LP, a.RQ, ncc ? reinterpret_cast<const int32_t*>(a.RS) : a.E2, a.PART, a.SC};
+    fast_kernel_fn fn = fast_pick(ps[0].cost, g.R, g.hs);
+    if (!fn) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
     if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
-    fast_pick(p.cost, p.R, g.K)<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
-    if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; }
+    fn<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
+    if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; ctx->hot_jobs += n; }
     ctx->hot_total++;
-    if (ncc)
-        fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
-            a.PART, g, A, p.ref.step, B, p.tgt.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
-    else
-        fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows), 128, 0, st>>>(
-            a.PART, g, A, p.ref.step, p.disp.ptr, p.disp.step, p.disp.elem, p.best.ptr, p.best.step);
+    if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp);
+    else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp);
     ctx->last_launches += 6;
     SB_CUDA(cudaGetLastError());
     return STEREO_OK;
 }
+
+static inline int run_fast(stereo_ctx* ctx, const Problem& p, cudaStream_t st) { return run_fast_batch(ctx, &p, 1, st); }
 
 } // namespace sb

@@ -34,8 +34,10 @@ constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
 constexpr int FRPS = 8;         // operand rows per pipeline stage
-constexpr int FNST = 8;         // pipeline stages
-constexpr int FWARPS_MAX = 12;   // warps per CTA: 8 (K=24, <=255 regs) or 12 (K=16, <=168 regs)
+constexpr int FNST_MAX = 8;     // pipeline stages (fewer when the tile rows are wide, FastGeom::nst)
+constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kernel may use
+constexpr int FWARPS = 8;       // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers)
+constexpr int FMAXJOBS = 8;     // directions (jobs) one launch sequence can carry
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone
@@ -54,45 +56,55 @@ __host__ __device__ static inline uint32_t key_invalid_threshold(int R) {
 // Geometry shared by host and device
 // ---------------------------------------------------------------------------------------------------
 struct FastGeom {
-    // problem
-    int rows, cols, R, dmin, dmax, cost;
+    // problem (shared by every job of a launch)
+    int rows, cols, R, D, cost;   // D = candidates per pixel (max_disp - min_disp + 1)
     int rb, re;            // output band
     int ar0, ar1;          // image rows present in the caller's buffers (full image: 0, rows); reads clamp into it
-    int K;                 // pixels per thread (strip width): 24 or 16
-    int nw;                // warps per CTA: 8 (K=24) or 12 (K=16)
+    int K;                 // pixels per thread (strip width): 24
+    int nw;                // warps per CTA: 8
+    int hs;                // strips per warp: 1 (a warp = 24 px x 128 disparities) or 2 (2 x 24 px x 64 disparities, D <= 64)
     // derived
-    int G;                 // number of 128-disparity groups
+    int dg;                // disparities per strip and warp = 128 / hs
+    int G;                 // number of dg-disparity groups
     int gc;                // groups per CTA (1 or 2)
-    int spc;               // strips per CTA = FWARPS / gc
-    int nstrips;           // ceil(cols / FK)
+    int spc;               // strips per CTA = nw * hs / gc
+    int nstrips;           // ceil(cols / K)
     int tilesX;            // ceil(nstrips / spc)
-    int gblocks;           // ceil(G / gc)
+    int gblocks;           // G / gc
     int base_y;            // step row of operand row 0 (multiple of FRPS, <= rb - (2R+1))
     int J;                 // operand rows (multiple of FRPS)
-    int qoff, eoff;        // column offsets of the RQ / E2 arrays
-    int lp_pitch, rq_pitch, e2_pitch;   // words
+    int lp_pitch, rq_pitch, e2_pitch;   // words (maximum over the jobs)
     int lpw, rqw, e2w;     // tile widths in words (multiples of 4)
-    int wpart;             // partial-key map width (= tilesX*spc*FK)
+    int nst;               // pipeline stages that fit in shared memory (<= FNST_MAX)
+    int wpart;             // partial-key map width (= tilesX*spc*K)
     int nrows;             // re - rb
+    int njobs;             // directions in this launch
     int ctas;              // grid size
-    long long total;       // tile-rows
+    long long total;       // tile-rows (all jobs)
     long long L;           // tile-rows per CTA
-    // valid centre columns (unpadded coordinates)
-    int cmin, cmax;
+};
+
+// One direction of one image pair inside a launch.  All jobs of a launch share FastGeom; what depends
+// on the sign of the search range (offsets, legal centre columns) and every pointer is per job.
+struct FastJob {
+    const uint8_t* A; size_t a_step;    // reference image (the one whose pixels get a disparity)
+    const uint8_t* B; size_t b_step;    // target image (searched)
+    int dmin, dmax;
+    int qoff, eoff;        // column offsets of the RQ / E2 arrays
+    int cmin, cmax;        // legal centre columns (unpadded coordinates)
+    void* disp; size_t disp_step; int elem;
+    void* best; size_t best_step;
+    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
+    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
+    int32_t* E2;       // [J][e2_pitch]   SSD: BIAS + 128*ER + position, or KEY_INVALID;  NCC: ER
+    int32_t* PART;     // [G][nrows][wpart] winning keys
+    int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
+    float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
+    float* SC;         // NCC: [strip][nrows] magic = 2^ceil(log2 sqrt(max EL of the strip row))
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
-
-struct FastArrays {
-    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
-    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
-    int32_t* E2;       // [J][e2_pitch]   BIAS + 128*ER + position, or KEY_INVALID
-    int32_t* PART;     // [G][nrows][wpart] winning keys
-    int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
-    float* RS;         // NCC: 1/sqrt(ER) per position   [J][e2_pitch]
-    float* SC;         // NCC: [nstrips][nrows] magic = 2^ceil(log2 sqrt(max EL of the strip row))
-};
 
 // ---------------------------------------------------------------------------------------------------
 // Device helpers
@@ -138,11 +150,7 @@ __device__ __forceinline__ int4 lds128(const int* p) { return *reinterpret_cast<
 // ---------------------------------------------------------------------------------------------------
 struct FastKernelParams {
     FastGeom g;
-    const int32_t* LP;
-    const uint32_t* RQ;
-    const int32_t* E2;   // SSD: key offsets; NCC: the RS array (f32 bit patterns)
-    int32_t* PART;
-    const float* SC;     // NCC: [strip][output row] power-of-two magic (see fast_row)
+    FastJob job[FMAXJOBS];
 };
 
 template <int R, int K>
@@ -183,10 +191,14 @@ constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
 constexpr int NCC_KEY_SHIFT = 9;                  // mantissa -> bits 9..31
 constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses every unsigned max)
 
-template <int R, int K, int PAR, int MODE, int COST>
+//
+// HS > 1 (narrow searches, D <= 128/HS): the warp is cut into HS sub-warps of 32/HS lanes, each with its
+// own K-pixel strip; `sub` is the lane's sub-warp, `ll` its lane index inside it.  The per-pixel warp
+// reduction then runs once per sub-warp over the full warp with the other lanes neutralised.
+template <int R, int K, int PAR, int MODE, int COST, int HS>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
-                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int lane, int cbase,
+                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int ll, int sub, int cbase,
                                          int cols, float magic) {
     using S = RowShape<R, K>;
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
@@ -268,51 +280,66 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         if (!NCC) {
             best = min(min(key[0], key[1]), min(key[2], key[3]));
             if (MODE == 2) best |= lane_or;
-            res[k & 3] = __reduce_min_sync(0xffffffffu, best);
         } else {
             best = max(max(key[0], key[1]), max(key[2], key[3]));
             if (MODE == 2) best = mmax < 0 ? NCC_KEY_NONE : best;
-            res[k & 3] = __reduce_max_sync(0xffffffffu, best);
         }
-        if ((k & 3) == 3 && lane == 0)
+        if (HS == 1) {
+            res[k & 3] = NCC ? __reduce_max_sync(0xffffffffu, best) : __reduce_min_sync(0xffffffffu, best);
+        } else {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int h = 0; h < HS; ++h) {
+                const uint32_t v = (sub == h) ? best : (NCC ? NCC_KEY_NONE : KEY_INVALID);
+                const uint32_t r = NCC ? __reduce_max_sync(0xffffffffu, v) : __reduce_min_sync(0xffffffffu, v);
+                if (sub == h) mine = r;
+            }
+            res[k & 3] = mine;
+        }
+        if ((k & 3) == 3 && ll == 0)
             *reinterpret_cast<uint4*>(out_row + k - 3) = make_uint4(res[0], res[1], res[2], res[3]);
     }
 }
 
-template <int R, int K, int NW, int COST>
-__global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelParams P) {
+template <int R, int K, int NW, int COST, int HS>
+__global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
+    constexpr int LS = 32 / HS;                 // lanes per strip
+    constexpr int DG = FM * LS;                 // disparities per strip and warp
     using S = RowShape<R, K>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const FastGeom& g = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane / LS, ll = lane % LS;
+    const int nst = g.nst;
 
     const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
     const int stage_words = lp_stage + rq_stage + e2_stage;
     int* smem = reinterpret_cast<int*>(smem_raw);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(FNST) * stage_words * 4);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nst) * stage_words * 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST_MAX);
 
     if (tid == 0) {
-        for (int i = 0; i < FNST; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }
+        for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // ---- this CTA's share of the (tile, row) space -------------------------------------------------
+    // ---- this CTA's share of the (job, tile, row) space ----------------------------------------------
     const long long lin_begin = (long long)blockIdx.x * g.L;
     long long lin_end = lin_begin + g.L;
     if (lin_end > g.total) lin_end = g.total;
     if (lin_begin >= lin_end) return;
     const int w = 2 * R + 1;
+    const int tpj = g.tilesX * g.gblocks;        // tiles per job
 
-    // producer: EVERY warp iterates the same stage sequence, FNST-2 stages ahead, warp-uniformly (all lanes
+    // producer: EVERY warp iterates the same stage sequence, nst-2 stages ahead, warp-uniformly (all lanes
     // wait on the empty barrier), and its lane 0 issues the warp's share of the stage's row copies (row r of
     // a stage belongs to warp r mod NW).
     long long p_lin = lin_begin;   // start of the producer's current segment
     int p_sj = 0, p_sj_end = -1;   // stage range of the producer's segment
     int p_tile = 0;
-    int pn = 0;                    // loads issued
+    int p_slot = 0, p_round = 0;   // ring position of the next load
     auto producer_open_segment = [&]() {
         p_tile = int(p_lin / g.nrows);
         const int r0 = int(p_lin % g.nrows);
@@ -327,12 +354,15 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
             if (p_lin >= lin_end) return false;
             producer_open_segment();
         }
-        const int slot = pn % FNST;
-        if (pn >= FNST) mbar_wait(empty0 + 8 * slot, ((pn / FNST) - 1) & 1);
-        const int xt = p_tile % g.tilesX, gb = p_tile / g.tilesX;
+        const int slot = p_slot;
+        if (p_round > 0) mbar_wait(empty0 + 8 * slot, (p_round - 1) & 1);
+        const int jb = p_tile / tpj, t2 = p_tile - jb * tpj;
+        const FastJob& job = P.job[jb];
+        const int xt = t2 % g.tilesX, gb = t2 / g.tilesX;
         const int p0 = xt * g.spc * K;
-        const int q0 = p0 + g.dmin + FGROUP * gb * g.gc + g.R + g.qoff;
-        const int q20 = p0 + g.dmin + FGROUP * gb * g.gc + g.eoff;
+        const int q0 = p0 + job.dmin + g.dg * gb * g.gc + g.R + job.qoff;
+        const int q20 = p0 + job.dmin + g.dg * gb * g.gc + job.eoff;
+        const int32_t* e2src = NCC ? reinterpret_cast<const int32_t*>(job.RS) : job.E2;
         const uint32_t bar = full0 + 8 * slot;
         int* st = smem + size_t(slot) * stage_words;
         constexpr int NLP = (FRPS - 1) / NW + 1, NRQ = (FRPS / 2 - 1) / NW + 1;       // copies per warp, upper bounds
@@ -348,27 +378,28 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
             for (int i = 0; i < NLP; ++i) {
                 const int r = warp + i * NW;
                 if (r < FRPS) {
-                    tma_load_1d(smem_u32(st + r * g.lpw), P.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
-                    tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), P.E2 + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
+                    tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
+                    tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
                 }
             }
 #pragma unroll
             for (int i = 0; i < NRQ; ++i) {
                 const int r = warp + i * NW;
                 if (r < FRPS / 2)
-                    tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), P.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+                    tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), job.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
             }
         }
         // reconverge here: without it lane 0 runs the following row on its own, up to the first warp
         // reduction, and every row instruction of that stretch issues twice
         __syncwarp();
-        ++pn; ++p_sj;
+        ++p_sj;
+        if (++p_slot == nst) { p_slot = 0; ++p_round; }
         return true;
     };
-    for (int i = 0; i < FNST - 2; ++i) if (!producer_issue()) break;
+    for (int i = 0; i < nst - 2; ++i) if (!producer_issue()) break;
 
     // ---- consumers -----------------------------------------------------------------------------------
-    int n = 0;                      // stages consumed
+    int c_slot = 0, c_round = 0;    // ring position of the next stage to consume
     long long lin = lin_begin;
     int col[FM][S::NC];
     while (lin < lin_end) {
@@ -377,40 +408,44 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
         const long long rem = lin_end - lin;
         const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
         lin += r1 - r0;
-        const int xt = tile % g.tilesX, gb = tile / g.tilesX;
-        const int strip = xt * g.spc + warp / g.gc;
+        const int jb = tile / tpj, t2 = tile - jb * tpj;
+        const FastJob& job = P.job[jb];
+        const int xt = t2 % g.tilesX, gb = t2 / g.tilesX;
+        const int wstrip = (warp / g.gc) * HS;                          // first strip of this warp inside the tile
+        const int strip = xt * g.spc + wstrip + sub;
         const int grp = gb * g.gc + warp % g.gc;
         const int x0 = strip * K;
-        const bool active = (x0 < g.cols) && (grp < g.G);
+        const int x0w = (xt * g.spc + wstrip) * K;                       // first pixel of the warp (warp-uniform)
+        const bool active = (x0w < g.cols) && (grp < g.G);               // warp-uniform: the row code holds warp collectives
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
-        // which flavour of candidate masking this warp's (24 pixels x 128 disparities) block needs
-        const int dlo = g.dmin + FGROUP * grp;                         // first disparity of the group
-        const bool pos_invalid = (x0 + dlo < g.cmin) || (x0 + K - 1 + dlo + FGROUP - 1 > g.cmax);
-        const bool lane_invalid = dlo + FGROUP - 1 > g.dmax;
-        const bool partial_lane = lane_invalid && (((g.dmax - dlo + 1) % FM) != 0);
+        // which flavour of candidate masking this warp's (HS x 24 pixels x DG disparities) block needs
+        const int dlo = job.dmin + DG * grp;                              // first disparity of the group
+        const bool pos_invalid = (x0w + dlo < job.cmin) || (x0w + HS * K - 1 + dlo + DG - 1 > job.cmax);
+        const bool lane_invalid = dlo + DG - 1 > job.dmax;
+        const bool partial_lane = lane_invalid && (((job.dmax - dlo + 1) % FM) != 0);
         // NCC: an illegal search position carries RS = 0, i.e. the score-0 key of its position; it can only win
         // when every legal candidate scores exactly 0 too, which the merge recognises (winner outside the image
         // -> first legal candidate, cv::minMaxLoc's first maximum).  So NCC never needs the explicit selects
         // for border positions, and SSD only for R > 5.
         const int mode = (partial_lane || (pos_invalid && !NCC && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
-        const int mmax = g.dmax - dlo - FM * lane;                      // m <= mmax are inside [dmin, dmax]
+        const int mmax = job.dmax - dlo - FM * ll;                        // m <= mmax are inside [dmin, dmax]
         // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
-        const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * lane) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
-        const float* sc_row = NCC ? P.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
-        const int cbase = x0 + dlo + FM * lane;                          // centre column of candidate (k=0, m=0)
-        const int lp_off = (warp / g.gc) * K;
-        const int rq_off = (warp / g.gc) * K + FGROUP * (warp % g.gc) + FM * lane;
-        int32_t* part = P.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
+        const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * ll) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
+        const float* sc_row = NCC ? job.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
+        const int cbase = x0 + dlo + FM * ll;                             // centre column of candidate (k=0, m=0)
+        const int lp_off = (wstrip + sub) * K;
+        const int rq_off = lp_off + DG * (warp % g.gc) + FM * ll;
+        int32_t* part = job.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
 #pragma unroll
         for (int m = 0; m < FM; ++m)
 #pragma unroll
             for (int c = 0; c < S::NC; ++c) col[m][c] = 0;
 
-        for (int sj = js / FRPS; sj <= (je - 1) / FRPS; ++sj, ++n) {
+        for (int sj = js / FRPS; sj <= (je - 1) / FRPS; ++sj) {
             producer_issue();
-            const int slot = n % FNST;
-            mbar_wait(full0 + 8 * slot, (n / FNST) & 1);
+            const int slot = c_slot;
+            mbar_wait(full0 + 8 * slot, c_round & 1);
             if (active) {
                 const int* st = smem + size_t(slot) * stage_words;
                 const int jlo = max(js, sj * FRPS), jhi = min(je, sj * FRPS + FRPS);
@@ -422,7 +457,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
                     const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
-#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, lane, cbase, g.cols, magic)
+#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, ll, sub, cbase, g.cols, magic)
                     if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
                     else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
                     else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
@@ -432,25 +467,28 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const FastKernelP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+            if (++c_slot == nst) { c_slot = 0; ++c_round; }
         }
     }
 }
 
 typedef void (*fast_kernel_fn)(const FastKernelParams);
-// The hot-kernel instantiations live in fast_inst.cu, compiled once per part (SB_PART = 0..7: cost x window
-// radius subset) so that the translation units build in parallel; each part exports a lookup function.
-constexpr int FAST_PARTS = 8;
-fast_kernel_fn fast_pick_part0(int R, int K); fast_kernel_fn fast_pick_part1(int R, int K);
-fast_kernel_fn fast_pick_part2(int R, int K); fast_kernel_fn fast_pick_part3(int R, int K);
-fast_kernel_fn fast_pick_part4(int R, int K); fast_kernel_fn fast_pick_part5(int R, int K);
-fast_kernel_fn fast_pick_part6(int R, int K); fast_kernel_fn fast_pick_part7(int R, int K);
-static inline fast_kernel_fn fast_pick(int cost, int R, int K) {
+// The hot-kernel instantiations live in fast_inst.cu, compiled once per part (SB_PART = 0..15: cost x window
+// radius subset x strips per warp) so that the translation units build in parallel; each part exports a
+// lookup function.
+constexpr int FAST_PARTS = 16;
+#define SB_DECL_PART(n) fast_kernel_fn fast_pick_part##n(int R, int hs);
+SB_DECL_PART(0) SB_DECL_PART(1) SB_DECL_PART(2) SB_DECL_PART(3) SB_DECL_PART(4) SB_DECL_PART(5) SB_DECL_PART(6) SB_DECL_PART(7)
+SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(12) SB_DECL_PART(13) SB_DECL_PART(14) SB_DECL_PART(15)
+#undef SB_DECL_PART
+static inline fast_kernel_fn fast_pick(int cost, int R, int hs) {
     typedef fast_kernel_fn (*part_fn)(int, int);
     static const part_fn parts[FAST_PARTS] = {fast_pick_part0, fast_pick_part1, fast_pick_part2, fast_pick_part3,
-                                              fast_pick_part4, fast_pick_part5, fast_pick_part6, fast_pick_part7};
-    const int first = cost == STEREO_COST_SSD ? 0 : FAST_PARTS / 2;
-    for (int i = first; i < first + FAST_PARTS / 2; ++i)
-        if (fast_kernel_fn fn = parts[i](R, K)) return fn;
+                                              fast_pick_part4, fast_pick_part5, fast_pick_part6, fast_pick_part7,
+                                              fast_pick_part8, fast_pick_part9, fast_pick_part10, fast_pick_part11,
+                                              fast_pick_part12, fast_pick_part13, fast_pick_part14, fast_pick_part15};
+    for (int i = 0; i < FAST_PARTS; ++i)
+        if (fast_kernel_fn fn = parts[i](R, hs | (cost << 8))) return fn;
     return nullptr;
 }
 

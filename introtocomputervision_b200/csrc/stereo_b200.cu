@@ -189,12 +189,39 @@ static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_a
     return run_exact(ctx, p, st);
 }
 
+// Enqueues `n` u8 problems that all take the packed path, several directions per launch sequence where they
+// are batchable (same shape, band, window, cost and candidate count).  `batch_budget` bounds the scratch one
+// launch sequence may hold.
+static int run_fast_jobs(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st) {
+    const size_t budget = size_t(3) << 30;
+    int i = 0;
+    while (i < n) {
+        const size_t per_job = fast_scratch_bytes(ctx, ps[i]);
+        int m = 1;
+        while (i + m < n && m < FMAXJOBS && fast_batchable(ps[i], ps[i + m]) && size_t(m + 1) * per_job <= budget) ++m;
+        const size_t need = size_t(m) * per_job;
+        if (need > ctx->arena.cap) {
+            SB_CUDA(cudaStreamSynchronize(st));
+            SB_CUDA(cudaStreamSynchronize(ctx->stream));
+            int rc = ctx->arena.reserve(need);
+            if (rc != STEREO_OK) return rc;
+        }
+        ctx->arena.reset();
+        ctx->last_path = STEREO_PATH_FAST_U8;
+        int rc = run_fast_batch(ctx, ps + i, m, st);
+        if (rc != STEREO_OK) return rc;
+        i += m;
+    }
+    return STEREO_OK;
+}
+
 static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
     ctx->last_launches = 0;
     ctx->last_ms = -1.f;
     ctx->last_path = STEREO_PATH_NONE;
     ctx->hot_used = 0;
     ctx->hot_total = 0;
+    ctx->hot_jobs = 0;
     cudaEventRecord(ctx->ev0, st);
 }
 static void end_call(stereo_ctx* ctx, cudaStream_t st) {
@@ -288,7 +315,7 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
         if (rc != STEREO_OK) return rc;
         if (!fast_supported(full)) return PIPE_NOT_APPLICABLE;
         Problem band = full; band.row_end = band_rows < rows ? band_rows : rows;
-        const size_t need = fast_scratch_bytes(ctx, band);
+        const size_t need = size_t(n_dirs) * fast_scratch_bytes(ctx, band);
         scratch = need > scratch ? need : scratch;
     }
     int rc = ensure_pipe(ctx, 3 * n_pairs * nb + 4);
@@ -362,15 +389,21 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
                 ctx->last_launches += 2;
             }
             if (up_hi > uploaded) uploaded = up_hi;
-            for (int d = 0; d < n_dirs; ++d) {
-                Problem p = full;
-                p.row_begin = rb; p.row_end = re;
-                p.dmin = dirs[d].dmin; p.dmax = dirs[d].dmax;
-                p.ref = ImageView{dirs[d].swap ? sl.r8 : sl.l8, u8_pitch, PixType::U8};
-                p.tgt = ImageView{dirs[d].swap ? sl.l8 : sl.r8, u8_pitch, PixType::U8};
-                p.disp = OutView{sl.out[d] + size_t(rb) * d_pitch, d_pitch, elem};
+            {
+                Problem pd[2];
+                for (int d = 0; d < n_dirs; ++d) {
+                    Problem& p = pd[d];
+                    p = full;
+                    p.row_begin = rb; p.row_end = re;
+                    p.dmin = dirs[d].dmin; p.dmax = dirs[d].dmax;
+                    p.ref = ImageView{dirs[d].swap ? sl.r8 : sl.l8, u8_pitch, PixType::U8};
+                    p.tgt = ImageView{dirs[d].swap ? sl.l8 : sl.r8, u8_pitch, PixType::U8};
+                    p.disp = OutView{sl.out[d] + size_t(rb) * d_pitch, d_pitch, elem};
+                }
+                const bool together = n_dirs == 2 && fast_batchable(pd[0], pd[1]);
                 ctx->arena.reset();
-                rc = run_fast(ctx, p, s_cmp);
+                rc = together ? run_fast_batch(ctx, pd, 2, s_cmp) : run_fast(ctx, pd[0], s_cmp);
+                if (rc == STEREO_OK && n_dirs == 2 && !together) { ctx->arena.reset(); rc = run_fast(ctx, pd[1], s_cmp); }
                 if (rc != STEREO_OK) return rc;
             }
             SB_CUDA(cudaEventRecord(ev(i, b, 1), s_cmp));
@@ -599,6 +632,8 @@ float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measure
     return total;
 }
 
+int stereo_ctx_last_hot_jobs(const stereo_ctx* ctx) { return ctx ? ctx->hot_jobs : 0; }
+
 int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
     if (!ctx || path < 0 || path > STEREO_PATH_FAST_U8) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->force_path = path;
@@ -686,21 +721,44 @@ int stereo_band_halo_rows(int rows, int row_begin, int row_end, int window_rad, 
 
 // ---- pairs: L->R over [-range, 0], then R->L with images swapped over [0, +range] (main.cpp:21-48) ----
 
+static void pair_problems(Problem* p, int cost, PixType type, const void* left, size_t left_step, const void* right,
+                          size_t right_step, int rows, int cols, int R, int range, void* disp_left, void* disp_right,
+                          size_t disp_step, int elem) {
+    p[0] = Problem{};
+    p[0].cost = cost;
+    p[0].rows = rows; p[0].cols = cols; p[0].row_begin = 0; p[0].row_end = rows; p[0].avail_begin = 0; p[0].avail_end = rows; p[0].R = R;
+    p[0].best = OutView{nullptr, 0, 4};
+    p[1] = p[0];
+    p[0].ref = ImageView{left, left_step, type}; p[0].tgt = ImageView{right, right_step, type};
+    p[0].dmin = -range; p[0].dmax = 0; p[0].disp = OutView{disp_left, disp_step, elem};
+    p[1].ref = ImageView{right, right_step, type}; p[1].tgt = ImageView{left, left_step, type};
+    p[1].dmin = 0; p[1].dmax = range; p[1].disp = OutView{disp_right, disp_step, elem};
+}
+
+// true when every problem can go straight to the packed kernels (u8 images, supported window / range)
+static bool all_fast(const stereo_ctx* ctx, const Problem* ps, int n) {
+    if (ctx->force_path == STEREO_PATH_EXACT_F32) return false;
+    for (int i = 0; i < n; ++i)
+        if (ps[i].ref.type != PixType::U8 || ps[i].tgt.type != PixType::U8 || !fast_supported(ps[i])) return false;
+    return true;
+}
+
 static int pair_device(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
                        size_t right_step, int rows, int cols, int R, int range, void* disp_left, void* disp_right,
                        size_t disp_step, int elem, cudaStream_t st) {
     if (range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
-    Problem p{};
-    p.cost = cost;
-    p.rows = rows; p.cols = cols; p.row_begin = 0; p.row_end = rows; p.avail_begin = 0; p.avail_end = rows; p.R = R;
-    p.best = OutView{nullptr, 0, 4};
-    p.ref = ImageView{left, left_step, type}; p.tgt = ImageView{right, right_step, type};
-    p.dmin = -range; p.dmax = 0; p.disp = OutView{disp_left, disp_step, elem};
-    int rc = run_problem(ctx, p, st);
+    Problem p[2];
+    pair_problems(p, cost, type, left, left_step, right, right_step, rows, cols, R, range, disp_left, disp_right, disp_step, elem);
+    if (all_fast(ctx, p, 2)) {       // both directions in one launch sequence
+        for (int d = 0; d < 2; ++d) {
+            int rc = validate(p[d], size_t(cols), size_t(cols));
+            if (rc != STEREO_OK) return rc;
+        }
+        return run_fast_jobs(ctx, p, 2, st);
+    }
+    int rc = run_problem(ctx, p[0], st);
     if (rc != STEREO_OK) return rc;
-    p.ref = ImageView{right, right_step, type}; p.tgt = ImageView{left, left_step, type};
-    p.dmin = 0; p.dmax = range; p.disp = OutView{disp_right, disp_step, elem};
-    return run_problem(ctx, p, st);
+    return run_problem(ctx, p[1], st);
 }
 
 static int pair_host(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
@@ -786,12 +844,31 @@ int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs
     if (n_pairs <= 0) { set_error("n_pairs must be positive"); return STEREO_ERR_INVALID_ARG; }
     if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    if (disparity_range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
     begin_call(ctx, st);
-    for (int i = 0; i < n_pairs && rc == STEREO_OK; ++i) {
-        rc = pair_device(ctx, cost, PixType::U8, left + size_t(i) * pair_stride, img_step,
-                         right + size_t(i) * pair_stride, img_step, rows, cols, window_rad, disparity_range,
-                         static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride,
-                         static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, disp_elem_bytes, st);
+    // jobs of FMAXJOBS/2 pairs at a time: up to FMAXJOBS directions share one launch sequence
+    constexpr int CHUNK = FMAXJOBS / 2;
+    Problem ps[FMAXJOBS];
+    for (int i0 = 0; i0 < n_pairs && rc == STEREO_OK; i0 += CHUNK) {
+        const int np = (n_pairs - i0 < CHUNK) ? n_pairs - i0 : CHUNK;
+        // left-referenced maps first, then right-referenced ones: jobs with the same range sign are neighbours
+        for (int k = 0; k < np; ++k) {
+            Problem two[2];
+            const int i = i0 + k;
+            pair_problems(two, cost, PixType::U8, left + size_t(i) * pair_stride, img_step, right + size_t(i) * pair_stride, img_step,
+                          rows, cols, window_rad, disparity_range, static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride,
+                          static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, disp_elem_bytes);
+            ps[k] = two[0]; ps[np + k] = two[1];
+        }
+        if (all_fast(ctx, ps, 2 * np)) {
+            for (int k = 0; k < 2 * np && rc == STEREO_OK; ++k) rc = validate(ps[k], size_t(cols), size_t(cols));
+            if (rc == STEREO_OK) rc = run_fast_jobs(ctx, ps, 2 * np, st);
+        } else {
+            for (int k = 0; k < np && rc == STEREO_OK; ++k) {
+                rc = run_problem(ctx, ps[k], st);
+                if (rc == STEREO_OK) rc = run_problem(ctx, ps[np + k], st);
+            }
+        }
     }
     end_call(ctx, st);
     return rc;

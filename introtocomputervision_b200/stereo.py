@@ -96,6 +96,11 @@ class Context:
         ms = float(_capi.lib().stereo_ctx_last_hot_kernel_ms(self._h, C.byref(n)))
         return ms, int(n.value)
 
+    @property
+    def last_hot_jobs(self) -> int:
+        """Directions (one disparity map each) the measured hot launches of the last call covered."""
+        return int(_capi.lib().stereo_ctx_last_hot_jobs(self._h))
+
     def force_path(self, path: int) -> None:
         _check(_capi.lib().stereo_ctx_force_path(self._h, int(path)), "stereo_ctx_force_path")
 

@@ -144,6 +144,58 @@ def test_pair_equals_two_singles_and_batch_equals_pairs(ctx):
             assert np.array_equal(bl[i], dl) and np.array_equal(br[i], dr)
 
 
+@pytest.mark.parametrize("n,rng,R", [(5, 63, 4), (9, 40, 2), (6, 150, 5), (4, 127, 7)])
+def test_device_batch_launch_chunks_vs_oracle(ctx, n, rng, R):
+    """Device batches share launch sequences (up to 8 directions each): chunk boundaries (4+1, 4+4+1 pairs),
+    2-strips-per-warp kernels (<= 64 candidates), one and two 128-disparity groups — all against the oracle."""
+    import torch
+    from introtocomputervision_b200 import _capi
+    import ctypes as C
+    rows, cols = 45, 250
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(rows, cols, min(64, rng), 900 + 17 * i + n)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    dl_, dr_ = torch.from_numpy(Ls).cuda(), torch.from_numpy(Rs).cuda()
+    for cost in (sb.COST_SSD, sb.COST_NCORR):
+        ol = torch.zeros((n, rows, cols), dtype=torch.int16, device="cuda")
+        orr = torch.zeros_like(ol)
+        rc = _capi.lib().stereo_disparity_pair_batch_u8_device(
+            ctx.handle, cost, n, dl_.data_ptr(), dr_.data_ptr(), cols, rows * cols, rows, cols, R, rng,
+            ol.data_ptr(), orr.data_ptr(), cols * 2, rows * cols * 2, 2, None)
+        assert rc == 0, _capi.last_error()
+        ctx.synchronize()
+        assert ctx.last_path == sb.PATH_FAST_U8
+        bl, br = ol.cpu().numpy(), orr.cpu().numpy()
+        for i in range(n):
+            Lf, Rf = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+            if cost == sb.COST_SSD:
+                assert np.array_equal(bl[i], oracle.ssd_fast(Lf, Rf, R, -rng, 0)), f"pair {i} L->R"
+                assert np.array_equal(br[i], oracle.ssd_fast(Rf, Lf, R, 0, rng)), f"pair {i} R->L"
+            else:
+                assert float(np.mean(bl[i] == oracle.ncorr_fast(Lf, Rf, R, -rng, 0))) >= 0.999
+                assert float(np.mean(br[i] == oracle.ncorr_fast(Rf, Lf, R, 0, rng))) >= 0.999
+
+
+def test_config5_shape_batch_pairs_vs_oracle(ctx):
+    """BASELINE config 5's shape (1280x720, 64 disparities, 9x9) on a few pairs: the 2-strips-per-warp kernels."""
+    n = 3
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(720, 1280, 64, 2000 + i)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, 63)
+    for i in range(n):
+        Lf, Rf = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+        assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 4, -63, 0)))
+        assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 4, 0, 63)))
+    nl, nr = ctx.disparity_pair_batch(sb.COST_NCORR, Ls[:1], Rs[:1], 4, 63)
+    assert float(np.mean(nl[0] == oracle.narrow_i8(oracle.ncorr_fast(Ls[0].astype(np.float32), Rs[0].astype(np.float32), 4, -63, 0)))) >= 0.999
+    assert float(np.mean(nr[0] == oracle.narrow_i8(oracle.ncorr_fast(Rs[0].astype(np.float32), Ls[0].astype(np.float32), 4, 0, 63)))) >= 0.999
+
+
 def test_wide_disparity_needs_wide_output(ctx):
     # > 127 disparities: int16 holds the true value, int8 wraps exactly like the reference's char store
     L, Rt, _ = synth.make_pair(16, 400, 200, 77)
