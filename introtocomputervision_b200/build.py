@@ -39,6 +39,14 @@ def units():
     return u
 
 
+def _deps(src: Path):
+    """Files a translation unit is rebuilt for: the hot-kernel parts only include fast_kernel.cuh / common.cuh."""
+    api = list((PKG.parent / "include").glob("*.h"))
+    if src.name == "fast_inst.cu":
+        return [src, CSRC / "fast_kernel.cuh", CSRC / "common.cuh", *api]
+    return [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *api]
+
+
 def sources():
     return sorted(CSRC.glob("*.cu"))
 
@@ -60,6 +68,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(unit):
         name, src, extra = unit
+        obj = OBJ / name
+        if not force and obj.exists() and all(d.stat().st_mtime <= obj.stat().st_mtime for d in _deps(src)):
+            return ""
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", str(OBJ / name), str(src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -149,6 +149,165 @@ __global__ void __launch_bounds__(PE_COLS) prep_e2_kernel(const __grid_constant_
     }
 }
 
+// Fused target-side prep (replaces prep_rq + prep_v + prep_e2 on the default path): ONE pass over the
+// extended target image produces the packed RQ rows AND the window-energy rows E2 / RS.
+//   * a thread owns one extended column (V column x <-> ext column e = x - eoff + R <-> RQ column x + delta,
+//     delta = qoff - eoff + R, a multiple of 4 and >= 0) and walks down PT_ROWS operand rows of its CTA;
+//     the four bytes of an RQ word (entering / leaving rows of two consecutive step rows) are exactly the
+//     bytes the vertical running sum of squares needs, so each image byte is fetched once per role;
+//   * every 4 rows the vertical sums go through a double-buffered shared-memory tile and come back as
+//     horizontal (2R+1)-sums, 4 adjacent centres per thread (LDS.128 in, sliding adds, STG.128 out).
+// A CTA of 256 columns yields PT_TS(R) = (256 - 2R) & ~3 centre columns.
+constexpr int PT_THREADS = 256;
+constexpr int PT_ROWS = 64;                   // operand rows per CTA (multiple of 4; the host halves it for small grids)
+constexpr int PT_VSTRIDE = PT_THREADS + 16;   // words per shared-memory row (slack for the sliding window reads)
+__host__ __device__ constexpr int pt_ts(int R) { return (PT_THREADS - 2 * R) & ~3; }
+
+template <int R, bool INTERIOR>
+__device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& job, int rows_per_cta, int (&vs)[2][4][PT_VSTRIDE]) {
+    const uint8_t* __restrict__ B = job.B; const size_t step = job.b_step;
+    uint32_t* __restrict__ RQ = job.RQ;
+    constexpr int TS = pt_ts(R);
+    constexpr int NV = 2 * R + 4;              // vertical sums a thread of the horizontal stage touches
+    constexpr int NVEC = (NV + 3) / 4;
+    const int t = threadIdx.x;
+    const int delta = job.qoff - job.eoff + R;
+    const int x0 = -delta + int(blockIdx.x) * TS;          // first V column of this CTA (multiple of 4)
+    const int x = x0 + t;
+    // column mapping of bext(): which source column, and whether the flat index falls into a neighbouring row
+    const int Wp = g.cols + 2 * R;
+    const int c = x - job.eoff;                            // padded column (e - R)
+    int shift = 0, scol;
+    if (c < 0) { shift = -1; scol = g.cols - 1; }
+    else if (c >= Wp) { shift = 1; scol = 0; }
+    else scol = clampi(c - R, 0, g.cols - 1);
+    const uint8_t* __restrict__ Bc = B + scol;
+    const int rows = g.rows, ar0 = g.ar0, ar1 = g.ar1;
+    auto load = [&](int i) -> int {                        // == bext(B, step, rows, cols, R, i, x - eoff + R, ar0, ar1)
+        if (INTERIOR) return Bc[size_t(i + shift) * step]; // every row the CTA touches (+-1) lies inside the image
+        if (shift < 0 && i + R - 1 < 0) return 0;
+        if (shift > 0 && i + R + 1 > rows + 2 * R - 1) return 0;
+        const int r = clampi(clampi(i + shift, 0, rows - 1), ar0, ar1 - 1);
+        return Bc[size_t(r) * step];
+    };
+    const int j0 = int(blockIdx.y) * rows_per_cta;
+    const int j1 = min(g.J, j0 + rows_per_cta);
+    const bool ncc = g.cost != STEREO_COST_SSD;
+    // vertical sum of squares of the row above the first one
+    int v = 0;
+    {
+        const int y = g.base_y + j0 - 1;
+#pragma unroll
+        for (int i = -R; i <= R; ++i) { const int b = load(y + i); v += b * b; }
+    }
+    const int q = x + delta;                               // RQ column
+    const bool rq_ok = t < TS && q < g.rq_pitch;           // q >= 0 by construction
+    // horizontal stage: thread -> (row hr of the group, 4 centres from column c4)
+    const int hr = t >> 6, c4 = (t & 63) * 4;
+    const int q2 = x0 + c4;
+    const bool h_ok = c4 < TS && q2 >= 0 && q2 < g.e2_pitch;
+    const bool all_valid = (q2 - job.eoff >= job.cmin) && (q2 + 3 - job.eoff <= job.cmax);
+    const uint32_t bias = key_bias(R);
+    // entering rows (ye+R, ye+1+R) and leaving rows (ye-R-1, ye-R) of the two step-row pairs of a 4-row group
+    const uint8_t* pn = nullptr; const uint8_t* po = nullptr;
+    if (INTERIOR) {
+        pn = Bc + size_t(g.base_y + j0 + R + shift) * step;
+        po = Bc + size_t(g.base_y + j0 - R - 1 + shift) * step;
+    }
+    int nb[8];
+    auto fetch = [&](int jj) {
+        if (INTERIOR) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                nb[4 * h] = pn[0]; nb[4 * h + 2] = pn[step]; nb[4 * h + 1] = po[0]; nb[4 * h + 3] = po[step];
+                pn += 2 * step; po += 2 * step;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ye = g.base_y + jj + 2 * h;
+                nb[4 * h] = load(ye + R); nb[4 * h + 1] = load(ye - R - 1); nb[4 * h + 2] = load(ye + 1 + R); nb[4 * h + 3] = load(ye - R);
+            }
+        }
+    };
+    fetch(j0);
+    int buf = 0;
+    for (int jj = j0; jj < j1; jj += 4, buf ^= 1) {
+        int cb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cb[i] = nb[i];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b0 = cb[4 * h], b1 = cb[4 * h + 1], b2 = cb[4 * h + 2], b3 = cb[4 * h + 3];
+            if (rq_ok) RQ[size_t((jj >> 1) + h) * g.rq_pitch + q] = uint32_t(b0) | (uint32_t(b1) << 8) | (uint32_t(b2) << 16) | (uint32_t(b3) << 24);
+            v += b0 * b0 - b1 * b1;
+            vs[buf][2 * h][t] = v;
+            v += b2 * b2 - b3 * b3;
+            vs[buf][2 * h + 1][t] = v;
+        }
+        if (jj + 4 < j1) fetch(jj + 4);                     // in flight across the barrier and the horizontal stage
+        __syncthreads();
+        const int y = g.base_y + jj + hr;
+        if (h_ok && y >= g.rb && y < g.re) {
+            int w[NVEC * 4];
+#pragma unroll
+            for (int i = 0; i < NVEC; ++i) {
+                const int4 u = *reinterpret_cast<const int4*>(&vs[buf][hr][c4 + 4 * i]);
+                w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+            }
+            int er[4];
+            er[0] = 0;
+#pragma unroll
+            for (int i = 0; i <= 2 * R; ++i) er[0] += w[i];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) er[k] = er[k - 1] + w[2 * R + k] - w[k - 1];
+            const size_t o = size_t(jj + hr) * g.e2_pitch + q2;
+            if (!ncc) {
+                int key[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int uc = q2 + k - job.eoff;
+                    const bool valid = all_valid || (uc >= job.cmin && uc <= job.cmax);
+                    key[k] = valid ? int(bias + (uint32_t(er[k]) << FKEY_BITS) + uint32_t(q2 + k)) : int(KEY_INVALID);
+                }
+                *reinterpret_cast<int4*>(job.E2 + o) = make_int4(key[0], key[1], key[2], key[3]);
+            } else {
+                float rs[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int uc = q2 + k - job.eoff;
+                    const bool valid = all_valid || (uc >= job.cmin && uc <= job.cmax);
+                    rs[k] = (valid && er[k] > 0) ? float(1.0 / sqrt(double(er[k]))) : 0.f;
+                }
+                *reinterpret_cast<float4*>(job.RS + o) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+            }
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(PT_THREADS) prep_tgt_kernel(const __grid_constant__ FastKernelParams P, int rows_per_cta) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    __shared__ __align__(16) int vs[2][4][PT_VSTRIDE];
+    // rows this CTA reads: base_y + j0 - R - 2 .. base_y + j1 + R (one more either side for the row-wrap columns)
+    const int j0 = int(blockIdx.y) * rows_per_cta, j1 = min(g.J, j0 + rows_per_cta);
+    const int ilo = g.base_y + j0 - R - 2, ihi = g.base_y + j1 + R;
+    const bool interior = ilo >= max(0, g.ar0) && ihi <= min(g.rows, g.ar1) - 1;
+    if (interior) prep_tgt_body<R, true>(g, job, rows_per_cta, vs);
+    else prep_tgt_body<R, false>(g, job, rows_per_cta, vs);
+}
+
+typedef void (*prep_tgt_fn)(const FastKernelParams, int);
+static inline prep_tgt_fn prep_tgt_pick(int R) {
+    switch (R) {
+        case 0: return prep_tgt_kernel<0>; case 1: return prep_tgt_kernel<1>; case 2: return prep_tgt_kernel<2>;
+        case 3: return prep_tgt_kernel<3>; case 4: return prep_tgt_kernel<4>; case 5: return prep_tgt_kernel<5>;
+        case 6: return prep_tgt_kernel<6>; case 7: return prep_tgt_kernel<7>;
+    }
+    return nullptr;
+}
+
 // NCC: per strip (K pixels) and output row, the power of two just above sqrt(max EL) — the binade the
 // fixed-point keys of that strip row live in.  V holds the vertical (2R+1)-sums of squares of the
 // replicate-padded REFERENCE image: V column c = padded column c, so EL(x) = sum V[yy][x .. x+2R].
@@ -179,100 +338,144 @@ __global__ void __launch_bounds__(128) prep_scale_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------------
 // Merge: winning key per group -> disparity (+ cost), in the caller's layout
 // ---------------------------------------------------------------------------------------------------
-__global__ void fast_merge_ssd_kernel(const __grid_constant__ FastKernelParams P) {
+// Stores 4 consecutive disparities of one row (vector store when the caller's layout allows it).
+__device__ __forceinline__ void store_disp4(void* disp_out, size_t disp_step, int elem, int yy, int x, int cols, const int (&d)[4]) {
+    char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
+    if (x + 3 < cols) {
+        if (elem == 2 && ((reinterpret_cast<uintptr_t>(drow) + 2 * size_t(x)) & 7) == 0) {
+            const uint32_t lo = (uint32_t(d[0]) & 0xFFFFu) | (uint32_t(d[1]) << 16), hi = (uint32_t(d[2]) & 0xFFFFu) | (uint32_t(d[3]) << 16);
+            *reinterpret_cast<uint2*>(drow + 2 * size_t(x)) = make_uint2(lo, hi);
+            return;
+        }
+        if (elem == 1 && ((reinterpret_cast<uintptr_t>(drow) + size_t(x)) & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(drow + x) = (uint32_t(d[0]) & 0xFFu) | ((uint32_t(d[1]) & 0xFFu) << 8) | ((uint32_t(d[2]) & 0xFFu) << 16) | (uint32_t(d[3]) << 24);
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (x + k >= cols) break;
+        if (elem == 1) reinterpret_cast<int8_t*>(drow)[x + k] = int8_t(uint8_t(uint32_t(d[k]) & 0xFFu));
+        else if (elem == 2) reinterpret_cast<int16_t*>(drow)[x + k] = int16_t(d[k]);
+        else reinterpret_cast<int32_t*>(drow)[x + k] = d[k];
+    }
+}
+
+// 4 pixels per thread: 16-byte loads of the partial keys, vector stores of the disparities.
+__global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_constant__ FastKernelParams P) {
     const FastGeom& g = P.g;
     const FastJob& job = P.job[blockIdx.z];
     const int32_t* __restrict__ PART = job.PART;
     const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
-    void* disp_out = job.disp; const size_t disp_step = job.disp_step; const int elem = job.elem;
     void* best_out = job.best; const size_t best_step = job.best_step;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int yy = blockIdx.y;
-    if (x >= g.cols) return;
-    int bestc = INT_MAX, bestd = 0;
-    bool found = false;
+    if (x4 >= g.cols) return;
+    int bestc[4], bestd[4];
+    bool found[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { bestc[k] = INT_MAX; bestd[k] = 0; found[k] = false; }
     const uint32_t thresh = key_invalid_threshold(g.R), bias = key_bias(g.R);
     for (int grp = 0; grp < g.G; ++grp) {
-        const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
-        if (key >= thresh) continue;                               // no legal candidate in this group
-        const uint32_t qlo = uint32_t(x + job.dmin + g.dg * grp + job.eoff);   // position of the group's first candidate
-        const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
-        const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
-        if (!found || c < bestc) { bestc = c; bestd = int(q2) - job.eoff - x; found = true; }
-    }
-    int cost = 99999999;                                           // DisparitySSD.cpp:37
-    // EL(x), the window energy of the reference image (replicate padding), is only needed to report
-    // the cost and to honour the 99999999 threshold; with (2R+1)^2 * 255^2 < 99999999 (R <= 19) the
-    // threshold can never bind, so the energy is computed only when the caller asked for costs.
-    if (found && best_out) {
-        int el = 0;
-        const int y = g.rb + yy;
-        for (int wy = -g.R; wy <= g.R; ++wy) {
-            const uint8_t* row = A + size_t(clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * a_step;
-            for (int wx = -g.R; wx <= g.R; ++wx) { const int v = row[clampi(x + wx, 0, g.cols - 1)]; el += v * v; }
+        const int4 kv = *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4);
+        const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t key = keys[k];
+            if (key >= thresh) continue;                               // no legal candidate in this group
+            const int x = x4 + k;
+            const uint32_t qlo = uint32_t(x + job.dmin + g.dg * grp + job.eoff);   // position of the group's first candidate
+            const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
+            const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
+            if (!found[k] || c < bestc[k]) { bestc[k] = c; bestd[k] = int(q2) - job.eoff - x; found[k] = true; }
         }
-        cost = bestc + el;
     }
-    char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
-    if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(bestd) & 0xFFu));
-    else if (elem == 2) reinterpret_cast<int16_t*>(drow)[x] = int16_t(bestd);
-    else reinterpret_cast<int32_t*>(drow)[x] = bestd;
-    if (best_out) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = cost;
+    store_disp4(job.disp, job.disp_step, job.elem, yy, x4, g.cols, bestd);
+    // EL(x), the window energy of the reference image (replicate padding), is only needed to report
+    // the cost and to honour the 99999999 threshold (DisparitySSD.cpp:37); with (2R+1)^2 * 255^2 < 99999999
+    // (R <= 19) the threshold can never bind, so the energy is computed only when the caller asked for costs.
+    if (best_out) {
+        const int y = g.rb + yy;
+        for (int k = 0; k < 4 && x4 + k < g.cols; ++k) {
+            const int x = x4 + k;
+            int cost = 99999999;
+            if (found[k]) {
+                int el = 0;
+                for (int wy = -g.R; wy <= g.R; ++wy) {
+                    const uint8_t* row = A + size_t(clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * a_step;
+                    for (int wx = -g.R; wx <= g.R; ++wx) { const int v = row[clampi(x + wx, 0, g.cols - 1)]; el += v * v; }
+                }
+                cost = bestc[k] + el;
+            }
+            reinterpret_cast<int32_t*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = cost;
+        }
+    }
 }
 
 // NCC: winning key per group -> first maximum over the groups -> disparity with the reference's
 // alignment rule (DisparityNCorr.cpp:67) and, on request, the winning score recomputed exactly with
 // TM_CCORR_NORMED's arithmetic (float32 numerator, double energies; see ncorr_exact_kernel).
-__global__ void fast_merge_ncc_kernel(const __grid_constant__ FastKernelParams P) {
+__global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_constant__ FastKernelParams P) {
     const FastGeom& g = P.g;
     const FastJob& job = P.job[blockIdx.z];
     const int32_t* __restrict__ PART = job.PART;
     const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
     const uint8_t* __restrict__ B = job.B; const size_t b_step = job.b_step;
-    void* disp_out = job.disp; const size_t disp_step = job.disp_step; const int elem = job.elem;
     void* best_out = job.best; const size_t best_step = job.best_step;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int yy = blockIdx.y;
-    if (x >= g.cols) return;
-    long long bestv = -1; int bestd = 0;
+    if (x4 >= g.cols) return;
+    long long bestv[4]; int bestd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { bestv[k] = -1; bestd[k] = 0; }
     for (int grp = 0; grp < g.G; ++grp) {
-        const uint32_t key = uint32_t(PART[(size_t(grp) * g.nrows + yy) * g.wpart + x]);
-        if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
-        const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
-        if (v > bestv) { bestv = v; bestd = job.dmin + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+        const int4 kv = *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4);
+        const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t key = keys[k];
+            if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
+            const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
+            if (v > bestv[k]) { bestv[k] = v; bestd[k] = job.dmin + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+        }
     }
-    const int startc = max(0, x + job.dmin), endc = min(g.cols - 1, x + job.dmax);
-    int centre = x + bestd;                                         // winning window centre (unpadded column)
-    // Illegal positions (centre outside the image) carry the score-0 key of their position (RS = 0).  One of
-    // them winning means every legal candidate scored exactly 0 (a non-zero C*rs never quantises to 0:
-    // rs >= 1/sqrt(Emax) > magic * 2^-24), and the first maximum of an all-zero result row is its first entry.
-    if (centre < startc || centre > endc) centre = startc;
     const bool right_aligned = (job.dmin <= 0 && job.dmax <= 0);
-    const int disp = (centre - startc) - (right_aligned ? endc - startc : 0);
-    char* drow = reinterpret_cast<char*>(disp_out) + size_t(yy) * disp_step;
-    if (elem == 1) reinterpret_cast<int8_t*>(drow)[x] = int8_t(uint8_t(uint32_t(disp) & 0xFFu));
-    else if (elem == 2) reinterpret_cast<int16_t*>(drow)[x] = int16_t(disp);
-    else reinterpret_cast<int32_t*>(drow)[x] = disp;
+    int disp[4], centre[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        const int startc = max(0, x + job.dmin), endc = min(g.cols - 1, x + job.dmax);
+        centre[k] = x + bestd[k];                                       // winning window centre (unpadded column)
+        // Illegal positions (centre outside the image) carry the score-0 key of their position (RS = 0).  One of
+        // them winning means every legal candidate scored exactly 0 (a non-zero C*rs never quantises to 0:
+        // rs >= 1/sqrt(Emax) > magic * 2^-24), and the first maximum of an all-zero result row is its first entry.
+        if (centre[k] < startc || centre[k] > endc) centre[k] = startc;
+        disp[k] = (centre[k] - startc) - (right_aligned ? endc - startc : 0);
+    }
+    store_disp4(job.disp, job.disp_step, job.elem, yy, x4, g.cols, disp);
     if (best_out) {
         const int y = g.rb + yy;
-        int c = 0, el = 0, er = 0;
-        for (int wy = -g.R; wy <= g.R; ++wy) {
-            const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
-            const uint8_t* arow = A + size_t(wr) * a_step;
-            const uint8_t* brow = B + size_t(wr) * b_step;
-            for (int wx = -g.R; wx <= g.R; ++wx) {
-                const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre + wx, 0, g.cols - 1)];
-                c += l * r; el += l * l; er += r * r;
+        for (int k = 0; k < 4 && x4 + k < g.cols; ++k) {
+            const int x = x4 + k;
+            int c = 0, el = 0, er = 0;
+            for (int wy = -g.R; wy <= g.R; ++wy) {
+                const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+                const uint8_t* arow = A + size_t(wr) * a_step;
+                const uint8_t* brow = B + size_t(wr) * b_step;
+                for (int wx = -g.R; wx <= g.R; ++wx) {
+                    const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre[k] + wx, 0, g.cols - 1)];
+                    c += l * r; el += l * l; er += r * r;
+                }
             }
+            double num = double(float(c));
+            const double wnd = double(er);
+            const double lim = fmin(0.5, 10 * double(FLT_EPSILON) * wnd);
+            const double t = (wnd <= lim) ? 0 : sqrt(wnd) * sqrt(double(el));
+            if (fabs(num) < t) num /= t;
+            else if (fabs(num) < t * 1.125) num = num > 0 ? 1 : -1;
+            else num = 0;
+            reinterpret_cast<float*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = float(num);
         }
-        double num = double(float(c));
-        const double wnd = double(er);
-        const double lim = fmin(0.5, 10 * double(FLT_EPSILON) * wnd);
-        const double t = (wnd <= lim) ? 0 : sqrt(wnd) * sqrt(double(el));
-        if (fabs(num) < t) num /= t;
-        else if (fabs(num) < t * 1.125) num = num > 0 ? 1 : -1;
-        else num = 0;
-        reinterpret_cast<float*>(reinterpret_cast<char*>(best_out) + size_t(yy) * best_step)[x] = float(num);
     }
 }
 
@@ -439,10 +642,22 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     }
     const unsigned nz = unsigned(n);
     prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, nz), 256, 0, st>>>(kp);
-    prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
-    prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
-    const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
-    prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
+    static const bool legacy_prep = [] { const char* e = getenv("STEREO_PREP_LEGACY"); return e && atoi(e) != 0; }();
+    if (!legacy_prep) {
+        int delta_max = 0;
+        for (int i = 0; i < n; ++i) { const int d = kp.job[i].qoff - kp.job[i].eoff + g.R; if (d > delta_max) delta_max = d; }
+        const int span = g.rq_pitch > g.e2_pitch + delta_max ? g.rq_pitch : g.e2_pitch + delta_max;
+        const int tiles = int(div_round_up(span, pt_ts(g.R)));
+        int rpc = PT_ROWS;                          // fewer rows per CTA while the grid would leave SMs idle
+        while (rpc > 16 && (long long)tiles * div_round_up(g.J, rpc) * n < 6LL * ctx->sm_count) rpc /= 2;
+        prep_tgt_pick(g.R)<<<dim3(tiles, div_round_up(g.J, rpc), nz), PT_THREADS, 0, st>>>(kp, rpc);
+        ctx->last_launches -= 2;
+    } else {   // three-pass version (debug knob): RQ rows, vertical sums in HBM, horizontal sums
+        prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
+        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
+        const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
+        prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
+    }
     if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
         prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 1);
         prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
@@ -455,8 +670,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     fn<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
     if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; ctx->hot_jobs += n; }
     ctx->hot_total++;
-    if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp);
-    else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp);
+    if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
+    else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
     ctx->last_launches += 6;
     SB_CUDA(cudaGetLastError());
     return STEREO_OK;
