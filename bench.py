@@ -9,12 +9,15 @@
 A step = one pass of the hot path over one batch of synthetic stereo pairs (both directions per
 pair, like the reference's disparitySSDPair, main.cpp:21-48).  Workload at every N: per GPU a batch
 of B synthetic 3840x2160 pairs, 256 disparities, 11x11 window, SSD (BASELINE config 4's shape and
-the config the north-star target is quoted on), pairs sharded by rank (weak scaling); for N > 1 the
-per-rank disparity maps are all-gathered over NCCL inside the timed step (BASELINE config 5's
-"sharded by pair ... with NCCL gather").
+the config the north-star target is quoted on), pairs sharded by rank (weak scaling); for N > 1 every
+rank's disparity maps are gathered on every rank inside the timed region (BASELINE config 5's "sharded
+by pair ... with ... gather"): by default with copy-engine pushes over NVLink into peer-mapped buffers
+(--gather p2p; they overlap the next step's kernels, which an SM-resident collective cannot because the
+hot kernel is persistent and fills every SM), or with an NCCL all_gather (--gather nccl).
 
-`value`   : whole-job Mpix x disp / s with inputs resident in HBM, CUDA events on the launching stream,
-            L2 flushed between steps, max over ranks.
+`value`   : whole-job Mpix x disp / s with inputs resident in HBM, one CUDA event pair on the launching stream
+            around all timed steps (joined with the copy-engine streams), inputs rotating over more sets
+            than the L2 holds, max over ranks.
 `e2e`     : the same metric through the reference-facing C-ABI call with HOST float32 (CV_32FC1)
             buffers — H2D and D2H copies inside the timed region, wall clock, max over ranks.
 `roofline`: the hot kernel (fast_ssd_kernel) against the FP32/INT32 issue roofline of SURVEY.md §8d
@@ -205,33 +208,54 @@ def run_ours(args, wl):
         return run_bands(args, wl, lib, ctx, cost, dev, rank, world, local)
     B = args.pairs
     elem_dtype, elem = (torch.int8, 1) if nd <= 128 else (torch.int16, 2)
+    from introtocomputervision_b200 import sharding
 
-    # synthetic pairs of this rank (pair-sharded batch: rank r owns pairs r*B .. r*B+B-1)
+    # synthetic pairs of this rank (pair-sharded batch: rank r owns pairs r*B .. r*B+B-1).  The inputs rotate
+    # over S sets whose total size exceeds the L2, so no step finds its images cached from the step before
+    # (set 0 is generated, the others are its rows rolled: throughput is data-independent, only residency matters).
     Ls, Rs = [], []
     for i in range(B):
         L, Rt, _ = synth.make_pair(rows, cols, nd, wl["seed"] + rank * B + i)
         Ls.append(L), Rs.append(Rt)
     h_left = torch.from_numpy(np.stack(Ls))
     h_right = torch.from_numpy(np.stack(Rs))
-    d_left, d_right = h_left.to(dev), h_right.to(dev)
-    d_dl = torch.empty((B, rows, cols), dtype=elem_dtype, device=dev)
-    d_dr = torch.empty_like(d_dl)
-    gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev) if world > 1 else None
-    mine = torch.empty((2, B, rows, cols), dtype=elem_dtype, device=dev) if world > 1 else None
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    props = torch.cuda.get_device_properties(dev)
+    l2_bytes = int(getattr(props, "L2_cache_size", 126 << 20))
+    set_bytes = 2 * B * rows * cols
+    S = max(2, -(-int(1.25 * l2_bytes) // set_bytes) + 1)
+    d_left = torch.stack([torch.roll(h_left, 17 * s_, dims=1) for s_ in range(S)]).to(dev)     # S x B x rows x cols
+    d_right = torch.stack([torch.roll(h_right, 17 * s_, dims=1) for s_ in range(S)]).to(dev)
+    d_out = torch.empty((2, 2, B, rows, cols), dtype=elem_dtype, device=dev)                    # [parity][direction][pair]
+    map_bytes = 2 * B * rows * cols * elem                                                      # one rank's maps of one step
     stream = torch.cuda.Stream(device=dev)              # a real (non-default) stream: the library enqueues on it
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    gather = args.gather if world > 1 else "none"
+    pg, gathered, tickets = None, None, {}
+    if gather == "p2p":
+        # every rank's buffer: [parity][rank][direction][pair][rows][cols]; filled by copy-engine pushes
+        pg = sharding.PeerGather(ctx, 2 * world * map_bytes)
+    elif gather == "nccl":
+        gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev)
 
-    def step_device():
+    def step_device(k):
+        par, s_ = k & 1, k % S
+        if pg is not None and k - 2 in tickets:
+            pg.wait(tickets.pop(k - 2), stream.cuda_stream)       # the pushes that read d_out[par] two steps ago
         rc = lib.stereo_disparity_pair_batch_u8_device(
-            ctx.handle, cost, B, d_left.data_ptr(), d_right.data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
-            d_dl.data_ptr(), d_dr.data_ptr(), cols * elem, rows * cols * elem, elem, sp)
+            ctx.handle, cost, B, d_left[s_].data_ptr(), d_right[s_].data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
+            d_out[par, 0].data_ptr(), d_out[par, 1].data_ptr(), cols * elem, rows * cols * elem, elem, sp)
         if rc != 0:
             raise RuntimeError(_capi.last_error())
-        if world > 1:       # the batch config's exchange step: gather every rank's maps
-            mine[0].copy_(d_dl), mine[1].copy_(d_dr)
-            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))   # bytes: NCCL has no int16
+        if pg is not None:      # the batch config's exchange step: every rank receives every rank's maps
+            pg.push((par * world + rank) * map_bytes, d_out[par].data_ptr(), map_bytes, stream.cuda_stream)
+            tickets[k] = pg.mark()
+        elif gathered is not None:
+            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), d_out[par].view(torch.uint8).view(-1))   # bytes: NCCL has no int16
+
+    def join_pushes():
+        for k in sorted(tickets):
+            pg.wait(tickets.pop(k), stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -239,26 +263,32 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     units_rank = B * 2 * rows * cols * nd
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    nwarm = max(3, args.warmup)
+    for k in range(nwarm):
+        step_device(k)
+    if pg is not None:
+        join_pushes()
     barrier()
+    if pg is not None and rank == 0:      # the gather delivers: rank 0's buffer holds the last warm-up step's maps of every rank
+        par = (nwarm - 1) & 1
+        got = pg.local_bytes(dev)[(par * world + rank) * map_bytes:(par * world + rank + 1) * map_bytes]
+        assert torch.equal(got, d_out[par].view(torch.uint8).view(-1)), "peer gather: own slot differs from the computed maps"
 
     sampler = ClockSampler(local)
     sampler.start()
-    evs = []
     hot_ms, hot_n, launches = 0.0, 0, 0
     barrier()
-    for _ in range(args.steps):
-        flush.zero_()                                     # L2 flush, outside the per-step event pair
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step_device()
-        e1.record(stream)
-        evs.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        step_device(nwarm + k)
         launches += ctx.last_launches
+    if pg is not None:
+        join_pushes()                                    # the timed region ends when every push has landed
+    e1.record(stream)
     barrier()
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = e0.elapsed_time(e1)
     # hot-kernel time of the last step (events recorded by the library on the same stream)
     ms, nmeas = ctx.last_hot_kernel_ms()
     hot_jobs = ctx.last_hot_jobs
@@ -269,6 +299,13 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = world * units_rank * args.steps / (dev_ms * 1e-3) / 1e6
+    if pg is not None:      # cross-rank check after the barrier: every slot of the last step equals what that rank computed
+        par = (nwarm + args.steps - 1) & 1
+        sums = pg.local_bytes(dev)[par * world * map_bytes:(par + 1) * world * map_bytes].view(world, -1).to(torch.int64).sum(dim=1)
+        mine_sum = d_out[par].view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
+        all_sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_sums, mine_sum)
+        assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's maps"
 
     # ---- e2e: reference-facing host call, float32 (CV_32FC1) host buffers, copies inside the timed region
     hf_left = h_left.to(torch.float32).pin_memory()
@@ -358,8 +395,12 @@ def run_ours(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (int32 accumulate)", "data": "synthetic",
             "config": {"workload": args.workload + f"_{args.cost}_pair", "rows": rows, "cols": cols, "ndisp": nd,
                        "window": 2 * R + 1, "pairs_per_gpu_per_step": B, "directions": 2,
-                       "sharding": "by pair" + (", NCCL all_gather of maps inside the step" if world > 1 else ""),
-                       "l2": "flushed between steps (512 MiB memset outside the per-step event pair)",
+                       "sharding": "by pair" + ({"p2p": ", every rank's maps pushed into every rank's gather buffer by the copy engines "
+                                                        "over NVLink (stereo_peer_push), overlapping the next step's kernels; "
+                                                        "all pushes joined inside the timed region",
+                                                 "nccl": ", NCCL all_gather of maps inside the step", "none": ""}[gather]),
+                       "l2": f"inputs rotate over {S} sets = {S * set_bytes >> 20} MiB > L2 ({l2_bytes >> 20} MiB); "
+                             f"one event pair around all timed steps",
                        "out_dtype": str(elem_dtype).replace("torch.", "")},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * 2 * rows * cols * 4,
@@ -369,6 +410,8 @@ def run_ours(args, wl):
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if pg is not None:
+        pg.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -458,6 +501,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pipe-bands", type=int, default=0, help="row bands per pair in the pipelined host entry points (0 = automatic)")
     ap.add_argument("--cost", default="ssd", choices=["ssd", "ncc"], help="window cost (the headline line is ssd)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the ranks' maps are gathered (copy-engine peer pushes, or an NCCL all_gather)")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
                     help="pairs: batch sharded by pair, weak scaling (default, the driver's line); "
                          "bands: ONE image sharded by row band with halo, strong scaling (BASELINE config 4)")

@@ -211,6 +211,28 @@ int stereo_disparity_band_halo_u8_device(stereo_ctx* ctx, int cost,
  * arithmetic, no device). */
 int stereo_band_halo_rows(int rows, int row_begin, int row_end, int window_rad, int* halo_begin, int* halo_end);
 
+/* ---- peer gather: the exchange step of the sharded configs, on the copy engines -----------------------
+ * The reference has no multi-GPU path; BASELINE configs 4 and 5 gather the per-rank maps.
+ * The hot kernel is persistent (one CTA per SM, full register file), so a collective that needs SMs cannot
+ * overlap it.  These calls let each rank push its finished maps straight into every other rank's gather
+ * buffer with device-to-device copies over NVLink (copy engines, no SM), stream-ordered after the kernels
+ * that produced them, while the SMs already work on the next launch sequence.
+ *   create  : device buffer other processes of this box can map + the 64-byte handle to send them
+ *   open    : map a peer's buffer from its handle (a different process; never the creating one)
+ *   push    : once `after_stream` reaches this point, copy src -> dst_ptrs[i] + dst_offset for every i
+ *             (NULL entries are skipped; pointers may be local or opened peers)
+ *   mark    : returns a ticket that completes when every push enqueued so far has finished
+ *   wait    : makes `cuda_stream` wait for a ticket (at most 64 tickets are live) */
+#define STEREO_IPC_HANDLE_BYTES 64
+int stereo_peer_buffer_create(stereo_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char* handle_out);
+int stereo_peer_buffer_open(stereo_ctx* ctx, const unsigned char* handle, void** peer_ptr);
+int stereo_peer_buffer_close(stereo_ctx* ctx, void* peer_ptr);
+int stereo_peer_buffer_destroy(stereo_ctx* ctx, void* dev_ptr);
+int stereo_peer_push(stereo_ctx* ctx, void* const* dst_ptrs, int n_dst, size_t dst_offset, const void* src, size_t bytes,
+                     void* after_stream);
+int stereo_peer_mark(stereo_ctx* ctx, int* ticket_out);
+int stereo_peer_wait(stereo_ctx* ctx, int ticket, void* cuda_stream);
+
 /* Blocks until everything enqueued on `cuda_stream` (NULL = the context's stream) has finished and
  * returns any asynchronous error. */
 int stereo_ctx_synchronize(stereo_ctx* ctx, void* cuda_stream);

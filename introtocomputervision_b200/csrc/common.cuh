@@ -100,4 +100,10 @@ struct stereo_ctx {
     int hot_used = 0;          // event pairs recorded by the last call
     int hot_total = 0;         // hot-kernel launches of the last call (may exceed HOT_EVENTS)
     int hot_jobs = 0;          // directions (jobs) covered by the measured hot launches
+    // peer gather (stereo_peer_*): copy-engine pushes of finished maps into other ranks' buffers over NVLink
+    static constexpr int PEER_STREAMS = 2, PEER_TICKETS = 64;
+    cudaStream_t s_peer[PEER_STREAMS] = {};
+    cudaEvent_t peer_ready = nullptr;                            // "producer stream reached this point"
+    cudaEvent_t peer_done[PEER_TICKETS][PEER_STREAMS] = {};      // ring of completion marks
+    int peer_next_stream = 0, peer_next_ticket = 0;
 };

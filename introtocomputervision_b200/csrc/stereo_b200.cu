@@ -594,6 +594,10 @@ void stereo_ctx_destroy(stereo_ctx* ctx) {
     }
     for (int i = 0; i < ctx->pipe_ev_cap; ++i) cudaEventDestroy(ctx->pipe_ev[i]);
     delete[] ctx->pipe_ev;
+    for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) if (ctx->s_peer[i]) { cudaStreamSynchronize(ctx->s_peer[i]); cudaStreamDestroy(ctx->s_peer[i]); }
+    if (ctx->peer_ready) cudaEventDestroy(ctx->peer_ready);
+    for (int t = 0; t < stereo_ctx::PEER_TICKETS; ++t)
+        for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) if (ctx->peer_done[t][i]) cudaEventDestroy(ctx->peer_done[t][i]);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -643,6 +647,96 @@ int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
 int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands) {
     if (!ctx || bands < 0 || bands > 4096) { set_error("bad pipe_bands argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->pipe_bands = bands;
+    return STEREO_OK;
+}
+
+// ---- peer gather: results pushed into other ranks' buffers by the copy engines ---------------------
+static int ensure_peer(stereo_ctx* ctx) {
+    if (ctx->peer_ready) return STEREO_OK;
+    for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) SB_CUDA(cudaStreamCreateWithFlags(&ctx->s_peer[i], cudaStreamNonBlocking));
+    for (int t = 0; t < stereo_ctx::PEER_TICKETS; ++t)
+        for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) SB_CUDA(cudaEventCreateWithFlags(&ctx->peer_done[t][i], cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ctx->peer_ready, cudaEventDisableTiming));
+    return STEREO_OK;
+}
+
+int stereo_peer_buffer_create(stereo_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char* handle_out) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!dev_ptr || !handle_out || bytes == 0) { set_error("bad peer buffer arguments"); return STEREO_ERR_INVALID_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == STEREO_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); set_error("peer buffer of %zu bytes: out of device memory", bytes); return STEREO_ERR_ALLOC; }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return STEREO_OK;
+}
+
+int stereo_peer_buffer_open(stereo_ctx* ctx, const unsigned char* handle, void** peer_ptr) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!handle || !peer_ptr) { set_error("bad peer buffer arguments"); return STEREO_ERR_INVALID_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return STEREO_OK;
+}
+
+int stereo_peer_buffer_close(stereo_ctx* ctx, void* peer_ptr) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (peer_ptr) SB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return STEREO_OK;
+}
+
+int stereo_peer_buffer_destroy(stereo_ctx* ctx, void* dev_ptr) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (dev_ptr) SB_CUDA(cudaFree(dev_ptr));
+    return STEREO_OK;
+}
+
+int stereo_peer_push(stereo_ctx* ctx, void* const* dst_ptrs, int n_dst, size_t dst_offset, const void* src, size_t bytes,
+                     void* after_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!dst_ptrs || n_dst < 0 || (!src && bytes)) { set_error("bad peer push arguments"); return STEREO_ERR_INVALID_ARG; }
+    rc = ensure_peer(ctx);
+    if (rc != STEREO_OK) return rc;
+    cudaStream_t producer = after_stream ? static_cast<cudaStream_t>(after_stream) : ctx->stream;
+    SB_CUDA(cudaEventRecord(ctx->peer_ready, producer));
+    for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) SB_CUDA(cudaStreamWaitEvent(ctx->s_peer[i], ctx->peer_ready, 0));
+    for (int i = 0; i < n_dst; ++i) {
+        if (!dst_ptrs[i]) continue;
+        cudaStream_t s = ctx->s_peer[ctx->peer_next_stream];
+        ctx->peer_next_stream = (ctx->peer_next_stream + 1) % stereo_ctx::PEER_STREAMS;
+        SB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst_ptrs[i]) + dst_offset, src, bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    return STEREO_OK;
+}
+
+int stereo_peer_mark(stereo_ctx* ctx, int* ticket_out) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!ticket_out) { set_error("ticket_out is null"); return STEREO_ERR_INVALID_ARG; }
+    rc = ensure_peer(ctx);
+    if (rc != STEREO_OK) return rc;
+    const int t = ctx->peer_next_ticket;
+    ctx->peer_next_ticket = (t + 1) % stereo_ctx::PEER_TICKETS;
+    for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) SB_CUDA(cudaEventRecord(ctx->peer_done[t][i], ctx->s_peer[i]));
+    *ticket_out = t;
+    return STEREO_OK;
+}
+
+int stereo_peer_wait(stereo_ctx* ctx, int ticket, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (ticket < 0 || ticket >= stereo_ctx::PEER_TICKETS || !ctx->peer_ready) { set_error("bad peer ticket"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    for (int i = 0; i < stereo_ctx::PEER_STREAMS; ++i) SB_CUDA(cudaStreamWaitEvent(s, ctx->peer_done[ticket][i], 0));
     return STEREO_OK;
 }
 

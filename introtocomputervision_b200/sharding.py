@@ -9,8 +9,9 @@ The path has no exchange step inside the computation — every 
   [r0, r1) and reads input rows [r0-R-1, r1+R+1) clamped to the image — R rows of window plus one more
   for the neighbouring padded row the reference's SSD reads through its flat index.
 
-The only collective is the gather of the per-rank results (``all_gather_into_tensor``; NCCL over NVLink
-on GPUs, gloo in the CPU tests).  The compute itself is a call into libstereo_b200.so per rank; a
+The only exchange is the gather of the per-rank results: ``all_gather_into_tensor`` (NCCL over NVLink on
+GPUs, gloo in the CPU tests) or, on the GPUs of one box, copy-engine pushes into every rank's buffer
+(``PeerGather``), which overlap the persistent hot kernel where a collective cannot.  The compute itself is a call into libstereo_b200.so per rank; a
 ``compute`` object can be injected so that the partition/gather logic is testable without a GPU.
 """
 from __future__ import annotations
@@ -94,20 +95,133 @@ class GpuCompute:
         return out
 
 
+class _RawDeviceBytes:
+    """Lets torch view a raw device pointer (a buffer owned by libstereo_b200.so) as a uint8 tensor."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """Gather buffer filled by copy-engine pushes over NVLink (``stereo_peer_*`` in include/stereo_b200.h).
+
+    Every rank owns a buffer of ``nbytes``; ``push(offset, src_ptr, n, stream)`` copies n bytes of this rank's
+    device memory into EVERY rank's buffer at ``offset`` (its own included), stream-ordered after the work
+    already enqueued on ``stream`` and without using an SM — the persistent hot kernel occupies every SM, so
+    an NCCL collective could only run between its launches, a copy-engine push runs underneath them.
+    ``torch.distributed`` (NCCL on GPUs) is used for the plumbing: the exchange of the 64-byte buffer handles
+    and the barrier that makes a gather complete."""
+
+    def __init__(self, ctx, nbytes: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.ctx, self.group = torch, dist, ctx, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nbytes = int(nbytes)
+        lib = _capi.lib()
+        local = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        self._check(lib.stereo_peer_buffer_create(ctx.handle, self.nbytes, C.byref(local), handle))
+        self.local_ptr = int(local.value)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs = (C.c_void_p * self.world)()
+        self._opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs[r] = self.local_ptr
+            else:
+                peer = C.c_void_p()
+                self._check(lib.stereo_peer_buffer_open(ctx.handle, (C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(peer)))
+                self.ptrs[r] = peer.value
+                self._opened.append(int(peer.value))
+
+    @staticmethod
+    def _check(st):
+        if st != _capi.STEREO_OK:
+            raise RuntimeError(_capi.last_error())
+
+    def push(self, offset: int, src_ptr: int, nbytes: int, stream: int) -> None:
+        if offset < 0 or offset + nbytes > self.nbytes:
+            raise ValueError("push outside the gather buffer")
+        self._check(_capi.lib().stereo_peer_push(self.ctx.handle, self.ptrs, self.world, int(offset), C.c_void_p(int(src_ptr)),
+                                                 int(nbytes), C.c_void_p(int(stream) or CUDA_STREAM_LEGACY)))
+
+    def mark(self) -> int:
+        t = C.c_int(-1)
+        self._check(_capi.lib().stereo_peer_mark(self.ctx.handle, C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int, stream: int) -> None:
+        self._check(_capi.lib().stereo_peer_wait(self.ctx.handle, int(ticket), C.c_void_p(int(stream) or CUDA_STREAM_LEGACY)))
+
+    def local_bytes(self, device):
+        """This rank's gather buffer as a uint8 tensor (no copy)."""
+        return self.torch.as_tensor(_RawDeviceBytes(self.local_ptr, self.nbytes), device=device)
+
+    def complete(self, stream: int) -> None:
+        """Blocks until every rank's pushes so far have landed everywhere (local join + barrier)."""
+        self.wait(self.mark(), stream)
+        self._check(_capi.lib().stereo_ctx_synchronize(self.ctx.handle, C.c_void_p(int(stream) or CUDA_STREAM_LEGACY)))
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        lib = _capi.lib()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)            # nobody may still be pushing into a buffer that goes away
+        for p in self._opened:
+            lib.stereo_peer_buffer_close(self.ctx.handle, C.c_void_p(p))
+        self._opened = []
+        if self.local_ptr:
+            lib.stereo_peer_buffer_destroy(self.ctx.handle, C.c_void_p(self.local_ptr))
+            self.local_ptr = 0
+
+
 class ShardedStereo:
     """Row-band and pair sharding over the ranks of a ``torch.distributed`` process group."""
 
-    def __init__(self, compute, group=None):
+    def __init__(self, compute, group=None, gather: str = "collective"):
+        """gather = "collective": ``all_gather_into_tensor`` (NCCL / gloo);  "peer": copy-engine pushes into every
+        rank's buffer (PeerGather; GPUs of one box only)."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.compute, self.group = compute, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if gather not in ("collective", "peer"):
+            raise ValueError("gather must be 'collective' or 'peer'")
+        self.gather_mode = gather
+        self._pg = None
+
+    def _gather_peer(self, mine):
+        mine = mine.contiguous()
+        n = mine.numel() * mine.element_size()
+        if self._pg is None or self._pg.nbytes != self.world * n:
+            if self._pg is not None:
+                self._pg.close()
+            self._pg = PeerGather(self.compute.ctx, self.world * n, group=self.group)
+        stream = self.torch.cuda.current_stream(mine.device).cuda_stream
+        self._pg.push(self.rank * n, mine.data_ptr(), n, stream)
+        self._pg.complete(stream)
+        out = self._pg.local_bytes(mine.device).clone()      # the buffer is reused by the next call
+        if self.world > 1:
+            self.dist.barrier(group=self.group)               # everyone has read before anyone pushes again
+        return out.view(mine.dtype).view((self.world,) + tuple(mine.shape))
+
+    def close(self):
+        if self._pg is not None:
+            self._pg.close()
+            self._pg = None
 
     def _gather(self, mine):
         if self.world == 1:
             return mine.unsqueeze(0)
+        if self.gather_mode == "peer":
+            return self._gather_peer(mine)
         # output = the ranks' tensors concatenated along dim 0 (the layout both NCCL and gloo accept)
         # gathered as raw bytes: the maps are int8/int16/int32 and gloo has no int16 collectives
         mine = mine.contiguous()
