@@ -57,6 +57,19 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(workload: str, cost: str, jobs_per_launch: float):
+    """DRAM bytes (read + write) of ONE hot-kernel launch from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); None when no
+    capture of this workload / cost / directions-per-launch exists."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if not p.exists():
+        return None
+    for e in json.loads(p.read_text()).get("captures", []):
+        if e["workload"] == workload and e["cost"] == cost and abs(e["directions_per_launch"] - jobs_per_launch) < 1e-9:
+            return int(e["dram_bytes_read"] + e["dram_bytes_write"])
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -380,7 +393,7 @@ def run_ours(args, wl):
                 "directions_per_launch": jobs_per_launch,
                 "launch_ms": round(hot_ms / hot_n, 4), "launches_timed": hot_n,
                 "peak_def": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
-                "traffic": None,
+                "traffic": ncu_traffic(args.workload, args.cost, jobs_per_launch),
                 "hbm": {"achieved": round(alg_bytes / (hot_ms / hot_n * 1e-3) / 1e9, 2), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": round(alg_bytes / (hot_ms / hot_n * 1e-3) / 1e9 / peaks["hbm_gbs"], 5),
                         "algorithmic_bytes_per_launch": alg_bytes, "of": peaks["source"]},
