@@ -19,12 +19,14 @@ hot kernel is persistent and fills every SM), or with an NCCL all_gather (--gath
             around all timed steps (joined with the copy-engine streams), inputs rotating over more sets
             than the L2 holds, max over ranks.
 `e2e`     : the same metric through the reference-facing C-ABI call with HOST float32 (CV_32FC1)
-            buffers — H2D and D2H copies inside the timed region, wall clock, max over ranks.
+            buffers — H2D and D2H copies inside the timed region, wall clock, max over ranks.  One
+            stereo_disparity_pair_batch_f32_host call per step; `per_pair_calls_value` is the same work as
+            separate synchronous stereo_disparity_pair_f32_host calls, `u8_host_api_value` the uint8 entry.
 `roofline`: the hot kernel (fast_ssd_kernel) against the FP32/INT32 issue roofline of SURVEY.md §8d
             (8 algorithmic lane-ops per pixel x disparity; peak = SMs x 128 lanes x max SM clock), plus
             the HBM view (algorithmic bytes / kernel time vs the measured copy bandwidth).
-`cpu_baseline`: the reference's own serial::disparitySSD (compiled in place into oracle/_ref) on a
-            bounded sample of the same workload on this box's host cores.
+`cpu_baseline`: the reference's own serial::disparitySSD / serial::disparityNCorr (compiled in place into
+            oracle/_ref) on a bounded sample of the same workload on this box's host cores.
 """
 from __future__ import annotations
 
@@ -132,10 +134,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # the reference's CPU implementation on host cores (bounded sample)
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_sample(wl, rows_per_thread: int, threads: int):
-    """Times the reference's serial::disparitySSD (oracle/_ref; falls back to the C port when the
-    compiled reference is absent) on `threads` disjoint full-width row bands of the workload's
-    left->right problem.  Returns (Mpix*disp/s, description dict)."""
+def cpu_reference_sample(wl, rows_per_thread: int, threads: int, cost: str = "ssd"):
+    """Times the reference's serial::disparitySSD / serial::disparityNCorr (oracle/_ref; falls back to the C port
+    when the compiled reference is absent) on `threads` disjoint full-width row bands of the workload's
+    left->right problem.  Returns (Mpix*disp/s, seconds, description dict)."""
     import oracle
     from introtocomputervision_b200 import synth
 
@@ -143,27 +145,30 @@ def cpu_reference_sample(wl, rows_per_thread: int, threads: int):
     band = max(1, rows_per_thread)
     L, Rt, _ = synth.make_pair(band * threads, wl["cols"], nd, wl["seed"])
     Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
-    kind = "reference" if oracle.have_ref() else "port"
+    have = oracle.have_ref() if cost == "ssd" else oracle.have_ref_ncc()
+    kind = "reference" if have else "port"
     oracle.set_num_threads(1)
+    fn = {("ssd", "reference"): oracle.ref_ssd, ("ssd", "port"): oracle.ssd,
+          ("ncc", "reference"): oracle.ref_ncorr, ("ncc", "port"): oracle.ncorr}[(cost, kind)]
 
     def work(i):
         a = np.ascontiguousarray(Lf[i * band:(i + 1) * band])
         b = np.ascontiguousarray(Rf[i * band:(i + 1) * band])
-        if kind == "reference":
-            oracle.ref_ssd(a, b, R, -(nd - 1), 0)
-        else:
-            oracle.ssd(a, b, R, -(nd - 1), 0)
+        fn(a, b, R, -(nd - 1), 0)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(work, range(threads)))
     dt = time.perf_counter() - t0
     units = threads * band * wl["cols"] * nd          # every row of every band is computed
+    what = {("ssd", "reference"): "reference serial::disparitySSD compiled -O2 from /root/reference (oracle/_ref)",
+            ("ssd", "port"): "C port of serial::disparitySSD (oracle/stereo_oracle.c)",
+            ("ncc", "reference"): "reference serial::disparityNCorr compiled -O2 from /root/reference (oracle/_ref) over the "
+                                  "shim's direct-sum cv::matchTemplate (OpenCV itself is not installed in C++)",
+            ("ncc", "port"): "C port of serial::disparityNCorr (oracle/stereo_oracle.c)"}[(cost, kind)]
     desc = {"kind": kind, "cores": threads,
             "sample": f"{threads} threads x {band}-row full-width bands ({wl['cols']} cols, {nd} disparities, "
-                      f"{2 * R + 1}x{2 * R + 1} window), L->R SSD, "
-                      + ("reference serial::disparitySSD compiled -O2 from /root/reference (oracle/_ref)"
-                         if kind == "reference" else "C port of serial::disparitySSD (oracle/stereo_oracle.c)")}
+                      f"{2 * R + 1}x{2 * R + 1} window), L->R {cost.upper()}, " + what}
     return units / dt / 1e6, dt, desc
 
 
@@ -173,18 +178,19 @@ def run_reference_arm(args, wl):
         return
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_reference_sample(wl, 1, threads)
+        cpu_reference_sample(wl, 1, threads, args.cost)
     vals, times = [], []
     for _ in range(args.steps):
-        v, dt, desc = cpu_reference_sample(wl, args.ref_rows, threads)
+        v, dt, desc = cpu_reference_sample(wl, args.ref_rows, threads, args.cost)
         vals.append(v), times.append(dt)
     total_units = sum(v * t for v, t in zip(vals, times))
     value = total_units / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32->int32", "data": "synthetic",
-        "config": {"workload": args.workload + "_ssd", **{k: wl[k] for k in ("rows", "cols", "ndisp")},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32->int32" if args.cost == "ssd" else "f32 (f64 window energies)", "data": "synthetic",
+        "config": {"workload": args.workload + f"_{args.cost}", **{k: wl[k] for k in ("rows", "cols", "ndisp")},
                    "window": 2 * wl["R"] + 1, "sample_rows_per_thread": args.ref_rows},
         "cpu_baseline": {**desc, "value": round(value, 3), "unit": UNIT},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -327,6 +333,16 @@ def run_ours(args, wl):
     h_dr = torch.empty((B, rows, cols), dtype=elem_dtype).pin_memory()
 
     def step_host():
+        # ONE call of the public host API per step: the step's batch of pairs as CV_32FC1 host images in, both
+        # disparity maps of every pair out (a batch of the reference's disparitySSDPair calls, main.cpp:21-48)
+        rc = lib.stereo_disparity_pair_batch_f32_host(
+            ctx.handle, cost, B, hf_left.data_ptr(), hf_right.data_ptr(), cols * 4, rows * cols * 4, rows, cols, R, nd - 1,
+            h_dl.data_ptr(), h_dr.data_ptr(), cols * elem, rows * cols * elem, elem)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+
+    def step_host_per_pair():
+        # the same work as B separate synchronous pair calls (the reference's calling pattern, one pair at a time)
         for i in range(B):
             rc = lib.stereo_disparity_pair_f32_host(
                 ctx.handle, cost, hf_left[i].data_ptr(), cols * 4, hf_right[i].data_ptr(), cols * 4, rows, cols, R, nd - 1,
@@ -348,7 +364,21 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * units_rank * e2e_steps / e2e_s / 1e6
-    e2e_launches = ctx.last_launches * B * e2e_steps
+    e2e_launches = ctx.last_launches * e2e_steps
+
+    def timed_host(fn):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * units_rank * e2e_steps / float(tt.item()) / 1e6
+
+    e2e_pp_value = timed_host(step_host_per_pair)
 
     # u8 host entry (same computation for callers that hold 8-bit images)
     hu_l, hu_r = h_left.pin_memory(), h_right.pin_memory()
@@ -360,17 +390,17 @@ def run_ours(args, wl):
         if rc != 0:
             raise RuntimeError(_capi.last_error())
 
-    step_host_u8()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host_u8()
-    barrier()
-    e2e8_s = time.perf_counter() - t0
-    t = torch.tensor([e2e8_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e8_value = world * units_rank * e2e_steps / float(t.item()) / 1e6
+    e2e8_value = timed_host(step_host_u8)
+
+    # self-check outside every timed region: the host API's maps equal the device path's on the same pairs (set 0)
+    step_host()
+    if pg is not None:
+        join_pushes()
+    step_device(2 * S)                  # even step number: parity 0, input set 0 (the un-rolled images)
+    if pg is not None:
+        join_pushes()
+    torch.cuda.synchronize()
+    assert torch.equal(d_out[0, 0].cpu(), h_dl) and torch.equal(d_out[0, 1].cpu(), h_dr), "host and device entry points disagree"
 
     if rank == 0:
         peaks = measured_peaks()
@@ -400,7 +430,7 @@ def run_ours(args, wl):
             }
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, dt, desc = cpu_reference_sample(wl, args.ref_rows, os.cpu_count() or 1)
+            v, dt, desc = cpu_reference_sample(wl, args.ref_rows, os.cpu_count() or 1, args.cost)
             cpu = {**desc, "value": round(v, 3), "unit": UNIT, "seconds": round(dt, 2)}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -418,8 +448,9 @@ def run_ours(args, wl):
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": B * 2 * rows * cols * 4,
                     "d2h_bytes_per_step": B * 2 * rows * cols * elem, "steps": e2e_steps,
-                    "api": "stereo_disparity_pair_f32_host (CV_32FC1 host images, pinned)",
-                    "u8_host_api_value": round(e2e8_value, 1)},
+                    "api": "stereo_disparity_pair_batch_f32_host: one call per step, the step's pairs as pinned CV_32FC1 host "
+                           "images in, int8/int16 host maps out",
+                    "per_pair_calls_value": round(e2e_pp_value, 1), "u8_host_api_value": round(e2e8_value, 1)},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -185,6 +185,16 @@ int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs,
                                         int disparity_range, void* disp_left, void* disp_right,
                                         size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes);
 
+/* The same for CV_32FC1 host images (the type the reference's entry points take, DisparitySSD.cu:150): a batch
+ * of the reference's disparitySSDPair / disparityNCorrPair calls (main.cpp:21-78) in one call.  img_step and
+ * pair_stride are in BYTES.  8-bit-valued images ride the packed kernels with uploads, conversion, compute and
+ * downloads overlapped across pairs; anything else is computed pair by pair on the exact path. */
+int stereo_disparity_pair_batch_f32_host(stereo_ctx* ctx, int cost, int n_pairs,
+                                         const float* left, const float* right, size_t img_step,
+                                         size_t pair_stride, int rows, int cols, int window_rad,
+                                         int disparity_range, void* disp_left, void* disp_right,
+                                         size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes);
+
 /* ---- row-band form for sharding one large image across GPUs (BASELINE config 4) -------------- */
 /* Computes output rows [row_begin, row_end) of the full rows x cols problem.  `ref`/`tgt` point at
  * FULL images (device); only rows within the band's halo are read.  disp_out points at the band's

@@ -295,6 +295,18 @@ static int pipe_bands(const stereo_ctx* ctx, int n_pairs, int rows) {
     return nb < 1 ? 1 : (nb > 8 ? 8 : nb);
 }
 
+// Pairs per work item of the pipeline.  Small images (BASELINE config 5: 1280x720, 64 disparities) ride several
+// pairs per item so that one launch sequence carries up to FMAXJOBS directions, as the device batch entry point
+// does; large images stay one pair (or one band of a pair) per item.
+static int pipe_chunk_pairs(int n_pairs, int nb, int rows, int cols) {
+    if (nb > 1) return 1;
+    const long long px = (long long)rows * cols;
+    long long cp = ((4ll << 20) + px - 1) / px;           // ~4 Mpix of reference image per item
+    if (cp > FMAXJOBS / 2) cp = FMAXJOBS / 2;
+    if (cp > n_pairs / 3) cp = n_pairs / 3;               // keep at least three items in flight
+    return cp < 1 ? 1 : int(cp);
+}
+
 static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
                                 const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
     if (ctx->force_path == STEREO_PATH_EXACT_F32) return PIPE_NOT_APPLICABLE;
@@ -308,6 +320,8 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
     full.disp = OutView{ctx, d_pitch, elem}; full.best = OutView{nullptr, 0, 4};
     const int nb = pipe_bands(ctx, n_pairs, rows);
     const int band_rows = (rows + nb - 1) / nb;
+    const int cp = pipe_chunk_pairs(n_pairs, nb, rows, cols);
+    const int n_items = (n_pairs + cp - 1) / cp;
     size_t scratch = 0;
     for (int d = 0; d < n_dirs; ++d) {
         full.dmin = dirs[d].dmin; full.dmax = dirs[d].dmax;
@@ -315,37 +329,42 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
         if (rc != STEREO_OK) return rc;
         if (!fast_supported(full)) return PIPE_NOT_APPLICABLE;
         Problem band = full; band.row_end = band_rows < rows ? band_rows : rows;
-        const size_t need = size_t(n_dirs) * fast_scratch_bytes(ctx, band);
+        const size_t need = size_t(n_dirs) * cp * fast_scratch_bytes(ctx, band);
         scratch = need > scratch ? need : scratch;
     }
-    int rc = ensure_pipe(ctx, 3 * n_pairs * nb + 4);
+    int rc = ensure_pipe(ctx, 3 * n_items * nb + 4);
     if (rc != STEREO_OK) return rc;
     cudaStream_t s_in = ctx->s_in, s_cmp = ctx->stream, s_out = ctx->s_out;
 
-    const int S = n_pairs < 3 ? n_pairs : 3;            // device slots (ring)
-    const size_t slot_bytes = 2 * align256(in_pitch * rows) + (type == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
+    const int S = n_items < 3 ? n_items : 3;            // device slots (ring), one work item each
+    const size_t pair_bytes = 2 * align256(in_pitch * rows) + (type == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
                               + size_t(n_dirs) * align256(d_pitch * rows);
+    const size_t slot_bytes = size_t(cp) * pair_bytes;
     if (size_t(S) * slot_bytes + 1024 > ctx->io.cap || scratch > ctx->arena.cap) {
         SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
         if (size_t(S) * slot_bytes + 1024 > ctx->io.cap) { rc = ctx->io.reserve(size_t(S) * slot_bytes + 1024); if (rc != STEREO_OK) return rc; }
         if (scratch > ctx->arena.cap) { rc = ctx->arena.reserve(scratch); if (rc != STEREO_OK) return rc; }
     }
     ctx->io.reset();
-    struct Slot { char* l; char* r; uint8_t* l8; uint8_t* r8; char* out[2]; } slot[3] = {};
-    for (int k = 0; k < S; ++k) {
-        slot[k].l = static_cast<char*>(ctx->io.take(in_pitch * rows));
-        slot[k].r = static_cast<char*>(ctx->io.take(in_pitch * rows));
-        if (type == PixType::F32) {
-            slot[k].l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
-            slot[k].r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
-        } else {
-            slot[k].l8 = reinterpret_cast<uint8_t*>(slot[k].l);
-            slot[k].r8 = reinterpret_cast<uint8_t*>(slot[k].r);
+    struct Slot { char* l; char* r; uint8_t* l8; uint8_t* r8; char* out[2]; };
+    constexpr int CPMAX = FMAXJOBS / 2;
+    Slot slot[3][CPMAX] = {};
+    for (int k = 0; k < S; ++k)
+        for (int c = 0; c < cp; ++c) {
+            Slot& sl = slot[k][c];
+            sl.l = static_cast<char*>(ctx->io.take(in_pitch * rows));
+            sl.r = static_cast<char*>(ctx->io.take(in_pitch * rows));
+            if (type == PixType::F32) {
+                sl.l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+                sl.r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+            } else {
+                sl.l8 = reinterpret_cast<uint8_t*>(sl.l);
+                sl.r8 = reinterpret_cast<uint8_t*>(sl.r);
+            }
+            for (int d = 0; d < n_dirs; ++d) sl.out[d] = static_cast<char*>(ctx->io.take(d_pitch * rows));
+            if (!sl.l || !sl.r || !sl.l8 || !sl.r8 || !sl.out[n_dirs - 1]) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
         }
-        for (int d = 0; d < n_dirs; ++d) slot[k].out[d] = static_cast<char*>(ctx->io.take(d_pitch * rows));
-        if (!slot[k].l || !slot[k].r || !slot[k].l8 || !slot[k].r8 || !slot[k].out[n_dirs - 1]) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
-    }
-    auto ev = [&](int pair, int band, int kind) { return ctx->pipe_ev[3 * (pair * nb + band) + kind + 1]; };   // kind: 0 in, 1 cmp, 2 out
+    auto ev = [&](int item, int band, int kind) { return ctx->pipe_ev[3 * (item * nb + band) + kind + 1]; };   // kind: 0 in, 1 cmp, 2 out
 
     begin_call(ctx, s_cmp);
     // copy streams start after whatever the context's stream was doing with these buffers
@@ -355,64 +374,76 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
     if (type == PixType::F32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s_cmp));
     ctx->last_path = STEREO_PATH_FAST_U8;
 
-    for (int i = 0; i < n_pairs; ++i) {
-        const Slot& sl = slot[i % S];
+    for (int w = 0; w < n_items; ++w) {
+        const Slot* sl = slot[w % S];
+        const int i0 = w * cp, np = (n_pairs - i0 < cp) ? n_pairs - i0 : cp;     // pairs i0 .. i0+np-1 ride this item
         int uploaded = 0;
         for (int b = 0; b < nb; ++b) {
             const int rb = b * band_rows, re = (rb + band_rows < rows) ? rb + band_rows : rows;
             if (rb >= re) {           // (rows not divisible: trailing empty band) keep the event chain intact
-                SB_CUDA(cudaEventRecord(ev(i, b, 0), s_in)); SB_CUDA(cudaEventRecord(ev(i, b, 1), s_cmp)); SB_CUDA(cudaEventRecord(ev(i, b, 2), s_out));
+                SB_CUDA(cudaEventRecord(ev(w, b, 0), s_in)); SB_CUDA(cudaEventRecord(ev(w, b, 1), s_cmp)); SB_CUDA(cudaEventRecord(ev(w, b, 2), s_out));
                 continue;
             }
             // ---- upload the rows this band adds: window halo R, the +1 row of the SSD flat-index wrap, and the
             //      operand rows the FRPS-row pipeline stages round up to
             const int up_hi = (b == nb - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
-            if (b == 0 && i >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(i - S, nb - 1, 1), 0));   // slot inputs free again
-            if (up_hi > uploaded) {
-                const int nr = up_hi - uploaded;
-                SB_CUDA(cudaMemcpy2DAsync(sl.l + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(in[i].left) + size_t(uploaded) * in[i].left_step,
-                                          in[i].left_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
-                SB_CUDA(cudaMemcpy2DAsync(sl.r + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(in[i].right) + size_t(uploaded) * in[i].right_step,
-                                          in[i].right_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
-            }
-            SB_CUDA(cudaEventRecord(ev(i, b, 0), s_in));
-            // ---- compute
-            SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(i, b, 0), 0));
-            if (b == 0 && i >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(i - S, nb - 1, 2), 0));  // slot outputs downloaded
-            if (type == PixType::F32 && up_hi > uploaded) {
-                const int nr = up_hi - uploaded;
-                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8));
-                classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl.l + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
-                                                             sl.l8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
-                classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl.r + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
-                                                             sl.r8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
-                ctx->last_launches += 2;
-            }
-            if (up_hi > uploaded) uploaded = up_hi;
-            {
-                Problem pd[2];
-                for (int d = 0; d < n_dirs; ++d) {
-                    Problem& p = pd[d];
-                    p = full;
-                    p.row_begin = rb; p.row_end = re;
-                    p.dmin = dirs[d].dmin; p.dmax = dirs[d].dmax;
-                    p.ref = ImageView{dirs[d].swap ? sl.r8 : sl.l8, u8_pitch, PixType::U8};
-                    p.tgt = ImageView{dirs[d].swap ? sl.l8 : sl.r8, u8_pitch, PixType::U8};
-                    p.disp = OutView{sl.out[d] + size_t(rb) * d_pitch, d_pitch, elem};
+            const int nr = up_hi - uploaded;
+            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(w - S, nb - 1, 1), 0));   // slot inputs free again
+            if (nr > 0)
+                for (int c = 0; c < np; ++c) {
+                    const HostPairIn& hp = in[i0 + c];
+                    SB_CUDA(cudaMemcpy2DAsync(sl[c].l + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(hp.left) + size_t(uploaded) * hp.left_step,
+                                              hp.left_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
+                    SB_CUDA(cudaMemcpy2DAsync(sl[c].r + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(hp.right) + size_t(uploaded) * hp.right_step,
+                                              hp.right_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
                 }
-                const bool together = n_dirs == 2 && fast_batchable(pd[0], pd[1]);
-                ctx->arena.reset();
-                rc = together ? run_fast_batch(ctx, pd, 2, s_cmp) : run_fast(ctx, pd[0], s_cmp);
-                if (rc == STEREO_OK && n_dirs == 2 && !together) { ctx->arena.reset(); rc = run_fast(ctx, pd[1], s_cmp); }
+            SB_CUDA(cudaEventRecord(ev(w, b, 0), s_in));
+            // ---- compute
+            SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w, b, 0), 0));
+            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w - S, nb - 1, 2), 0));  // slot outputs downloaded
+            if (type == PixType::F32 && nr > 0) {
+                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8));
+                for (int c = 0; c < np; ++c) {
+                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].l + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
+                                                                 sl[c].l8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
+                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].r + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
+                                                                 sl[c].r8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
+                    ctx->last_launches += 2;
+                }
+            }
+            if (nr > 0) uploaded = up_hi;
+            {
+                // direction-major: jobs with the same range sign are neighbours (they share offsets and pitches)
+                Problem pd[FMAXJOBS];
+                for (int d = 0; d < n_dirs; ++d)
+                    for (int c = 0; c < np; ++c) {
+                        Problem& p = pd[d * np + c];
+                        p = full;
+                        p.row_begin = rb; p.row_end = re;
+                        p.dmin = dirs[d].dmin; p.dmax = dirs[d].dmax;
+                        p.ref = ImageView{dirs[d].swap ? sl[c].r8 : sl[c].l8, u8_pitch, PixType::U8};
+                        p.tgt = ImageView{dirs[d].swap ? sl[c].l8 : sl[c].r8, u8_pitch, PixType::U8};
+                        p.disp = OutView{sl[c].out[d] + size_t(rb) * d_pitch, d_pitch, elem};
+                    }
+                const int nj = n_dirs * np;
+                bool together = true;
+                for (int k = 1; k < nj; ++k) together = together && fast_batchable(pd[0], pd[k]);
+                if (together) {
+                    ctx->arena.reset();
+                    rc = run_fast_batch(ctx, pd, nj, s_cmp);
+                } else {
+                    for (int k = 0; k < nj && rc == STEREO_OK; ++k) { ctx->arena.reset(); rc = run_fast(ctx, pd[k], s_cmp); }
+                }
                 if (rc != STEREO_OK) return rc;
             }
-            SB_CUDA(cudaEventRecord(ev(i, b, 1), s_cmp));
+            SB_CUDA(cudaEventRecord(ev(w, b, 1), s_cmp));
             // ---- download
-            SB_CUDA(cudaStreamWaitEvent(s_out, ev(i, b, 1), 0));
-            for (int d = 0; d < n_dirs; ++d)
-                SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(dirs[d].out[i]) + size_t(rb) * disp_step, disp_step, sl.out[d] + size_t(rb) * d_pitch, d_pitch,
-                                          size_t(cols) * elem, re - rb, cudaMemcpyDeviceToHost, s_out));
-            SB_CUDA(cudaEventRecord(ev(i, b, 2), s_out));
+            SB_CUDA(cudaStreamWaitEvent(s_out, ev(w, b, 1), 0));
+            for (int c = 0; c < np; ++c)
+                for (int d = 0; d < n_dirs; ++d)
+                    SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(dirs[d].out[i0 + c]) + size_t(rb) * disp_step, disp_step, sl[c].out[d] + size_t(rb) * d_pitch, d_pitch,
+                                              size_t(cols) * elem, re - rb, cudaMemcpyDeviceToHost, s_out));
+            SB_CUDA(cudaEventRecord(ev(w, b, 2), s_out));
         }
     }
     if (type == PixType::F32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
@@ -968,18 +999,21 @@ int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs
     return rc;
 }
 
-int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
-                                        const uint8_t* right, size_t img_step, size_t pair_stride, int rows, int cols,
-                                        int window_rad, int disparity_range, void* disp_left, void* disp_right,
-                                        size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes) {
+// Host batches, both pixel types.  Strides are in bytes.
+static int pair_batch_host(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const void* left_v, const void* right_v,
+                           size_t img_step, size_t pair_stride, int rows, int cols, int window_rad, int disparity_range,
+                           void* disp_left, void* disp_right, size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes) {
     int rc = check_ctx(ctx);
     if (rc != STEREO_OK) return rc;
+    const char* left = static_cast<const char*>(left_v);
+    const char* right = static_cast<const char*>(right_v);
+    const size_t px = type == PixType::F32 ? 4 : 1;
     if (n_pairs <= 0) { set_error("n_pairs must be positive"); return STEREO_ERR_INVALID_ARG; }
     if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
-    if (rows <= 0 || cols <= 0 || img_step < size_t(cols) || disp_step < size_t(cols) * disp_elem_bytes) { set_error("bad size/step"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768 || img_step < size_t(cols) * px || disp_step < size_t(cols) * disp_elem_bytes) { set_error("bad size/step"); return STEREO_ERR_INVALID_ARG; }
     if (disp_elem_bytes != 1 && disp_elem_bytes != 2 && disp_elem_bytes != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
     if (disparity_range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
-    {   // pipelined: pair i+1 uploads while pair i computes and pair i-1 downloads (3 device slots)
+    {   // pipelined: item i+1 uploads while item i computes and item i-1 downloads (3 device slots)
         std::vector<HostPairIn> in(n_pairs);
         std::vector<void*> outs_l(n_pairs), outs_r(n_pairs);
         for (int i = 0; i < n_pairs; ++i) {
@@ -988,40 +1022,37 @@ int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs, 
             outs_r[i] = static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride;
         }
         const HostDir dirs[2] = {{false, -disparity_range, 0, outs_l.data()}, {true, 0, disparity_range, outs_r.data()}};
-        rc = pairs_host_pipelined(ctx, cost, PixType::U8, n_pairs, in.data(), dirs, 2, rows, cols, window_rad, disp_step, disp_elem_bytes);
+        rc = pairs_host_pipelined(ctx, cost, type, n_pairs, in.data(), dirs, 2, rows, cols, window_rad, disp_step, disp_elem_bytes);
         if (rc <= STEREO_OK) return rc;
     }
-    cudaStream_t st = ctx->stream;
-    // Sequential fallback (parameters the packed kernels do not cover): stage the whole batch on the device.
-    const size_t in_pitch = align256(cols), d_pitch = align256(size_t(cols) * disp_elem_bytes);
-    const size_t in_pair = in_pitch * rows, d_pair = d_pitch * rows;
-    const size_t need = size_t(n_pairs) * (2 * in_pair + 2 * d_pair) + 4096;
-    if (need > ctx->io.cap) {
-        SB_CUDA(cudaStreamSynchronize(st));
-        rc = ctx->io.reserve(need);
+    // Sequential fallback (parameters the packed kernels do not cover, or float images that are not 8-bit):
+    // pair by pair through the single-pair host path (which picks the exact kernels where needed).
+    int launches = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        rc = pair_host(ctx, cost, type, left + size_t(i) * pair_stride, img_step, right + size_t(i) * pair_stride, img_step, rows, cols,
+                       window_rad, disparity_range, static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride,
+                       static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, disp_elem_bytes);
         if (rc != STEREO_OK) return rc;
+        launches += ctx->last_launches;
     }
-    ctx->io.reset();
-    uint8_t* d_l = static_cast<uint8_t*>(ctx->io.take(size_t(n_pairs) * in_pair));
-    uint8_t* d_r = static_cast<uint8_t*>(ctx->io.take(size_t(n_pairs) * in_pair));
-    char* d_dl = static_cast<char*>(ctx->io.take(size_t(n_pairs) * d_pair));
-    char* d_dr = static_cast<char*>(ctx->io.take(size_t(n_pairs) * d_pair));
-    begin_call(ctx, st);
-    for (int i = 0; i < n_pairs && rc == STEREO_OK; ++i) {
-        SB_CUDA(cudaMemcpy2DAsync(d_l + i * in_pair, in_pitch, left + size_t(i) * pair_stride, img_step, cols, rows, cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemcpy2DAsync(d_r + i * in_pair, in_pitch, right + size_t(i) * pair_stride, img_step, cols, rows, cudaMemcpyHostToDevice, st));
-        rc = pair_device(ctx, cost, PixType::U8, d_l + i * in_pair, in_pitch, d_r + i * in_pair, in_pitch, rows, cols,
-                         window_rad, disparity_range, d_dl + i * d_pair, d_dr + i * d_pair, d_pitch, disp_elem_bytes, st);
-        if (rc != STEREO_OK) break;
-        SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(disp_left) + size_t(i) * disp_pair_stride, disp_step, d_dl + i * d_pair, d_pitch,
-                                  size_t(cols) * disp_elem_bytes, rows, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(disp_right) + size_t(i) * disp_pair_stride, disp_step, d_dr + i * d_pair, d_pitch,
-                                  size_t(cols) * disp_elem_bytes, rows, cudaMemcpyDeviceToHost, st));
-    }
-    end_call(ctx, st);
-    if (rc != STEREO_OK) return rc;
-    SB_CUDA(cudaStreamSynchronize(st));
+    ctx->last_launches = launches;
     return STEREO_OK;
+}
+
+int stereo_disparity_pair_batch_u8_host(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
+                                        const uint8_t* right, size_t img_step, size_t pair_stride, int rows, int cols,
+                                        int window_rad, int disparity_range, void* disp_left, void* disp_right,
+                                        size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes) {
+    return pair_batch_host(ctx, cost, PixType::U8, n_pairs, left, right, img_step, pair_stride, rows, cols, window_rad,
+                           disparity_range, disp_left, disp_right, disp_step, disp_pair_stride, disp_elem_bytes);
+}
+
+int stereo_disparity_pair_batch_f32_host(stereo_ctx* ctx, int cost, int n_pairs, const float* left,
+                                         const float* right, size_t img_step, size_t pair_stride, int rows, int cols,
+                                         int window_rad, int disparity_range, void* disp_left, void* disp_right,
+                                         size_t disp_step, size_t disp_pair_stride, int disp_elem_bytes) {
+    return pair_batch_host(ctx, cost, PixType::F32, n_pairs, left, right, img_step, pair_stride, rows, cols, window_rad,
+                           disparity_range, disp_left, disp_right, disp_step, disp_pair_stride, disp_elem_bytes);
 }
 
 } // extern "C"

@@ -139,19 +139,27 @@ class Context:
 
     def disparity_pair_batch(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int,
                              disparity_range: int, dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
-        """left/right: uint8 arrays of shape (n_pairs, rows, cols)."""
-        left = np.ascontiguousarray(left, np.uint8)
-        right = np.ascontiguousarray(right, np.uint8)
+        """left/right: arrays of shape (n_pairs, rows, cols), both uint8 or both float32 (CV_32FC1 images, the
+        type the reference's entry points take): a batch of ``disparitySSDPair`` / ``disparityNCorrPair`` calls."""
+        left, right = np.asarray(left), np.asarray(right)
+        if left.dtype == np.float32 and right.dtype == np.float32:
+            kind, name = np.float32, "stereo_disparity_pair_batch_f32_host"
+        elif left.dtype == np.uint8 and right.dtype == np.uint8:
+            kind, name = np.uint8, "stereo_disparity_pair_batch_u8_host"
+        else:
+            raise TypeError("batch images must both be float32 (CV_32FC1) or both uint8")
+        left = np.ascontiguousarray(left, kind)
+        right = np.ascontiguousarray(right, kind)
         if left.ndim != 3 or left.shape != right.shape:
-            raise ValueError("batch inputs must be (n, rows, cols) uint8 arrays of equal shape")
+            raise ValueError("batch inputs must be (n, rows, cols) arrays of equal shape")
         n, rows, cols = left.shape
         dt = np.dtype(dtype)
         dl = np.empty((n, rows, cols), dt)
         dr = np.empty((n, rows, cols), dt)
-        st = _capi.lib().stereo_disparity_pair_batch_u8_host(
+        st = getattr(_capi.lib(), name)(
             self._h, int(cost), n, left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], rows, cols,
             int(window_rad), int(disparity_range), dl.ctypes.data, dr.ctypes.data, dl.strides[1], dl.strides[0], _ELEM[dt])
-        _check(st, "stereo_disparity_pair_batch_u8_host")
+        _check(st, name)
         return dl, dr
 
 

@@ -8,9 +8,11 @@ from .oracle import (  # noqa: F401
     OracleError,
     build,
     have_ref,
+    have_ref_ncc,
     narrow_i8,
     ncorr,
     ncorr_fast,
+    ref_ncorr,
     ref_ssd,
     set_num_threads,
     num_threads,

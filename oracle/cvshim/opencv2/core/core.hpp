@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY (oracle/): a minimal stand-in for the parts of OpenCV's cv::Mat API that
-// /root/reference/ProblemSets/ps2_cpp/lib/DisparitySSD.cpp touches, so that the reference's own
-// translation unit can be compiled *in place, unmodified* into oracle/_ref/ (OpenCV C++ is not
-// installed in this image).  Nothing under oracle/ is linked into, or called by, the product.
+// /root/reference/ProblemSets/ps2_cpp/lib/DisparitySSD.cpp and lib/DisparityNCorr.cpp touch, so that
+// the reference's own translation units can be compiled *in place, unmodified* into oracle/_ref/
+// (OpenCV C++ is not installed in this image).  Nothing under oracle/ is linked into, or called by, the product.
 //
 // Behavioural notes that matter for parity:
 //  * Mat::at<T>(r, c) is unchecked, exactly like release-mode OpenCV: data + r*step + c*sizeof(T).
@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <stdexcept>
 #include <string>
 
 #define CV_8U 0
@@ -27,6 +28,15 @@
 namespace cv {
 
 enum BorderTypes { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1 };
+
+struct Point { int x = 0, y = 0; Point() = default; Point(int x_, int y_) : x(x_), y(y_) {} };
+// Like cv::Rect_<int>: any integral argument mix narrows to int (DisparityNCorr.cpp:46,52 pass size_t).
+struct Rect {
+    int x = 0, y = 0, width = 0, height = 0;
+    Rect() = default;
+    template <typename A, typename B, typename C, typename D>
+    Rect(A x_, B y_, C w_, D h_) : x(int(x_)), y(int(y_)), width(int(w_)), height(int(h_)) {}
+};
 
 class Mat {
 public:
@@ -66,6 +76,23 @@ public:
     }
     template <typename T> const T& at(int r, int c) const {
         return *reinterpret_cast<const T*>(data + ptrdiff_t(r) * ptrdiff_t(step) + ptrdiff_t(c) * ptrdiff_t(sizeof(T)));
+    }
+
+    // Region of interest: a header onto the same buffer (DisparityNCorr.cpp:47,53).  OpenCV asserts that the
+    // rectangle lies inside the matrix and throws otherwise; the shim does the same.
+    Mat operator()(const Rect& r) const {
+        if (r.x < 0 || r.y < 0 || r.width < 0 || r.height < 0 || r.x + r.width > cols || r.y + r.height > rows)
+            throw std::out_of_range("cv::Mat::operator()(Rect): roi outside the matrix");
+        Mat m;
+        m.rows = r.height; m.cols = r.width; m.step = step; m._type = _type; m._buf = _buf;
+        m.data = data + size_t(r.y) * step + size_t(r.x) * elemSize();
+        return m;
+    }
+    Mat clone() const {
+        Mat m(rows, cols, _type);
+        const size_t es = elemSize();
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data + size_t(r) * m.step, data + size_t(r) * step, size_t(cols) * es);
+        return m;
     }
 
     static constexpr size_t GUARD = 1 << 16;   // zero bytes either side of the pixel buffer

@@ -4,6 +4,9 @@
 * ``_ref/libref_ssd.so``   — the reference's own ``serial::disparitySSD``
   (``/root/reference/ProblemSets/ps2_cpp/lib/DisparitySSD.cpp``) compiled in place by
   ``oracle/Makefile``; exists wherever it was built (it travels to the GPU box as a binary).
+* ``_ref/libref_ncc.so``   — the reference's own ``serial::disparityNCorr``
+  (``lib/DisparityNCorr.cpp``) compiled in place likewise; its ``cv::matchTemplate`` / ``cv::minMaxLoc``
+  are the shim's restatement of OpenCV's TM_CCORR_NORMED arithmetic (``cvshim/opencv2/imgproc/imgproc.hpp``).
 """
 from __future__ import annotations
 
@@ -18,6 +21,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = _HERE / "libstereo_oracle.so"
 _REF = _HERE / "_ref" / "libref_ssd.so"
 _REF_O0 = _HERE / "_ref" / "libref_ssd_O0.so"
+_REF_NCC = _HERE / "_ref" / "libref_ncc.so"
 
 
 class OracleError(RuntimeError):
@@ -30,7 +34,7 @@ def build(force: bool = False) -> None:
     if need:
         subprocess.run(["make", "-C", str(_HERE), "libstereo_oracle.so"], check=True, capture_output=True)
     ref_src = Path("/root/reference/ProblemSets/ps2_cpp/lib/DisparitySSD.cpp")
-    if ref_src.exists() and (force or not _REF.exists()):
+    if ref_src.exists() and (force or not _REF.exists() or not _REF_NCC.exists()):
         subprocess.run(["make", "-C", str(_HERE), "ref"], check=True, capture_output=True)
 
 
@@ -57,6 +61,10 @@ def _load():
 
 def have_ref() -> bool:
     return _REF.exists()
+
+
+def have_ref_ncc() -> bool:
+    return _REF_NCC.exists()
 
 
 def _f32(a):
@@ -138,4 +146,28 @@ def ref_ssd(ref, tgt, window_rad, min_disp, max_disp, opt: str = "O2"):
                                       out.ctypes.data_as(C.POINTER(C.c_int8)))
     if st != 0:
         raise OracleError(f"ref_serial_disparity_ssd failed with status {st}")
+    return out
+
+
+def ref_ncorr(ref, tgt, window_rad, min_disp, max_disp):
+    """The reference's own compiled serial::disparityNCorr (DisparityNCorr.cpp:12-71) over the shim's
+    matchTemplate; returns int8 (CV_8SC1) like the reference.  O(rows*cols*D*w^2): small cases only."""
+    if not _REF_NCC.exists():
+        raise OracleError(f"{_REF_NCC} not built (reference sources absent?)")
+    lib = _ref.get("ncc")
+    if lib is None:
+        lib = C.CDLL(str(_REF_NCC))
+        lib.ref_serial_disparity_ncorr.restype = C.c_int
+        lib.ref_serial_disparity_ncorr.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int8)]
+        _ref["ncc"] = lib
+    ref, tgt = _f32(ref), _f32(tgt)
+    if ref.shape != tgt.shape:
+        raise OracleError("shape mismatch")
+    rows, cols = ref.shape
+    out = np.empty((rows, cols), np.int8)
+    st = lib.ref_serial_disparity_ncorr(_fp(ref), _fp(tgt), rows, cols, int(window_rad), int(min_disp), int(max_disp),
+                                        out.ctypes.data_as(C.POINTER(C.c_int8)))
+    if st != 0:
+        raise OracleError(f"ref_serial_disparity_ncorr failed with status {st}")
     return out

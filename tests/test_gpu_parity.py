@@ -301,6 +301,44 @@ def test_pipelined_batch_reuses_device_slots(ctx, bands):
         assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 4, 0, 23))), i
 
 
+@pytest.mark.parametrize("n,kind", [(13, np.float32), (13, np.uint8), (6, np.float32), (2, np.float32)])
+def test_host_batch_chunked_items_vs_oracle(ctx, n, kind):
+    """Host batches of small images ride several pairs per pipeline item (13 pairs -> items of 4+4+4+1 pairs, 8
+    directions per launch sequence; 6 pairs -> items of 2), CV_32FC1 and uint8 inputs, SSD and NCC."""
+    rows, cols, R, rng = 37, 130, 3, 21
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(rows, cols, 16, 5100 + 3 * i + n)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls).astype(kind), np.stack(Rs).astype(kind)
+    for cost in (sb.COST_SSD, sb.COST_NCORR):
+        bl, br = ctx.disparity_pair_batch(cost, Ls, Rs, R, rng, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_FAST_U8
+        for i in range(n):
+            Lf, Rf = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+            if cost == sb.COST_SSD:
+                assert np.array_equal(bl[i], oracle.ssd_fast(Lf, Rf, R, -rng, 0)), f"pair {i} L->R"
+                assert np.array_equal(br[i], oracle.ssd_fast(Rf, Lf, R, 0, rng)), f"pair {i} R->L"
+            else:
+                assert float(np.mean(bl[i] == oracle.ncorr_fast(Lf, Rf, R, -rng, 0))) >= NCC_DISP_AGREE
+                assert float(np.mean(br[i] == oracle.ncorr_fast(Rf, Lf, R, 0, rng))) >= NCC_DISP_AGREE
+
+
+def test_host_batch_f32_non_8bit_pair_falls_back_to_exact(ctx):
+    # one noisy pair in a CV_32FC1 batch: the whole batch is redone pair by pair, the noisy one on the exact kernels
+    n, rows, cols, R, rng = 5, 30, 110, 2, 17
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(rows, cols, 12, 6100 + i)
+        Ls.append(L.astype(np.float32)), Rs.append(Rt.astype(np.float32))
+    Ls[3] = synth.noisy_variant(Ls[3].astype(np.uint8), 5)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, R, rng, dtype=np.int8)
+    for i in range(n):
+        assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(Ls[i], Rs[i], R, -rng, 0))), i
+        assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rs[i], Ls[i], R, 0, rng))), i
+
+
 def test_pipelined_host_non_8bit_falls_back_to_exact(ctx):
     # the 8-bit flag is only known after the pipelined pass: a noisy image must be redone on the exact path
     L, Rt, _ = synth.make_pair(60, 200, 30, 31)

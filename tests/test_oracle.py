@@ -51,6 +51,50 @@ def test_ssd_restatement_matches_compiled_reference_random(seed):
     assert np.array_equal(lit, oracle.ssd_fast(L, Rt, R, a, b))
 
 
+@pytest.mark.skipif(not oracle.have_ref_ncc(), reason="oracle/_ref/libref_ncc.so not built (reference sources absent)")
+@pytest.mark.parametrize("seed", range(8))
+def test_ncc_restatement_matches_compiled_reference_random(seed):
+    """The reference's own DisparityNCorr.cpp loop (compiled in place over the shim's matchTemplate) against the
+    C restatement: search-rectangle clamping, result width, the `- (result.cols - 1)` rule of :67 for searches
+    that end at the pixel, mixed-sign ranges, the char store."""
+    rng = np.random.default_rng(50 + seed)
+    rows, cols = int(rng.integers(5, 20)), int(rng.integers(12, 60))
+    R = int(rng.integers(0, 5))
+    a, b = [(-14, 0), (0, 14), (-9, 0), (0, 5), (-6, 7), (-3, 0), (0, 21), (-30, 0)][seed]
+    L, Rt, _ = synth.make_pair(rows, cols, 8, 300 + seed)
+    if seed % 3 == 1:
+        L, Rt = synth.noisy_variant(L, seed), synth.contrast_variant(Rt)
+    elif seed % 3 == 2:
+        L = L.astype(np.float32); L[2:9, 5:30] = 0          # zero-energy templates and windows: score 0, first candidate
+        Rt = Rt.astype(np.float32); Rt[0:6, 10:40] = 0
+    else:
+        L, Rt = L.astype(np.float32), Rt.astype(np.float32)
+    ref = oracle.ref_ncorr(L, Rt, R, a, b)
+    lit = oracle.ncorr(L, Rt, R, a, b)
+    assert np.array_equal(ref, oracle.narrow_i8(lit))
+
+
+@pytest.mark.skipif(not oracle.have_ref_ncc(), reason="oracle/_ref/libref_ncc.so not built")
+@pytest.mark.parametrize("name,R,dmin,dmax", _cases("ncc"))
+def test_ncc_compiled_reference_matches_opencv_golden(golden, name, R, dmin, dmax):
+    """Closes the loop: reference loop + shim arithmetic == the fixtures produced by EXECUTED OpenCV
+    (cv2.matchTemplate / cv2.minMaxLoc inside a mirror of the same loop, tests/golden/make_golden.py)."""
+    g = golden.get("ncc", name)
+    if g["left"].size * (dmax - dmin + 1) > 3_000_000:
+        pytest.skip("too large for the O(w^2) reference loop")
+    L, Rt = g["left"].astype(np.float32), g["right"].astype(np.float32)
+    ref = oracle.ref_ncorr(L, Rt, R, dmin, dmax)
+    agree = float(np.mean(ref == oracle.narrow_i8(g["disp"])))
+    assert agree >= 0.999, agree      # float32 DFT numerator (OpenCV) vs exactly rounded sum: near-ties may flip
+
+
+@pytest.mark.skipif(not oracle.have_ref_ncc(), reason="oracle/_ref/libref_ncc.so not built")
+def test_ncc_compiled_reference_throws_where_restatement_rejects():
+    img = np.ones((8, 16), np.float32)
+    with pytest.raises(oracle.OracleError):
+        oracle.ref_ncorr(img, img, 1, 3, 5)
+
+
 def test_ssd_known_answer_shift():
     # right(x) = left(x + k)  =>  interior L->R disparity = -k   (SURVEY.md §8c KAT)
     rng = np.random.default_rng(3)
