@@ -251,10 +251,14 @@ def run_ours(args, wl):
     sp = C.c_void_p(stream.cuda_stream)
     gather = args.gather if world > 1 else "none"
     pg, gathered, tickets = None, None, {}
+    gather_note = ""
     if gather == "p2p":
         # every rank's buffer: [parity][rank][direction][pair][rows][cols]; filled by copy-engine pushes
-        pg = sharding.PeerGather(ctx, 2 * world * map_bytes)
-    elif gather == "nccl":
+        try:
+            pg = sharding.PeerGather(ctx, 2 * world * map_bytes)
+        except sharding.PeerGatherUnavailable as e:       # raised on every rank together
+            gather, gather_note = "nccl", f" (peer buffers unavailable: {e})"
+    if gather == "nccl":
         gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev)
 
     def step_device(k):
@@ -441,7 +445,7 @@ def run_ours(args, wl):
                        "sharding": "by pair" + ({"p2p": ", every rank's maps pushed into every rank's gather buffer by the copy engines "
                                                         "over NVLink (stereo_peer_push), overlapping the next step's kernels; "
                                                         "all pushes joined inside the timed region",
-                                                 "nccl": ", NCCL all_gather of maps inside the step", "none": ""}[gather]),
+                                                 "nccl": ", NCCL all_gather of maps inside the step" + gather_note, "none": ""}[gather]),
                        "l2": f"inputs rotate over {S} sets = {S * set_bytes >> 20} MiB > L2 ({l2_bytes >> 20} MiB); "
                              f"one event pair around all timed steps",
                        "out_dtype": str(elem_dtype).replace("torch.", "")},

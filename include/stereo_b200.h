@@ -109,6 +109,14 @@ int stereo_ctx_force_path(stereo_ctx* ctx, int path);
  * (DisparitySSD.cu:171-206). */
 int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands);
 
+/* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the problem allows
+ * it (SSD, window_rad <= 5, disparity_range + 1 a multiple of 128) — the reference's disparitySSDPair always wants
+ * both (main.cpp:21-48) and SSD_LR(x, d) and SSD_RL(x + d, -d) are the same window sum.  Results are identical
+ * either way; on (the default) is faster.  0 switches back to one cost volume per direction. */
+int stereo_ctx_set_fuse_pairs(stereo_ctx* ctx, int on);
+/* Image pairs of the last call whose two maps came out of one cost volume. */
+int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx);
+
 /* ---- single direction, HOST buffers (the drop-in form) ------------------------------------ */
 /*
  * One disparity map for reference image `ref` searched in `tgt` over [min_disp, max_disp].

@@ -35,6 +35,8 @@ SIGNATURES = {
     "stereo_ctx_last_hot_jobs": (_i, [_vp]),
     "stereo_ctx_force_path": (_i, [_vp, _i]),
     "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
+    "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
+    "stereo_ctx_last_fused_pairs": (_i, [_vp]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),
     "stereo_disparity_f32_host": (_i, _SINGLE_HOST),
     "stereo_disparity_u8_host": (_i, _SINGLE_HOST),

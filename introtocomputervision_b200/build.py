@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = CSRC / "_build"
 LIB = PKG / "libstereo_b200.so"
-FAST_PARTS = 16
+FAST_PARTS = 19          # 16 cost x radius x strips-per-warp parts + 3 fused pair kernel parts
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -94,12 +94,14 @@ struct stereo_ctx {
     float last_ms = -1.f;
     int force_path = 0;
     int pipe_bands = 0;       // 0 = automatic
+    int fuse_pairs = 1;       // both maps of a pair from one cost volume where the problem allows it
     // device time of the hot kernels only (fast_*_kernel), per direction, for the roofline report
     static constexpr int HOT_EVENTS = 16;
     cudaEvent_t hot0[HOT_EVENTS] = {}, hot1[HOT_EVENTS] = {};
     int hot_used = 0;          // event pairs recorded by the last call
     int hot_total = 0;         // hot-kernel launches of the last call (may exceed HOT_EVENTS)
     int hot_jobs = 0;          // directions (jobs) covered by the measured hot launches
+    int fused_pairs_done = 0;  // image pairs of the last call whose two maps came out of one cost volume
     // peer gather (stereo_peer_*): copy-engine pushes of finished maps into other ranks' buffers over NVLink
     static constexpr int PEER_STREAMS = 2, PEER_TICKETS = 64;
     cudaStream_t s_peer[PEER_STREAMS] = {};

@@ -46,11 +46,19 @@ __global__ void __launch_bounds__(256) prep_lp_kernel(const __grid_constant__ Fa
     const int y = g.base_y + j;
     const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
     const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+    // Fused pair launches: padded columns past the end of the row (the windows of the partner direction's candidates
+    // centred in the right padding, DisparitySSD.cpp:39-40,50) alias the next padded row, exactly as in the
+    // extended TARGET image of an unfused launch (bext).  The direction's own pixels never read those columns.
+    const bool ext = g.npairs > 0 && p4 + 3 >= g.cols + 2 * g.R;
     int v[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int col = clampi(p4 + t - g.R, 0, g.cols - 1);
-        const int lnew = rnew[col], lold = rold[col];
+        int lnew = rnew[col], lold = rold[col];
+        if (ext) {
+            lnew = bext(A, step, g.rows, g.cols, g.R, y + g.R, p4 + t + g.R, g.ar0, g.ar1);
+            lold = bext(A, step, g.rows, g.cols, g.R, y - g.R - 1, p4 + t + g.R, g.ar0, g.ar1);
+        }
         // SSD: (-l_new, +l_old) so the running sums hold -C; NCC: (+l_new, -l_old), sums hold +C
         const int a_new = g.cost == STEREO_COST_SSD ? -lnew : lnew, a_old = g.cost == STEREO_COST_SSD ? lold : -lold;
         v[t] = int(uint32_t(uint16_t(int16_t(a_new))) | (uint32_t(uint16_t(int16_t(a_old))) << 16));
@@ -66,7 +74,7 @@ __global__ void __launch_bounds__(256) prep_rq_kernel(const __grid_constant__ Fa
     uint32_t* __restrict__ RQ = job.RQ;
     const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int jp = blockIdx.y;
-    if (q4 >= g.rq_pitch) return;
+    if (q4 >= g.rq_pitch || !RQ) return;
     const int ye = g.base_y + 2 * jp;
     uint32_t v[4];
 #pragma unroll
@@ -201,7 +209,7 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
         for (int i = -R; i <= R; ++i) { const int b = load(y + i); v += b * b; }
     }
     const int q = x + delta;                               // RQ column
-    const bool rq_ok = t < TS && q < g.rq_pitch;           // q >= 0 by construction
+    const bool rq_ok = t < TS && q < g.rq_pitch && RQ != nullptr;   // q >= 0 by construction; fused partner jobs have no RQ
     // horizontal stage: thread -> (row hr of the group, 4 centres from column c4)
     const int hr = t >> 6, c4 = (t & 63) * 4;
     const int q2 = x0 + c4;
@@ -499,6 +507,18 @@ static inline bool fast_batchable(const Problem& a, const Problem& b) {
            a.tgt.type == PixType::U8 && b.tgt.type == PixType::U8;
 }
 
+// A left-referenced and a right-referenced problem of the SAME image pair whose maps can come out of one cost
+// volume (fused pair launch): SSD, R <= 5 (masking through the keys alone), mirrored ranges [-r, 0] / [0, r] with
+// r + 1 a multiple of 128 (whole disparity groups, so the partner's groups are this direction's groups reversed).
+static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
+    static const bool off = [] { const char* e = getenv("STEREO_FUSE_PAIRS"); return e && atoi(e) == 0; }();
+    if (off || !fast_batchable(a, b)) return false;
+    const int range = -a.dmin;
+    return a.cost == STEREO_COST_SSD && a.R <= FFREE_MASK_R && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
+           (range + 1) % FGROUP == 0 && a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step &&
+           a.tgt.step == b.ref.step;
+}
+
 // Strips per warp: 2 for searches of at most 64 candidates (a warp then covers 2 x 24 pixels x 64 disparities
 // instead of leaving half its lanes idle).  STEREO_FAST_HS=1 forces the single-strip kernels (debug knob).
 static inline int fast_pick_hs(int D) {
@@ -508,18 +528,22 @@ static inline int fast_pick_hs(int D) {
 }
 
 static inline size_t fast_stage_bytes(const FastGeom& g) {
-    return (size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w) * 4;
+    return (size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w + size_t(FRPS) * g.elw) * 4;
 }
 
 // Geometry of a launch over `n` batchable problems; fills the per-job offsets of `jobs` (pointers are the
 // caller's business).
-static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs) {
+// `fused_pairs` > 0: a fused pair launch over n = 2*fused_pairs problems, left-referenced directions first; the hot
+// kernel walks the first half only and produces the partners' partial keys on the way.
+static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs, int fused_pairs = 0) {
     const Problem& p = ps[0];
     g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.cost = p.cost;
     g.D = p.dmax - p.dmin + 1;
     g.rb = p.row_begin; g.re = p.row_end; g.nrows = g.re - g.rb;
     g.ar0 = p.avail_begin; g.ar1 = p.avail_end;
     g.njobs = n;
+    g.npairs = fused_pairs;
+    g.elw = 0;
     g.K = FK_DEFAULT;
     g.nw = FWARPS;
     g.hs = fast_pick_hs(g.D);
@@ -533,13 +557,15 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         g.lpw = round_up(tile_px + 2 * p.R, 4);
         g.rqw = round_up(tile_px + 2 * p.R + g.dg * g.gc + FM, 4);
         g.e2w = round_up(tile_px + g.dg * g.gc + FM, 4);
-        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16) / fast_stage_bytes(g));
+        g.elw = fused_pairs > 0 ? tile_px : 0;
+        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16 - (fused_pairs > 0 ? FWARPS * 128 : 0)) / fast_stage_bytes(g));
         if (g.nst > FNST_MAX) g.nst = FNST_MAX;
         if (g.nst >= 4 || g.hs == 1) break;
         g.hs = 1;                                  // tile rows too wide for a useful pipeline: single-strip kernels
     }
     const int tile_px = g.spc * g.K;
-    g.nstrips = (p.cols + g.K - 1) / g.K;
+    // fused: the strips also cover the R columns of right padding the partner direction may centre a window on
+    g.nstrips = (p.cols + (fused_pairs > 0 ? p.R : 0) + g.K - 1) / g.K;
     g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
     g.gblocks = g.G / g.gc;
     g.base_y = floor_div(g.rb - w, FRPS) * FRPS;
@@ -555,6 +581,8 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         jb.dmin = q.dmin; jb.dmax = q.dmax;
         if (q.cost == STEREO_COST_SSD) { jb.cmin = -q.R; jb.cmax = q.cols - 1 + q.R; }
         else { jb.cmin = 0; jb.cmax = q.cols - 1; }
+        // fused partner: its energy rows feed the diagonal minima; candidates left of the image do not exist for it
+        if (fused_pairs > 0 && i >= fused_pairs) jb.cmin = 0;
         // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
         int qo = -(q.dmin + q.R); if (qo < 0) qo = 0;
         while (((q.dmin + q.R + qo) & 3) != 0) ++qo;
@@ -567,7 +595,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         if (rqp > g.rq_pitch) g.rq_pitch = rqp;
         if (e2p > g.e2_pitch) g.e2_pitch = e2p;
     }
-    g.total = (long long)n * g.tilesX * g.gblocks * g.nrows;
+    g.total = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks * g.nrows;
     // grid: one CTA per SM, but keep segments long enough that the (2R+1)-row warm-up stays small
     long long min_rows = 4LL * w; if (min_rows < 32) min_rows = 32;
     long long ctas = g.total / min_rows; if (ctas < 1) ctas = 1;
@@ -577,7 +605,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
 }
 
 static inline size_t fast_smem_bytes(const FastGeom& g) {
-    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16;
+    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + (g.elw ? FWARPS * 128 : 0);
 }
 
 static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64); }
@@ -609,15 +637,23 @@ static inline int fast_ctx_init(stereo_ctx*) {
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
             }
+    for (int R = 0; R <= FFREE_MASK_R; ++R) {
+        fast_kernel_fn fn = fast_pick_fused(R);
+        if (!fn) { set_error("fused pair kernel (R %d) missing from the build", R); return STEREO_ERR_UNSUPPORTED; }
+        cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+    }
     return STEREO_OK;
 }
 
 // One launch sequence (prep x4-6, hot kernel, merge) over `n` <= FMAXJOBS batchable problems.
-static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st) {
-    if (n < 1 || n > FMAXJOBS) { set_error("bad job count (internal)"); return STEREO_ERR_INVALID_ARG; }
+// `fused_pairs` > 0: ps holds fused_pairs left-referenced problems followed by their right-referenced partners
+// (fast_pair_fusable pairwise); ONE hot launch over the left-referenced directions yields both maps of every pair.
+static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st, int fused_pairs = 0) {
+    if (n < 1 || n > FMAXJOBS || (fused_pairs && n != 2 * fused_pairs)) { set_error("bad job count (internal)"); return STEREO_ERR_INVALID_ARG; }
     FastKernelParams kp{};
     FastGeom& g = kp.g;
-    fast_geometry(ctx, ps, n, g, kp.job);
+    fast_geometry(ctx, ps, n, g, kp.job, fused_pairs);
     const bool ncc = ps[0].cost == STEREO_COST_NCORR;
     const int vpitch = fast_vpitch(g);
     for (int i = 0; i < n; ++i) {
@@ -627,6 +663,15 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         jb.B = static_cast<const uint8_t*>(p.tgt.ptr); jb.b_step = p.tgt.step;
         jb.disp = p.disp.ptr; jb.disp_step = p.disp.step; jb.elem = p.disp.elem;
         jb.best = p.best.ptr; jb.best_step = p.best.step;
+        const bool partner = fused_pairs > 0 && i >= fused_pairs;      // only its energy rows and partial keys exist
+        if (partner) {
+            jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+            jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
+            if (!jb.E2 || !jb.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+            // every strip merges into the partner's partial keys with RED.MIN: start from "no candidate"
+            SB_CUDA(cudaMemsetAsync(jb.PART, 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
+            continue;
+        }
         jb.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
         jb.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
         jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
@@ -641,9 +686,9 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         }
     }
     const unsigned nz = unsigned(n);
-    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, nz), 256, 0, st>>>(kp);
+    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, fused_pairs ? unsigned(fused_pairs) : nz), 256, 0, st>>>(kp);
     static const bool legacy_prep = [] { const char* e = getenv("STEREO_PREP_LEGACY"); return e && atoi(e) != 0; }();
-    if (!legacy_prep) {
+    if (!legacy_prep || fused_pairs) {
         int delta_max = 0;
         for (int i = 0; i < n; ++i) { const int d = kp.job[i].qoff - kp.job[i].eoff + g.R; if (d > delta_max) delta_max = d; }
         const int span = g.rq_pitch > g.e2_pitch + delta_max ? g.rq_pitch : g.e2_pitch + delta_max;
@@ -663,8 +708,12 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
         ctx->last_launches += 2;
     }
-    fast_kernel_fn fn = fast_pick(ps[0].cost, g.R, g.hs);
-    if (!fn) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
+    fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R) : fast_pick(ps[0].cost, g.R, g.hs);
+    if (!fn || (fused_pairs && g.hs != 1)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
+    if (fused_pairs) {
+        ctx->last_launches += fused_pairs;         // the memsets
+        ctx->fused_pairs_done += fused_pairs;
+    }
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
     if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
     fn<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);

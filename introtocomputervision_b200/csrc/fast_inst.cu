@@ -1,10 +1,12 @@
 // Instantiations of the hot kernel (fast_kernel.cuh), one translation unit per SB_PART so they compile in parallel:
 //   SB_PART = hs_index * 8 + cost * 4 + radius subset;  hs_index 0 -> 1 strip per warp, 1 -> 2 strips per warp;
 //   cost 0 = SSD, 1 = NCC;  radius subsets {0,1,2,3}, {4}, {5}, {6,7}.
+//   SB_PART = 16, 17, 18: the fused pair kernels (SSD, both maps of a pair from one cost volume), radius subsets
+//   {0,1,2,3}, {4}, {5}.
 #include "fast_kernel.cuh"
 
 #ifndef SB_PART
-#error "compile with -DSB_PART=0..15"
+#error "compile with -DSB_PART=0..18"
 #endif
 
 namespace sb {
@@ -12,6 +14,23 @@ namespace sb {
 #define SB_CAT2(a, b) a##b
 #define SB_CAT(a, b) SB_CAT2(a, b)
 
+#if SB_PART >= 16
+#if SB_PART == 16
+fast_kernel_fn fast_pick_fused_a(int R) {
+    switch (R) {
+    case 0: return fast_cost_kernel<0, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 1: return fast_cost_kernel<1, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 2: return fast_cost_kernel<2, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 3: return fast_cost_kernel<3, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
+    }
+    return nullptr;
+}
+#elif SB_PART == 17
+fast_kernel_fn fast_pick_fused_b(int R) { return R == 4 ? fast_cost_kernel<4, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+#else
+fast_kernel_fn fast_pick_fused_c(int R) { return R == 5 ? fast_cost_kernel<5, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+#endif
+#else
 // `key` = strips per warp | cost << 8
 fast_kernel_fn SB_CAT(fast_pick_part, SB_PART)(int R, int key) {
     constexpr int HS = (SB_PART / 8) ? 2 : 1;
@@ -35,5 +54,6 @@ fast_kernel_fn SB_CAT(fast_pick_part, SB_PART)(int R, int key) {
     }
     return nullptr;
 }
+#endif
 
 } // namespace sb

@@ -79,6 +79,9 @@ struct FastGeom {
     int wpart;             // partial-key map width (= tilesX*spc*K)
     int nrows;             // re - rb
     int njobs;             // directions in this launch
+    int npairs;            // fused launches: image pairs (jobs 0..npairs-1 are the L->R directions the hot kernel
+                           // walks, job i+npairs is the R->L partner of job i); 0 otherwise
+    int elw;               // fused launches: tile width (words) of the partner's energy rows (= spc*K); 0 otherwise
     int ctas;              // grid size
     long long total;       // tile-rows (all jobs)
     long long L;           // tile-rows per CTA
@@ -195,11 +198,23 @@ constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses
 // HS > 1 (narrow searches, D <= 128/HS): the warp is cut into HS sub-warps of 32/HS lanes, each with its
 // own K-pixel strip; `sub` is the lane's sub-warp, `ll` its lane index inside it.  The per-pixel warp
 // reduction then runs once per sub-warp over the full warp with the other lanes neutralised.
-template <int R, int K, int PAR, int MODE, int COST, int HS>
+//
+// FUSED (SSD, one strip per warp, D a multiple of 128, R <= 5): the R->L map of the same image pair comes out of
+// the same cross terms.  C(x, d) serves the L->R pixel x AND the R->L pixel x' = x + d, whose
+// candidate -d it is (main.cpp:33,43: the second call swaps the images and mirrors the range).  A lane's four
+// candidates at pixel step k lie on the diagonals t = k + 4*lane + m of the (x, x') plane (t = x' - x0 - dlo), so
+// the warp keeps the running minimum of 128 live diagonals in registers, 4 per lane: every step each lane merges
+// its four keys  key2 = EL2[x] + 256*s  (EL2 = the partner direction's energy/position term for candidate x), hands
+// the diagonal it will not touch again to the lane below (one SHFL) and lane 0 retires one finished diagonal into
+// a 24-word shared-memory tail.  At the end of the row the tail and the 128 live diagonals are merged into the
+// partner's partial-key map with RED.MIN (several strips contribute to one x').
+template <int R, int K, int PAR, int MODE, int COST, int HS, bool FUSED = false>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
                                          int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int ll, int sub, int cbase,
-                                         int cols, float magic) {
+                                         int cols, float magic, const int* __restrict__ el_row = nullptr,
+                                         uint32_t* __restrict__ tail = nullptr, uint32_t* __restrict__ part2_row = nullptr,
+                                         int x2base = 0) {
     using S = RowShape<R, K>;
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr bool BIASED = NCC && (R <= NCC_BIAS_MAX_R);
@@ -245,9 +260,20 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         for (int m = 0; m < FM; ++m) s[m] += col[m][c];
     }
     uint32_t res[4];
+    uint32_t acc[FM];            // FUSED: running minima of the diagonals k + 4*ll + m
+    int elv[4];
+    if (FUSED) {
+#pragma unroll
+        for (int m = 0; m < FM; ++m) acc[m] = KEY_INVALID;
+    }
+    const uint32_t top_or = (FUSED && ll == 31) ? KEY_INVALID : 0u;   // lane 31 opens a fresh diagonal every step
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         update(k + 2 * R);
+        if (FUSED && (k & 3) == 0) {
+            const int4 v = lds128(el_row + k);
+            elv[0] = v.x; elv[1] = v.y; elv[2] = v.z; elv[3] = v.w;
+        }
         uint32_t key[FM];
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
@@ -264,6 +290,12 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 }
                 if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
                 key[m] = kv;
+                if (FUSED) {
+                    // the partner direction's key of the same cross term: BIAS + 128*(EL(x) - 2C) + x; pixels x beyond its
+                    // legal centres (x > cols-1+R) carry EL2 = KEY_INVALID and lose like illegal search positions do (R <= 5)
+                    const uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                    acc[m] = min(acc[m], k2);
+                }
             } else {
                 const float rs = __int_as_float(e2v[k + m]);
                 // BIASED: s is the float 2^23 + C, so C*rs + magic = fma(s, rs, magic - 2^23*rs); the addend is exact
@@ -298,11 +330,33 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         }
         if ((k & 3) == 3 && ll == 0)
             *reinterpret_cast<uint4*>(out_row + k - 3) = make_uint4(res[0], res[1], res[2], res[3]);
+        if (FUSED) {
+            // diagonal k + 4*ll is complete for this lane: it moves to the lane below (lane 0: into the tail);
+            // the lane's other three diagonals move down one slot and the slot on top takes over lane ll+1's
+            const uint32_t done = acc[0];
+            const uint32_t in = __shfl_down_sync(0xffffffffu, done, 1) | top_or;
+            if (ll == 0) tail[k] = done;
+            acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
+        }
+    }
+    if (FUSED) {
+        // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
+        __syncwarp();
+        const uint32_t tv = (ll < K) ? tail[ll] : KEY_INVALID;
+        const int xt = x2base + ll;
+        if (ll < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tv);
+#pragma unroll
+        for (int m = 0; m < FM; ++m) {
+            const int xa = x2base + K + FM * ll + m;
+            if (unsigned(xa) < unsigned(cols)) atomicMin(part2_row + xa, acc[m]);
+        }
+        __syncwarp();             // the next row overwrites the tail
     }
 }
 
-template <int R, int K, int NW, int COST, int HS>
+template <int R, int K, int NW, int COST, int HS, bool FUSED = false>
 __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
+    static_assert(!FUSED || (COST == STEREO_COST_SSD && HS == 1 && R <= FFREE_MASK_R && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, one strip per warp, R <= 5");
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr int LS = 32 / HS;                 // lanes per strip
     constexpr int DG = FM * LS;                 // disparities per strip and warp
@@ -314,10 +368,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     const int nst = g.nst;
 
     const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
-    const int stage_words = lp_stage + rq_stage + e2_stage;
+    const int el_stage = FUSED ? FRPS * g.elw : 0;
+    const int stage_words = lp_stage + rq_stage + e2_stage + el_stage;
     int* smem = reinterpret_cast<int*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nst) * stage_words * 4);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST_MAX);
+    uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * 32;     // FUSED: 32 words per warp
 
     if (tid == 0) {
         for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }
@@ -332,6 +388,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     if (lin_begin >= lin_end) return;
     const int w = 2 * R + 1;
     const int tpj = g.tilesX * g.gblocks;        // tiles per job
+    const int npair = FUSED ? g.npairs : 0;      // the partner of job jb is job jb + npair
 
     // producer: EVERY warp iterates the same stage sequence, nst-2 stages ahead, warp-uniformly (all lanes
     // wait on the empty barrier), and its lane 0 issues the warp's share of the stage's row copies (row r of
@@ -368,7 +425,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         constexpr int NLP = (FRPS - 1) / NW + 1, NRQ = (FRPS / 2 - 1) / NW + 1;       // copies per warp, upper bounds
         uint32_t mine = 0;
 #pragma unroll
-        for (int i = 0; i < NLP; ++i) if (warp + i * NW < FRPS) mine += uint32_t(g.lpw + g.e2w) * 4u;
+        for (int i = 0; i < NLP; ++i) if (warp + i * NW < FRPS) mine += uint32_t(g.lpw + g.e2w + (FUSED ? g.elw : 0)) * 4u;
 #pragma unroll
         for (int i = 0; i < NRQ; ++i) if (warp + i * NW < FRPS / 2) mine += uint32_t(g.rqw) * 4u;
         const int j0 = p_sj * FRPS;
@@ -380,6 +437,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                 if (r < FRPS) {
                     tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
                     tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
+                    if (FUSED)      // the partner's energy rows: E2'[j][x], x = pixel column (its eoff is 0)
+                        tma_load_1d(smem_u32(st + lp_stage + rq_stage + e2_stage + r * g.elw), P.job[jb + npair].E2 + size_t(j0 + r) * g.e2_pitch + p0,
+                                    uint32_t(g.elw) * 4u, bar);
                 }
             }
 #pragma unroll
@@ -416,7 +476,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int grp = gb * g.gc + warp % g.gc;
         const int x0 = strip * K;
         const int x0w = (xt * g.spc + wstrip) * K;                       // first pixel of the warp (warp-uniform)
-        const bool active = (x0w < g.cols) && (grp < g.G);               // warp-uniform: the row code holds warp collectives
+        // warp-uniform: the row code holds warp collectives.  FUSED: strips reach R columns into the right padding,
+        // where the partner direction's last candidates are centred.
+        const bool active = (x0w < g.cols + (FUSED ? R : 0)) && (grp < g.G);
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
         // which flavour of candidate masking this warp's (HS x 24 pixels x DG disparities) block needs
@@ -437,6 +499,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int lp_off = (wstrip + sub) * K;
         const int rq_off = lp_off + DG * (warp % g.gc) + FM * ll;
         int32_t* part = job.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
+        // FUSED: the partner's candidates -d of this group are its group G-1-grp (D is a multiple of 128)
+        uint32_t* part2 = FUSED ? reinterpret_cast<uint32_t*>(P.job[jb + npair].PART) + (size_t(g.G - 1 - grp) * g.nrows) * g.wpart : nullptr;
+        const int x2base = x0 + dlo;                                      // partner pixel of diagonal 0
 #pragma unroll
         for (int m = 0; m < FM; ++m)
 #pragma unroll
@@ -458,11 +523,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                     const int par = j & 1;
                     const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
 #define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, ll, sub, cbase, g.cols, magic)
+#define SB_ROWF(P_) fast_row<R, K, P_, 1, COST, HS, true>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
+                                                          st + lp_stage + rq_stage + e2_stage + r * g.elw + lp_off, tail, \
+                                                          part2 + size_t(j - (g.rb - g.base_y)) * g.wpart, x2base)
                     if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
+                    else if constexpr (FUSED) { if (par) SB_ROWF(1); else SB_ROWF(0); }   // the host only fuses launches whose blocks are all mode 1
                     else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
                     else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
                     else                { if (par) SB_ROW(1, 3); else SB_ROW(0, 3); }
 #undef SB_ROW
+#undef SB_ROWF
                 }
             }
             __syncwarp();
@@ -481,6 +551,15 @@ constexpr int FAST_PARTS = 16;
 SB_DECL_PART(0) SB_DECL_PART(1) SB_DECL_PART(2) SB_DECL_PART(3) SB_DECL_PART(4) SB_DECL_PART(5) SB_DECL_PART(6) SB_DECL_PART(7)
 SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(12) SB_DECL_PART(13) SB_DECL_PART(14) SB_DECL_PART(15)
 #undef SB_DECL_PART
+// Fused pair kernels (SSD, R <= 5, one strip per warp): part 16 + radius subset (fast_inst.cu).
+fast_kernel_fn fast_pick_fused_a(int R);
+fast_kernel_fn fast_pick_fused_b(int R);
+fast_kernel_fn fast_pick_fused_c(int R);
+static inline fast_kernel_fn fast_pick_fused(int R) {
+    if (fast_kernel_fn fn = fast_pick_fused_a(R)) return fn;
+    if (fast_kernel_fn fn = fast_pick_fused_b(R)) return fn;
+    return fast_pick_fused_c(R);
+}
 static inline fast_kernel_fn fast_pick(int cost, int R, int hs) {
     typedef fast_kernel_fn (*part_fn)(int, int);
     static const part_fn parts[FAST_PARTS] = {fast_pick_part0, fast_pick_part1, fast_pick_part2, fast_pick_part3,

@@ -192,8 +192,34 @@ static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_a
 // Enqueues `n` u8 problems that all take the packed path, several directions per launch sequence where they
 // are batchable (same shape, band, window, cost and candidate count).  `batch_budget` bounds the scratch one
 // launch sequence may hold.
+// True when ps = n/2 left-referenced problems followed by their right-referenced partners, each pair fusable.
+static bool fused_layout(const stereo_ctx* ctx, const Problem* ps, int n) {
+    if (!ctx->fuse_pairs || n < 2 || (n & 1) || n > FMAXJOBS) return false;
+    const int np = n / 2;
+    for (int k = 0; k < np; ++k)
+        if (!fast_pair_fusable(ps[k], ps[np + k]) || !fast_batchable(ps[0], ps[k])) return false;
+    return true;
+}
+
+// One launch sequence over batchable problems, fused when they are whole pairs.
+static int run_fast_auto(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st) {
+    return run_fast_batch(ctx, ps, n, st, fused_layout(ctx, ps, n) ? n / 2 : 0);
+}
+
 static int run_fast_jobs(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t st) {
     const size_t budget = size_t(3) << 30;
+    if (fused_layout(ctx, ps, n)) {          // (n <= FMAXJOBS: one launch sequence)
+        const size_t need = size_t(n) * fast_scratch_bytes(ctx, ps[0]);
+        if (need > ctx->arena.cap) {
+            SB_CUDA(cudaStreamSynchronize(st));
+            SB_CUDA(cudaStreamSynchronize(ctx->stream));
+            int rc = ctx->arena.reserve(need);
+            if (rc != STEREO_OK) return rc;
+        }
+        ctx->arena.reset();
+        ctx->last_path = STEREO_PATH_FAST_U8;
+        return run_fast_batch(ctx, ps, n, st, n / 2);
+    }
     int i = 0;
     while (i < n) {
         const size_t per_job = fast_scratch_bytes(ctx, ps[i]);
@@ -222,6 +248,7 @@ static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
     ctx->hot_used = 0;
     ctx->hot_total = 0;
     ctx->hot_jobs = 0;
+    ctx->fused_pairs_done = 0;
     cudaEventRecord(ctx->ev0, st);
 }
 static void end_call(stereo_ctx* ctx, cudaStream_t st) {
@@ -430,7 +457,7 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
                 for (int k = 1; k < nj; ++k) together = together && fast_batchable(pd[0], pd[k]);
                 if (together) {
                     ctx->arena.reset();
-                    rc = run_fast_batch(ctx, pd, nj, s_cmp);
+                    rc = run_fast_auto(ctx, pd, nj, s_cmp);
                 } else {
                     for (int k = 0; k < nj && rc == STEREO_OK; ++k) { ctx->arena.reset(); rc = run_fast(ctx, pd[k], s_cmp); }
                 }
@@ -678,6 +705,14 @@ int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
 int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands) {
     if (!ctx || bands < 0 || bands > 4096) { set_error("bad pipe_bands argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->pipe_bands = bands;
+    return STEREO_OK;
+}
+
+int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx) { return ctx ? ctx->fused_pairs_done : 0; }
+
+int stereo_ctx_set_fuse_pairs(stereo_ctx* ctx, int on) {
+    if (!ctx) { set_error("null context"); return STEREO_ERR_INVALID_ARG; }
+    ctx->fuse_pairs = on ? 1 : 0;
     return STEREO_OK;
 }
 

@@ -102,6 +102,10 @@ class _RawDeviceBytes:
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+class PeerGatherUnavailable(RuntimeError):
+    """Raised on every rank of the group when any rank could not create or map a gather buffer."""
+
+
 class PeerGather:
     """Gather buffer filled by copy-engine pushes over NVLink (``stereo_peer_*`` in include/stereo_b200.h).
 
@@ -122,21 +126,46 @@ class PeerGather:
         lib = _capi.lib()
         local = C.c_void_p()
         handle = (C.c_ubyte * 64)()
-        self._check(lib.stereo_peer_buffer_create(ctx.handle, self.nbytes, C.byref(local), handle))
-        self.local_ptr = int(local.value)
-        handles = [None] * self.world
+        # Set-up is collective and fails on EVERY rank or on none: a rank that cannot create or map a buffer
+        # (no peer access between two GPUs, IPC disabled in a container) still takes part in both exchanges.
+        err = None
+        self.local_ptr = 0
+        if lib.stereo_peer_buffer_create(ctx.handle, self.nbytes, C.byref(local), handle) == _capi.STEREO_OK:
+            self.local_ptr = int(local.value)
+        else:
+            err = _capi.last_error()
+        handles = [bytes(handle) if err is None else None]
         if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle), group=group)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
         self.ptrs = (C.c_void_p * self.world)()
         self._opened = []
-        for r in range(self.world):
-            if r == self.rank:
-                self.ptrs[r] = self.local_ptr
-            else:
+        if all(h is not None for h in handles):
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs[r] = self.local_ptr
+                    continue
                 peer = C.c_void_p()
-                self._check(lib.stereo_peer_buffer_open(ctx.handle, (C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(peer)))
+                if lib.stereo_peer_buffer_open(ctx.handle, (C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(peer)) != _capi.STEREO_OK:
+                    err = err or f"rank {self.rank} cannot map rank {r}'s buffer: {_capi.last_error()}"
+                    break
                 self.ptrs[r] = peer.value
                 self._opened.append(int(peer.value))
+        else:
+            err = err or "another rank could not create its gather buffer"
+        errs = [err]
+        if self.world > 1:
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+        bad = [e for e in errs if e]
+        if bad:
+            for p_ in self._opened:
+                lib.stereo_peer_buffer_close(ctx.handle, C.c_void_p(p_))
+            self._opened = []
+            if self.local_ptr:
+                lib.stereo_peer_buffer_destroy(ctx.handle, C.c_void_p(self.local_ptr))
+                self.local_ptr = 0
+            raise PeerGatherUnavailable(bad[0])
 
     @staticmethod
     def _check(st):

@@ -108,6 +108,15 @@ class Context:
         """Row bands per image pair in the pipelined host entry points (0 = automatic)."""
         _check(_capi.lib().stereo_ctx_set_pipe_bands(self._h, int(bands)), "stereo_ctx_set_pipe_bands")
 
+    @property
+    def last_fused_pairs(self) -> int:
+        """Image pairs of the last call whose two maps came out of one cost volume."""
+        return int(_capi.lib().stereo_ctx_last_fused_pairs(self._h))
+
+    def set_fuse_pairs(self, on: bool) -> None:
+        """Pair calls: both maps from one cost volume where possible (default on; results identical either way)."""
+        _check(_capi.lib().stereo_ctx_set_fuse_pairs(self._h, int(bool(on))), "stereo_ctx_set_fuse_pairs")
+
     def synchronize(self, stream: int = 0) -> None:
         _check(_capi.lib().stereo_ctx_synchronize(self._h, C.c_void_p(stream)), "stereo_ctx_synchronize")
 

@@ -339,6 +339,94 @@ def test_host_batch_f32_non_8bit_pair_falls_back_to_exact(ctx):
         assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rs[i], Ls[i], R, 0, rng))), i
 
 
+# ---- fused pair launches: both maps of a pair from one cost volume --------------------------
+
+FUSED_SHAPES = [
+    # rows, cols, R, range      (range + 1 a multiple of 128)
+    (30, 300, 2, 127),          # cols not a multiple of the 24-pixel strip, one disparity group
+    (26, 500, 5, 255),          # two groups in one CTA; the last 255 columns see candidates in the right padding
+    (40, 96, 3, 127),           # image narrower than the range: every R->L pixel has right-padding candidates
+    (19, 700, 0, 127),          # 1x1 window
+    (22, 410, 4, 383),          # three groups (gc = 1)
+    (64, 1000, 5, 255),
+    (9, 130, 1, 127),           # fewer rows than a pipeline stage
+]
+
+
+@pytest.mark.parametrize("rows,cols,R,rng", FUSED_SHAPES)
+def test_fused_pair_equals_oracle_and_unfused(ctx, rows, cols, R, rng):
+    L, Rt, _ = synth.make_pair(rows, cols, min(rng + 1, 64), 8000 + rows + cols)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l, ref_r = oracle.ssd_fast(Lf, Rf, R, -rng, 0), oracle.ssd_fast(Rf, Lf, R, 0, rng)
+    try:
+        ctx.set_fuse_pairs(True)
+        fl, fr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_FAST_U8
+        assert ctx.last_fused_pairs == 1, "the fused pair launch did not run"
+        ctx.set_fuse_pairs(False)
+        ul, ur = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+        assert ctx.last_fused_pairs == 0
+    finally:
+        ctx.set_fuse_pairs(True)
+    assert np.array_equal(ul, ref_l) and np.array_equal(ur, ref_r)
+    assert np.array_equal(fl, ref_l), "fused L->R"
+    bad = np.argwhere(fr != ref_r)
+    assert bad.size == 0, f"fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
+
+
+def test_fused_pair_ties_flat_images(ctx):
+    # flat and banded images: every candidate ties; first-minimum order must survive the diagonal minima
+    rows, cols, R, rng = 24, 400, 3, 127
+    flat = np.full((rows, cols), 9, np.uint8)
+    band = np.tile((np.arange(cols) // 37 % 2 * 200).astype(np.uint8), (rows, 1))
+    for L, Rt in ((flat, flat), (band, band), (band, flat)):
+        Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+        fl, fr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+        assert ctx.last_fused_pairs == 1
+        assert np.array_equal(fl, oracle.ssd_fast(Lf, Rf, R, -rng, 0))
+        assert np.array_equal(fr, oracle.ssd_fast(Rf, Lf, R, 0, rng))
+
+
+def test_fused_pair_bands_and_batches(ctx):
+    # host pipeline in row bands (seams: the +1 halo row of the SSD row wrap) and a chunked batch of pairs
+    rows, cols, R, rng = 150, 520, 5, 127
+    L, Rt, _ = synth.make_pair(rows, cols, 64, 4242)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l, ref_r = oracle.ssd_fast(Lf, Rf, R, -rng, 0), oracle.ssd_fast(Rf, Lf, R, 0, rng)
+    try:
+        for bands in (1, 3, 4):
+            ctx.set_pipe_bands(bands)
+            dl, dr = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, R, rng, dtype=np.int16)
+            assert ctx.last_fused_pairs == bands
+            assert np.array_equal(dl, ref_l) and np.array_equal(dr, ref_r), bands
+    finally:
+        ctx.set_pipe_bands(0)
+    n = 7
+    Ls, Rs = [], []
+    for i in range(n):
+        a, b, _ = synth.make_pair(33, 330, 64, 7000 + i)
+        Ls.append(a), Rs.append(b)
+    Ls, Rs = np.stack(Ls), np.stack(Rs)
+    bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, 127, dtype=np.int8)
+    assert ctx.last_fused_pairs == n
+    for i in range(n):
+        a, b = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+        assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(a, b, 4, -127, 0))), i
+        assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(b, a, 4, 0, 127))), i
+
+
+def test_fused_pair_with_costs_matches_single_calls(ctx):
+    rows, cols, R, rng = 28, 280, 2, 127
+    L, Rt, _ = synth.make_pair(rows, cols, 48, 99)
+    dl, dr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+    assert ctx.last_fused_pairs == 1
+    sl, cl = ctx.disparity(sb.COST_SSD, L, Rt, R, -rng, 0, dtype=np.int16, return_best=True)
+    sr, cr = ctx.disparity(sb.COST_SSD, Rt, L, R, 0, rng, dtype=np.int16, return_best=True)
+    assert np.array_equal(dl, sl) and np.array_equal(dr, sr)
+    _, ol = oracle.ssd_fast(L.astype(np.float32), Rt.astype(np.float32), R, -rng, 0, return_cost=True)
+    assert np.array_equal(cl, ol)
+
+
 def test_pipelined_host_non_8bit_falls_back_to_exact(ctx):
     # the 8-bit flag is only known after the pipelined pass: a noisy image must be redone on the exact path
     L, Rt, _ = synth.make_pair(60, 200, 30, 31)

@@ -88,6 +88,16 @@ def _worker(rank, world, port, q):
             a, b = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
             ok &= bool(np.array_equal(dl[i].numpy(), oracle.narrow_i8(oracle.ssd_fast(a, b, 2, -7, 0))))
             ok &= bool(np.array_equal(dr[i].numpy(), oracle.narrow_i8(oracle.ssd_fast(b, a, 2, 0, 7))))
+        # peer gather set-up is collective: without a device no rank can create a buffer, and EVERY rank gets the
+        # same PeerGatherUnavailable instead of one rank raising while the others wait in an exchange
+        class NoDeviceCtx:
+            handle = None
+        try:
+            sharding.PeerGather(NoDeviceCtx(), 1024)
+            ok = False
+        except sharding.PeerGatherUnavailable:
+            pass
+        dist.barrier()
         q.put((rank, ok))
     except Exception as exc:      # report instead of leaving the parent waiting on the queue
         q.put((rank, f"{type(exc).__name__}: {exc}"))
