@@ -50,6 +50,10 @@ if str(ROOT) not in sys.path:
 METRIC = "disparity Mpix x disparities/s"
 UNIT = "Mpix*disp/s"
 OPS_PER_UNIT = {"ssd": 8, "ncc": 9}          # SURVEY.md §8d algorithmic lane-ops per pixel x disparity
+# Fused pair launches compute ONE cost volume for both maps of a pair: of the 8 SSD ops per pixel x
+# disparity, the 6 that build the window sum (sub, mul, 2 vertical adds, 2 horizontal adds) are shared by the two
+# directions' units and only the 2 winner-take-all ops are per unit: (6 + 2 * 2) / 2 = 5 lane-ops per unit.
+OPS_PER_UNIT_FUSED = {"ssd": 5}
 
 WORKLOADS = {
     # name: rows, cols, n_disp, window_rad, seed
@@ -315,8 +319,23 @@ def run_ours(args, wl):
     # hot-kernel time of the last step (events recorded by the library on the same stream)
     ms, nmeas = ctx.last_hot_kernel_ms()
     hot_jobs = ctx.last_hot_jobs
+    fused = ctx.last_fused_pairs > 0
     if nmeas > 0:
         hot_ms, hot_n = ms, nmeas
+    # the same batch with one cost volume per direction (untimed: one step, for the roofline of the unfused kernel)
+    unfused = None
+    if fused:
+        ctx.set_fuse_pairs(False)
+        if pg is not None:
+            join_pushes()
+        step_device(nwarm + args.steps + (nwarm + args.steps) % 2)
+        if pg is not None:
+            join_pushes()
+        torch.cuda.synchronize()
+        ms_u, n_u = ctx.last_hot_kernel_ms()
+        if n_u > 0:
+            unfused = (ms_u, n_u, ctx.last_hot_jobs)
+        ctx.set_fuse_pairs(True)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -371,7 +390,7 @@ def run_ours(args, wl):
     e2e_launches = ctx.last_launches * e2e_steps
 
     def timed_host(fn):
-        fn()
+        fn(), fn()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -416,14 +435,16 @@ def run_ours(args, wl):
             jobs_per_launch = hot_jobs / hot_n                              # directions one hot launch covers
             units_hot = hot_jobs * rows * cols * nd
             t_hot = hot_ms * 1e-3
-            achieved = OPS_PER_UNIT[args.cost] * units_hot / t_hot
+            opu = OPS_PER_UNIT_FUSED[args.cost] if fused else OPS_PER_UNIT[args.cost]
+            achieved = opu * units_hot / t_hot
             b_in, b_out = 1, elem
             alg_bytes = int(jobs_per_launch * rows * cols * (2 * b_in + b_out))   # per launch
             roof = {
-                "bound": "alu", "kernel": f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>",
+                "bound": "alu", "kernel": (f"fast_cost_kernel<R={R},K=20,NW=8,SSD,fused pair>" if fused
+                                           else f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>"),
                 "achieved": round(achieved / 1e12, 3), "peak": round(peak_lane_ops / 1e12, 3), "unit": "Tlane-op/s",
                 "frac": round(achieved / peak_lane_ops, 4),
-                "ops_per_unit": OPS_PER_UNIT[args.cost], "units_per_launch": int(jobs_per_launch * rows * cols * nd),
+                "ops_per_unit": opu, "units_per_launch": int(jobs_per_launch * rows * cols * nd),
                 "directions_per_launch": jobs_per_launch,
                 "launch_ms": round(hot_ms / hot_n, 4), "launches_timed": hot_n,
                 "peak_def": f"{sms} SMs x 128 lanes x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
@@ -432,6 +453,17 @@ def run_ours(args, wl):
                         "frac": round(alg_bytes / (hot_ms / hot_n * 1e-3) / 1e9 / peaks["hbm_gbs"], 5),
                         "algorithmic_bytes_per_launch": alg_bytes, "of": peaks["source"]},
             }
+            if fused:
+                roof["note"] = ("fused pair launch: one cost volume serves both maps of a pair, so a unit costs 5 algorithmic "
+                                "lane-ops instead of SURVEY.md 8d's 8 (6 shared window-sum ops / 2 + 2 WTA ops); at 8 ops per unit "
+                                "the same launch would read frac = %.4f" % (OPS_PER_UNIT[args.cost] * units_hot / t_hot / peak_lane_ops))
+                if unfused is not None:
+                    ms_u, n_u, jobs_u = unfused
+                    ach_u = OPS_PER_UNIT[args.cost] * jobs_u * rows * cols * nd / (ms_u * 1e-3)
+                    roof["unfused_kernel"] = {"kernel": f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>", "ops_per_unit": OPS_PER_UNIT[args.cost],
+                                              "launch_ms": round(ms_u / n_u, 4), "directions_per_launch": jobs_u / n_u,
+                                              "achieved": round(ach_u / 1e12, 3), "frac": round(ach_u / peak_lane_ops, 4),
+                                              "how": "same batch, one untimed step with stereo_ctx_set_fuse_pairs(0)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             v, dt, desc = cpu_reference_sample(wl, args.ref_rows, os.cpu_count() or 1, args.cost)
@@ -442,6 +474,7 @@ def run_ours(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 (int32 accumulate)", "data": "synthetic",
             "config": {"workload": args.workload + f"_{args.cost}_pair", "rows": rows, "cols": cols, "ndisp": nd,
                        "window": 2 * R + 1, "pairs_per_gpu_per_step": B, "directions": 2,
+                       "pair_fusion": "both maps of a pair from one cost volume" if fused else "one cost volume per direction",
                        "sharding": "by pair" + ({"p2p": ", every rank's maps pushed into every rank's gather buffer by the copy engines "
                                                         "over NVLink (stereo_peer_push), overlapping the next step's kernels; "
                                                         "all pushes joined inside the timed region",

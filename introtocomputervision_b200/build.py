@@ -18,6 +18,8 @@ LIB = PKG / "libstereo_b200.so"
 FAST_PARTS = 19          # 16 cost x radius x strips-per-warp parts + 3 fused pair kernel parts
 
 NVCC_FLAGS = [
+    *([f"-DSB_FK_FUSED={os.environ['SB_FK_FUSED']}"] if os.environ.get("SB_FK_FUSED") else []),
+    *([f"-DSB_FK_DEFAULT={os.environ['SB_FK_DEFAULT']}"] if os.environ.get("SB_FK_DEFAULT") else []),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -544,7 +544,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
     g.njobs = n;
     g.npairs = fused_pairs;
     g.elw = 0;
-    g.K = FK_DEFAULT;
+    g.K = fused_pairs > 0 ? FK_FUSED : FK_DEFAULT;
     g.nw = FWARPS;
     g.hs = fast_pick_hs(g.D);
     const int w = 2 * p.R + 1;
@@ -610,21 +610,27 @@ static inline size_t fast_smem_bytes(const FastGeom& g) {
 
 static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64); }
 
-// Scratch of ONE job of a launch over problems shaped like `p`.
+// Scratch of ONE job of a launch over problems shaped like `p` (the larger of the plain and the fused-pair geometry:
+// fused launches add R columns of strips and may use another strip width).
 static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
-    FastGeom g; FastJob jb{};
-    fast_geometry(ctx, &p, 1, g, &jb);
-    // pitches may grow by one alignment step when jobs with other range signs join the launch
-    g.rq_pitch += 64; g.e2_pitch += 64;
-    size_t b = 0;
-    auto add = [&](size_t bytes) { b += ((bytes + 255) & ~size_t(255)); };
-    add(size_t(g.J) * g.lp_pitch * 4);
-    add(size_t(g.J / 2) * g.rq_pitch * 4);
-    add(size_t(g.J) * g.e2_pitch * 4);
-    add(size_t(g.G) * g.nrows * g.wpart * 4);
-    add(size_t(g.nrows) * fast_vpitch(g) * 4);
-    if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
-    return b + 4096;
+    size_t best = 0;
+    for (int fused = 0; fused <= 1; ++fused) {
+        if (fused && (p.cost != STEREO_COST_SSD || p.R > FFREE_MASK_R)) break;
+        FastGeom g; FastJob jb{};
+        fast_geometry(ctx, &p, 1, g, &jb, fused);
+        // pitches may grow by one alignment step when jobs with other range signs join the launch
+        g.rq_pitch += 64; g.e2_pitch += 64;
+        size_t b = 0;
+        auto add = [&](size_t bytes) { b += ((bytes + 255) & ~size_t(255)); };
+        add(size_t(g.J) * g.lp_pitch * 4);
+        add(size_t(g.J / 2) * g.rq_pitch * 4);
+        add(size_t(g.J) * g.e2_pitch * 4);
+        add(size_t(g.G) * g.nrows * g.wpart * 4);
+        add(size_t(g.nrows) * fast_vpitch(g) * 4);
+        if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
+        if (b > best) best = b;
+    }
+    return best + 4096;
 }
 
 static inline int fast_ctx_init(stereo_ctx*) {

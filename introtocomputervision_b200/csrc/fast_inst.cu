@@ -18,17 +18,17 @@ namespace sb {
 #if SB_PART == 16
 fast_kernel_fn fast_pick_fused_a(int R) {
     switch (R) {
-    case 0: return fast_cost_kernel<0, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 1: return fast_cost_kernel<1, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 2: return fast_cost_kernel<2, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 3: return fast_cost_kernel<3, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 0: return fast_cost_kernel<0, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 1: return fast_cost_kernel<1, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 2: return fast_cost_kernel<2, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 3: return fast_cost_kernel<3, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
     }
     return nullptr;
 }
 #elif SB_PART == 17
-fast_kernel_fn fast_pick_fused_b(int R) { return R == 4 ? fast_cost_kernel<4, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+fast_kernel_fn fast_pick_fused_b(int R) { return R == 4 ? fast_cost_kernel<4, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
 #else
-fast_kernel_fn fast_pick_fused_c(int R) { return R == 5 ? fast_cost_kernel<5, FK_DEFAULT, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+fast_kernel_fn fast_pick_fused_c(int R) { return R == 5 ? fast_cost_kernel<5, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
 #endif
 #else
 // `key` = strips per warp | cost << 8

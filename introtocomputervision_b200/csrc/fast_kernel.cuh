@@ -29,7 +29,10 @@
 
 namespace sb {
 
-constexpr int FK_DEFAULT = 24;  // pixels per thread (strip width); template parameter K of the kernels
+#ifndef SB_FK_DEFAULT
+#define SB_FK_DEFAULT 24
+#endif
+constexpr int FK_DEFAULT = SB_FK_DEFAULT;  // pixels per thread (strip width); template parameter K of the kernels
 constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
