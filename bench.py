@@ -520,11 +520,11 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     sp = C.c_void_p(stream.cuda_stream)
 
     def step():
-        for k, (a, b, dmin, dmax) in enumerate(((d_l, d_r, -(nd - 1), 0), (d_r, d_l, 0, nd - 1))):
-            rc = lib.stereo_disparity_band_halo_u8_device(ctx.handle, cost, a.data_ptr(), cols, b.data_ptr(), cols, rows, cols,
-                                                          r0, r1, h0, h1, R, dmin, dmax, mine[k].data_ptr(), cols * elem, elem, sp)
-            if rc != 0:
-                raise RuntimeError(_capi.last_error())
+        rc = lib.stereo_disparity_pair_band_halo_u8_device(ctx.handle, cost, d_l.data_ptr(), cols, d_r.data_ptr(), cols, rows, cols,
+                                                           r0, r1, h0, h1, R, nd - 1, mine[0].data_ptr(), mine[1].data_ptr(),
+                                                           cols * elem, elem, sp)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
         if world > 1:
             dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))
 
@@ -560,10 +560,11 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
                 "data": "synthetic",
                 "config": {"workload": args.workload + f"_{args.cost}_pair_bands", "rows": rows, "cols": cols, "ndisp": nd,
                            "window": 2 * R + 1, "band_rows": band, "halo_rows": R + 1, "directions": 2,
+                           "pair_fusion": "both maps of a band from one cost volume" if ctx.last_fused_pairs else "one cost volume per direction",
                            "sharding": "by row band, slab with halo resident per rank"
                                        + (", NCCL all_gather of the bands inside the step" if world > 1 else ""),
                            "l2": "flushed between steps"},
-                "gpu_launches": ctx.last_launches * 2 * args.steps, "clocks": clocks}
+                "gpu_launches": ctx.last_launches * args.steps, "clocks": clocks}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

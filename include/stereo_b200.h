@@ -225,6 +225,16 @@ int stereo_disparity_band_halo_u8_device(stereo_ctx* ctx, int cost,
                                          int window_rad, int min_disp, int max_disp,
                                          void* disp_out, size_t disp_step, int disp_elem_bytes, void* cuda_stream);
 
+/* Both maps of the band in one call (a rank's share of a row-band sharded pair): left-referenced map over
+ * [-disparity_range, 0] into disp_left, right-referenced map over [0, +disparity_range] into disp_right, each
+ * pointing at the band's first output row; from one cost volume where stereo_ctx_set_fuse_pairs allows it. */
+int stereo_disparity_pair_band_halo_u8_device(stereo_ctx* ctx, int cost,
+                                              const uint8_t* left_halo, size_t left_step, const uint8_t* right_halo, size_t right_step,
+                                              int rows, int cols, int row_begin, int row_end, int halo_begin, int halo_end,
+                                              int window_rad, int disparity_range,
+                                              void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes,
+                                              void* cuda_stream);
+
 /* Input rows [*halo_begin, *halo_end) a band [row_begin, row_end) of a rows-high image needs (pure host
  * arithmetic, no device). */
 int stereo_band_halo_rows(int rows, int row_begin, int row_end, int window_rad, int* halo_begin, int* halo_end);

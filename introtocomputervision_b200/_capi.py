@@ -49,6 +49,7 @@ SIGNATURES = {
     "stereo_disparity_pair_batch_u8_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
     "stereo_disparity_pair_batch_f32_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
     "stereo_disparity_band_halo_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "stereo_disparity_pair_band_halo_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i, _vp]),
     "stereo_band_halo_rows": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "stereo_peer_buffer_create": (_i, [_vp, _sz, C.POINTER(_vp), _vp]),
     "stereo_peer_buffer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),

@@ -33,6 +33,11 @@ namespace sb {
 #define SB_FK_DEFAULT 24
 #endif
 constexpr int FK_DEFAULT = SB_FK_DEFAULT;  // pixels per thread (strip width); template parameter K of the kernels
+#ifndef SB_FK_FUSED
+#define SB_FK_FUSED 20
+#endif
+constexpr int FK_FUSED = SB_FK_FUSED;      // strip width of the fused pair kernels: their 8 extra live registers per thread
+                                           // make 24-pixel strips spill (ncu: 2.07 ms vs 1.82 ms per two 4K/256 pairs)
 constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group

@@ -994,6 +994,36 @@ int stereo_disparity_pair_u8_device(stereo_ctx* ctx, int cost, const uint8_t* le
     return rc;
 }
 
+// Both maps of a row band from one launch sequence (one rank's share of a row-band sharded PAIR, BASELINE config 4).
+int stereo_disparity_pair_band_halo_u8_device(stereo_ctx* ctx, int cost, const uint8_t* left_halo, size_t left_step,
+                                              const uint8_t* right_halo, size_t right_step, int rows, int cols,
+                                              int row_begin, int row_end, int halo_begin, int halo_end, int window_rad,
+                                              int disparity_range, void* disp_left, void* disp_right, size_t disp_step,
+                                              int disp_elem_bytes, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!left_halo || !right_halo || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (halo_begin < 0 || halo_end > rows || halo_begin >= halo_end) { set_error("bad halo rows [%d, %d)", halo_begin, halo_end); return STEREO_ERR_INVALID_ARG; }
+    if (disparity_range < 0) { set_error("disparity_range must be >= 0"); return STEREO_ERR_INVALID_RANGE; }
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    const uint8_t* l0 = left_halo - size_t(halo_begin) * left_step;       // full-image origins, see above
+    const uint8_t* r0 = right_halo - size_t(halo_begin) * right_step;
+    Problem p[2];
+    pair_problems(p, cost, PixType::U8, l0, left_step, r0, right_step, rows, cols, window_rad, disparity_range, disp_left, disp_right,
+                  disp_step, disp_elem_bytes);
+    for (int d = 0; d < 2; ++d) { p[d].row_begin = row_begin; p[d].row_end = row_end; p[d].avail_begin = halo_begin; p[d].avail_end = halo_end; }
+    begin_call(ctx, st);
+    if (all_fast(ctx, p, 2)) {
+        for (int d = 0; d < 2 && rc == STEREO_OK; ++d) rc = validate(p[d], size_t(cols), size_t(cols));
+        if (rc == STEREO_OK) rc = run_fast_jobs(ctx, p, 2, st);
+    } else {
+        rc = run_problem(ctx, p[0], st);
+        if (rc == STEREO_OK) rc = run_problem(ctx, p[1], st);
+    }
+    end_call(ctx, st);
+    return rc;
+}
+
 int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
                                           const uint8_t* right, size_t img_step, size_t pair_stride, int rows,
                                           int cols, int window_rad, int disparity_range, void* disp_left,

@@ -77,6 +77,21 @@ class GpuCompute:
             raise RuntimeError(_capi.last_error())
         return out
 
+    def pair_band(self, cost, left_slab, right_slab, rows, cols, r0, r1, h0, h1, window_rad, disparity_range, dtype):
+        """Both maps of the band [r0, r1) in one launch sequence: (2, r1 - r0, cols)."""
+        torch = self.torch
+        dl = torch.as_tensor(np.ascontiguousarray(left_slab)).to(self.device, non_blocking=True)
+        dr = torch.as_tensor(np.ascontiguousarray(right_slab)).to(self.device, non_blocking=True)
+        out = torch.empty((2, r1 - r0, cols), dtype=dtype, device=self.device)
+        e = self._elem[dtype]
+        stream = torch.cuda.current_stream(self.device).cuda_stream or CUDA_STREAM_LEGACY
+        st = _capi.lib().stereo_disparity_pair_band_halo_u8_device(
+            self.ctx.handle, int(cost), dl.data_ptr(), cols, dr.data_ptr(), cols, rows, cols, r0, r1, h0, h1,
+            int(window_rad), int(disparity_range), out[0].data_ptr(), out[1].data_ptr(), cols * e, e, C.c_void_p(stream))
+        if st != _capi.STEREO_OK:
+            raise RuntimeError(_capi.last_error())
+        return out
+
     def pair_batch(self, cost, lefts, rights, window_rad, disparity_range, dtype):
         torch = self.torch
         n, rows, cols = lefts.shape
@@ -275,6 +290,23 @@ class ShardedStereo:
             mine[:r1 - r0] = self.compute.band(cost, left[h0:h1], right[h0:h1], rows, cols, r0, r1, h0, h1,
                                                window_rad, min_disp, max_disp, dtype)
         return self._gather(mine).reshape(self.world * band, cols)[:rows]
+
+    def disparity_pair_bands(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, disparity_range: int,
+                             dtype=None):
+        """(left-referenced map, right-referenced map), each rows x cols, on every rank; every rank computes both
+        maps of its row band in one launch sequence (BASELINE config 4 for a pair)."""
+        torch = self.torch
+        dtype = dtype or torch.int16
+        rows, cols = left.shape
+        band = -(-rows // self.world)
+        r0, r1 = band_shard(rows, self.world, self.rank)
+        mine = torch.zeros((2, band, cols), dtype=dtype, device=getattr(self.compute, "device", "cpu"))
+        if r1 > r0:
+            h0, h1 = band_halo(rows, r0, r1, window_rad)
+            mine[:, :r1 - r0] = self.compute.pair_band(cost, left[h0:h1], right[h0:h1], rows, cols, r0, r1, h0, h1,
+                                                       window_rad, disparity_range, dtype)
+        g = self._gather(mine)                                        # world x 2 x band x cols
+        return g[:, 0].reshape(self.world * band, cols)[:rows], g[:, 1].reshape(self.world * band, cols)[:rows]
 
     # -- batches, sharded by pair (BASELINE config 5) ---------------------------------------------------
     def disparity_pair_batch(self, cost: int, lefts: np.ndarray, rights: np.ndarray, window_rad: int,

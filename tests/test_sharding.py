@@ -48,6 +48,11 @@ class OracleCompute:
         d = fn(left_slab.astype(np.float32), right_slab.astype(np.float32), R, dmin, dmax)
         return torch.from_numpy(d[r0 - h0:r1 - h0].astype(np.int32)).to(dtype)
 
+    def pair_band(self, cost, left_slab, right_slab, rows, cols, r0, r1, h0, h1, R, rng, dtype):
+        import torch
+        return torch.stack([self.band(cost, left_slab, right_slab, rows, cols, r0, r1, h0, h1, R, -rng, 0, dtype),
+                            self.band(cost, right_slab, left_slab, rows, cols, r0, r1, h0, h1, R, 0, rng, dtype)])
+
     def pair_batch(self, cost, lefts, rights, R, rng, dtype):
         import torch
         fn = oracle.ssd_fast if cost == sb.COST_SSD else oracle.ncorr_fast
@@ -80,6 +85,10 @@ def _worker(rank, world, port, q):
                 full = sh.disparity_bands(cost, a, b, 3, dmin, dmax, dtype=torch.int16).numpy()
                 ref = fn(a.astype(np.float32), b.astype(np.float32), 3, dmin, dmax)
                 ok &= bool(np.array_equal(full, ref.astype(np.int16)))
+        # both maps of a pair, row-band sharded
+        pl, pr = sh.disparity_pair_bands(sb.COST_SSD, L, Rt, 3, 11, dtype=torch.int16)
+        ok &= bool(np.array_equal(pl.numpy(), oracle.ssd_fast(L.astype(np.float32), Rt.astype(np.float32), 3, -11, 0).astype(np.int16)))
+        ok &= bool(np.array_equal(pr.numpy(), oracle.ssd_fast(Rt.astype(np.float32), L.astype(np.float32), 3, 0, 11).astype(np.int16)))
         # pair batch: 5 pairs over the ranks
         Ls = np.stack([synth.make_pair(20, 64, 8, 300 + i)[0] for i in range(5)])
         Rs = np.stack([synth.make_pair(20, 64, 8, 300 + i)[1] for i in range(5)])
@@ -141,6 +150,18 @@ def test_gpu_sharding_single_rank_and_slab_api(ctx):
     sh = sharding.ShardedStereo(comp)
     out = sh.disparity_bands(sb.COST_SSD, L, Rt, 5, -39, 0, dtype=torch.int16)
     assert np.array_equal(out.cpu().numpy(), ctx.disparity(sb.COST_SSD, L, Rt, 5, -39, 0, dtype=np.int16))
+    # both maps of every band of a 3-way split from one (fused) launch sequence each == the full-image pair call
+    Lw, Rw, _ = synth.make_pair(101, 420, 64, 6)
+    full_l, full_r = ctx.disparity_pair(sb.COST_SSD, Lw, Rw, 4, 127, dtype=np.int16)
+    for rank in range(3):
+        r0, r1 = sharding.band_shard(101, 3, rank)
+        h0, h1 = sharding.band_halo(101, r0, r1, 4)
+        both = comp.pair_band(sb.COST_SSD, Lw[h0:h1].copy(), Rw[h0:h1].copy(), 101, 420, r0, r1, h0, h1, 4, 127, torch.int16)
+        torch.cuda.synchronize()
+        assert ctx.last_fused_pairs == 1
+        assert np.array_equal(both[0].cpu().numpy(), full_l[r0:r1]) and np.array_equal(both[1].cpu().numpy(), full_r[r0:r1]), rank
+    pl, pr = sh.disparity_pair_bands(sb.COST_SSD, Lw, Rw, 4, 127, dtype=torch.int16)
+    assert np.array_equal(pl.cpu().numpy(), full_l) and np.array_equal(pr.cpu().numpy(), full_r)
     Ls, Rs = np.stack([L[:64, :128], L[64:128, :128]]), np.stack([Rt[:64, :128], Rt[64:128, :128]])
     dl, dr = sh.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 3, 15, dtype=torch.int8)
     bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 3, 15)
