@@ -507,24 +507,25 @@ static inline bool fast_batchable(const Problem& a, const Problem& b) {
            a.tgt.type == PixType::U8 && b.tgt.type == PixType::U8;
 }
 
-// A left-referenced and a right-referenced problem of the SAME image pair whose maps can come out of one cost
-// volume (fused pair launch): SSD, R <= 5 (masking through the keys alone), mirrored ranges [-r, 0] / [0, r] with
-// r + 1 a multiple of 128 (whole disparity groups, so the partner's groups are this direction's groups reversed).
-static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
-    static const bool off = [] { const char* e = getenv("STEREO_FUSE_PAIRS"); return e && atoi(e) == 0; }();
-    if (off || !fast_batchable(a, b)) return false;
-    const int range = -a.dmin;
-    return a.cost == STEREO_COST_SSD && a.R <= FFREE_MASK_R && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
-           (range + 1) % FGROUP == 0 && a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step &&
-           a.tgt.step == b.ref.step;
-}
-
 // Strips per warp: 2 for searches of at most 64 candidates (a warp then covers 2 x 24 pixels x 64 disparities
 // instead of leaving half its lanes idle).  STEREO_FAST_HS=1 forces the single-strip kernels (debug knob).
 static inline int fast_pick_hs(int D) {
     static const int forced = [] { const char* e = getenv("STEREO_FAST_HS"); return e ? atoi(e) : 0; }();
     if (forced == 1) return 1;
     return D <= 64 ? 2 : 1;
+}
+
+// A left-referenced and a right-referenced problem of the SAME image pair whose maps can come out of one cost
+// volume (fused pair launch): SSD, R <= 5 (masking through the keys alone), mirrored ranges [-r, 0] / [0, r] with
+// r + 1 a multiple of the disparities per group (128, or 64 for searches of at most 64 candidates: whole groups, so
+// the partner's groups are this direction's groups reversed).  The launch geometry must agree (fast_fused_geometry_ok).
+static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
+    static const bool off = [] { const char* e = getenv("STEREO_FUSE_PAIRS"); return e && atoi(e) == 0; }();
+    if (off || !fast_batchable(a, b)) return false;
+    const int range = -a.dmin;
+    return a.cost == STEREO_COST_SSD && a.R <= FFREE_MASK_R && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
+           (range + 1) % (FGROUP / fast_pick_hs(range + 1)) == 0 && a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step &&
+           a.tgt.step == b.ref.step;
 }
 
 static inline size_t fast_stage_bytes(const FastGeom& g) {
@@ -558,7 +559,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         g.rqw = round_up(tile_px + 2 * p.R + g.dg * g.gc + FM, 4);
         g.e2w = round_up(tile_px + g.dg * g.gc + FM, 4);
         g.elw = fused_pairs > 0 ? tile_px : 0;
-        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16 - (fused_pairs > 0 ? FWARPS * 128 : 0)) / fast_stage_bytes(g));
+        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16 - (fused_pairs > 0 ? FWARPS * 256 : 0)) / fast_stage_bytes(g));
         if (g.nst > FNST_MAX) g.nst = FNST_MAX;
         if (g.nst >= 4 || g.hs == 1) break;
         g.hs = 1;                                  // tile rows too wide for a useful pipeline: single-strip kernels
@@ -604,8 +605,16 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
     g.ctas = int((g.total + g.L - 1) / g.L);
 }
 
+// The fused kernels need whole disparity groups under the geometry the launch will really use (the strips-per-warp
+// choice can fall back to 1 when the tile rows get too wide for a useful pipeline).
+static inline bool fast_fused_geometry_ok(const stereo_ctx* ctx, const Problem* ps, int n) {
+    FastKernelParams kp{};
+    fast_geometry(ctx, ps, n, kp.g, kp.job, n / 2);
+    return kp.g.D % kp.g.dg == 0;
+}
+
 static inline size_t fast_smem_bytes(const FastGeom& g) {
-    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + (g.elw ? FWARPS * 128 : 0);
+    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + (g.elw ? FWARPS * 256 : 0);
 }
 
 static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64); }
@@ -643,9 +652,10 @@ static inline int fast_ctx_init(stereo_ctx*) {
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
             }
-    for (int R = 0; R <= FFREE_MASK_R; ++R) {
-        fast_kernel_fn fn = fast_pick_fused(R);
-        if (!fn) { set_error("fused pair kernel (R %d) missing from the build", R); return STEREO_ERR_UNSUPPORTED; }
+    for (int R = 0; R <= FFREE_MASK_R; ++R)
+      for (int hs = 1; hs <= 2; ++hs) {
+        fast_kernel_fn fn = fast_pick_fused(R, hs);
+        if (!fn) { set_error("fused pair kernel (R %d, hs %d) missing from the build", R, hs); return STEREO_ERR_UNSUPPORTED; }
         cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
     }
@@ -714,8 +724,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
         ctx->last_launches += 2;
     }
-    fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R) : fast_pick(ps[0].cost, g.R, g.hs);
-    if (!fn || (fused_pairs && g.hs != 1)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
+    fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R, g.hs) : fast_pick(ps[0].cost, g.R, g.hs);
+    if (!fn || (fused_pairs && g.D % g.dg != 0)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {
         ctx->last_launches += fused_pairs;         // the memsets
         ctx->fused_pairs_done += fused_pairs;

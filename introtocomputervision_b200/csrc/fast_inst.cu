@@ -1,12 +1,12 @@
 // Instantiations of the hot kernel (fast_kernel.cuh), one translation unit per SB_PART so they compile in parallel:
 //   SB_PART = hs_index * 8 + cost * 4 + radius subset;  hs_index 0 -> 1 strip per warp, 1 -> 2 strips per warp;
 //   cost 0 = SSD, 1 = NCC;  radius subsets {0,1,2,3}, {4}, {5}, {6,7}.
-//   SB_PART = 16, 17, 18: the fused pair kernels (SSD, both maps of a pair from one cost volume), radius subsets
-//   {0,1,2,3}, {4}, {5}.
+//   SB_PART = 16..21: the fused pair kernels (SSD, both maps of a pair from one cost volume), radius subsets
+//   {0,1,2,3}, {4}, {5}; 16-18 one strip per warp, 19-21 two strips per warp.
 #include "fast_kernel.cuh"
 
 #ifndef SB_PART
-#error "compile with -DSB_PART=0..18"
+#error "compile with -DSB_PART=0..21"
 #endif
 
 namespace sb {
@@ -15,20 +15,31 @@ namespace sb {
 #define SB_CAT(a, b) SB_CAT2(a, b)
 
 #if SB_PART >= 16
+#define SB_FUSED_KERNEL(R_, HS_) fast_cost_kernel<R_, FK_FUSED, FWARPS, STEREO_COST_SSD, HS_, true>
+#if SB_PART == 16 || SB_PART == 19
 #if SB_PART == 16
 fast_kernel_fn fast_pick_fused_a(int R) {
+    constexpr int HS = 1;
+#else
+fast_kernel_fn fast_pick_fused2_a(int R) {
+    constexpr int HS = 2;
+#endif
     switch (R) {
-    case 0: return fast_cost_kernel<0, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 1: return fast_cost_kernel<1, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 2: return fast_cost_kernel<2, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
-    case 3: return fast_cost_kernel<3, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true>;
+    case 0: return SB_FUSED_KERNEL(0, HS);
+    case 1: return SB_FUSED_KERNEL(1, HS);
+    case 2: return SB_FUSED_KERNEL(2, HS);
+    case 3: return SB_FUSED_KERNEL(3, HS);
     }
     return nullptr;
 }
 #elif SB_PART == 17
-fast_kernel_fn fast_pick_fused_b(int R) { return R == 4 ? fast_cost_kernel<4, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+fast_kernel_fn fast_pick_fused_b(int R) { return R == 4 ? SB_FUSED_KERNEL(4, 1) : nullptr; }
+#elif SB_PART == 18
+fast_kernel_fn fast_pick_fused_c(int R) { return R == 5 ? SB_FUSED_KERNEL(5, 1) : nullptr; }
+#elif SB_PART == 20
+fast_kernel_fn fast_pick_fused2_b(int R) { return R == 4 ? SB_FUSED_KERNEL(4, 2) : nullptr; }
 #else
-fast_kernel_fn fast_pick_fused_c(int R) { return R == 5 ? fast_cost_kernel<5, FK_FUSED, FWARPS, STEREO_COST_SSD, 1, true> : nullptr; }
+fast_kernel_fn fast_pick_fused2_c(int R) { return R == 5 ? SB_FUSED_KERNEL(5, 2) : nullptr; }
 #endif
 #else
 // `key` = strips per warp | cost << 8

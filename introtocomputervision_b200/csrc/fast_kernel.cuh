@@ -207,7 +207,7 @@ constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses
 // own K-pixel strip; `sub` is the lane's sub-warp, `ll` its lane index inside it.  The per-pixel warp
 // reduction then runs once per sub-warp over the full warp with the other lanes neutralised.
 //
-// FUSED (SSD, one strip per warp, D a multiple of 128, R <= 5): the R->L map of the same image pair comes out of
+// FUSED (SSD, D a multiple of the 128 / HS disparities of a group, R <= 5): the R->L map of the same image pair comes out of
 // the same cross terms.  C(x, d) serves the L->R pixel x AND the R->L pixel x' = x + d, whose
 // candidate -d it is (main.cpp:33,43: the second call swaps the images and mirrors the range).  A lane's four
 // candidates at pixel step k lie on the diagonals t = k + 4*lane + m of the (x, x') plane (t = x' - x0 - dlo), so
@@ -274,7 +274,8 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 #pragma unroll
         for (int m = 0; m < FM; ++m) acc[m] = KEY_INVALID;
     }
-    const uint32_t top_or = (FUSED && ll == 31) ? KEY_INVALID : 0u;   // lane 31 opens a fresh diagonal every step
+    constexpr int LSF = 32 / HS;                                          // lanes per strip
+    const uint32_t top_or = (FUSED && ll == LSF - 1) ? KEY_INVALID : 0u;  // the top lane of a strip opens a fresh diagonal every step
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         update(k + 2 * R);
@@ -342,17 +343,20 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             // diagonal k + 4*ll is complete for this lane: it moves to the lane below (lane 0: into the tail);
             // the lane's other three diagonals move down one slot and the slot on top takes over lane ll+1's
             const uint32_t done = acc[0];
-            const uint32_t in = __shfl_down_sync(0xffffffffu, done, 1) | top_or;
-            if (ll == 0) tail[k] = done;
+            const uint32_t in = __shfl_down_sync(0xffffffffu, done, 1, LSF) | top_or;
+            if (ll == 0) tail[32 * sub + k] = done;
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
         }
     }
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
-        const uint32_t tv = (ll < K) ? tail[ll] : KEY_INVALID;
-        const int xt = x2base + ll;
-        if (ll < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tv);
+        const int lane = sub * LSF + ll;
+#pragma unroll
+        for (int h = 0; h < HS; ++h) {                   // strip h of the warp: its tail, one entry per lane
+            const int xt = x2base + (h - sub) * K + lane;
+            if (lane < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tail[32 * h + lane]);
+        }
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             const int xa = x2base + K + FM * ll + m;
@@ -364,7 +368,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 
 template <int R, int K, int NW, int COST, int HS, bool FUSED = false>
 __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
-    static_assert(!FUSED || (COST == STEREO_COST_SSD && HS == 1 && R <= FFREE_MASK_R && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, one strip per warp, R <= 5");
+    static_assert(!FUSED || (COST == STEREO_COST_SSD && R <= FFREE_MASK_R && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, R <= 5");
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr int LS = 32 / HS;                 // lanes per strip
     constexpr int DG = FM * LS;                 // disparities per strip and warp
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     int* smem = reinterpret_cast<int*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nst) * stage_words * 4);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST_MAX);
-    uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * 32;     // FUSED: 32 words per warp
+    uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * 64;     // FUSED: 32 words per strip of the warp
 
     if (tid == 0) {
         for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int lp_off = (wstrip + sub) * K;
         const int rq_off = lp_off + DG * (warp % g.gc) + FM * ll;
         int32_t* part = job.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
-        // FUSED: the partner's candidates -d of this group are its group G-1-grp (D is a multiple of 128)
+        // FUSED: the partner's candidates -d of this group are its group G-1-grp (D is a multiple of the group size)
         uint32_t* part2 = FUSED ? reinterpret_cast<uint32_t*>(P.job[jb + npair].PART) + (size_t(g.G - 1 - grp) * g.nrows) * g.wpart : nullptr;
         const int x2base = x0 + dlo;                                      // partner pixel of diagonal 0
 #pragma unroll
@@ -563,7 +567,15 @@ SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(1
 fast_kernel_fn fast_pick_fused_a(int R);
 fast_kernel_fn fast_pick_fused_b(int R);
 fast_kernel_fn fast_pick_fused_c(int R);
-static inline fast_kernel_fn fast_pick_fused(int R) {
+fast_kernel_fn fast_pick_fused2_a(int R);     // two strips per warp (64 disparities)
+fast_kernel_fn fast_pick_fused2_b(int R);
+fast_kernel_fn fast_pick_fused2_c(int R);
+static inline fast_kernel_fn fast_pick_fused(int R, int hs) {
+    if (hs == 2) {
+        if (fast_kernel_fn fn = fast_pick_fused2_a(R)) return fn;
+        if (fast_kernel_fn fn = fast_pick_fused2_b(R)) return fn;
+        return fast_pick_fused2_c(R);
+    }
     if (fast_kernel_fn fn = fast_pick_fused_a(R)) return fn;
     if (fast_kernel_fn fn = fast_pick_fused_b(R)) return fn;
     return fast_pick_fused_c(R);

@@ -198,7 +198,7 @@ static bool fused_layout(const stereo_ctx* ctx, const Problem* ps, int n) {
     const int np = n / 2;
     for (int k = 0; k < np; ++k)
         if (!fast_pair_fusable(ps[k], ps[np + k]) || !fast_batchable(ps[0], ps[k])) return false;
-    return true;
+    return fast_fused_geometry_ok(ctx, ps, n);
 }
 
 // One launch sequence over batchable problems, fused when they are whole pairs.

@@ -350,6 +350,9 @@ FUSED_SHAPES = [
     (22, 410, 4, 383),          # three groups (gc = 1)
     (64, 1000, 5, 255),
     (9, 130, 1, 127),           # fewer rows than a pipeline stage
+    (33, 450, 4, 63),           # 64 candidates: two strips per warp, 16-lane diagonal chains
+    (21, 97, 2, 63),
+    (50, 1280, 5, 63),
 ]
 
 
@@ -407,12 +410,13 @@ def test_fused_pair_bands_and_batches(ctx):
         a, b, _ = synth.make_pair(33, 330, 64, 7000 + i)
         Ls.append(a), Rs.append(b)
     Ls, Rs = np.stack(Ls), np.stack(Rs)
-    bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, 127, dtype=np.int8)
-    assert ctx.last_fused_pairs == n
-    for i in range(n):
-        a, b = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
-        assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(a, b, 4, -127, 0))), i
-        assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(b, a, 4, 0, 127))), i
+    for rng in (127, 63):
+        bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, rng, dtype=np.int8)
+        assert ctx.last_fused_pairs == n
+        for i in range(n):
+            a, b = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+            assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(a, b, 4, -rng, 0))), (rng, i)
+            assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(b, a, 4, 0, rng))), (rng, i)
 
 
 def test_fused_pair_with_costs_matches_single_calls(ctx):
