@@ -118,7 +118,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def start(self):
         if self.nv is not None:
@@ -440,7 +440,7 @@ def run_ours(args, wl):
             b_in, b_out = 1, elem
             alg_bytes = int(jobs_per_launch * rows * cols * (2 * b_in + b_out))   # per launch
             roof = {
-                "bound": "alu", "kernel": (f"fast_cost_kernel<R={R},K=20,NW=8,SSD,fused pair>" if fused
+                "bound": "alu", "kernel": (f"fast_cost_kernel<R={R},K={16 if nd <= 64 else 20},NW=8,SSD,fused pair>" if fused
                                            else f"fast_cost_kernel<R={R},K=24,NW=8,{args.cost.upper()}>"),
                 "achieved": round(achieved / 1e12, 3), "peak": round(peak_lane_ops / 1e12, 3), "unit": "Tlane-op/s",
                 "frac": round(achieved / peak_lane_ops, 4),

@@ -545,11 +545,12 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
     g.njobs = n;
     g.npairs = fused_pairs;
     g.elw = 0;
-    g.K = fused_pairs > 0 ? FK_FUSED : FK_DEFAULT;
+    g.K = FK_DEFAULT;
     g.nw = FWARPS;
     g.hs = fast_pick_hs(g.D);
     const int w = 2 * p.R + 1;
     for (;;) {
+        if (fused_pairs > 0) g.K = g.hs == 2 ? FK_FUSED2 : FK_FUSED;
         g.dg = FGROUP / g.hs;
         g.G = (g.D + g.dg - 1) / g.dg;
         g.gc = (g.hs == 1 && g.G % 2 == 0) ? 2 : 1;

@@ -15,7 +15,7 @@ namespace sb {
 #define SB_CAT(a, b) SB_CAT2(a, b)
 
 #if SB_PART >= 16
-#define SB_FUSED_KERNEL(R_, HS_) fast_cost_kernel<R_, FK_FUSED, FWARPS, STEREO_COST_SSD, HS_, true>
+#define SB_FUSED_KERNEL(R_, HS_) fast_cost_kernel<R_, (HS_ == 2 ? FK_FUSED2 : FK_FUSED), FWARPS, STEREO_COST_SSD, HS_, true>
 #if SB_PART == 16 || SB_PART == 19
 #if SB_PART == 16
 fast_kernel_fn fast_pick_fused_a(int R) {

@@ -33,11 +33,16 @@ namespace sb {
 #define SB_FK_DEFAULT 24
 #endif
 constexpr int FK_DEFAULT = SB_FK_DEFAULT;  // pixels per thread (strip width); template parameter K of the kernels
+// Strip width of the fused pair kernels.  Their 8 extra live registers per thread make 24-pixel strips spill (ncu: 2.07 ms
+// vs 1.82 ms per two 4K/256 pairs).  One strip per warp: 20 pixels (255 registers, no spills for R = 5, 24 bytes for R = 4);
+// two strips per warp: 16 pixels (20 spills there; 0.150 vs 0.167 ms per four 720p/64 pairs).
 #ifndef SB_FK_FUSED
 #define SB_FK_FUSED 20
 #endif
-constexpr int FK_FUSED = SB_FK_FUSED;      // strip width of the fused pair kernels: their 8 extra live registers per thread
-                                           // make 24-pixel strips spill (ncu: 2.07 ms vs 1.82 ms per two 4K/256 pairs)
+#ifndef SB_FK_FUSED2
+#define SB_FK_FUSED2 16
+#endif
+constexpr int FK_FUSED = SB_FK_FUSED, FK_FUSED2 = SB_FK_FUSED2;
 constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
@@ -343,19 +348,26 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             // diagonal k + 4*ll is complete for this lane: it moves to the lane below (lane 0: into the tail);
             // the lane's other three diagonals move down one slot and the slot on top takes over lane ll+1's
             const uint32_t done = acc[0];
-            const uint32_t in = __shfl_down_sync(0xffffffffu, done, 1, LSF) | top_or;
-            if (ll == 0) tail[32 * sub + k] = done;
+            uint32_t in;
+            if (HS == 1) { in = __shfl_down_sync(0xffffffffu, done, 1) | top_or; if (ll == 0) tail[k] = done; }
+            else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF) | top_or; if (ll == 0) tail[32 * sub + k] = done; }
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
         }
     }
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
-        const int lane = sub * LSF + ll;
+        if (HS == 1) {
+            const uint32_t tv = (ll < K) ? tail[ll] : KEY_INVALID;
+            const int xt = x2base + ll;
+            if (ll < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tv);
+        } else {
+            const int lane = sub * LSF + ll;
 #pragma unroll
-        for (int h = 0; h < HS; ++h) {                   // strip h of the warp: its tail, one entry per lane
-            const int xt = x2base + (h - sub) * K + lane;
-            if (lane < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tail[32 * h + lane]);
+            for (int h = 0; h < HS; ++h) {               // strip h of the warp: its tail, one entry per lane
+                const int xt = x2base + (h - sub) * K + lane;
+                if (lane < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tail[32 * h + lane]);
+            }
         }
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     int* smem = reinterpret_cast<int*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nst) * stage_words * 4);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST_MAX);
-    uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * 64;     // FUSED: 32 words per strip of the warp
+    uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * (32 * HS);     // FUSED: 32 words per strip of the warp
 
     if (tid == 0) {
         for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }

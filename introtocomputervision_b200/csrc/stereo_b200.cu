@@ -317,7 +317,8 @@ static int ensure_pipe(stereo_ctx* ctx, int events) {
 
 static int pipe_bands(const stereo_ctx* ctx, int n_pairs, int rows) {
     if (ctx->pipe_bands > 0) return ctx->pipe_bands < rows ? ctx->pipe_bands : rows;
-    if (n_pairs >= 4 || rows < 512) return 1;           // enough pairs in flight / too small to be worth cutting
+    if (rows < 512) return 1;                           // too small to be worth cutting
+    if (n_pairs >= 4) return rows >= 1024 ? 2 : 1;      // enough pairs in flight; two bands shorten the fill and the drain (tools/e2e_sweep.py)
     int nb = (rows + 255) / 512;                        // ~512-row bands: the (2R+1)-row warm-up stays < 3 %
     return nb < 1 ? 1 : (nb > 8 ? 8 : nb);
 }
