@@ -135,6 +135,24 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_cpus(index: int):
+    """Multi-rank runs: keep this rank's threads (and, by first touch, its pinned host buffers) on the CPUs NVML
+    reports as local to its GPU.  Returns the number of CPUs bound to, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 1) + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and cpus != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------
 # the reference's CPU implementation on host cores (bounded sample)
 # ---------------------------------------------------------------------------------------------------
@@ -219,6 +237,7 @@ def run_ours(args, wl):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bound_cpus = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _capi.lib()
@@ -487,7 +506,8 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": B * 2 * rows * cols * elem, "steps": e2e_steps,
                     "api": "stereo_disparity_pair_batch_f32_host: one call per step, the step's pairs as pinned CV_32FC1 host "
                            "images in, int8/int16 host maps out",
-                    "per_pair_calls_value": round(e2e_pp_value, 1), "u8_host_api_value": round(e2e8_value, 1)},
+                    "per_pair_calls_value": round(e2e_pp_value, 1), "u8_host_api_value": round(e2e8_value, 1),
+                    "host_cpus_bound_per_rank": bound_cpus},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
@@ -512,21 +532,38 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     h0, h1 = sharding.band_halo(rows, r0, r1, R)
     band = -(-rows // world)
     d_l, d_r = torch.from_numpy(L[h0:h1].copy()).to(dev), torch.from_numpy(Rt[h0:h1].copy()).to(dev)   # this rank's slab only
-    mine = torch.zeros((2, band, cols), dtype=elem_dtype, device=dev)
-    gathered = torch.empty((world, 2, band, cols), dtype=elem_dtype, device=dev)
+    mine = torch.zeros((2, 2, band, cols), dtype=elem_dtype, device=dev)          # [parity][direction]
+    band_bytes = 2 * band * cols * elem
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    gather = args.gather if world > 1 else "none"
+    pg, gathered, gather_note = None, None, ""
+    if gather == "p2p":          # every rank's buffer: [parity][rank][direction][band rows][cols], filled by copy-engine pushes
+        try:
+            pg = sharding.PeerGather(ctx, 2 * world * band_bytes)
+        except sharding.PeerGatherUnavailable as e:
+            gather, gather_note = "nccl", f" (peer buffers unavailable: {e})"
+    if gather == "nccl":
+        gathered = torch.empty((world, 2, band, cols), dtype=elem_dtype, device=dev)
+    state = {"k": 0}
 
     def step():
+        # ONE image pair per step: the gather is part of the step (strong scaling has nothing to overlap it with), so a
+        # step ends when this rank's pushes have landed / the collective has finished
+        par = state["k"] & 1
+        state["k"] += 1
         rc = lib.stereo_disparity_pair_band_halo_u8_device(ctx.handle, cost, d_l.data_ptr(), cols, d_r.data_ptr(), cols, rows, cols,
-                                                           r0, r1, h0, h1, R, nd - 1, mine[0].data_ptr(), mine[1].data_ptr(),
+                                                           r0, r1, h0, h1, R, nd - 1, mine[par, 0].data_ptr(), mine[par, 1].data_ptr(),
                                                            cols * elem, elem, sp)
         if rc != 0:
             raise RuntimeError(_capi.last_error())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))
+        if pg is not None:
+            pg.push((par * world + rank) * band_bytes, mine[par].data_ptr(), band_bytes, stream.cuda_stream)
+            pg.wait(pg.mark(), stream.cuda_stream)
+        elif gathered is not None:
+            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine[par].view(torch.uint8).view(-1))
 
     def barrier():
         if world > 1:
@@ -562,10 +599,23 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
                            "window": 2 * R + 1, "band_rows": band, "halo_rows": R + 1, "directions": 2,
                            "pair_fusion": "both maps of a band from one cost volume" if ctx.last_fused_pairs else "one cost volume per direction",
                            "sharding": "by row band, slab with halo resident per rank"
-                                       + (", NCCL all_gather of the bands inside the step" if world > 1 else ""),
+                                       + {"p2p": ", every rank's band pushed into every rank's gather buffer by the copy engines over "
+                                                 "NVLink (stereo_peer_push), joined inside the step",
+                                          "nccl": ", NCCL all_gather of the bands inside the step" + gather_note, "none": ""}[gather],
                            "l2": "flushed between steps"},
                 "gpu_launches": ctx.last_launches * args.steps, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    if pg is not None:
+        # cross-rank check: every slot of the last step equals what that rank computed
+        par = (state["k"] - 1) & 1
+        dist.barrier()
+        torch.cuda.synchronize()
+        sums = pg.local_bytes(dev)[par * world * band_bytes:(par + 1) * world * band_bytes].view(world, -1).to(torch.int64).sum(dim=1)
+        mine_sum = mine[par].view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
+        all_sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_sums, mine_sum)
+        assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's band"
+        pg.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -727,8 +727,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     }
     fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R, g.hs) : fast_pick(ps[0].cost, g.R, g.hs);
     if (!fn || (fused_pairs && g.D % g.dg != 0)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
-    if (fused_pairs) {
-        ctx->last_launches += fused_pairs;         // the memsets
+    if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
         ctx->fused_pairs_done += fused_pairs;
     }
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
