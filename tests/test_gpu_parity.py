@@ -377,6 +377,26 @@ def test_fused_pair_equals_oracle_and_unfused(ctx, rows, cols, R, rng):
     assert bad.size == 0, f"fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
 
 
+@pytest.mark.parametrize("seed", range(14))
+def test_fused_pair_random_shapes(ctx, seed):
+    """Seeded random shapes through the fused pair launch: images narrower than a strip or than the search range, a
+    single row, every radius 0..5, 64 / 128 / 256 candidates, uint8 and CV_32FC1 inputs."""
+    rng = np.random.default_rng(9000 + seed)
+    rows = int(rng.integers(1, 48))
+    cols = int(rng.choice([3, 17, 40, 95, 129, 257, 600])) + int(rng.integers(0, 7))
+    R = int(rng.integers(0, 6))
+    r = int(rng.choice([63, 127, 255]))
+    L, Rt, _ = synth.make_pair(rows, cols, min(r + 1, max(2, cols // 2)), 9100 + seed)
+    if seed % 3 == 0:                       # low-texture image: many exact ties
+        L, Rt = (L // 64 * 64).astype(np.uint8), (Rt // 64 * 64).astype(np.uint8)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    a, b = (Lf, Rf) if seed % 2 else (L, Rt)
+    dl, dr = ctx.disparity_pair(sb.COST_SSD, a, b, R, r, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs >= 1
+    assert np.array_equal(dl, oracle.ssd_fast(Lf, Rf, R, -r, 0)), (rows, cols, R, r)
+    assert np.array_equal(dr, oracle.ssd_fast(Rf, Lf, R, 0, r)), (rows, cols, R, r)
+
+
 def test_fused_pair_ties_flat_images(ctx):
     # flat and banded images: every candidate ties; first-minimum order must survive the diagonal minima
     rows, cols, R, rng = 24, 400, 3, 127
