@@ -8,7 +8,7 @@
 
 A step = one pass of the hot path over one batch of synthetic stereo pairs (both directions per
 pair, like the reference's disparitySSDPair, main.cpp:21-48).  Workload at every N: per GPU a batch
-of B synthetic 3840x2160 pairs, 256 disparities, 11x11 window, SSD (BASELINE config 4's shape and
+of B = 4 synthetic 3840x2160 pairs, 256 disparities, 11x11 window, SSD (BASELINE config 4's shape and
 the config the north-star target is quoted on), pairs sharded by rank (weak scaling); for N > 1 every
 rank's disparity maps are gathered on every rank inside the timed region (BASELINE config 5's "sharded
 by pair ... with ... gather"): by default with copy-engine pushes over NVLink into peer-mapped buffers
@@ -628,7 +628,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k_d256_w11", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=2, help="stereo pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=4, help="stereo pairs per GPU per step (4 pairs = 8 directions = one launch sequence)")
     ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--pipe-bands", type=int, default=0, help="row bands per pair in the pipelined host entry points (0 = automatic)")
