@@ -134,6 +134,38 @@ inline void run(int cost, const MatT& left, const MatT& right, size_t windowRad,
 }
 } // namespace detail
 
+// Both maps of a pair in ONE call: what the reference's disparitySSDPair / disparityNCorrPair (src/main.cpp:21-78)
+// do with two calls — left-referenced map over [-range, 0], then the images swapped and [0, +range].  SSD pairs come
+// out of one cost volume where the library can fuse them (stereo_ctx_set_fuse_pairs); results are the two calls'.
+inline void run_pair(int cost, const MatT& left, const MatT& right, size_t windowRad, int disparityRange,
+                     MatT& disparityLeft, MatT& disparityRight, int out_type, stereo_ctx* ctx) {
+    if (left.rows != right.rows || left.cols != right.cols || left.type() != right.type())
+        check(STEREO_ERR_INVALID_ARG, "disparity pair: left/right differ in size or type (main.cpp:27-28)");
+    if (!ctx) ctx = default_ctx();
+    disparityLeft.create(left.rows, left.cols, out_type);
+    disparityRight.create(left.rows, left.cols, out_type);
+    const int elem = out_type == S16C1 ? 2 : 1;
+    int st;
+    if (left.type() == F32C1)
+        st = stereo_disparity_pair_f32_host(ctx, cost, reinterpret_cast<const float*>(left.data), left.step,
+                                            reinterpret_cast<const float*>(right.data), right.step, left.rows, left.cols,
+                                            int(windowRad), disparityRange, disparityLeft.data, disparityRight.data,
+                                            disparityLeft.step, elem);
+    else if (left.type() == U8C1)
+        st = stereo_disparity_pair_u8_host(ctx, cost, left.data, left.step, right.data, right.step, left.rows, left.cols,
+                                           int(windowRad), disparityRange, disparityLeft.data, disparityRight.data,
+                                           disparityLeft.step, elem);
+    else
+        st = STEREO_ERR_INVALID_ARG;
+    check(st, cost == STEREO_COST_SSD ? "disparitySSDPair" : "disparityNCorrPair");
+}
+inline void disparitySSDPair(const MatT& l, const MatT& r, size_t rad, int range, MatT& dl, MatT& dr, bool wide = false, stereo_ctx* ctx = nullptr) {
+    run_pair(STEREO_COST_SSD, l, r, rad, range, dl, dr, wide ? S16C1 : S8C1, ctx);
+}
+inline void disparityNCorrPair(const MatT& l, const MatT& r, size_t rad, int range, MatT& dl, MatT& dr, bool wide = false, stereo_ctx* ctx = nullptr) {
+    run_pair(STEREO_COST_NCORR, l, r, rad, range, dl, dr, wide ? S16C1 : S8C1, ctx);
+}
+
 // int16 outputs for > 127 disparities (the reference's CV_8SC1 wraps)
 inline void disparitySSDWide(const MatT& l, const MatT& r, size_t rad, int dmin, int dmax, MatT& d, stereo_ctx* ctx = nullptr) {
     detail::run(STEREO_COST_SSD, l, r, rad, dmin, dmax, d, S16C1, ctx);
