@@ -16,7 +16,12 @@
 // The cost volume never exists in memory: a thread owns K=24 pixels x M=4 disparities, a warp
 // 24 pixels x 128 disparities, and only the winning key per pixel and 128-disparity group leaves
 // the SM.  Operand rows are staged in shared memory with TMA bulk copies (cp.async.bulk, SASS
-// UBLKCP) through a 4-stage mbarrier ring; all warps of a CTA share the staged rows.
+// UBLKCP) through a ring of up to 8 stages of 8 rows (full / empty mbarriers); all warps of a CTA share
+// the staged rows.
+//
+// Pair launches (FUSED): the same cross terms also give the map of the OTHER direction of the image pair
+// (C(x, d) is candidate -d of the partner pixel x + d), kept as running minima along the diagonals of the
+// (x, x + d) plane - see fast_row.  Strips are 20 (16) pixels wide there instead of 24.
 //
 // Reference semantics reproduced: replicate padding, the clamped candidate
 // range in padded coordinates, the flat-index row wrap of the SSD target reads (realised by building
