@@ -109,6 +109,11 @@ int stereo_ctx_force_path(stereo_ctx* ctx, int path);
  * (DisparitySSD.cu:171-206). */
 int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands);
 
+/* How the pipelined host entry points cut a call of `n_pairs` rows x cols pairs into work items: row bands per pair
+ * (bands_override = stereo_ctx_set_pipe_bands' value, 0 = automatic) and pairs per item (small images ride several
+ * pairs per launch sequence).  Pure host arithmetic, no device needed. */
+int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_override, int* bands_per_pair, int* pairs_per_item);
+
 /* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the problem allows
  * it (SSD, window_rad <= 5, disparity_range + 1 a multiple of 128) — the reference's disparitySSDPair always wants
  * both (main.cpp:21-48) and SSD_LR(x, d) and SSD_RL(x + d, -d) are the same window sum.  Results are identical

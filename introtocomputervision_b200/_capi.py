@@ -35,6 +35,7 @@ SIGNATURES = {
     "stereo_ctx_last_hot_jobs": (_i, [_vp]),
     "stereo_ctx_force_path": (_i, [_vp, _i]),
     "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
+    "stereo_host_pipeline_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
     "stereo_ctx_last_fused_pairs": (_i, [_vp]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),

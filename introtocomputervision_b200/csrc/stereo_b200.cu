@@ -709,6 +709,19 @@ int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands) {
     return STEREO_OK;
 }
 
+// Pure host arithmetic (no device): how a host batch call is cut into pipeline items.
+int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_override, int* bands_per_pair, int* pairs_per_item) {
+    if (n_pairs <= 0 || rows <= 0 || cols <= 0 || bands_override < 0 || !bands_per_pair || !pairs_per_item) {
+        set_error("bad arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    stereo_ctx tmp;
+    tmp.pipe_bands = bands_override;
+    const int nb = pipe_bands(&tmp, n_pairs, rows);
+    *bands_per_pair = nb;
+    *pairs_per_item = pipe_chunk_pairs(n_pairs, nb, rows, cols);
+    return STEREO_OK;
+}
+
 int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx) { return ctx ? ctx->fused_pairs_done : 0; }
 
 int stereo_ctx_set_fuse_pairs(stereo_ctx* ctx, int on) {

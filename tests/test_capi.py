@@ -79,3 +79,26 @@ def test_headline_hot_kernels_do_not_spill():
         m = re.search(r"fast_cost_kernel" + kernel + r".*?\n\s*REG:(\d+) STACK:(\d+)", out, flags=re.S)
         assert m, f"kernel {kernel} not found in part {part}"
         assert int(m.group(2)) == 0, f"fast_cost_kernel{kernel} spills: STACK:{m.group(2)}"
+
+
+def test_host_pipeline_plan():
+    """The cut of a host batch into pipeline items (pure host arithmetic): large single pairs go in ~512-row bands,
+    batches of large images in two bands, batches of small images several pairs per item (<= 4 = 8 directions per launch
+    sequence) with at least three items in flight."""
+    lib = _capi.lib()
+
+    def plan(n, rows, cols, override=0):
+        b, c = C.c_int(), C.c_int()
+        assert lib.stereo_host_pipeline_plan(n, rows, cols, override, C.byref(b), C.byref(c)) == 0
+        return b.value, c.value
+
+    assert plan(1, 2160, 3840) == (4, 1)
+    assert plan(2, 2160, 3840) == (4, 1)
+    assert plan(4, 2160, 3840) == (2, 1)
+    assert plan(1, 1080, 1920) == (2, 1)
+    assert plan(1, 128, 128) == (1, 1)
+    assert plan(16, 720, 1280) == (1, 4)
+    assert plan(6, 720, 1280) == (1, 2)
+    assert plan(512, 720, 1280) == (1, 4)
+    assert plan(3, 2160, 3840, override=7) == (7, 1)
+    assert lib.stereo_host_pipeline_plan(0, 10, 10, 0, None, None) != 0
