@@ -488,6 +488,71 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Fused pair launches: the partner's candidates centred in the right padding, evaluated directly
+// ---------------------------------------------------------------------------------------------------
+// The fused hot kernel gives the right-referenced pixel x' every candidate centred on an image column.  The reference
+// also searches the right padding (DisparitySSD.cpp:39-40: the clamp is colsP-1): centres pos in
+// [cols, min(x' + range, cols-1+R)], whose windows run past the end of the padded row and alias the next row through
+// the flat index (bext).  Normally the strips simply extend R columns (LP rows built with bext); when those R columns
+// would cost a whole extra tile (narrow images: 1280 columns = 4 tiles of 320, +4 columns = a fifth), the <= R
+// candidates of the last `range` pixels of every row are evaluated here instead - one thread per pixel, the window
+// of the reference image and the 3R extended target columns of each window row in registers - and merged into the
+// same partial-key map (RED.MIN) with the key the hot kernel would have produced: BIAS + 128*(ER - 2C) + pos.
+template <int R>
+__global__ void __launch_bounds__(128) fused_border_kernel(const __grid_constant__ FastKernelParams P) {
+    constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1;
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[g.npairs + blockIdx.z];          // the right-referenced direction: A = right image, B = left image
+    const int range = job.dmax;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xp = g.cols - 1 - idx;                            // the pixel x'
+    const int yy = blockIdx.y, y = g.rb + yy;
+    if (idx >= range || xp < 0) return;
+    const int ncand = min(xp + range, g.cols - 1 + R) - g.cols + 1;
+    if (ncand <= 0) return;
+    const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
+    int ssd[NCAND], eref = 0;
+#pragma unroll
+    for (int c = 0; c < NCAND; ++c) ssd[c] = 0;
+    // the 3R extended target columns right of unpadded column cols-R-1 are: R image columns, R times the replicated
+    // last column, R times the aliased first column of the next padded row (zero past the last padded row) - bext()
+#pragma unroll 1
+    for (int wy = -R; wy <= R; ++wy) {
+        const int ra = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+        const uint8_t* arow = A + size_t(ra) * job.a_step;
+        const uint8_t* brow = B + size_t(ra) * job.b_step;
+        int a[W], b[NB];
+#pragma unroll
+        for (int i = 0; i < W; ++i) { a[i] = arow[clampi(xp - R + i, 0, g.cols - 1)]; eref += a[i] * a[i]; }
+        const int edge = brow[g.cols - 1];
+        const int wrap = bext(B, job.b_step, g.rows, g.cols, R, y + wy, g.cols + 4 * R, g.ar0, g.ar1);     // padded column cols + 3R >= Wp
+#pragma unroll
+        for (int i = 0; i < R; ++i) { b[i] = brow[max(g.cols - R + i, 0)]; b[R + i] = edge; b[2 * R + i] = wrap; }
+#pragma unroll
+        for (int c = 0; c < R; ++c)
+#pragma unroll
+            for (int i = 0; i < W; ++i) { const int d = a[i] - b[c + i]; ssd[c] += d * d; }
+    }
+    uint32_t* __restrict__ PART2 = reinterpret_cast<uint32_t*>(job.PART);
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+        if (c >= ncand) break;
+        const int pos = g.cols + c;
+        const uint32_t key = key_bias(R) + (uint32_t(ssd[c] - eref) << FKEY_BITS) + uint32_t(pos);
+        atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
+    }
+}
+
+typedef void (*fused_border_fn)(const FastKernelParams);
+static inline fused_border_fn fused_border_pick(int R) {
+    switch (R) {
+        case 1: return fused_border_kernel<1>; case 2: return fused_border_kernel<2>; case 3: return fused_border_kernel<3>;
+        case 4: return fused_border_kernel<4>; case 5: return fused_border_kernel<5>;
+    }
+    return nullptr;      // R = 0: the padding is empty
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
 static inline bool fast_supported(const Problem& p) {
@@ -545,6 +610,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
     g.njobs = n;
     g.npairs = fused_pairs;
     g.elw = 0;
+    g.border = 0;
     g.K = FK_DEFAULT;
     g.nw = FWARPS;
     g.hs = fast_pick_hs(g.D);
@@ -566,8 +632,15 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         g.hs = 1;                                  // tile rows too wide for a useful pipeline: single-strip kernels
     }
     const int tile_px = g.spc * g.K;
-    // fused: the strips also cover the R columns of right padding the partner direction may centre a window on
-    g.nstrips = (p.cols + (fused_pairs > 0 ? p.R : 0) + g.K - 1) / g.K;
+    // fused: the strips also cover the R columns of right padding the partner direction may centre a window on -
+    // unless that costs a whole tile of a narrow image (>= 1/8 more work); then fused_border_kernel takes them
+    g.nstrips = (p.cols + g.K - 1) / g.K;
+    if (fused_pairs > 0 && p.R > 0) {
+        const int ext_strips = (p.cols + p.R + g.K - 1) / g.K;
+        const int t0 = (g.nstrips + g.spc - 1) / g.spc, t1 = (ext_strips + g.spc - 1) / g.spc;
+        if (t1 > t0 && t0 <= 8) g.border = 1;
+        else g.nstrips = ext_strips;
+    }
     g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
     g.gblocks = g.G / g.gc;
     g.base_y = floor_div(g.rb - w, FRPS) * FRPS;
@@ -584,7 +657,8 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         if (q.cost == STEREO_COST_SSD) { jb.cmin = -q.R; jb.cmax = q.cols - 1 + q.R; }
         else { jb.cmin = 0; jb.cmax = q.cols - 1; }
         // fused partner: its energy rows feed the diagonal minima; candidates left of the image do not exist for it
-        if (fused_pairs > 0 && i >= fused_pairs) jb.cmin = 0;
+        // (and, when fused_border_kernel takes the right padding, none beyond the last image column either)
+        if (fused_pairs > 0 && i >= fused_pairs) { jb.cmin = 0; if (g.border) jb.cmax = q.cols - 1; }
         // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
         int qo = -(q.dmin + q.R); if (qo < 0) qo = 0;
         while (((q.dmin + q.R + qo) & 3) != 0) ++qo;
@@ -728,6 +802,13 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R, g.hs) : fast_pick(ps[0].cost, g.R, g.hs);
     if (!fn || (fused_pairs && g.D % g.dg != 0)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
+        if (g.border) {
+            if (fused_border_fn bf = fused_border_pick(g.R)) {
+                const int bt = -ps[0].dmin <= 64 ? 64 : 128;          // one thread per pixel of the last `range` columns
+                bf<<<dim3(div_round_up(-ps[0].dmin, bt), g.nrows, unsigned(fused_pairs)), bt, 0, st>>>(kp);
+                ctx->last_launches += 1;
+            }
+        }
         ctx->fused_pairs_done += fused_pairs;
     }
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;

@@ -100,6 +100,8 @@ struct FastGeom {
     int npairs;            // fused launches: image pairs (jobs 0..npairs-1 are the L->R directions the hot kernel
                            // walks, job i+npairs is the R->L partner of job i); 0 otherwise
     int elw;               // fused launches: tile width (words) of the partner's energy rows (= spc*K); 0 otherwise
+    int border;            // fused launches: 1 = the partner's candidates centred in the right padding come from
+                           // fused_border_kernel instead of R extra columns of strips (when those would cost a whole tile)
     int ctas;              // grid size
     long long total;       // tile-rows (all jobs)
     long long L;           // tile-rows per CTA
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int x0w = (xt * g.spc + wstrip) * K;                       // first pixel of the warp (warp-uniform)
         // warp-uniform: the row code holds warp collectives.  FUSED: strips reach R columns into the right padding,
         // where the partner direction's last candidates are centred.
-        const bool active = (x0w < g.cols + (FUSED ? R : 0)) && (grp < g.G);
+        const bool active = (x0w < g.cols + ((FUSED && !g.border) ? R : 0)) && (grp < g.G);
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
         // which flavour of candidate masking this warp's (HS x 24 pixels x DG disparities) block needs

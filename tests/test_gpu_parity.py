@@ -352,7 +352,12 @@ FUSED_SHAPES = [
     (9, 130, 1, 127),           # fewer rows than a pipeline stage
     (33, 450, 4, 63),           # 64 candidates: two strips per warp, 16-lane diagonal chains
     (21, 97, 2, 63),
-    (50, 1280, 5, 63),
+    (50, 1280, 5, 63),          # 5 tiles of 256 columns exactly: the right-padding candidates come from fused_border_kernel
+    (25, 320, 3, 127),          # border-kernel mode, one strip per warp, one group per CTA (2 tiles of 160)
+    (31, 400, 5, 255),          # border-kernel mode, two groups per CTA (5 tiles of 80), every pixel has padding candidates
+    (20, 512, 5, 63),           # border-kernel mode, two strips per warp
+    (17, 160, 1, 127),          # border-kernel mode, R = 1
+    (12, 320, 0, 127),          # R = 0: no padding at all
 ]
 
 
@@ -408,6 +413,22 @@ def test_fused_pair_ties_flat_images(ctx):
         assert ctx.last_fused_pairs == 1
         assert np.array_equal(fl, oracle.ssd_fast(Lf, Rf, R, -rng, 0))
         assert np.array_equal(fr, oracle.ssd_fast(Rf, Lf, R, 0, rng))
+
+
+def test_fused_pair_border_kernel_in_bands(ctx):
+    # border-kernel mode (1280 columns, 64 candidates) through the banded host pipeline: band seams see the +1 halo row
+    rows, cols, R, rng = 90, 1280, 4, 63
+    L, Rt, _ = synth.make_pair(rows, cols, 64, 777)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l, ref_r = oracle.ssd_fast(Lf, Rf, R, -rng, 0), oracle.ssd_fast(Rf, Lf, R, 0, rng)
+    try:
+        for bands in (1, 3):
+            ctx.set_pipe_bands(bands)
+            dl, dr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+            assert ctx.last_fused_pairs == bands
+            assert np.array_equal(dl, ref_l) and np.array_equal(dr, ref_r), bands
+    finally:
+        ctx.set_pipe_bands(0)
 
 
 def test_fused_pair_bands_and_batches(ctx):
