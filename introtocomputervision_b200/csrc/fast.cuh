@@ -343,6 +343,36 @@ __global__ void __launch_bounds__(128) prep_scale_kernel(const __grid_constant__
     SC[size_t(strip) * g.nrows + yy] = magic;
 }
 
+// The same for launches that hold BOTH directions of every image pair (jobs i and i + npairs mirror each other): the
+// reference image of a job is its partner's target image, whose window energies prep_tgt_kernel has just turned into
+// the partner's RS rows (1/sqrt(E), 0 for E = 0 or an illegal centre).  max EL over a strip = 1 / min nonzero RS, so the
+// separate vertical pass over the reference image (prep_v_kernel) is not needed.
+__global__ void __launch_bounds__(128) prep_scale_pair_kernel(const __grid_constant__ FastKernelParams P, int npairs) {
+    const FastGeom& g = P.g;
+    const int z = blockIdx.z;
+    const FastJob& job = P.job[z];
+    const FastJob& partner = P.job[z < npairs ? z + npairs : z - npairs];
+    float* __restrict__ SC = job.SC;
+    const int strip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (strip >= g.tilesX * g.spc) return;
+    const int x0 = strip * g.K;
+    float magic = 1.f;
+    if (x0 < g.cols) {
+        const float* rs = partner.RS + size_t(g.rb + yy - g.base_y) * g.e2_pitch + partner.eoff + x0;
+        const int x1 = min(g.K, g.cols - x0);
+        float rsmin = 0.f;                                   // min over the nonzero entries
+        for (int x = 0; x < x1; ++x) { const float v = rs[x]; if (v > 0.f && (rsmin == 0.f || v < rsmin)) rsmin = v; }
+        if (rsmin > 0.f) {
+            // smallest power of two strictly above sqrt(elmax) * (1 + 2^-20); 1/rs is sqrt(E) to within 2^-23 relative
+            const float bound = float((1.0 / double(rsmin)) * (1.0 + 1.0 / 1048576.0));
+            int e; frexpf(bound, &e);
+            magic = ldexpf(1.f, e);
+        }
+    }
+    SC[size_t(strip) * g.nrows + yy] = magic;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Merge: winning key per group -> disparity (+ cost), in the caller's layout
 // ---------------------------------------------------------------------------------------------------
@@ -593,6 +623,18 @@ static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
            a.tgt.step == b.ref.step;
 }
 
+// Jobs i and i + n/2 of a launch are the two directions of one image pair (any cost): left-referenced problems first.
+static inline bool fast_launch_is_pairs(const Problem* ps, int n) {
+    if (n < 2 || (n & 1)) return false;
+    const int np = n / 2;
+    for (int k = 0; k < np; ++k) {
+        const Problem& a = ps[k]; const Problem& b = ps[np + k];
+        if (!(a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step && a.tgt.step == b.ref.step &&
+              a.dmax == 0 && b.dmin == 0 && b.dmax == -a.dmin)) return false;
+    }
+    return true;
+}
+
 static inline size_t fast_stage_bytes(const FastGeom& g) {
     return (size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w + size_t(FRPS) * g.elw) * 4;
 }
@@ -794,7 +836,11 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
         prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
     }
-    if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
+    if (ncc && (!legacy_prep) && fast_launch_is_pairs(ps, n)) {
+        // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
+        prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
+        ctx->last_launches += 1;
+    } else if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
         prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 1);
         prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
         ctx->last_launches += 2;
