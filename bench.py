@@ -525,7 +525,8 @@ def run_ours(args, wl):
 
 def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     """BASELINE config 4: one synthetic pair, output rows sharded over the ranks (R+1 halo rows from the
-    rank's own slab, no neighbour exchange), maps all-gathered over NCCL inside the timed step."""
+    rank's own slab, no neighbour exchange), both maps of the band from one launch sequence, every rank's band
+    delivered to every rank inside the timed step (copy-engine peer pushes, or --gather nccl)."""
     import torch
     import torch.distributed as dist
     from introtocomputervision_b200 import _capi, sharding, synth
