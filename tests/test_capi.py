@@ -102,3 +102,25 @@ def test_host_pipeline_plan():
     assert plan(512, 720, 1280) == (1, 4)
     assert plan(3, 2160, 3840, override=7) == (7, 1)
     assert lib.stereo_host_pipeline_plan(0, 10, 10, 0, None, None) != 0
+
+
+def test_docs_name_only_real_entry_points():
+    """Every stereo_* identifier INTEGRATION.md, DESIGN.md and README.md mention is declared in include/stereo_b200.h
+    (families written with braces or a trailing * are expanded / matched as prefixes)."""
+    names = set(header_functions())
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = (ROOT / doc).read_text()
+        for m in re.finditer(r"\bstereo_[a-z0-9_{},*]+", text):
+            tok = m.group(0).rstrip(",")
+            if tok in ("stereo_ctx", "stereo_b200", "stereo_cost", "stereo_oracle", "stereo_b200_") or tok.startswith(("stereo_b200.", "stereo_oracle.")):
+                continue
+            if "{" in tok:                     # e.g. stereo_disparity_pair_batch_{u8,f32}_{host,device}
+                parts = re.split(r"[{}]", tok)
+                expanded = [""]
+                for i, part in enumerate(parts):
+                    expanded = [e + alt for e in expanded for alt in (part.split(",") if i % 2 else [part])]
+                assert any(e in names for e in expanded), f"{doc}: none of {expanded} is declared in the header"
+            elif tok.endswith("*") or tok.endswith("_"):
+                assert any(n.startswith(tok.rstrip("*")) for n in names), f"{doc}: no entry point starts with {tok}"
+            else:
+                assert tok in names or any(n.startswith(tok) for n in names), f"{doc}: {tok} is not declared in the header"
