@@ -95,6 +95,20 @@ def test_ncc_compiled_reference_throws_where_restatement_rejects():
         oracle.ref_ncorr(img, img, 1, 3, 5)
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("rows,cols,R,rng", [(14, 300, 2, 127), (9, 96, 3, 127), (8, 130, 1, 127), (10, 97, 2, 63),
+                                             (7, 160, 5, 63), (6, 40, 4, 255), (12, 320, 0, 127)])
+def test_ssd_restatement_matches_compiled_reference_on_pair_ranges(rows, cols, R, rng):
+    """The mirrored ranges of the pair helpers (main.cpp:33,43) at the candidate counts the fused pair kernels take
+    (64 / 128 / 256): the fast restatement the GPU tests compare against equals the reference's own compiled code, both
+    directions - including the right-referenced map's candidates centred in the right padding (row-wrap reads, §A.1)
+    and images narrower than the search range."""
+    L, Rt, _ = synth.make_pair(rows, cols, min(rng + 1, 32), 400 + rows + cols)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    assert np.array_equal(oracle.ref_ssd(Lf, Rf, R, -rng, 0), oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, R, -rng, 0)))
+    assert np.array_equal(oracle.ref_ssd(Rf, Lf, R, 0, rng), oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, R, 0, rng)))
+
+
 def test_ssd_known_answer_shift():
     # right(x) = left(x + k)  =>  interior L->R disparity = -k   (SURVEY.md §8c KAT)
     rng = np.random.default_rng(3)
