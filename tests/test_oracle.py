@@ -109,6 +109,17 @@ def test_ssd_restatement_matches_compiled_reference_on_pair_ranges(rows, cols, R
     assert np.array_equal(oracle.ref_ssd(Rf, Lf, R, 0, rng), oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, R, 0, rng)))
 
 
+@pytest.mark.skipif(not oracle.have_ref_ncc(), reason="oracle/_ref/libref_ncc.so not built")
+@pytest.mark.parametrize("rows,cols,R,rng", [(8, 200, 2, 127), (6, 96, 3, 63), (7, 130, 1, 127), (5, 70, 4, 63)])
+def test_ncc_fast_restatement_matches_compiled_reference_on_pair_ranges(rows, cols, R, rng):
+    """The O(rows*cols*D) NCC restatement the GPU tests compare against, on the pair helpers' mirrored ranges, against
+    the reference's own compiled loop (both directions; images narrower than the range clip the search strip)."""
+    L, Rt, _ = synth.make_pair(rows, cols, min(rng + 1, 32), 500 + rows + cols)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    assert np.array_equal(oracle.ref_ncorr(Lf, Rf, R, -rng, 0), oracle.narrow_i8(oracle.ncorr_fast(Lf, Rf, R, -rng, 0)))
+    assert np.array_equal(oracle.ref_ncorr(Rf, Lf, R, 0, rng), oracle.narrow_i8(oracle.ncorr_fast(Rf, Lf, R, 0, rng)))
+
+
 def test_ssd_known_answer_shift():
     # right(x) = left(x + k)  =>  interior L->R disparity = -k   (SURVEY.md §8c KAT)
     rng = np.random.default_rng(3)
