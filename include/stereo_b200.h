@@ -35,6 +35,10 @@
  *     reference re-allocates per call, DisparitySSD.cu:171-178).  A context is not thread-safe;
  *     use one per host thread.  Different contexts are independent (the reference's file-scope
  *     texture references, DisparitySSD.cu:19-20, made it non-reentrant).
+ *   - Calls on one context execute in call order even when they are enqueued on different CUDA
+ *     streams: all of them share the context's scratch arena, so a call enqueued on another stream
+ *     than its predecessor first waits (on the device) for the predecessor's last kernel.  Use one
+ *     context per stream for concurrent execution.
  */
 #ifndef STEREO_B200_H_
 #define STEREO_B200_H_
@@ -89,7 +93,10 @@ void stereo_ctx_destroy(stereo_ctx* ctx);
 /* Kernel family used by the most recent compute call on this context (stereo_path). */
 int stereo_ctx_last_path(const stereo_ctx* ctx);
 /* Device time of the most recent compute call's kernels in milliseconds (cudaEvent pair; the
- * reference logs the same quantity, DisparitySSD.cu:192-203).  <0 if unavailable. */
+ * reference logs the same quantity, DisparitySSD.cu:192-203).  <0 if unavailable.  For the pipelined
+ * HOST entry points the pair brackets the compute stream, which waits for every band's upload: the
+ * figure then includes upload time the kernels were blocked on (stereo_ctx_last_hot_kernel_ms is
+ * kernels only). */
 float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
 /* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels; one launch
  * covers up to 8 directions of equally shaped problems), summed over the launches that were measured

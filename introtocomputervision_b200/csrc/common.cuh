@@ -83,6 +83,8 @@ struct stereo_ctx {
     int pipe_ev_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_pending = false;
+    bool have_prev_call = false;                    // ev1 marks the end of the previous call ...
+    cudaStream_t prev_stream = nullptr;             // ... which was enqueued on this stream
     sb::Arena arena;          // per-call scratch (padded images, packed rows, partial keys)
     sb::Arena io;             // device staging of host-API inputs/outputs
     void* pinned = nullptr;   // pinned host staging

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
             const uint32_t key = keys[k];
             if (key >= thresh) continue;                               // no legal candidate in this group
             const int x = x4 + k;
-            const uint32_t qlo = uint32_t(x + job.dmin + g.dg * grp + job.eoff);   // position of the group's first candidate
+            const uint32_t qlo = uint32_t(x + job.dlo0 + g.dg * grp + job.eoff);   // position of the group's first candidate
             const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
             const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
             if (!found[k] || c < bestc[k]) { bestc[k] = c; bestd[k] = int(q2) - job.eoff - x; found[k] = true; }
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
             const uint32_t key = keys[k];
             if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
             const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
-            if (v > bestv[k]) { bestv[k] = v; bestd[k] = job.dmin + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+            if (v > bestv[k]) { bestv[k] = v; bestd[k] = job.dlo0 + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
         }
     }
     const bool right_aligned = (job.dmin <= 0 && job.dmax <= 0);
@@ -577,7 +577,8 @@ typedef void (*fused_border_fn)(const FastKernelParams);
 static inline fused_border_fn fused_border_pick(int R) {
     switch (R) {
         case 1: return fused_border_kernel<1>; case 2: return fused_border_kernel<2>; case 3: return fused_border_kernel<3>;
-        case 4: return fused_border_kernel<4>; case 5: return fused_border_kernel<5>;
+        case 4: return fused_border_kernel<4>; case 5: return fused_border_kernel<5>; case 6: return fused_border_kernel<6>;
+        case 7: return fused_border_kernel<7>;
     }
     return nullptr;      // R = 0: the padding is empty
 }
@@ -611,16 +612,15 @@ static inline int fast_pick_hs(int D) {
 }
 
 // A left-referenced and a right-referenced problem of the SAME image pair whose maps can come out of one cost
-// volume (fused pair launch): SSD, R <= 5 (masking through the keys alone), mirrored ranges [-r, 0] / [0, r] with
-// r + 1 a multiple of the disparities per group (128, or 64 for searches of at most 64 candidates: whole groups, so
-// the partner's groups are this direction's groups reversed).  The launch geometry must agree (fast_fused_geometry_ok).
+// volume (fused pair launch): SSD, any supported window, mirrored ranges [-r, 0] / [0, r].  The walked direction's
+// disparity groups are aligned to the TOP of its range (FastJob::dlo0), so the partner's groups are those groups
+// reversed whatever the candidate count; the candidates below -r of the lowest group are masked in both maps.
 static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
     static const bool off = [] { const char* e = getenv("STEREO_FUSE_PAIRS"); return e && atoi(e) == 0; }();
     if (off || !fast_batchable(a, b)) return false;
     const int range = -a.dmin;
-    return a.cost == STEREO_COST_SSD && a.R <= FFREE_MASK_R && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
-           (range + 1) % (FGROUP / fast_pick_hs(range + 1)) == 0 && a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step &&
-           a.tgt.step == b.ref.step;
+    return a.cost == STEREO_COST_SSD && a.R <= FMAXR && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
+           a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step && a.tgt.step == b.ref.step;
 }
 
 // Jobs i and i + n/2 of a launch are the two directions of one image pair (any cost): left-referenced problems first.
@@ -643,7 +643,7 @@ static inline size_t fast_stage_bytes(const FastGeom& g) {
 // caller's business).
 // `fused_pairs` > 0: a fused pair launch over n = 2*fused_pairs problems, left-referenced directions first; the hot
 // kernel walks the first half only and produces the partners' partial keys on the way.
-static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs, int fused_pairs = 0) {
+static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs, int fused_pairs, int nw) {
     const Problem& p = ps[0];
     g.rows = p.rows; g.cols = p.cols; g.R = p.R; g.cost = p.cost;
     g.D = p.dmax - p.dmin + 1;
@@ -653,12 +653,11 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
     g.npairs = fused_pairs;
     g.elw = 0;
     g.border = 0;
-    g.K = FK_DEFAULT;
-    g.nw = FWARPS;
+    g.nw = nw;
     g.hs = fast_pick_hs(g.D);
     const int w = 2 * p.R + 1;
     for (;;) {
-        if (fused_pairs > 0) g.K = g.hs == 2 ? FK_FUSED2 : FK_FUSED;
+        g.K = fast_k(p.R, fused_pairs > 0, g.hs);
         g.dg = FGROUP / g.hs;
         g.G = (g.D + g.dg - 1) / g.dg;
         g.gc = (g.hs == 1 && g.G % 2 == 0) ? 2 : 1;
@@ -696,38 +695,54 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
         FastJob& jb = jobs[i];
         const Problem& q = ps[i];
         jb.dmin = q.dmin; jb.dmax = q.dmax;
+        // group layout: from dmin upwards; the walked directions of a fused launch from dmax downwards (whole groups)
+        jb.dlo0 = (fused_pairs > 0 && i < fused_pairs) ? q.dmax - (g.G * g.dg - 1) : q.dmin;
         if (q.cost == STEREO_COST_SSD) { jb.cmin = -q.R; jb.cmax = q.cols - 1 + q.R; }
         else { jb.cmin = 0; jb.cmax = q.cols - 1; }
         // fused partner: its energy rows feed the diagonal minima; candidates left of the image do not exist for it
         // (and, when fused_border_kernel takes the right padding, none beyond the last image column either)
         if (fused_pairs > 0 && i >= fused_pairs) { jb.cmin = 0; if (g.border) jb.cmax = q.cols - 1; }
         // RQ column q = e + qoff with e = x0 + dl + R + (c+m); first index must be >= 0 and 4-aligned
-        int qo = -(q.dmin + q.R); if (qo < 0) qo = 0;
-        while (((q.dmin + q.R + qo) & 3) != 0) ++qo;
+        int qo = -(jb.dlo0 + q.R); if (qo < 0) qo = 0;
+        while (((jb.dlo0 + q.R + qo) & 3) != 0) ++qo;
         jb.qoff = qo;
-        int eo = -q.dmin; if (eo < 0) eo = 0;
-        while (((q.dmin + eo) & 3) != 0) ++eo;
+        int eo = -jb.dlo0; if (eo < 0) eo = 0;
+        while (((jb.dlo0 + eo) & 3) != 0) ++eo;
         jb.eoff = eo;
-        const int rqp = round_up(last_p0 + q.dmin + gmax + q.R + jb.qoff + g.rqw, 64);
-        const int e2p = round_up(last_p0 + q.dmin + gmax + jb.eoff + g.e2w, 64);
+        const int rqp = round_up(last_p0 + jb.dlo0 + gmax + q.R + jb.qoff + g.rqw, 64);
+        const int e2p = round_up(last_p0 + jb.dlo0 + gmax + jb.eoff + g.e2w, 64);
         if (rqp > g.rq_pitch) g.rq_pitch = rqp;
         if (e2p > g.e2_pitch) g.e2_pitch = e2p;
     }
-    g.total = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks * g.nrows;
-    // grid: one CTA per SM, but keep segments long enough that the (2R+1)-row warm-up stays small
-    long long min_rows = 4LL * w; if (min_rows < 32) min_rows = 32;
-    long long ctas = g.total / min_rows; if (ctas < 1) ctas = 1;
-    if (ctas > ctx->sm_count) ctas = ctx->sm_count;
-    g.L = (g.total + ctas - 1) / ctas;
-    g.ctas = int((g.total + g.L - 1) / g.L);
+    // grid: one CTA per SM.  Fewer tiles than SMs (small images): every tile is cut into the same number of row segments
+    // of L rows, so no CTA pays the (2R+1)-row warm-up twice; otherwise the (tile, row) space is split evenly.
+    const long long ntiles = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks;
+    if (ntiles < ctx->sm_count) {
+        int spt = int(ctx->sm_count / ntiles);                 // segments per tile
+        int L = (g.nrows + spt - 1) / spt;
+        if (L < FRPS) L = FRPS;                                // at least one pipeline stage of rows per CTA
+        spt = (g.nrows + L - 1) / L;
+        g.L = L;
+        g.nrl = spt * L;
+        g.total = ntiles * g.nrl;
+        g.ctas = int(ntiles * spt);
+    } else {
+        g.nrl = g.nrows;
+        g.total = ntiles * g.nrows;
+        g.L = (g.total + ctx->sm_count - 1) / ctx->sm_count;
+        g.ctas = int((g.total + g.L - 1) / g.L);
+    }
 }
 
-// The fused kernels need whole disparity groups under the geometry the launch will really use (the strips-per-warp
-// choice can fall back to 1 when the tile rows get too wide for a useful pipeline).
-static inline bool fast_fused_geometry_ok(const stereo_ctx* ctx, const Problem* ps, int n) {
-    FastKernelParams kp{};
-    fast_geometry(ctx, ps, n, kp.g, kp.job, n / 2);
-    return kp.g.D % kp.g.dg == 0;
+// Warps per CTA: 8; 4 when the 8-warp tiles are fewer than half the SMs (small images: every tile is then cut into row
+// segments, each paying a (2R+1)-row warm-up - narrower tiles halve what that warm-up costs).  STEREO_FAST_NW forces it.
+static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs, int fused_pairs = 0) {
+    static const int forced = [] { const char* e = getenv("STEREO_FAST_NW"); return e ? atoi(e) : 0; }();
+    fast_geometry_nw(ctx, ps, n, g, jobs, fused_pairs, forced == FWARPS_SMALL ? FWARPS_SMALL : FWARPS);
+    if (forced == 0) {
+        const long long ntiles = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks;
+        if (2 * ntiles <= ctx->sm_count && g.gc == 1) fast_geometry_nw(ctx, ps, n, g, jobs, fused_pairs, FWARPS_SMALL);
+    }
 }
 
 static inline size_t fast_smem_bytes(const FastGeom& g) {
@@ -741,9 +756,10 @@ static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 
 static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     size_t best = 0;
     for (int fused = 0; fused <= 1; ++fused) {
-        if (fused && (p.cost != STEREO_COST_SSD || p.R > FFREE_MASK_R)) break;
+        if (fused && p.cost != STEREO_COST_SSD) break;
+      for (int nw = FWARPS_SMALL; nw <= FWARPS; nw += FWARPS - FWARPS_SMALL) {      // either tile width may be picked at launch
         FastGeom g; FastJob jb{};
-        fast_geometry(ctx, &p, 1, g, &jb, fused);
+        fast_geometry_nw(ctx, &p, 1, g, &jb, fused, nw);
         // pitches may grow by one alignment step when jobs with other range signs join the launch
         g.rq_pitch += 64; g.e2_pitch += 64;
         size_t b = 0;
@@ -755,6 +771,7 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
         add(size_t(g.nrows) * fast_vpitch(g) * 4);
         if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
         if (b > best) best = b;
+      }
     }
     return best + 4096;
 }
@@ -769,7 +786,7 @@ static inline int fast_ctx_init(stereo_ctx*) {
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
             }
-    for (int R = 0; R <= FFREE_MASK_R; ++R)
+    for (int R = 0; R <= FMAXR; ++R)
       for (int hs = 1; hs <= 2; ++hs) {
         fast_kernel_fn fn = fast_pick_fused(R, hs);
         if (!fn) { set_error("fused pair kernel (R %d, hs %d) missing from the build", R, hs); return STEREO_ERR_UNSUPPORTED; }
@@ -846,7 +863,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         ctx->last_launches += 2;
     }
     fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R, g.hs) : fast_pick(ps[0].cost, g.R, g.hs);
-    if (!fn || (fused_pairs && g.D % g.dg != 0)) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
+    if (!fn) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
         if (g.border) {
             if (fused_border_fn bf = fused_border_pick(g.R)) {

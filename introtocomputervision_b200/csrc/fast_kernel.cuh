@@ -48,6 +48,18 @@ constexpr int FK_DEFAULT = SB_FK_DEFAULT;  // pixels per thread (strip width); t
 #define SB_FK_FUSED2 16
 #endif
 constexpr int FK_FUSED = SB_FK_FUSED, FK_FUSED2 = SB_FK_FUSED2;
+// Wide windows (R = 6, 7; the reference's own config/ps2.yaml:19-41 uses nothing else): a thread keeps K + 2R column sums
+// per disparity, so the strips narrow by 4 pixels to stay inside the register file (K = 24 spilled 100-136 bytes there).
+#ifndef SB_FK_WIDE
+#define SB_FK_WIDE 20
+#endif
+#ifndef SB_FK_FUSED_WIDE
+#define SB_FK_FUSED_WIDE 16
+#endif
+constexpr int FK_WIDE_R = 6;    // first radius that takes the narrower strips
+__host__ __device__ constexpr int fast_k(int R, bool fused, int hs) {
+    return fused ? (hs == 2 ? FK_FUSED2 : (R >= FK_WIDE_R ? SB_FK_FUSED_WIDE : FK_FUSED)) : (R >= FK_WIDE_R ? SB_FK_WIDE : FK_DEFAULT);
+}
 constexpr int FM = 4;           // disparities per thread
 constexpr int FGROUP = 32 * FM; // disparities per warp ("group")
 constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candidates inside a group
@@ -55,6 +67,8 @@ constexpr int FRPS = 8;         // operand rows per pipeline stage
 constexpr int FNST_MAX = 8;     // pipeline stages (fewer when the tile rows are wide, FastGeom::nst)
 constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kernel may use
 constexpr int FWARPS = 8;       // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers)
+constexpr int FWARPS_SMALL = 4; // ... of launches whose tiles are fewer than half the SMs (small images): narrower tiles, so that
+                                // each CTA's (2R+1)-row warm-up is paid on half the pixels (FastGeom::nw, a launch parameter)
 constexpr int FMAXJOBS = 8;     // directions (jobs) one launch sequence can carry
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
@@ -79,7 +93,7 @@ struct FastGeom {
     int rb, re;            // output band
     int ar0, ar1;          // image rows present in the caller's buffers (full image: 0, rows); reads clamp into it
     int K;                 // pixels per thread (strip width): 24
-    int nw;                // warps per CTA: 8
+    int nw;                // warps per CTA: 8, or 4 for small images (blockDim.x / 32; the kernels are compiled for up to 8)
     int hs;                // strips per warp: 1 (a warp = 24 px x 128 disparities) or 2 (2 x 24 px x 64 disparities, D <= 64)
     // derived
     int dg;                // disparities per strip and warp = 128 / hs
@@ -103,8 +117,10 @@ struct FastGeom {
     int border;            // fused launches: 1 = the partner's candidates centred in the right padding come from
                            // fused_border_kernel instead of R extra columns of strips (when those would cost a whole tile)
     int ctas;              // grid size
-    long long total;       // tile-rows (all jobs)
-    long long L;           // tile-rows per CTA
+    int nrl;               // rows of a tile in the linear (tile, row) space the CTAs split: nrows, or nrows padded up to a
+                           // multiple of L when there are fewer tiles than SMs (then no CTA straddles two tiles)
+    long long total;       // tiles x nrl (all jobs)
+    long long L;           // linear rows per CTA
 };
 
 // One direction of one image pair inside a launch.  All jobs of a launch share FastGeom; what depends
@@ -113,6 +129,9 @@ struct FastJob {
     const uint8_t* A; size_t a_step;    // reference image (the one whose pixels get a disparity)
     const uint8_t* B; size_t b_step;    // target image (searched)
     int dmin, dmax;
+    int dlo0;              // first disparity of group 0: dmin, or (fused pair launches, the direction the kernel walks)
+                           // dmax - (G*dg - 1), i.e. groups aligned to the TOP of the range so that the partner's groups are
+                           // this direction's groups reversed for any candidate count; candidates below dmin are masked
     int qoff, eoff;        // column offsets of the RQ / E2 arrays
     int cmin, cmax;        // legal centre columns (unpadded coordinates)
     void* disp; size_t disp_step; int elem;
@@ -231,7 +250,7 @@ constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses
 template <int R, int K, int PAR, int MODE, int COST, int HS, bool FUSED = false>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
-                                         int32_t* __restrict__ out_row, int mmax, uint32_t lane_or, int ll, int sub, int cbase,
+                                         int32_t* __restrict__ out_row, int mmin, int mmax, uint32_t lane_or, int ll, int sub, int cbase,
                                          int cols, float magic, const int* __restrict__ el_row = nullptr,
                                          uint32_t* __restrict__ tail = nullptr, uint32_t* __restrict__ part2_row = nullptr,
                                          int x2base = 0) {
@@ -289,11 +308,17 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     constexpr int LSF = 32 / HS;                                          // lanes per strip
     const uint32_t top_or = (FUSED && ll == LSF - 1) ? KEY_INVALID : 0u;  // the top lane of a strip opens a fresh diagonal every step
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k) {                 // [pixel-loop-begin] (tests/test_capi.py checks that nothing spills in here)
         update(k + 2 * R);
         if (FUSED && (k & 3) == 0) {
             const int4 v = lds128(el_row + k);
             elv[0] = v.x; elv[1] = v.y; elv[2] = v.z; elv[3] = v.w;
+            // a lane outside [dmin, dmax] contributes to neither map; for R <= 5 the partner's key of such a lane loses
+            // through its energy term alone (KEY_INVALID - 256*C stays above every valid key), one OR per pixel
+            if (MODE == 2 && R <= FFREE_MASK_R) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) elv[i] = int(uint32_t(elv[i]) | lane_or);
+            }
         }
         uint32_t key[FM];
 #pragma unroll
@@ -309,12 +334,15 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 } else {                                // IMAD (immediate) on the FMA-heavy pipe
                     kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
                 }
-                if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax) ? KEY_INVALID : kv;
+                if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : kv;
                 key[m] = kv;
                 if (FUSED) {
                     // the partner direction's key of the same cross term: BIAS + 128*(EL(x) - 2C) + x; pixels x beyond its
-                    // legal centres (x > cols-1+R) carry EL2 = KEY_INVALID and lose like illegal search positions do (R <= 5)
-                    const uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                    // legal centres (x > cols-1+R) carry EL2 = KEY_INVALID and lose like illegal search positions do (R <= 5;
+                    // wider windows take the explicit selects of MODE 3 in the blocks that hold such pixels)
+                    uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                    if (MODE == 3) k2 = (uint32_t(elv[k & 3]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : k2;
+                    if (MODE == 2 && R > FFREE_MASK_R) k2 |= lane_or;
                     acc[m] = min(acc[m], k2);
                 }
             } else {
@@ -325,7 +353,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                                        : __fmaf_rn(__int2float_rn(s[m]), rs, magic);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
                 uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
-                if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax) ? NCC_KEY_NONE : kv;
+                if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax || m < mmin) ? NCC_KEY_NONE : kv;
                 key[m] = kv;
             }
         }
@@ -360,7 +388,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF) | top_or; if (ll == 0) tail[32 * sub + k] = done; }
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
         }
-    }
+    }                                             // [pixel-loop-end]
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
@@ -387,7 +415,8 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 
 template <int R, int K, int NW, int COST, int HS, bool FUSED = false>
 __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
-    static_assert(!FUSED || (COST == STEREO_COST_SSD && R <= FFREE_MASK_R && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, R <= 5");
+    static_assert(!FUSED || (COST == STEREO_COST_SSD && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, strips of 4k <= 32 pixels");
+    static_assert(NW == 8, "the per-warp copy counts below assume 4 or 8 warps per CTA");
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr int LS = 32 / HS;                 // lanes per strip
     constexpr int DG = FM * LS;                 // disparities per strip and warp
@@ -397,6 +426,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane / LS, ll = lane % LS;
     const int nst = g.nst;
+    const int nw = g.nw;                        // warps of this launch (blockDim.x / 32): 8, or 4 for small images
 
     const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
     const int el_stage = FUSED ? FRPS * g.elw : 0;
@@ -407,12 +437,14 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     uint32_t* tail = reinterpret_cast<uint32_t*>(bars + 2 * FNST_MAX) + warp * (32 * HS);     // FUSED: 32 words per strip of the warp
 
     if (tid == 0) {
-        for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, NW); mbar_init(empty0 + 8 * i, NW); }
+        for (int i = 0; i < nst; ++i) { mbar_init(full0 + 8 * i, nw); mbar_init(empty0 + 8 * i, nw); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // ---- this CTA's share of the (job, tile, row) space ----------------------------------------------
+    // Linear index = tile * nrl + row with nrl >= nrows (rows nrows..nrl-1 of a tile are padding: when the launch has fewer
+    // tiles than SMs, nrl is a multiple of L and every CTA's share lies inside one tile).
     const long long lin_begin = (long long)blockIdx.x * g.L;
     long long lin_end = lin_begin + g.L;
     if (lin_end > g.total) lin_end = g.total;
@@ -420,27 +452,33 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     const int w = 2 * R + 1;
     const int tpj = g.tilesX * g.gblocks;        // tiles per job
     const int npair = FUSED ? g.npairs : 0;      // the partner of job jb is job jb + npair
+    // next non-empty segment [r0, r1) of one tile at or after `lin`; false when the share is exhausted
+    auto next_segment = [&](long long& lin, int& tile, int& r0, int& r1) -> bool {
+        while (lin < lin_end) {
+            tile = int(lin / g.nrl);
+            r0 = int(lin % g.nrl);
+            const long long rem = lin_end - lin;
+            const int e = (rem > g.nrl - r0) ? g.nrl : r0 + int(rem);
+            lin += e - r0;
+            r1 = e < g.nrows ? e : g.nrows;
+            if (r0 < r1) return true;
+        }
+        return false;
+    };
 
     // producer: EVERY warp iterates the same stage sequence, nst-2 stages ahead, warp-uniformly (all lanes
     // wait on the empty barrier), and its lane 0 issues the warp's share of the stage's row copies (row r of
-    // a stage belongs to warp r mod NW).
-    long long p_lin = lin_begin;   // start of the producer's current segment
+    // a stage belongs to warp r mod nw).
+    long long p_lin = lin_begin;   // start of the producer's next segment
     int p_sj = 0, p_sj_end = -1;   // stage range of the producer's segment
     int p_tile = 0;
     int p_slot = 0, p_round = 0;   // ring position of the next load
-    auto producer_open_segment = [&]() {
-        p_tile = int(p_lin / g.nrows);
-        const int r0 = int(p_lin % g.nrows);
-        long long rem = lin_end - p_lin;
-        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
-        const int js = g.rb + r0 - w - g.base_y, je = g.rb + r1 - g.base_y;
-        p_sj = js / FRPS; p_sj_end = (je - 1) / FRPS;
-        p_lin += r1 - r0;
-    };
     auto producer_issue = [&]() -> bool {     // returns false when nothing is left
         if (p_sj > p_sj_end) {
-            if (p_lin >= lin_end) return false;
-            producer_open_segment();
+            int r0, r1;
+            if (!next_segment(p_lin, p_tile, r0, r1)) return false;
+            const int js = g.rb + r0 - w - g.base_y, je = g.rb + r1 - g.base_y;
+            p_sj = js / FRPS; p_sj_end = (je - 1) / FRPS;
         }
         const int slot = p_slot;
         if (p_round > 0) mbar_wait(empty0 + 8 * slot, (p_round - 1) & 1);
@@ -448,23 +486,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const FastJob& job = P.job[jb];
         const int xt = t2 % g.tilesX, gb = t2 / g.tilesX;
         const int p0 = xt * g.spc * K;
-        const int q0 = p0 + job.dmin + g.dg * gb * g.gc + g.R + job.qoff;
-        const int q20 = p0 + job.dmin + g.dg * gb * g.gc + job.eoff;
+        const int q0 = p0 + job.dlo0 + g.dg * gb * g.gc + g.R + job.qoff;
+        const int q20 = p0 + job.dlo0 + g.dg * gb * g.gc + job.eoff;
         const int32_t* e2src = NCC ? reinterpret_cast<const int32_t*>(job.RS) : job.E2;
         const uint32_t bar = full0 + 8 * slot;
         int* st = smem + size_t(slot) * stage_words;
-        constexpr int NLP = (FRPS - 1) / NW + 1, NRQ = (FRPS / 2 - 1) / NW + 1;       // copies per warp, upper bounds
+        constexpr int NLP = (FRPS - 1) / FWARPS_SMALL + 1, NRQ = (FRPS / 2 - 1) / FWARPS_SMALL + 1;       // copies per warp, upper bounds
         uint32_t mine = 0;
 #pragma unroll
-        for (int i = 0; i < NLP; ++i) if (warp + i * NW < FRPS) mine += uint32_t(g.lpw + g.e2w + (FUSED ? g.elw : 0)) * 4u;
+        for (int i = 0; i < NLP; ++i) if (warp + i * nw < FRPS) mine += uint32_t(g.lpw + g.e2w + (FUSED ? g.elw : 0)) * 4u;
 #pragma unroll
-        for (int i = 0; i < NRQ; ++i) if (warp + i * NW < FRPS / 2) mine += uint32_t(g.rqw) * 4u;
+        for (int i = 0; i < NRQ; ++i) if (warp + i * nw < FRPS / 2) mine += uint32_t(g.rqw) * 4u;
         const int j0 = p_sj * FRPS;
         if (lane == 0) {
             if (mine) mbar_expect_tx(bar, mine); else mbar_arrive(bar);
 #pragma unroll
             for (int i = 0; i < NLP; ++i) {
-                const int r = warp + i * NW;
+                const int r = warp + i * nw;
                 if (r < FRPS) {
                     tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
                     tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
@@ -475,7 +513,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
             }
 #pragma unroll
             for (int i = 0; i < NRQ; ++i) {
-                const int r = warp + i * NW;
+                const int r = warp + i * nw;
                 if (r < FRPS / 2)
                     tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), job.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
             }
@@ -493,12 +531,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     int c_slot = 0, c_round = 0;    // ring position of the next stage to consume
     long long lin = lin_begin;
     int col[FM][S::NC];
-    while (lin < lin_end) {
-        const int tile = int(lin / g.nrows);
-        const int r0 = int(lin % g.nrows);
-        const long long rem = lin_end - lin;
-        const int r1 = (rem > g.nrows - r0) ? g.nrows : r0 + int(rem);
-        lin += r1 - r0;
+    int tile, r0, r1;
+    while (next_segment(lin, tile, r0, r1)) {
         const int jb = tile / tpj, t2 = tile - jb * tpj;
         const FastJob& job = P.job[jb];
         const int xt = t2 % g.tilesX, gb = t2 / g.tilesX;
@@ -512,17 +546,21 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const bool active = (x0w < g.cols + ((FUSED && !g.border) ? R : 0)) && (grp < g.G);
         const int y0 = g.rb + r0, y1 = g.rb + r1;
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
-        // which flavour of candidate masking this warp's (HS x 24 pixels x DG disparities) block needs
-        const int dlo = job.dmin + DG * grp;                              // first disparity of the group
-        const bool pos_invalid = (x0w + dlo < job.cmin) || (x0w + HS * K - 1 + dlo + DG - 1 > job.cmax);
-        const bool lane_invalid = dlo + DG - 1 > job.dmax;
-        const bool partial_lane = lane_invalid && (((job.dmax - dlo + 1) % FM) != 0);
+        // which flavour of candidate masking this warp's (HS x K pixels x DG disparities) block needs
+        const int dlo = job.dlo0 + DG * grp;                              // first disparity of the group
+        bool pos_invalid = (x0w + dlo < job.cmin) || (x0w + HS * K - 1 + dlo + DG - 1 > job.cmax);
+        if (FUSED) pos_invalid = pos_invalid || (x0w + HS * K - 1 > P.job[jb + npair].cmax);   // pixels the partner cannot centre a window on
+        const bool hi_invalid = dlo + DG - 1 > job.dmax, lo_invalid = dlo < job.dmin;
+        const bool lane_invalid = hi_invalid || lo_invalid;
+        const bool partial_lane = (hi_invalid && (((job.dmax - dlo + 1) % FM) != 0)) || (lo_invalid && (((job.dmin - dlo) % FM) != 0));
         // NCC: an illegal search position carries RS = 0, i.e. the score-0 key of its position; it can only win
         // when every legal candidate scores exactly 0 too, which the merge recognises (winner outside the image
         // -> first legal candidate, cv::minMaxLoc's first maximum).  So NCC never needs the explicit selects
         // for border positions, and SSD only for R > 5.
         const int mode = (partial_lane || (pos_invalid && !NCC && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
-        const int mmax = job.dmax - dlo - FM * ll;                        // m <= mmax are inside [dmin, dmax]
+        const int mmin = job.dmin - dlo - FM * ll;                        // mmin <= m <= mmax are inside [dmin, dmax]
+        int mmax = job.dmax - dlo - FM * ll;
+        if (mmin > FM - 1) mmax = -1;                                     // the whole lane lies below dmin: dead, like one above dmax
         // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
         const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * ll) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
         const float* sc_row = NCC ? job.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
@@ -530,7 +568,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int lp_off = (wstrip + sub) * K;
         const int rq_off = lp_off + DG * (warp % g.gc) + FM * ll;
         int32_t* part = job.PART + (size_t(grp) * g.nrows) * g.wpart + x0;
-        // FUSED: the partner's candidates -d of this group are its group G-1-grp (D is a multiple of the group size)
+        // FUSED: the partner's candidates -d of this group are its group G-1-grp (the groups are aligned to the top of the range)
         uint32_t* part2 = FUSED ? reinterpret_cast<uint32_t*>(P.job[jb + npair].PART) + (size_t(g.G - 1 - grp) * g.nrows) * g.wpart : nullptr;
         const int x2base = x0 + dlo;                                      // partner pixel of diagonal 0
 #pragma unroll
@@ -553,12 +591,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
                     const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
-#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, ll, sub, cbase, g.cols, magic)
-#define SB_ROWF(P_) fast_row<R, K, P_, 1, COST, HS, true>(col, lp_row, rq_row, e2_row, out_row, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
+#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic)
+#define SB_ROWF(P_, M_) fast_row<R, K, P_, M_, COST, HS, true>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
                                                           st + lp_stage + rq_stage + e2_stage + r * g.elw + lp_off, tail, \
                                                           part2 + size_t(j - (g.rb - g.base_y)) * g.wpart, x2base)
                     if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
-                    else if constexpr (FUSED) { if (par) SB_ROWF(1); else SB_ROWF(0); }   // the host only fuses launches whose blocks are all mode 1
+                    else if constexpr (FUSED) {
+                        if (mode == 1)      { if (par) SB_ROWF(1, 1); else SB_ROWF(0, 1); }
+                        else if (mode == 2) { if (par) SB_ROWF(1, 2); else SB_ROWF(0, 2); }
+                        else                { if (par) SB_ROWF(1, 3); else SB_ROWF(0, 3); }
+                    }
                     else if (mode == 1) { if (par) SB_ROW(1, 1); else SB_ROW(0, 1); }
                     else if (mode == 2) { if (par) SB_ROW(1, 2); else SB_ROW(0, 2); }
                     else                { if (par) SB_ROW(1, 3); else SB_ROW(0, 3); }
@@ -582,22 +624,20 @@ constexpr int FAST_PARTS = 16;
 SB_DECL_PART(0) SB_DECL_PART(1) SB_DECL_PART(2) SB_DECL_PART(3) SB_DECL_PART(4) SB_DECL_PART(5) SB_DECL_PART(6) SB_DECL_PART(7)
 SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(12) SB_DECL_PART(13) SB_DECL_PART(14) SB_DECL_PART(15)
 #undef SB_DECL_PART
-// Fused pair kernels (SSD, R <= 5, one strip per warp): part 16 + radius subset (fast_inst.cu).
-fast_kernel_fn fast_pick_fused_a(int R);
-fast_kernel_fn fast_pick_fused_b(int R);
-fast_kernel_fn fast_pick_fused_c(int R);
-fast_kernel_fn fast_pick_fused2_a(int R);     // two strips per warp (64 disparities)
-fast_kernel_fn fast_pick_fused2_b(int R);
-fast_kernel_fn fast_pick_fused2_c(int R);
+// Fused pair kernels (SSD): parts 16..25 (fast_inst.cu).
+constexpr int FAST_FUSED_PARTS = 10;
+#define SB_DECL_FPART(n) fast_kernel_fn fast_pick_fused_part##n(int R, int hs);
+SB_DECL_FPART(16) SB_DECL_FPART(17) SB_DECL_FPART(18) SB_DECL_FPART(19) SB_DECL_FPART(20)
+SB_DECL_FPART(21) SB_DECL_FPART(22) SB_DECL_FPART(23) SB_DECL_FPART(24) SB_DECL_FPART(25)
+#undef SB_DECL_FPART
 static inline fast_kernel_fn fast_pick_fused(int R, int hs) {
-    if (hs == 2) {
-        if (fast_kernel_fn fn = fast_pick_fused2_a(R)) return fn;
-        if (fast_kernel_fn fn = fast_pick_fused2_b(R)) return fn;
-        return fast_pick_fused2_c(R);
-    }
-    if (fast_kernel_fn fn = fast_pick_fused_a(R)) return fn;
-    if (fast_kernel_fn fn = fast_pick_fused_b(R)) return fn;
-    return fast_pick_fused_c(R);
+    typedef fast_kernel_fn (*part_fn)(int, int);
+    static const part_fn parts[FAST_FUSED_PARTS] = {fast_pick_fused_part16, fast_pick_fused_part17, fast_pick_fused_part18, fast_pick_fused_part19,
+                                                    fast_pick_fused_part20, fast_pick_fused_part21, fast_pick_fused_part22, fast_pick_fused_part23,
+                                                    fast_pick_fused_part24, fast_pick_fused_part25};
+    for (int i = 0; i < FAST_FUSED_PARTS; ++i)
+        if (fast_kernel_fn fn = parts[i](R, hs)) return fn;
+    return nullptr;
 }
 static inline fast_kernel_fn fast_pick(int cost, int R, int hs) {
     typedef fast_kernel_fn (*part_fn)(int, int);

@@ -40,6 +40,7 @@ void Arena::release() {
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+static int quiesce(stereo_ctx* ctx, cudaStream_t st);
 
 // ---- validation ---------------------------------------------------------------------------------
 
@@ -145,8 +146,8 @@ static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_a
         need += u8_bytes;
     }
     if (need > ctx->arena.cap) {
-        SB_CUDA(cudaStreamSynchronize(st));
-        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        rc = quiesce(ctx, st);
+        if (rc != STEREO_OK) return rc;
         rc = ctx->arena.reserve(need);
         if (rc != STEREO_OK) return rc;
     }
@@ -198,7 +199,7 @@ static bool fused_layout(const stereo_ctx* ctx, const Problem* ps, int n) {
     const int np = n / 2;
     for (int k = 0; k < np; ++k)
         if (!fast_pair_fusable(ps[k], ps[np + k]) || !fast_batchable(ps[0], ps[k])) return false;
-    return fast_fused_geometry_ok(ctx, ps, n);
+    return true;
 }
 
 // One launch sequence over batchable problems, fused when they are whole pairs.
@@ -211,9 +212,9 @@ static int run_fast_jobs(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t
     if (fused_layout(ctx, ps, n)) {          // (n <= FMAXJOBS: one launch sequence)
         const size_t need = size_t(n) * fast_scratch_bytes(ctx, ps[0]);
         if (need > ctx->arena.cap) {
-            SB_CUDA(cudaStreamSynchronize(st));
-            SB_CUDA(cudaStreamSynchronize(ctx->stream));
-            int rc = ctx->arena.reserve(need);
+            int rc = quiesce(ctx, st);
+            if (rc != STEREO_OK) return rc;
+            rc = ctx->arena.reserve(need);
             if (rc != STEREO_OK) return rc;
         }
         ctx->arena.reset();
@@ -227,9 +228,9 @@ static int run_fast_jobs(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t
         while (i + m < n && m < FMAXJOBS && fast_batchable(ps[i], ps[i + m]) && size_t(m + 1) * per_job <= budget) ++m;
         const size_t need = size_t(m) * per_job;
         if (need > ctx->arena.cap) {
-            SB_CUDA(cudaStreamSynchronize(st));
-            SB_CUDA(cudaStreamSynchronize(ctx->stream));
-            int rc = ctx->arena.reserve(need);
+            int rc = quiesce(ctx, st);
+            if (rc != STEREO_OK) return rc;
+            rc = ctx->arena.reserve(need);
             if (rc != STEREO_OK) return rc;
         }
         ctx->arena.reset();
@@ -241,7 +242,11 @@ static int run_fast_jobs(stereo_ctx* ctx, const Problem* ps, int n, cudaStream_t
     return STEREO_OK;
 }
 
+// Every call of a context shares one scratch arena (and the classification flag), so calls are ordered: a call
+// enqueued on another stream than its predecessor first waits for the predecessor's end-of-call event.
 static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
+    if (ctx->have_prev_call && ctx->prev_stream != st) cudaStreamWaitEvent(st, ctx->ev1, 0);
+    ctx->prev_stream = st;
     ctx->last_launches = 0;
     ctx->last_ms = -1.f;
     ctx->last_path = STEREO_PATH_NONE;
@@ -254,6 +259,15 @@ static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
 static void end_call(stereo_ctx* ctx, cudaStream_t st) {
     cudaEventRecord(ctx->ev1, st);
     ctx->timing_pending = true;
+    ctx->have_prev_call = true;
+}
+
+// Before the scratch arena is reallocated: nothing enqueued by earlier calls may still use it.
+static int quiesce(stereo_ctx* ctx, cudaStream_t st) {
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->have_prev_call && ctx->prev_stream != st && ctx->prev_stream != ctx->stream) SB_CUDA(cudaEventSynchronize(ctx->ev1));
+    return STEREO_OK;
 }
 
 static int check_ctx(stereo_ctx* ctx) {
@@ -335,8 +349,25 @@ static int pipe_chunk_pairs(int n_pairs, int nb, int rows, int cols) {
     return cp < 1 ? 1 : int(cp);
 }
 
+static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
+                                     const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem);
+
+// Failures inside the pipeline leave asynchronous copies from / to the CALLER's host buffers queued on the three
+// streams: drain them before the error reaches the caller, who may free or reuse those buffers.
 static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
                                 const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
+    const int rc = pairs_host_pipelined_body(ctx, cost, type, n_pairs, in, dirs, n_dirs, rows, cols, R, disp_step, elem);
+    if (rc < STEREO_OK) {
+        if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+        (void)cudaGetLastError();
+    }
+    return rc;
+}
+
+static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
+                                     const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
     if (ctx->force_path == STEREO_PATH_EXACT_F32) return PIPE_NOT_APPLICABLE;
     const size_t px = type == PixType::F32 ? 4 : 1;
     const size_t in_pitch = align256(cols * px), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
@@ -356,9 +387,13 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
         int rc = validate(full, u8_pitch, u8_pitch);
         if (rc != STEREO_OK) return rc;
         if (!fast_supported(full)) return PIPE_NOT_APPLICABLE;
-        Problem band = full; band.row_end = band_rows < rows ? band_rows : rows;
-        const size_t need = size_t(n_dirs) * cp * fast_scratch_bytes(ctx, band);
-        scratch = need > scratch ? need : scratch;
+        // every band: the operand-row count depends on where the band starts relative to the FRPS-row stages
+        for (int b = 0; b < nb; ++b) {
+            Problem band = full; band.row_begin = b * band_rows; band.row_end = (b + 1) * band_rows < rows ? (b + 1) * band_rows : rows;
+            if (band.row_begin >= band.row_end) break;
+            const size_t need = size_t(n_dirs) * cp * fast_scratch_bytes(ctx, band);
+            scratch = need > scratch ? need : scratch;
+        }
     }
     int rc = ensure_pipe(ctx, 3 * n_items * nb + 4);
     if (rc != STEREO_OK) return rc;

@@ -185,8 +185,12 @@ def _prep_pair(a: np.ndarray, b: np.ndarray, f32_name: str, u8_name: str):
     else:
         # the reference: assert(left.type() == CV_32FC1 && right.type() == CV_32FC1) (DisparitySSD.cu:150)
         raise TypeError("images must both be float32 (CV_32FC1) or both uint8")
-    a = a if a.strides[1] == a.itemsize else np.ascontiguousarray(a, kind)
-    b = b if b.strides[1] == b.itemsize else np.ascontiguousarray(b, kind)
+    # cv::Mat layout only: unit column stride and a non-negative row step of at least one row (views such as
+    # img[::-1] or img[:, ::2] are copied; a negative step would wrap in the C ABI's size_t)
+    def _mat(v):
+        ok = v.strides[1] == v.itemsize and v.strides[0] >= v.shape[1] * v.itemsize
+        return v if ok else np.ascontiguousarray(v, kind)
+    a, b = _mat(a), _mat(b)
     return a, b, getattr(_capi.lib(), name)
 
 

@@ -653,3 +653,108 @@ def test_config3_full_size_ssd_and_ncc(ctx):
     d, s = ctx.disparity(sb.COST_NCORR, L, Rt, 4, -127, 0, dtype=np.int16, return_best=True)
     assert ctx.last_path == sb.PATH_FAST_U8
     assert_ncc_close(d, s, d_ref, s_ref)
+
+
+# ---- fused pair launches for any candidate count and every window radius ----------------------
+# The reference's own problems (config/ps2.yaml:19-41) are R = 6 / 7 with 4, 96 and 81 candidates: none of them is a
+# whole number of 128- (64-) disparity groups.  The walked direction's groups are aligned to the top of its range and the
+# candidates below -range are masked in both maps; R > 5 takes explicit selects at the image borders.
+
+GENERAL_FUSED_SHAPES = [
+    (20, 300, 7, 95), (20, 300, 6, 80), (16, 128, 6, 3), (12, 200, 5, 100), (9, 260, 3, 129), (14, 333, 7, 127),
+    (10, 150, 0, 1), (11, 700, 7, 255), (13, 90, 6, 40), (8, 64, 7, 63), (17, 257, 4, 64), (9, 1290, 6, 70),
+    (6, 30, 7, 95), (5, 9, 6, 200), (40, 640, 7, 95), (25, 513, 2, 33),
+]
+
+
+@pytest.mark.parametrize("rows,cols,R,rng", GENERAL_FUSED_SHAPES)
+def test_fused_pair_any_range_any_radius(ctx, rows, cols, R, rng):
+    L, Rt, _ = synth.make_pair(rows, cols, min(rng + 1, max(2, cols // 2)), 31000 + rows * 7 + cols)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l, ref_r = oracle.ssd_fast(Lf, Rf, R, -rng, 0), oracle.ssd_fast(Rf, Lf, R, 0, rng)
+    fl, fr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs == 1
+    bad = np.argwhere(fl != ref_l)
+    assert bad.size == 0, f"fused L->R differs at {bad[:5].tolist()} (of {len(bad)})"
+    bad = np.argwhere(fr != ref_r)
+    assert bad.size == 0, f"fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
+    ctx.set_fuse_pairs(False)
+    try:
+        ul, ur = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+        assert ctx.last_fused_pairs == 0
+    finally:
+        ctx.set_fuse_pairs(True)
+    assert np.array_equal(ul, ref_l) and np.array_equal(ur, ref_r)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fused_pair_random_any_range(ctx, seed):
+    rng = np.random.default_rng(12000 + seed)
+    rows = int(rng.integers(1, 40))
+    cols = int(rng.choice([5, 21, 47, 99, 160, 290, 640])) + int(rng.integers(0, 9))
+    R = int(rng.integers(0, 8))
+    r = int(rng.integers(1, 300))
+    L, Rt, _ = synth.make_pair(rows, cols, min(r + 1, max(2, cols // 2)), 12100 + seed)
+    if seed % 4 == 0:                       # low-texture image: many exact ties
+        L, Rt = (L // 64 * 64).astype(np.uint8), (Rt // 64 * 64).astype(np.uint8)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    a, b = (Lf, Rf) if seed % 2 else (L, Rt)
+    dl, dr = ctx.disparity_pair(sb.COST_SSD, a, b, R, r, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs >= 1
+    assert np.array_equal(dl, oracle.ssd_fast(Lf, Rf, R, -r, 0)), (rows, cols, R, r)
+    assert np.array_equal(dr, oracle.ssd_fast(Rf, Lf, R, 0, r)), (rows, cols, R, r)
+
+
+def test_fused_pair_any_range_ties_flat_images(ctx):
+    rows, cols = 18, 300
+    flat = np.full((rows, cols), 200, np.uint8)
+    band = np.tile((np.arange(cols) // 29 % 2 * 255).astype(np.uint8), (rows, 1))
+    for R, rng in ((7, 95), (6, 3), (5, 80)):
+        for L, Rt in ((flat, flat), (band, band), (band, flat)):
+            Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+            fl, fr = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, rng, dtype=np.int16)
+            assert ctx.last_fused_pairs == 1
+            assert np.array_equal(fl, oracle.ssd_fast(Lf, Rf, R, -rng, 0)), (R, rng)
+            assert np.array_equal(fr, oracle.ssd_fast(Rf, Lf, R, 0, rng)), (R, rng)
+
+
+# ---- the configurations the numbers are quoted on, at their real size ---------------------------------------------------
+
+def test_ps2_problem_shapes_full_size_clean(ctx):
+    """config/ps2.yaml:19-41 at the logged image sizes (ps2_cpu.log:6,12,49): pair0 128x128 R=6 range=3 SSD, pair1
+    511x640 R=7 range=95 SSD and NCC, pair2 529x640 R=7 range=80 NCC; synthetic stand-ins for the LFS-stubbed pixels."""
+    for rows, cols, R, rng, seed in ((128, 128, 6, 3, 10), (511, 640, 7, 95, 11)):
+        L, Rt, _ = synth.make_pair(rows, cols, rng + 1, seed)
+        Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+        dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(R, rng), ctx=ctx)
+        assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs == 1
+        assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, R, -rng, 0))), (rows, cols)
+        assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, R, 0, rng))), (rows, cols)
+    for rows, cols, R, rng, seed in ((511, 640, 7, 95, 11), (529, 640, 7, 80, 12)):
+        L, Rt, _ = synth.make_pair(rows, cols, rng + 1, seed)
+        Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+        for ref, tgt, lo, hi in ((Lf, Rf, -rng, 0), (Rf, Lf, 0, rng)):
+            d_ref, s_ref = oracle.ncorr_fast(ref, tgt, R, lo, hi, return_score=True)
+            d, s = ctx.disparity(sb.COST_NCORR, ref, tgt, R, lo, hi, dtype=np.int16, return_best=True)
+            assert ctx.last_path == sb.PATH_FAST_U8
+            assert_ncc_close(d, s, d_ref, s_ref)
+
+
+def test_config4_full_size_fused_pair_and_ncc(ctx):
+    """BASELINE config 4's shape on ONE GPU, the configuration the headline number is quoted on: 3840x2160, 256
+    disparities, 11x11.  SSD: both maps of the fused pair launch bit-exact against the oracle.  NCC: L->R within the
+    north-star tolerance."""
+    L, Rt, _ = synth.make_pair(2160, 3840, 256, 1002)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    dl, dr = ctx.disparity_pair(sb.COST_SSD, L, Rt, 5, 255, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs >= 1
+    ref_l = oracle.ssd_fast(Lf, Rf, 5, -255, 0)
+    bad = np.argwhere(dl != ref_l)
+    assert bad.size == 0, f"4K fused L->R differs at {bad[:5].tolist()} (of {len(bad)})"
+    ref_r = oracle.ssd_fast(Rf, Lf, 5, 0, 255)
+    bad = np.argwhere(dr != ref_r)
+    assert bad.size == 0, f"4K fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
+    d_ref, s_ref = oracle.ncorr_fast(Lf, Rf, 5, -255, 0, return_score=True)
+    d, s = ctx.disparity(sb.COST_NCORR, L, Rt, 5, -255, 0, dtype=np.int16, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    assert_ncc_close(d, s, d_ref, s_ref)
