@@ -226,6 +226,33 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def oracle_band_check(L, Rt, R, nd, cost, got_l, got_r, r0, n):
+    """Outside the timed region: rows [r0, r0 + n) of both maps of one pair against the oracle (oracle/ is the checker here,
+    never the thing measured).  The oracle runs on the slab of image rows the band depends on - window halo R plus the row
+    the SSD flat-index wrap reads - and its interior rows are compared.  got_l / got_r: numpy maps of the
+    whole image.  Returns a small report dict."""
+    import oracle
+    rows = L.shape[0]
+    lo, hi = max(0, r0 - R - 1), min(rows, r0 + n + R + 1)
+    Ls, Rs = np.ascontiguousarray(L[lo:hi]).astype(np.float32), np.ascontiguousarray(Rt[lo:hi]).astype(np.float32)
+    # slab borders that are not image borders see different padding: compare only rows whose halo lies inside the slab
+    a = r0 - lo if lo > 0 else 0
+    b = a + n
+    rep = {"rows": [r0, r0 + n], "oracle": "oracle.ssd_fast" if cost == "ssd" else "oracle.ncorr_fast"}
+    if cost == "ssd":
+        ref_l = oracle.ssd_fast(Ls, Rs, R, -(nd - 1), 0)[a:b]
+        ref_r = oracle.ssd_fast(Rs, Ls, R, 0, nd - 1)[a:b]
+        bad = int(np.count_nonzero(ref_l.astype(np.int64) != got_l[r0:r0 + n].astype(np.int64))
+                  + np.count_nonzero(ref_r.astype(np.int64) != got_r[r0:r0 + n].astype(np.int64)))
+        rep.update(pixels=int(2 * ref_l.size), mismatches=bad, ok=bad == 0, rule="bit-exact")
+    else:
+        ref_l = oracle.ncorr_fast(Ls, Rs, R, -(nd - 1), 0)[a:b]
+        ref_r = oracle.ncorr_fast(Rs, Ls, R, 0, nd - 1)[a:b]
+        agree = float((np.count_nonzero(ref_l == got_l[r0:r0 + n]) + np.count_nonzero(ref_r == got_r[r0:r0 + n])) / (2 * ref_l.size))
+        rep.update(pixels=int(2 * ref_l.size), agreement=round(agree, 6), ok=agree >= 0.999, rule=">= 99.9 % equal disparities")
+    return rep
+
+
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
@@ -449,6 +476,23 @@ def run_ours(args, wl):
     torch.cuda.synchronize()
     assert torch.equal(d_out[0, 0].cpu(), h_dl) and torch.equal(d_out[0, 1].cpu(), h_dr), "host and device entry points disagree"
 
+    # parity check outside every timed region (rank 0): a 64-row band of the step's maps - and, in multi-GPU runs, of a
+    # PEER rank's maps as they arrived in this rank's gather buffer - against the oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        r0 = max(0, min(rows - 64, (rows // 2) // 8 * 8 + 3))
+        nrow = min(64, rows)
+        mine_l, mine_r = d_out[0, 0, 0].cpu().numpy(), d_out[0, 1, 0].cpu().numpy()
+        parity = {"own_pair0": oracle_band_check(Ls[0], Rs[0], R, nd, args.cost, mine_l, mine_r, r0, nrow)}
+        if pg is not None and world > 1:
+            peer = 1
+            slot = pg.local_bytes(dev)[(0 * world + peer) * map_bytes:(0 * world + peer + 1) * map_bytes]      # parity 0, rank `peer`
+            maps = slot.view(elem_dtype).view(2, B, rows, cols)
+            pl, pr_ = maps[0, B - 1].cpu().numpy(), maps[1, B - 1].cpu().numpy()
+            PL, PR, _ = synth.make_pair(rows, cols, nd, wl["seed"] + peer * B + (B - 1))
+            parity[f"rank{peer}_pair{B - 1}_from_gather_buffer"] = oracle_band_check(PL, PR, R, nd, args.cost, pl, pr_, r0, nrow)
+        parity["ok"] = all(v["ok"] for v in parity.values())
+
     if rank == 0:
         peaks = measured_peaks()
         props = torch.cuda.get_device_properties(dev)
@@ -519,13 +563,172 @@ def run_ours(args, wl):
                     "per_pair_calls_value": round(e2e_pp_value, 1), "u8_host_api_value": round(e2e8_value, 1),
                     "host_cpus_bound_per_rank": bound_cpus},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
+            "parity_check": parity,
         }
+        if world == 1 and not args.no_suite:
+            # the other configurations, each a short device-resident run (same clocks sampler idea: one sample set around all)
+            s2 = ClockSampler(local)
+            s2.start()
+            lines = []
+            for wname, cname, b, st_ in (("4k_d256_w11", "ncc", 2, 5), ("1080p_d128_w9", "ssd", 4, 10), ("1080p_d128_w9", "ncc", 4, 10),
+                                         ("720p_d64_w9", "ssd", 16, 5), ("720p_d64_w9", "ncc", 16, 5)):
+                if wname == args.workload and cname == args.cost:
+                    continue
+                lines.append(suite_batch_line(torch, lib, ctx, dev, stream, wname, cname, b, st_, peak_lane_ops))
+            ps2 = suite_ps2_lines(torch, lib, ctx, dev, stream, 10, peak_lane_ops)
+            line["suite"] = {"batches": lines, "ps2": ps2, "clocks": s2.stop()}
         print(json.dumps(line), flush=True)
     if pg is not None:
         pg.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# suite: the other configurations next to the headline line (device-resident inputs, CUDA events)
+# ---------------------------------------------------------------------------------------------------
+# Published GTX 1080 kernel figures for the reference's own problems (output/ps2_gpu.log): Mpix*disp/s per map
+PS2_PUBLISHED = {
+    "p1_ssd_128x128_d4_w13": (226 + 256) / 2, "p2_ssd_511x640_d96_w15": (1628 + 1709) / 2,
+    "p3_ssd_noisy_511x640_d96_w15": (1651 + 1568) / 2, "p3_ssd_contrast_511x640_d96_w15": (1628 + 1542) / 2,
+    "p4_ncc_511x640_d96_w15": (1127 + 1081) / 2, "p4_ncc_noisy_511x640_d96_w15": (1199 + 1187) / 2,
+    "p4_ncc_contrast_511x640_d96_w15": (1198 + 1187) / 2, "p5_ncc_529x640_d81_w15": (1219 + 1295) / 2,
+}
+
+
+def _events_ms(torch, stream, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def suite_batch_line(torch, lib, ctx, dev, stream, wl_name, cost_name, B, steps, peak_lane_ops):
+    """One device-resident line like the headline's: B pairs per step of a WORKLOADS shape, inputs rotating over more sets
+    than the L2 holds."""
+    import introtocomputervision_b200 as sb
+    from introtocomputervision_b200 import _capi, synth
+    wl = WORKLOADS[wl_name]
+    rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
+    cost = sb.COST_SSD if cost_name == "ssd" else sb.COST_NCORR
+    elem_dtype, elem = (torch.int8, 1) if nd <= 128 else (torch.int16, 2)
+    Ls, Rs = zip(*[synth.make_pair(rows, cols, nd, wl["seed"] + i)[:2] for i in range(min(B, 4))])
+    h_l = torch.from_numpy(np.stack([Ls[i % len(Ls)] for i in range(B)]))
+    h_r = torch.from_numpy(np.stack([Rs[i % len(Rs)] for i in range(B)]))
+    l2 = int(getattr(torch.cuda.get_device_properties(dev), "L2_cache_size", 126 << 20))
+    set_bytes = 2 * B * rows * cols
+    S = max(2, -(-int(1.25 * l2) // set_bytes) + 1)
+    S = min(S, 64)
+    d_l = torch.stack([torch.roll(h_l, 17 * s_, dims=1) for s_ in range(S)]).to(dev)
+    d_r = torch.stack([torch.roll(h_r, 17 * s_, dims=1) for s_ in range(S)]).to(dev)
+    d_out = torch.empty((2, B, rows, cols), dtype=elem_dtype, device=dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    k = [0]
+
+    def step():
+        s_ = k[0] % S
+        k[0] += 1
+        rc = lib.stereo_disparity_pair_batch_u8_device(
+            ctx.handle, cost, B, d_l[s_].data_ptr(), d_r[s_].data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
+            d_out[0].data_ptr(), d_out[1].data_ptr(), cols * elem, rows * cols * elem, elem, sp)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+
+    ms = _events_ms(torch, stream, step, steps, 3)
+    hot_ms, hot_n = ctx.last_hot_kernel_ms()
+    units = B * 2 * rows * cols * nd
+    fused = ctx.last_fused_pairs > 0
+    opu = (OPS_PER_UNIT_FUSED if fused and cost_name in OPS_PER_UNIT_FUSED else OPS_PER_UNIT)[cost_name]
+    # last_hot_kernel_ms covers at most 16 launches of the last call; scale to the directions they covered
+    hot_units = ctx.last_hot_jobs * rows * cols * nd
+    line = {"workload": f"{wl_name}_{cost_name}_pair", "pairs_per_step": B, "ms_per_step": round(ms, 4),
+            "value": round(units / (ms * 1e-3) / 1e6, 1), "unit": UNIT,
+            "pair_fusion": bool(fused), "gpu_launches_per_step": ctx.last_launches,
+            "l2": f"inputs rotate over {S} sets = {S * set_bytes >> 20} MiB"}
+    if hot_n > 0:
+        line["hot_kernel_ms_per_step"] = round(hot_ms * (units / hot_units), 4)
+        line["hot_share_of_step"] = round(hot_ms * (units / hot_units) / ms, 3)
+        line["roofline_frac"] = round(opu * hot_units / (hot_ms * 1e-3) / peak_lane_ops, 4)
+        line["ops_per_unit"] = opu
+    del d_l, d_r, d_out
+    return line
+
+
+def suite_ps2_lines(torch, lib, ctx, dev, stream, steps, peak_lane_ops):
+    """The reference executable's own problems (config/ps2.yaml:19-41, main.cpp:80-330) as device-resident CV_32FC1 pair
+    calls (what the reference wrapper holds after its uploads): ms per pair call = two maps, Mpix*disp/s per map next to
+    the published GTX 1080 kernel figure."""
+    import introtocomputervision_b200 as sb
+    from introtocomputervision_b200 import _capi, synth
+    problems = []
+    L0, R0, _ = synth.make_pair(128, 128, 4, 10)
+    L1, R1, _ = synth.make_pair(511, 640, 96, 11)
+    L2, R2, _ = synth.make_pair(529, 640, 81, 12)
+    f = lambda a: a.astype(np.float32)
+    noisy = (synth.noisy_variant(L1, 12), synth.noisy_variant(R1, 13))
+    contrast = (synth.contrast_variant(L1), f(R1))
+    problems.append(("p1_ssd_128x128_d4_w13", sb.COST_SSD, f(L0), f(R0), 6, 3))
+    problems.append(("p2_ssd_511x640_d96_w15", sb.COST_SSD, f(L1), f(R1), 7, 95))
+    problems.append(("p3_ssd_noisy_511x640_d96_w15", sb.COST_SSD, *noisy, 7, 95))
+    problems.append(("p3_ssd_contrast_511x640_d96_w15", sb.COST_SSD, *contrast, 7, 95))
+    problems.append(("p4_ncc_511x640_d96_w15", sb.COST_NCORR, f(L1), f(R1), 7, 95))
+    problems.append(("p4_ncc_noisy_511x640_d96_w15", sb.COST_NCORR, *noisy, 7, 95))
+    problems.append(("p4_ncc_contrast_511x640_d96_w15", sb.COST_NCORR, *contrast, 7, 95))
+    problems.append(("p5_ncc_529x640_d81_w15", sb.COST_NCORR, f(L2), f(R2), 7, 80))
+    sp = C.c_void_p(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out, total_ms = [], 0.0
+    paths = {sb.PATH_EXACT_F32: "exact_f32 (brute force)", sb.PATH_FAST_U8: "fast_u8", sb.PATH_FAST_F32: "fast_f32"}
+    for name, cost, Lf, Rf, R, rng in problems:
+        rows, cols = Lf.shape
+        d_l, d_r = torch.from_numpy(Lf).to(dev), torch.from_numpy(Rf).to(dev)
+        d_dl = torch.empty((rows, cols), dtype=torch.int8, device=dev)
+        d_dr = torch.empty_like(d_dl)
+
+        def call():
+            rc = lib.stereo_disparity_pair_f32_device(ctx.handle, cost, d_l.data_ptr(), cols * 4, d_r.data_ptr(), cols * 4, rows, cols,
+                                                      R, rng, d_dl.data_ptr(), d_dr.data_ptr(), cols, 1, sp)
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        ms_call, ms_kern, ms_hot = [], [], []
+        for _ in range(steps):
+            flush.zero_()                                    # L2 flushed between the timed calls
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_call.append(e0.elapsed_time(e1))
+            ms_kern.append(ctx.last_kernel_ms)
+            h, n = ctx.last_hot_kernel_ms()
+            ms_hot.append(h if n > 0 else float("nan"))
+        ms = statistics.median(ms_call)
+        units_map = rows * cols * (rng + 1)
+        per_map = 2 * units_map / (ms * 1e-3) / 1e6 / 2            # Mpix*disp/s of one map at half the pair call's time
+        pub = PS2_PUBLISHED.get(name)
+        out.append({"problem": name, "cost": "ssd" if cost == sb.COST_SSD else "ncc", "rows": rows, "cols": cols,
+                    "ndisp": rng + 1, "window": 2 * R + 1, "path": paths.get(ctx.last_path, str(ctx.last_path)),
+                    "pair_fusion": bool(ctx.last_fused_pairs), "ms_per_pair_call": round(ms, 4), "ms_per_map": round(ms / 2, 4),
+                    "hot_kernel_ms": round(statistics.median(ms_hot), 4), "launches": ctx.last_launches,
+                    "value_per_map": round(per_map, 1), "unit": UNIT,
+                    "published_gtx1080_kernel": pub, "vs_baseline": round(per_map / pub, 1) if pub else None})
+        total_ms += ms * {"p3_ssd_noisy_511x640_d96_w15": 1, "p3_ssd_contrast_511x640_d96_w15": 1}.get(name, 1)
+    return {"problems": out, "all_problems_ms": round(total_ms, 4),
+            "timing": "device-resident CV_32FC1 images, CUDA events around one stereo_disparity_pair_f32_device call (classification, "
+                      "its 16-byte read-back, prep, hot and merge kernels), L2 flushed before every timed call, median of "
+                      f"{steps}; the reference's published figure is its kernel alone (GpuTimer, DisparitySSD.cu:192-203)"}
 
 
 def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
@@ -642,6 +845,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=4, help="stereo pairs per GPU per step (4 pairs = 8 directions = one launch sequence)")
     ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-suite", action="store_true", help="skip the suite of other configurations (N = 1 only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of a band of the step's maps")
     ap.add_argument("--pipe-bands", type=int, default=0, help="row bands per pair in the pipelined host entry points (0 = automatic)")
     ap.add_argument("--cost", default="ssd", choices=["ssd", "ncc"], help="window cost (the headline line is ssd)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],

@@ -70,8 +70,10 @@ typedef enum stereo_cost {
 /* Which kernel family served the last call (for tests and reports). */
 typedef enum stereo_path {
     STEREO_PATH_NONE = 0,
-    STEREO_PATH_EXACT_F32 = 1,  /* general float path: per-element reference arithmetic */
-    STEREO_PATH_FAST_U8 = 2     /* integer-valued 0..255 inputs: packed dot-product running sums */
+    STEREO_PATH_EXACT_F32 = 1,  /* any float input, window and range: per-element reference arithmetic, no running sums */
+    STEREO_PATH_FAST_U8 = 2,    /* integer-valued 0..255 inputs: packed dot-product running sums */
+    STEREO_PATH_FAST_F32 = 3    /* general float inputs of bounded range (noise / contrast variants, main.cpp:140-153,191-193):
+                                   per-element round((l-r)^2) as exact int32 running sums (SSD), float32 running sums (NCC) */
 } stereo_path;
 
 typedef struct stereo_ctx stereo_ctx;
@@ -186,6 +188,16 @@ int stereo_disparity_pair_u8_device(stereo_ctx* ctx, int cost,
                                     int rows, int cols, int window_rad, int disparity_range,
                                     void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes,
                                     void* cuda_stream);
+
+/* The same for CV_32FC1 device images (what the reference's wrapper holds after its uploads, DisparitySSD.cu:171-174).
+ * The kernel family depends on the pixel values (8-bit-valued, bounded float range, anything else), which the
+ * host learns from a device-side classification: this call synchronises `cuda_stream` once before it enqueues
+ * the matching kernels; the kernels themselves run asynchronously. */
+int stereo_disparity_pair_f32_device(stereo_ctx* ctx, int cost,
+                                     const float* left, size_t left_step, const float* right, size_t right_step,
+                                     int rows, int cols, int window_rad, int disparity_range,
+                                     void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes,
+                                     void* cuda_stream);
 
 /* ---- batches of equally-shaped pairs (BASELINE config 5) ------------------------------------ */
 /* `n_pairs` image pairs stored back to back: pair i's left image starts at left + i*pair_stride

@@ -13,7 +13,7 @@ LIB_PATH = Path(os.environ.get("STEREO_B200_LIB") or (Path(__file__).resolve().p
 STEREO_OK = 0
 ERR_INVALID_ARG, ERR_INVALID_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 COST_SSD, COST_NCORR = 0, 1
-PATH_NONE, PATH_EXACT_F32, PATH_FAST_U8 = 0, 1, 2
+PATH_NONE, PATH_EXACT_F32, PATH_FAST_U8, PATH_FAST_F32 = 0, 1, 2, 3
 
 _vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "stereo_disparity_pair_f32_host": (_i, _PAIR_HOST),
     "stereo_disparity_pair_u8_host": (_i, _PAIR_HOST),
     "stereo_disparity_pair_u8_device": (_i, _PAIR_HOST + [_vp]),
+    "stereo_disparity_pair_f32_device": (_i, _PAIR_HOST + [_vp]),
     "stereo_disparity_pair_batch_u8_device": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i, _vp]),
     "stereo_disparity_pair_batch_u8_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
     "stereo_disparity_pair_batch_f32_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),

@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = CSRC / "_build"
 LIB = PKG / "libstereo_b200.so"
-FAST_PARTS = 26          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused pair kernel parts
+FAST_PARTS = 38          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused pair parts + 3 x 4 float-operand parts
 
 NVCC_FLAGS = [
     *([f"-DSB_FK_FUSED={os.environ['SB_FK_FUSED']}"] if os.environ.get("SB_FK_FUSED") else []),

@@ -126,21 +126,49 @@ __global__ void store_output_kernel(const int32_t* __restrict__ disp, const uint
     }
 }
 
-// Is a float image exactly 8-bit (integral, 0..255)?  Writes the u8 copy and ORs 1 into *flag if
-// any pixel is not.  (convertTo(CV_32FC1) without scaling, main.cpp:87-88, produces such images;
+// Is a float image exactly 8-bit (integral, 0..255)?  Writes the u8 copy and ORs 1 into flag[0] if any pixel is not
+// (2 as well if a pixel is not finite).  (convertTo(CV_32FC1) without scaling, main.cpp:87-88, produces such images;
 // addNoise / *1.1f, main.cpp:140-153,191-193, do not.)
+// Blocks that hold a non-8-bit pixel also fold their pixel range into flag[1] (largest -v) and flag[2] (largest v), in an
+// order-preserving unsigned encoding whose zero is "nothing seen": together with [0, 255] for the clean blocks that bounds
+// the value range of the image, which decides whether the float running-sum kernels apply (fast.cuh).
+__device__ __forceinline__ unsigned f32_ordered(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+static inline float f32_from_ordered(unsigned u) {
+    const unsigned b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    float f; memcpy(&f, &b, 4); return f;
+}
 __global__ void classify_convert_kernel(const float* __restrict__ img, size_t step, int rows, int cols,
                                         uint8_t* __restrict__ out, size_t out_step, int* flag) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    bool bad = false;
+    bool bad = false, nonfinite = false;
+    float v = 0.f;
     if (x < cols && y < rows) {
-        const float v = reinterpret_cast<const float*>(reinterpret_cast<const char*>(img) + size_t(y) * step)[x];
+        v = reinterpret_cast<const float*>(reinterpret_cast<const char*>(img) + size_t(y) * step)[x];
         const float f = floorf(v);
         bad = !(v >= 0.f && v <= 255.f && f == v);
+        nonfinite = !(fabsf(v) <= 3.0e38f);
         out[size_t(y) * out_step + x] = bad ? 0 : uint8_t(int(v));
     }
-    if (__syncthreads_or(bad) && threadIdx.x == 0 && threadIdx.y == 0) atomicOr(flag, 1);
+    if (__syncthreads_or(bad)) {
+        __shared__ unsigned smax[2][8];
+        const float vv = nonfinite ? 0.f : v;
+        const unsigned hi = __reduce_max_sync(0xffffffffu, f32_ordered(vv)), lo = __reduce_max_sync(0xffffffffu, f32_ordered(-vv));
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, warp = tid >> 5;
+        if ((tid & 31) == 0) { smax[0][warp] = lo; smax[1][warp] = hi; }
+        const int anynf = __syncthreads_or(nonfinite);
+        if (tid == 0) {
+            unsigned l = 0, h = 0;
+            const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
+            for (int i = 0; i < nwarps && i < 8; ++i) { l = max(l, smax[0][i]); h = max(h, smax[1][i]); }
+            atomicOr(flag, anynf ? 3 : 1);
+            atomicMax(reinterpret_cast<unsigned*>(flag) + 1, l);
+            atomicMax(reinterpret_cast<unsigned*>(flag) + 2, h);
+        }
+    }
 }
 
 } // namespace sb

@@ -374,6 +374,130 @@ __global__ void __launch_bounds__(128) prep_scale_pair_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Float-operand path (general float32 images: the noise / contrast variants of main.cpp:140-153,191-193)
+// ---------------------------------------------------------------------------------------------------
+// bext() for float images: the value the reference reads at unpadded row i, extended column e (= unpadded column + 2R).
+__device__ __forceinline__ float bextf(const uint8_t* __restrict__ B, size_t step, int rows, int cols, int R, int i, int e,
+                                       int ar0, int ar1) {
+    const int Wp = cols + 2 * R;
+    const int c = e - R;                 // padded column, may be < 0 or >= Wp
+    int src_row = i, src_col;
+    if (c < 0) {                         // previous padded row, right padding
+        if (i + R - 1 < 0) return 0.f;
+        src_row = i - 1; src_col = cols - 1;
+    } else if (c >= Wp) {                // next padded row, left padding
+        if (i + R + 1 > rows + 2 * R - 1) return 0.f;
+        src_row = i + 1; src_col = 0;
+    } else {
+        src_col = clampi(c - R, 0, cols - 1);
+    }
+    src_row = clampi(clampi(src_row, 0, rows - 1), ar0, ar1 - 1);
+    return reinterpret_cast<const float*>(B + size_t(src_row) * step)[src_col];
+}
+
+// AF[jj][p]: rows of the replicate-padded reference image, array row jj <-> image row base_y - R - 1 + jj, p = padded
+// column.  Operand row j of the hot kernel = (entering row AF[j + 2R + 1], leaving row AF[j]).  Fused pair launches: the
+// columns past the padded row alias the next padded row exactly like the extended target image does (see prep_lp_kernel).
+__global__ void __launch_bounds__(256) prep_af_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int jj = blockIdx.y;
+    if (p4 >= g.lp_pitch) return;
+    const int i = g.base_y - g.R - 1 + jj;
+    const float* row = reinterpret_cast<const float*>(job.A + size_t(clampi(clampi(i, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * job.a_step);
+    const bool ext = g.npairs > 0 && p4 + 3 >= g.cols + 2 * g.R;
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        v[t] = ext ? bextf(job.A, job.a_step, g.rows, g.cols, g.R, i, p4 + t + g.R, g.ar0, g.ar1)
+                   : row[clampi(p4 + t - g.R, 0, g.cols - 1)];
+    }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.LP) + size_t(jj) * g.lp_pitch + p4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// BF[jj][q]: rows of the extended target image, column q <-> extended column e = q - qoff.
+__global__ void __launch_bounds__(256) prep_bf_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int jj = blockIdx.y;
+    if (q4 >= g.rq_pitch || !job.RQ) return;
+    const int i = g.base_y - g.R - 1 + jj;
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = bextf(job.B, job.b_step, g.rows, g.cols, g.R, i, q4 + t - job.qoff, g.ar0, g.ar1);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.RQ) + size_t(jj) * g.rq_pitch + q4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// Position / energy rows of the float path.  SSD: E2[j][q2] = q2 for a legal centre, KEY_INVALID otherwise (the key is
+// 128 * SSD + position, there is no energy term).  NCC: RS[j][q2] = 1 / sqrt(window energy of the extended target image),
+// summed in double like OpenCV's integral images (0 for an illegal centre or an empty window).
+__global__ void __launch_bounds__(128) prep_e2f_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (q2 >= g.e2_pitch) return;
+    const int uc = q2 - job.eoff;
+    const bool valid = uc >= job.cmin && uc <= job.cmax;
+    const size_t o = size_t(j) * g.e2_pitch + q2;
+    if (g.cost == STEREO_COST_SSD) {
+        job.E2[o] = valid ? q2 : int(KEY_INVALID);
+        return;
+    }
+    const int y = g.base_y + j;
+    float rs = 0.f;
+    if (valid && y >= g.rb && y < g.re) {
+        double er = 0;
+        for (int wy = -g.R; wy <= g.R; ++wy)
+            for (int t = 0; t <= 2 * g.R; ++t) {
+                const double b = bextf(job.B, job.b_step, g.rows, g.cols, g.R, y + wy, uc + g.R + t, g.ar0, g.ar1);
+                er += b * b;
+            }
+        rs = er > 0 ? float(1.0 / sqrt(er)) : 0.f;
+    }
+    job.RS[o] = rs;
+}
+
+// NCC, float path: window energies of the reference image per pixel (replicate padding, double sums) ...
+__global__ void __launch_bounds__(128) prep_elf_kernel(const __grid_constant__ FastKernelParams P, int vpitch) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (x >= g.cols) return;
+    const int y = g.rb + yy;
+    double el = 0;
+    for (int wy = -g.R; wy <= g.R; ++wy) {
+        const float* row = reinterpret_cast<const float*>(job.A + size_t(clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * job.a_step);
+        for (int wx = -g.R; wx <= g.R; ++wx) { const double a = row[clampi(x + wx, 0, g.cols - 1)]; el += a * a; }
+    }
+    reinterpret_cast<float*>(job.V)[size_t(yy) * vpitch + x] = float(el);
+}
+// ... and per strip row the key scale: 3 * 2^e with 2^e just above sqrt(max EL) - |C * rs| <= sqrt(EL) (Cauchy-Schwarz; 2^-10
+// of slack for the float32 running sums), so C * rs + 3 * 2^e lies in the binade [2 * 2^e, 4 * 2^e) whatever the sign of C.
+__global__ void __launch_bounds__(128) prep_scale_f_kernel(const __grid_constant__ FastKernelParams P, int vpitch) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int strip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y;
+    if (strip >= g.tilesX * g.spc) return;
+    const int x0 = strip * g.K;
+    float magic = 3.f;
+    if (x0 < g.cols) {
+        const float* v = reinterpret_cast<const float*>(job.V) + size_t(yy) * vpitch + x0;
+        const int x1 = min(g.K, g.cols - x0);
+        float elmax = 0.f;
+        for (int x = 0; x < x1; ++x) elmax = fmaxf(elmax, v[x]);
+        const float bound = float(sqrt(double(elmax)) * (1.0 + 1.0 / 1024.0));
+        int e; frexpf(bound, &e);                                       // bound = f * 2^e, f in [0.5, 1)
+        magic = elmax > 0.f ? 3.f * ldexpf(1.f, e) : 3.f;
+    }
+    job.SC[size_t(strip) * g.nrows + yy] = magic;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Merge: winning key per group -> disparity (+ cost), in the caller's layout
 // ---------------------------------------------------------------------------------------------------
 // Stores 4 consecutive disparities of one row (vector store when the caller's layout allows it).
@@ -413,7 +537,7 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
     bool found[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { bestc[k] = INT_MAX; bestd[k] = 0; found[k] = false; }
-    const uint32_t thresh = key_invalid_threshold(g.R), bias = key_bias(g.R);
+    const uint32_t thresh = g.opf ? KEY_INVALID : key_invalid_threshold(g.R), bias = key_bias(g.R);
     for (int grp = 0; grp < g.G; ++grp) {
         const int4 kv = *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4);
         const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
@@ -424,7 +548,8 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
             const int x = x4 + k;
             const uint32_t qlo = uint32_t(x + job.dlo0 + g.dg * grp + job.eoff);   // position of the group's first candidate
             const uint32_t q2 = qlo + ((key - qlo) & uint32_t(FGROUP - 1));
-            const int c = int(key - q2 - bias) >> FKEY_BITS;           // ER - 2C (exact: multiple of 128)
+            // packed: ER - 2C (exact: multiple of 128);  float operands: the SSD itself (key = 128 * SSD + position)
+            const int c = g.opf ? int((key - q2) >> FKEY_BITS) : (int(key - q2 - bias) >> FKEY_BITS);
             if (!found[k] || c < bestc[k]) { bestc[k] = c; bestd[k] = int(q2) - job.eoff - x; found[k] = true; }
         }
     }
@@ -437,7 +562,9 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
         for (int k = 0; k < 4 && x4 + k < g.cols; ++k) {
             const int x = x4 + k;
             int cost = 99999999;
-            if (found[k]) {
+            if (found[k] && g.opf) {
+                cost = bestc[k] < 99999999 ? bestc[k] : 99999999;
+            } else if (found[k]) {
                 int el = 0;
                 for (int wy = -g.R; wy <= g.R; ++wy) {
                     const uint8_t* row = A + size_t(clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * a_step;
@@ -495,20 +622,34 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
         const int y = g.rb + yy;
         for (int k = 0; k < 4 && x4 + k < g.cols; ++k) {
             const int x = x4 + k;
-            int c = 0, el = 0, er = 0;
-            for (int wy = -g.R; wy <= g.R; ++wy) {
-                const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
-                const uint8_t* arow = A + size_t(wr) * a_step;
-                const uint8_t* brow = B + size_t(wr) * b_step;
-                for (int wx = -g.R; wx <= g.R; ++wx) {
-                    const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre[k] + wx, 0, g.cols - 1)];
-                    c += l * r; el += l * l; er += r * r;
+            double num, wnd, eld;
+            if (g.opf) {       // float images: double sums (products of floats are exact in double), float32 numerator
+                double acc = 0, e1 = 0, e2 = 0;
+                for (int wy = -g.R; wy <= g.R; ++wy) {
+                    const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+                    const float* arow = reinterpret_cast<const float*>(A + size_t(wr) * a_step);
+                    const float* brow = reinterpret_cast<const float*>(B + size_t(wr) * b_step);
+                    for (int wx = -g.R; wx <= g.R; ++wx) {
+                        const double l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre[k] + wx, 0, g.cols - 1)];
+                        acc += l * r; e1 += l * l; e2 += r * r;
+                    }
                 }
+                num = double(float(acc)); wnd = e2; eld = e1;
+            } else {
+                int c = 0, el = 0, er = 0;
+                for (int wy = -g.R; wy <= g.R; ++wy) {
+                    const int wr = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+                    const uint8_t* arow = A + size_t(wr) * a_step;
+                    const uint8_t* brow = B + size_t(wr) * b_step;
+                    for (int wx = -g.R; wx <= g.R; ++wx) {
+                        const int l = arow[clampi(x + wx, 0, g.cols - 1)], r = brow[clampi(centre[k] + wx, 0, g.cols - 1)];
+                        c += l * r; el += l * l; er += r * r;
+                    }
+                }
+                num = double(float(c)); wnd = double(er); eld = double(el);
             }
-            double num = double(float(c));
-            const double wnd = double(er);
             const double lim = fmin(0.5, 10 * double(FLT_EPSILON) * wnd);
-            const double t = (wnd <= lim) ? 0 : sqrt(wnd) * sqrt(double(el));
+            const double t = (wnd <= lim) ? 0 : sqrt(wnd) * sqrt(eld);
             if (fabs(num) < t) num /= t;
             else if (fabs(num) < t * 1.125) num = num > 0 ? 1 : -1;
             else num = 0;
@@ -599,8 +740,7 @@ static inline bool fast_supported(const Problem& p) {
 static inline bool fast_batchable(const Problem& a, const Problem& b) {
     return a.cost == b.cost && a.rows == b.rows && a.cols == b.cols && a.R == b.R && a.row_begin == b.row_begin &&
            a.row_end == b.row_end && a.avail_begin == b.avail_begin && a.avail_end == b.avail_end &&
-           (a.dmax - a.dmin) == (b.dmax - b.dmin) && a.ref.type == PixType::U8 && b.ref.type == PixType::U8 &&
-           a.tgt.type == PixType::U8 && b.tgt.type == PixType::U8;
+           (a.dmax - a.dmin) == (b.dmax - b.dmin) && a.ref.type == a.tgt.type && b.ref.type == b.tgt.type && a.ref.type == b.ref.type;
 }
 
 // Strips per warp: 2 for searches of at most 64 candidates (a warp then covers 2 x 24 pixels x 64 disparities
@@ -636,6 +776,7 @@ static inline bool fast_launch_is_pairs(const Problem* ps, int n) {
 }
 
 static inline size_t fast_stage_bytes(const FastGeom& g) {
+    if (g.opf) return (size_t(2 * FRPS) * g.lpw + size_t(2 * FRPS) * g.rqw + size_t(FRPS) * g.e2w + size_t(FRPS) * g.elw) * 4;
     return (size_t(FRPS) * g.lpw + size_t(FRPS / 2) * g.rqw + size_t(FRPS) * g.e2w + size_t(FRPS) * g.elw) * 4;
 }
 
@@ -654,10 +795,11 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
     g.elw = 0;
     g.border = 0;
     g.nw = nw;
-    g.hs = fast_pick_hs(g.D);
+    g.opf = p.ref.type == PixType::F32 ? 1 : 0;
+    g.hs = g.opf ? 1 : fast_pick_hs(g.D);
     const int w = 2 * p.R + 1;
     for (;;) {
-        g.K = fast_k(p.R, fused_pairs > 0, g.hs);
+        g.K = g.opf ? fast_kf(p.R) : fast_k(p.R, fused_pairs > 0, g.hs);
         g.dg = FGROUP / g.hs;
         g.G = (g.D + g.dg - 1) / g.dg;
         g.gc = (g.hs == 1 && g.G % 2 == 0) ? 2 : 1;
@@ -679,7 +821,7 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
     if (fused_pairs > 0 && p.R > 0) {
         const int ext_strips = (p.cols + p.R + g.K - 1) / g.K;
         const int t0 = (g.nstrips + g.spc - 1) / g.spc, t1 = (ext_strips + g.spc - 1) / g.spc;
-        if (t1 > t0 && t0 <= 8) g.border = 1;
+        if (t1 > t0 && t0 <= 8 && !g.opf) g.border = 1;      // (the border kernel is 8-bit only)
         else g.nstrips = ext_strips;
     }
     g.tilesX = (g.nstrips + g.spc - 1) / g.spc;
@@ -714,36 +856,44 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
         if (rqp > g.rq_pitch) g.rq_pitch = rqp;
         if (e2p > g.e2_pitch) g.e2_pitch = e2p;
     }
-    // grid: one CTA per SM.  Fewer tiles than SMs (small images): every tile is cut into the same number of row segments
-    // of L rows, so no CTA pays the (2R+1)-row warm-up twice; otherwise the (tile, row) space is split evenly.
+    // grid: one CTA per SM, two ways to cut the (tile, row) space:
+    //   linear   - split evenly into sm_count shares; a share that crosses a tile boundary pays the (2R+1)-row warm-up twice
+    //   segments - (fewer tiles than SMs) every tile is cut into the same number of row segments, one CTA each: no share
+    //              straddles, but ntiles * spt CTAs may leave SMs idle
+    // whichever has the smaller modelled critical path (a warm-up row costs about half a regular row).
     const long long ntiles = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks;
+    const long long lin_total = ntiles * g.nrows;
+    const long long lin_L = (lin_total + ctx->sm_count - 1) / ctx->sm_count;
+    const double t_lin = double(lin_L) + w * 0.5 * (lin_L < g.nrows ? 2 : 1 + (lin_L + g.nrows - 1) / g.nrows);
+    int spt = 0, seg_L = 0;
+    double t_seg = 1e30;
     if (ntiles < ctx->sm_count) {
-        int spt = int(ctx->sm_count / ntiles);                 // segments per tile
-        int L = (g.nrows + spt - 1) / spt;
-        if (L < FRPS) L = FRPS;                                // at least one pipeline stage of rows per CTA
-        spt = (g.nrows + L - 1) / L;
-        g.L = L;
-        g.nrl = spt * L;
+        spt = int(ctx->sm_count / ntiles);                     // segments per tile
+        seg_L = (g.nrows + spt - 1) / spt;
+        if (seg_L < FRPS) seg_L = FRPS;                        // at least one pipeline stage of rows per CTA
+        spt = (g.nrows + seg_L - 1) / seg_L;
+        t_seg = double(seg_L) + w * 0.5;
+    }
+    if (t_seg < t_lin) {
+        g.L = seg_L;
+        g.nrl = spt * seg_L;
         g.total = ntiles * g.nrl;
         g.ctas = int(ntiles * spt);
     } else {
         g.nrl = g.nrows;
-        g.total = ntiles * g.nrows;
-        g.L = (g.total + ctx->sm_count - 1) / ctx->sm_count;
+        g.total = lin_total;
+        g.L = lin_L;
         g.ctas = int((g.total + g.L - 1) / g.L);
     }
 }
 
-// Warps per CTA: 8; 4 when the 8-warp tiles are fewer than half the SMs (small images: every tile is then cut into row
-// segments, each paying a (2R+1)-row warm-up - narrower tiles halve what that warm-up costs).  STEREO_FAST_NW forces it.
 static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n, FastGeom& g, FastJob* jobs, int fused_pairs = 0) {
-    static const int forced = [] { const char* e = getenv("STEREO_FAST_NW"); return e ? atoi(e) : 0; }();
-    fast_geometry_nw(ctx, ps, n, g, jobs, fused_pairs, forced == FWARPS_SMALL ? FWARPS_SMALL : FWARPS);
-    if (forced == 0) {
-        const long long ntiles = (long long)(fused_pairs > 0 ? fused_pairs : n) * g.tilesX * g.gblocks;
-        if (2 * ntiles <= ctx->sm_count && g.gc == 1) fast_geometry_nw(ctx, ps, n, g, jobs, fused_pairs, FWARPS_SMALL);
-    }
+    fast_geometry_nw(ctx, ps, n, g, jobs, fused_pairs, FWARPS);
 }
+
+// Fused launches whose blocks are all MODE 1 (whole disparity groups, masks free through the keys: R <= 5) take the
+// kernel compiled without the other row flavours.
+static inline bool fast_fused_all_mode1(const FastGeom& g) { return g.R <= FFREE_MASK_R && g.D % g.dg == 0; }
 
 static inline size_t fast_smem_bytes(const FastGeom& g) {
     return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + (g.elw ? FWARPS * 256 : 0);
@@ -757,15 +907,15 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     size_t best = 0;
     for (int fused = 0; fused <= 1; ++fused) {
         if (fused && p.cost != STEREO_COST_SSD) break;
-      for (int nw = FWARPS_SMALL; nw <= FWARPS; nw += FWARPS - FWARPS_SMALL) {      // either tile width may be picked at launch
+      {
         FastGeom g; FastJob jb{};
-        fast_geometry_nw(ctx, &p, 1, g, &jb, fused, nw);
+        fast_geometry(ctx, &p, 1, g, &jb, fused);
         // pitches may grow by one alignment step when jobs with other range signs join the launch
         g.rq_pitch += 64; g.e2_pitch += 64;
         size_t b = 0;
         auto add = [&](size_t bytes) { b += ((bytes + 255) & ~size_t(255)); };
-        add(size_t(g.J) * g.lp_pitch * 4);
-        add(size_t(g.J / 2) * g.rq_pitch * 4);
+        if (g.opf) { add(size_t(g.J + 2 * g.R + 1) * g.lp_pitch * 4); add(size_t(g.J + 2 * g.R + 1) * g.rq_pitch * 4); }
+        else { add(size_t(g.J) * g.lp_pitch * 4); add(size_t(g.J / 2) * g.rq_pitch * 4); }
         add(size_t(g.J) * g.e2_pitch * 4);
         add(size_t(g.G) * g.nrows * g.wpart * 4);
         add(size_t(g.nrows) * fast_vpitch(g) * 4);
@@ -787,12 +937,20 @@ static inline int fast_ctx_init(stereo_ctx*) {
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
             }
     for (int R = 0; R <= FMAXR; ++R)
-      for (int hs = 1; hs <= 2; ++hs) {
-        fast_kernel_fn fn = fast_pick_fused(R, hs);
-        if (!fn) { set_error("fused pair kernel (R %d, hs %d) missing from the build", R, hs); return STEREO_ERR_UNSUPPORTED; }
+      for (int hs = 1; hs <= 2; ++hs)
+        for (int gen = (R <= FFREE_MASK_R ? 0 : 1); gen <= 1; ++gen) {
+        fast_kernel_fn fn = fast_pick_fused(R, hs, gen);
+        if (!fn) { set_error("fused pair kernel (R %d, hs %d, gen %d) missing from the build", R, hs, gen); return STEREO_ERR_UNSUPPORTED; }
         cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
     }
+    for (int R = 0; R <= FMAXR; ++R)
+        for (int kind = 0; kind < 3; ++kind) {
+            fast_kernel_fn fn = fast_pick_opf(R, kind);
+            if (!fn) { set_error("float-operand kernel (R %d, kind %d) missing from the build", R, kind); return STEREO_ERR_UNSUPPORTED; }
+            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+        }
     return STEREO_OK;
 }
 
@@ -805,7 +963,10 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     FastGeom& g = kp.g;
     fast_geometry(ctx, ps, n, g, kp.job, fused_pairs);
     const bool ncc = ps[0].cost == STEREO_COST_NCORR;
+    const bool opf = g.opf != 0;
     const int vpitch = fast_vpitch(g);
+    const int w = 2 * g.R + 1;
+    const size_t lp_rows = opf ? size_t(g.J + w) : size_t(g.J), rq_rows = opf ? size_t(g.J + w) : size_t(g.J / 2);
     for (int i = 0; i < n; ++i) {
         FastJob& jb = kp.job[i];
         const Problem& p = ps[i];
@@ -822,8 +983,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
             SB_CUDA(cudaMemsetAsync(jb.PART, 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
             continue;
         }
-        jb.LP = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.lp_pitch * 4));
-        jb.RQ = static_cast<uint32_t*>(ctx->arena.take(size_t(g.J / 2) * g.rq_pitch * 4));
+        jb.LP = static_cast<int32_t*>(ctx->arena.take(lp_rows * g.lp_pitch * 4));
+        jb.RQ = static_cast<uint32_t*>(ctx->arena.take(rq_rows * g.rq_pitch * 4));
         jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
         jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
         jb.V = static_cast<int32_t*>(ctx->arena.take(size_t(g.nrows) * vpitch * 4));
@@ -835,35 +996,52 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
             set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC;
         }
     }
-    const unsigned nz = unsigned(n);
-    prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, fused_pairs ? unsigned(fused_pairs) : nz), 256, 0, st>>>(kp);
+    const unsigned nz = unsigned(n), nwalk = fused_pairs ? unsigned(fused_pairs) : nz;
     static const bool legacy_prep = [] { const char* e = getenv("STEREO_PREP_LEGACY"); return e && atoi(e) != 0; }();
-    if (!legacy_prep || fused_pairs) {
-        int delta_max = 0;
-        for (int i = 0; i < n; ++i) { const int d = kp.job[i].qoff - kp.job[i].eoff + g.R; if (d > delta_max) delta_max = d; }
-        const int span = g.rq_pitch > g.e2_pitch + delta_max ? g.rq_pitch : g.e2_pitch + delta_max;
-        const int tiles = int(div_round_up(span, pt_ts(g.R)));
-        int rpc = PT_ROWS;                          // fewer rows per CTA while the grid would leave SMs idle
-        while (rpc > 16 && (long long)tiles * div_round_up(g.J, rpc) * n < 6LL * ctx->sm_count) rpc /= 2;
-        prep_tgt_pick(g.R)<<<dim3(tiles, div_round_up(g.J, rpc), nz), PT_THREADS, 0, st>>>(kp, rpc);
-        ctx->last_launches -= 2;
-    } else {   // three-pass version (debug knob): RQ rows, vertical sums in HBM, horizontal sums
-        prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
-        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
-        const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
-        prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
-    }
-    if (ncc && (!legacy_prep) && fast_launch_is_pairs(ps, n)) {
-        // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
-        prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
+    fast_kernel_fn fn = nullptr;
+    if (opf) {
+        // float operand rows straight from the images (padding, row-wrap aliasing), position / energy rows
+        prep_af_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), unsigned(lp_rows), nwalk), 256, 0, st>>>(kp);
+        prep_bf_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), unsigned(rq_rows), nwalk), 256, 0, st>>>(kp);
+        prep_e2f_kernel<<<dim3(div_round_up(g.e2_pitch, 128), g.J, nz), 128, 0, st>>>(kp);
+        ctx->last_launches += 3;
+        if (ncc) {
+            prep_elf_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
+            prep_scale_f_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
+            ctx->last_launches += 2;
+        }
+        fn = fast_pick_opf(g.R, ncc ? OPF_NCC : (fused_pairs ? OPF_SSD_FUSED : OPF_SSD));
+    } else {
+        prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, nwalk), 256, 0, st>>>(kp);
         ctx->last_launches += 1;
-    } else if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
-        prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 1);
-        prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
-        ctx->last_launches += 2;
+        if (!legacy_prep || fused_pairs) {
+            int delta_max = 0;
+            for (int i = 0; i < n; ++i) { const int d = kp.job[i].qoff - kp.job[i].eoff + g.R; if (d > delta_max) delta_max = d; }
+            const int span = g.rq_pitch > g.e2_pitch + delta_max ? g.rq_pitch : g.e2_pitch + delta_max;
+            const int tiles = int(div_round_up(span, pt_ts(g.R)));
+            int rpc = PT_ROWS;                          // fewer rows per CTA while the grid would leave SMs idle
+            while (rpc > 16 && (long long)tiles * div_round_up(g.J, rpc) * n < 6LL * ctx->sm_count) rpc /= 2;
+            prep_tgt_pick(g.R)<<<dim3(tiles, div_round_up(g.J, rpc), nz), PT_THREADS, 0, st>>>(kp, rpc);
+            ctx->last_launches += 1;
+        } else {   // three-pass version (debug knob): RQ rows, vertical sums in HBM, horizontal sums
+            prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
+            prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
+            const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
+            prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
+            ctx->last_launches += 3;
+        }
+        if (ncc && (!legacy_prep) && fast_launch_is_pairs(ps, n)) {
+            // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
+            prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
+            ctx->last_launches += 1;
+        } else if (ncc) {   // window energies of the reference image -> per strip-row key binade (V is free again after prep_e2)
+            prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 1);
+            prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
+            ctx->last_launches += 2;
+        }
+        fn = fused_pairs ? fast_pick_fused(g.R, g.hs, fast_fused_all_mode1(g) ? 0 : 1) : fast_pick(ps[0].cost, g.R, g.hs);
     }
-    fast_kernel_fn fn = fused_pairs ? fast_pick_fused(g.R, g.hs) : fast_pick(ps[0].cost, g.R, g.hs);
-    if (!fn) { set_error("no hot kernel for R=%d hs=%d (internal)", g.R, g.hs); return STEREO_ERR_UNSUPPORTED; }
+    if (!fn) { set_error("no hot kernel for R=%d hs=%d opf=%d (internal)", g.R, g.hs, g.opf); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
         if (g.border) {
             if (fused_border_fn bf = fused_border_pick(g.R)) {
@@ -881,7 +1059,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     ctx->hot_total++;
     if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
     else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
-    ctx->last_launches += 6;
+    ctx->last_launches += 2;
     SB_CUDA(cudaGetLastError());
     return STEREO_OK;
 }

@@ -57,6 +57,8 @@ constexpr int FK_FUSED = SB_FK_FUSED, FK_FUSED2 = SB_FK_FUSED2;
 #define SB_FK_FUSED_WIDE 16
 #endif
 constexpr int FK_WIDE_R = 6;    // first radius that takes the narrower strips
+// float-operand kernels (OPF): K + 2R <= 30 column sums per disparity next to the operand words in flight
+__host__ __device__ constexpr int fast_kf(int R) { return R <= 3 ? 24 : (R <= 5 ? 20 : 16); }
 __host__ __device__ constexpr int fast_k(int R, bool fused, int hs) {
     return fused ? (hs == 2 ? FK_FUSED2 : (R >= FK_WIDE_R ? SB_FK_FUSED_WIDE : FK_FUSED)) : (R >= FK_WIDE_R ? SB_FK_WIDE : FK_DEFAULT);
 }
@@ -66,9 +68,9 @@ constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candida
 constexpr int FRPS = 8;         // operand rows per pipeline stage
 constexpr int FNST_MAX = 8;     // pipeline stages (fewer when the tile rows are wide, FastGeom::nst)
 constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kernel may use
-constexpr int FWARPS = 8;       // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers)
-constexpr int FWARPS_SMALL = 4; // ... of launches whose tiles are fewer than half the SMs (small images): narrower tiles, so that
-                                // each CTA's (2R+1)-row warm-up is paid on half the pixels (FastGeom::nw, a launch parameter)
+constexpr int FWARPS = 8;       // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers).  4-warp CTAs (narrower
+                                // tiles for small images) were measured: one warp per scheduler cannot hide the row code's
+                                // latencies (511x640/96 fused pair: 91 us against 54 us with 8 warps)
 constexpr int FMAXJOBS = 8;     // directions (jobs) one launch sequence can carry
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
@@ -93,7 +95,8 @@ struct FastGeom {
     int rb, re;            // output band
     int ar0, ar1;          // image rows present in the caller's buffers (full image: 0, rows); reads clamp into it
     int K;                 // pixels per thread (strip width): 24
-    int nw;                // warps per CTA: 8, or 4 for small images (blockDim.x / 32; the kernels are compiled for up to 8)
+    int nw;                // warps per CTA: 8
+    int opf;               // 1: float operand rows (general float32 images), 0: packed 8-bit operands
     int hs;                // strips per warp: 1 (a warp = 24 px x 128 disparities) or 2 (2 x 24 px x 64 disparities, D <= 64)
     // derived
     int dg;                // disparities per strip and warp = 128 / hs
@@ -136,8 +139,10 @@ struct FastJob {
     int cmin, cmax;        // legal centre columns (unpadded coordinates)
     void* disp; size_t disp_step; int elem;
     void* best; size_t best_step;
-    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1))
-    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R))
+    int32_t* LP;       // [J][lp_pitch]   s16x2: (-l(y+R), +l(y-R-1));   opf: [J+2R+1][lp_pitch] float rows of the padded reference
+                       //                 image, array row jj <-> image row base_y - R - 1 + jj
+    uint32_t* RQ;      // [J/2][rq_pitch] u8x4 : (r(ye+R), r(ye-R-1), r(ye+1+R), r(ye-R));   opf: [J+2R+1][rq_pitch] float rows of the
+                       //                 extended target image
     int32_t* E2;       // [J][e2_pitch]   SSD: BIAS + 128*ER + position, or KEY_INVALID;  NCC: ER
     int32_t* PART;     // [G][nrows][wpart] winning keys
     int32_t* V;        // [nrows][vpitch] vertical (2R+1)-sums of squares of the extended target image
@@ -247,29 +252,94 @@ constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses
 // the diagonal it will not touch again to the lane below (one SHFL) and lane 0 retires one finished diagonal into
 // a 24-word shared-memory tail.  At the end of the row the tail and the 128 live diagonals are merged into the
 // partner's partial-key map with RED.MIN (several strips contribute to one x').
-template <int R, int K, int PAR, int MODE, int COST, int HS, bool FUSED = false>
+// OPF (float operands): the images are general float32 (noise / contrast variants, main.cpp:140-153,191-193), the
+// operand rows are rows of the replicate-padded (extended) float images themselves - entering row and leaving row
+// of the reference image (lp_row / lp_old) and of the target image (rq_row / rq_old) - and
+//   SSD: col += q(l_new, r_new) - q(l_old, r_old) with q = the reference's per-element term (DisparitySSD.cpp:49-51)
+//        (int)round(f32((l - r)^2)): FSUB, FMUL (separately rounded, never fused), FADD.RZ +0.5, FADD.RZ +2^23 - the
+//        mantissa of the last sum IS floor(q + 0.5) = round-half-away(q) for q < 2^23 - 1, so the column sums are
+//        exact int32 sums of the bit patterns (the 2^23 biases cancel in new - old): ONE IADD3 per unit.
+//        key = 128 * SSD + position (no energy terms); illegal positions take the explicit selects of MODE 3.
+//   NCC: col += l_new*r_new - l_old*r_old in float32 (two FFMA); key from v = C * RS[pos] shifted by 3*magic into
+//        the binade [2*magic, 4*magic) because C may be negative for float images.
+// The host only takes this path when the value range of the two images keeps every term inside those bounds.
+__device__ __forceinline__ int ssd_q_bits(float a, float b) {
+    const float d = __fsub_rn(a, b);
+    const float q = __fmul_rn(d, d);
+    return __float_as_int(__fadd_rz(__fadd_rz(q, 0.5f), 8388608.0f));
+}
+constexpr uint32_t FKEY_MUL_F32 = 1u << FKEY_BITS;     // OPF SSD keys: 128 * cost + position
+
+template <int R, int K, int PAR, int MODE, int COST, int HS, bool FUSED = false, bool OPF = false>
 __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], const int* __restrict__ lp_row,
                                          const int* __restrict__ rq_row, const int* __restrict__ e2_row,
                                          int32_t* __restrict__ out_row, int mmin, int mmax, uint32_t lane_or, int ll, int sub, int cbase,
                                          int cols, float magic, const int* __restrict__ el_row = nullptr,
                                          uint32_t* __restrict__ tail = nullptr, uint32_t* __restrict__ part2_row = nullptr,
-                                         int x2base = 0) {
+                                         int x2base = 0, const int* __restrict__ lp_old = nullptr, const int* __restrict__ rq_old = nullptr) {
     using S = RowShape<R, K>;
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
-    constexpr bool BIASED = NCC && (R <= NCC_BIAS_MAX_R);
-    int lpv[S::NC4];
-    int rqv[S::NQ4];
+    constexpr bool BIASED = NCC && !OPF && (R <= NCC_BIAS_MAX_R);
+    constexpr uint32_t KEYMUL = OPF ? FKEY_MUL_F32 : uint32_t(2 << FKEY_BITS);
+    int lpv[S::NC4];               // packed: s16x2 (new, old) of the reference image;  OPF: the entering row (float bits)
+    int rqv[S::NQ4];               // packed: u8x4 of the target image;                 OPF: the entering row
+    int lov[OPF ? S::NC4 : 1];     // OPF: the leaving rows
+    int rov[OPF ? S::NQ4 : 1];
+    if (!OPF) {
 #pragma unroll
-    for (int i = 0; i < S::NC4 / 4; ++i) {
-        const int4 v = lds128(lp_row + 4 * i);
-        lpv[4 * i] = v.x; lpv[4 * i + 1] = v.y; lpv[4 * i + 2] = v.z; lpv[4 * i + 3] = v.w;
-    }
+        for (int i = 0; i < S::NC4 / 4; ++i) {
+            const int4 v = lds128(lp_row + 4 * i);
+            lpv[4 * i] = v.x; lpv[4 * i + 1] = v.y; lpv[4 * i + 2] = v.z; lpv[4 * i + 3] = v.w;
+        }
 #pragma unroll
-    for (int i = 0; i < S::NQ4 / 4; ++i) {
-        const int4 v = lds128(rq_row + 4 * i);
-        rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
+        for (int i = 0; i < S::NQ4 / 4; ++i) {
+            const int4 v = lds128(rq_row + 4 * i);
+            rqv[4 * i] = v.x; rqv[4 * i + 1] = v.y; rqv[4 * i + 2] = v.z; rqv[4 * i + 3] = v.w;
+        }
     }
+    // OPF: operands are fetched four columns at a time right before their first use (twice the operand words of the
+    // packed path would not fit next to the column sums)
+    auto fetch4 = [&](int (&dst)[OPF ? S::NC4 : 1], const int* row, int i) {
+        const int4 v = lds128(row + 4 * i);
+        dst[OPF ? 4 * i : 0] = v.x; dst[OPF ? 4 * i + 1 : 0] = v.y; dst[OPF ? 4 * i + 2 : 0] = v.z; dst[OPF ? 4 * i + 3 : 0] = v.w;
+    };
+    auto fetch4q = [&](int (&dst)[OPF ? S::NQ4 : 1], const int* row, int i) {
+        const int4 v = lds128(row + 4 * i);
+        dst[OPF ? 4 * i : 0] = v.x; dst[OPF ? 4 * i + 1 : 0] = v.y; dst[OPF ? 4 * i + 2 : 0] = v.z; dst[OPF ? 4 * i + 3 : 0] = v.w;
+    };
     auto update = [&](int c) {
+        if (OPF) {
+            if ((c & 3) == 0) {
+                {
+                    const int4 v = lds128(lp_row + c);
+                    lpv[c] = v.x; lpv[c + 1] = v.y; lpv[c + 2] = v.z; lpv[c + 3] = v.w;
+                }
+                if (MODE != 0) fetch4(lov, lp_old, c / 4);
+                if (c == 0) {
+                    const int4 v = lds128(rq_row);
+                    rqv[0] = v.x; rqv[1] = v.y; rqv[2] = v.z; rqv[3] = v.w;
+                    if (MODE != 0) fetch4q(rov, rq_old, 0);
+                }
+                if (c + 4 < S::NQ4) {
+                    const int4 v = lds128(rq_row + c + 4);
+                    rqv[c + 4] = v.x; rqv[c + 5] = v.y; rqv[c + 6] = v.z; rqv[c + 7] = v.w;
+                    if (MODE != 0) fetch4q(rov, rq_old, c / 4 + 1);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < FM; ++m) {
+                if (!NCC) {
+                    const int qn = ssd_q_bits(__int_as_float(lpv[c]), __int_as_float(rqv[c + m]));
+                    if (MODE == 0) col[m][c] += qn - NCC_FLOAT_BIAS;      // warm-up: entering row only (remove its 2^23 bias)
+                    else col[m][c] += qn - ssd_q_bits(__int_as_float(lov[OPF ? c : 0]), __int_as_float(rov[OPF ? c + m : 0]));
+                } else {
+                    float v = __fmaf_rn(__int_as_float(lpv[c]), __int_as_float(rqv[c + m]), __int_as_float(col[m][c]));
+                    if (MODE != 0) v = __fmaf_rn(-__int_as_float(lov[OPF ? c : 0]), __int_as_float(rov[OPF ? c + m : 0]), v);
+                    col[m][c] = __float_as_int(v);
+                }
+            }
+            return;
+        }
         const int a = (MODE == 0) ? (lpv[c] & 0xFFFF) : lpv[c];      // warm-up: entering row only
 #pragma unroll
         for (int m = 0; m < FM; ++m)
@@ -286,17 +356,21 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         const int4 v = lds128(e2_row + 4 * i);
         e2v[4 * i] = v.x; e2v[4 * i + 1] = v.y; e2v[4 * i + 2] = v.z; e2v[4 * i + 3] = v.w;
     }
-    int s[FM];
+    int s[FM];                   // horizontal window sums: int (packed, OPF SSD) or float bits (OPF NCC)
     int sbias = 0;
     // opaque to the compiler: a literal would be re-associated out of the running sums and re-added per use
     if (BIASED) asm("mov.b32 %0, 0x4B000000;" : "=r"(sbias));
 #pragma unroll
     for (int m = 0; m < FM; ++m) s[m] = sbias;
+    constexpr bool FSUM = OPF && NCC;           // float running sums
 #pragma unroll
     for (int c = 0; c < 2 * R; ++c) {
         update(c);
 #pragma unroll
-        for (int m = 0; m < FM; ++m) s[m] += col[m][c];
+        for (int m = 0; m < FM; ++m) {
+            if (FSUM) s[m] = __float_as_int(__fadd_rn(__int_as_float(s[m]), __int_as_float(col[m][c])));
+            else s[m] += col[m][c];
+        }
     }
     uint32_t res[4];
     uint32_t acc[FM];            // FUSED: running minima of the diagonals k + 4*ll + m
@@ -315,7 +389,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             elv[0] = v.x; elv[1] = v.y; elv[2] = v.z; elv[3] = v.w;
             // a lane outside [dmin, dmax] contributes to neither map; for R <= 5 the partner's key of such a lane loses
             // through its energy term alone (KEY_INVALID - 256*C stays above every valid key), one OR per pixel
-            if (MODE == 2 && R <= FFREE_MASK_R) {
+            if (MODE == 2 && R <= FFREE_MASK_R && !OPF) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) elv[i] = int(uint32_t(elv[i]) | lane_or);
             }
@@ -323,34 +397,42 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         uint32_t key[FM];
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
-            s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
+            if (FSUM) {
+                float t = __fadd_rn(__int_as_float(s[m]), __int_as_float(col[m][k + 2 * R]));
+                if (k > 0) t = __fsub_rn(t, __int_as_float(col[m][k - 1]));
+                s[m] = __float_as_int(t);
+            } else {
+                s[m] = s[m] + col[m][k + 2 * R] - (k > 0 ? col[m][k - 1] : 0);
+            }
             if (!NCC) {
-                // s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position.
+                // packed: s = -C (the packed operand carries -l): key = BIAS + 128*(ER - 2C) + position; OPF: s = SSD,
+                // key = 128*SSD + position.
                 // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
                 // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
                 uint32_t kv;
-                if (SB_KEY_LEA_MASK & (1 << m)) {      // shift-add on the ALU pipe
+                if (!OPF && (SB_KEY_LEA_MASK & (1 << m))) {      // shift-add on the ALU pipe
                     asm("{.reg .b32 t; shl.b32 t, %1, 8; add.s32 %0, t, %2;}" : "=r"(kv) : "r"(s[m]), "r"(e2v[k + m]));
                 } else {                                // IMAD (immediate) on the FMA-heavy pipe
-                    kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                    kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * KEYMUL;
                 }
                 if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : kv;
                 key[m] = kv;
                 if (FUSED) {
                     // the partner direction's key of the same cross term: BIAS + 128*(EL(x) - 2C) + x; pixels x beyond its
                     // legal centres (x > cols-1+R) carry EL2 = KEY_INVALID and lose like illegal search positions do (R <= 5;
-                    // wider windows take the explicit selects of MODE 3 in the blocks that hold such pixels)
-                    uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * uint32_t(2 << FKEY_BITS);
+                    // wider windows and float operands take the explicit selects of MODE 3 in the blocks that hold such pixels)
+                    uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * KEYMUL;
                     if (MODE == 3) k2 = (uint32_t(elv[k & 3]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : k2;
-                    if (MODE == 2 && R > FFREE_MASK_R) k2 |= lane_or;
+                    if (MODE == 2 && (R > FFREE_MASK_R || OPF)) k2 |= lane_or;
                     acc[m] = min(acc[m], k2);
                 }
             } else {
                 const float rs = __int_as_float(e2v[k + m]);
                 // BIASED: s is the float 2^23 + C, so C*rs + magic = fma(s, rs, magic - 2^23*rs); the addend is exact
                 // (Sterbenz / common-ulp argument: 2^23*rs >= 2990 > magic/2 for R <= 5), i.e. ONE rounding
+                // OPF: `magic` arrives as 3 * 2^e (C may be negative): r lies in [2*2^e, 4*2^e)
                 const float r = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, magic))
-                                       : __fmaf_rn(__int2float_rn(s[m]), rs, magic);
+                                       : __fmaf_rn(OPF ? __int_as_float(s[m]) : __int2float_rn(s[m]), rs, magic);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
                 uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
                 if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax || m < mmin) ? NCC_KEY_NONE : kv;
@@ -413,10 +495,15 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     }
 }
 
-template <int R, int K, int NW, int COST, int HS, bool FUSED = false>
+// GEN (fused kernels only): false = every block of the launch is MODE 1 (whole disparity groups, R <= 5: the masks come
+// free through the keys) - the kernel the 4K/256 and 1080p/128 configurations run, kept free of the other row flavours
+// so that their code does not weigh on its register allocation; true = any candidate count, any radius.
+// OPF: float operand rows (see fast_row): LP / RQ point at the extended float images, one row per image row; each
+// stage stages the entering AND the leaving rows of both images.
+template <int R, int K, int NW, int COST, int HS, bool FUSED = false, bool GEN = true, bool OPF = false>
 __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
     static_assert(!FUSED || (COST == STEREO_COST_SSD && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, strips of 4k <= 32 pixels");
-    static_assert(NW == 8, "the per-warp copy counts below assume 4 or 8 warps per CTA");
+    static_assert(!OPF || (HS == 1 && GEN && K % 4 == 0), "float operands: one strip per warp, general masks");
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr int LS = 32 / HS;                 // lanes per strip
     constexpr int DG = FM * LS;                 // disparities per strip and warp
@@ -426,11 +513,14 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane / LS, ll = lane % LS;
     const int nst = g.nst;
-    const int nw = g.nw;                        // warps of this launch (blockDim.x / 32): 8, or 4 for small images
+    constexpr int nw = NW;
 
-    const int lp_stage = FRPS * g.lpw, rq_stage = (FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;   // words
+    // stage layout (words): [lp (OPF: entering rows)] [OPF: lp leaving rows] [rq (OPF: entering)] [OPF: rq leaving] [e2] [FUSED: el]
+    constexpr int NOP = OPF ? 2 : 1;
+    const int lp_stage = FRPS * g.lpw, rq_stage = (OPF ? FRPS : FRPS / 2) * g.rqw, e2_stage = FRPS * g.e2w;
     const int el_stage = FUSED ? FRPS * g.elw : 0;
-    const int stage_words = lp_stage + rq_stage + e2_stage + el_stage;
+    const int rq_base = NOP * lp_stage, e2_base = NOP * (lp_stage + rq_stage), el_base = e2_base + e2_stage;
+    const int stage_words = el_base + el_stage;
     int* smem = reinterpret_cast<int*>(smem_raw);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + size_t(nst) * stage_words * 4);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + FNST_MAX);
@@ -491,12 +581,15 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int32_t* e2src = NCC ? reinterpret_cast<const int32_t*>(job.RS) : job.E2;
         const uint32_t bar = full0 + 8 * slot;
         int* st = smem + size_t(slot) * stage_words;
-        constexpr int NLP = (FRPS - 1) / FWARPS_SMALL + 1, NRQ = (FRPS / 2 - 1) / FWARPS_SMALL + 1;       // copies per warp, upper bounds
+        constexpr int NLP = (FRPS - 1) / NW + 1, NRQ = (FRPS / 2 - 1) / NW + 1;       // copies per warp, upper bounds
         uint32_t mine = 0;
 #pragma unroll
-        for (int i = 0; i < NLP; ++i) if (warp + i * nw < FRPS) mine += uint32_t(g.lpw + g.e2w + (FUSED ? g.elw : 0)) * 4u;
+        for (int i = 0; i < NLP; ++i)
+            if (warp + i * nw < FRPS) mine += uint32_t(NOP * g.lpw + (OPF ? 2 * g.rqw : 0) + g.e2w + (FUSED ? g.elw : 0)) * 4u;
+        if (!OPF) {
 #pragma unroll
-        for (int i = 0; i < NRQ; ++i) if (warp + i * nw < FRPS / 2) mine += uint32_t(g.rqw) * 4u;
+            for (int i = 0; i < NRQ; ++i) if (warp + i * nw < FRPS / 2) mine += uint32_t(g.rqw) * 4u;
+        }
         const int j0 = p_sj * FRPS;
         if (lane == 0) {
             if (mine) mbar_expect_tx(bar, mine); else mbar_arrive(bar);
@@ -504,18 +597,28 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
             for (int i = 0; i < NLP; ++i) {
                 const int r = warp + i * nw;
                 if (r < FRPS) {
-                    tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
-                    tma_load_1d(smem_u32(st + lp_stage + rq_stage + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
+                    if (!OPF) {
+                        tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
+                    } else {
+                        // image row of operand row j: leaving = array row j, entering = array row j + 2R + 1
+                        tma_load_1d(smem_u32(st + r * g.lpw), job.LP + size_t(j0 + r + w) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
+                        tma_load_1d(smem_u32(st + lp_stage + r * g.lpw), job.LP + size_t(j0 + r) * g.lp_pitch + p0, uint32_t(g.lpw) * 4u, bar);
+                        tma_load_1d(smem_u32(st + rq_base + r * g.rqw), job.RQ + size_t(j0 + r + w) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+                        tma_load_1d(smem_u32(st + rq_base + rq_stage + r * g.rqw), job.RQ + size_t(j0 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+                    }
+                    tma_load_1d(smem_u32(st + e2_base + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
                     if (FUSED)      // the partner's energy rows: E2'[j][x], x = pixel column (its eoff is 0)
-                        tma_load_1d(smem_u32(st + lp_stage + rq_stage + e2_stage + r * g.elw), P.job[jb + npair].E2 + size_t(j0 + r) * g.e2_pitch + p0,
+                        tma_load_1d(smem_u32(st + el_base + r * g.elw), P.job[jb + npair].E2 + size_t(j0 + r) * g.e2_pitch + p0,
                                     uint32_t(g.elw) * 4u, bar);
                 }
             }
+            if (!OPF) {
 #pragma unroll
-            for (int i = 0; i < NRQ; ++i) {
-                const int r = warp + i * nw;
-                if (r < FRPS / 2)
-                    tma_load_1d(smem_u32(st + lp_stage + r * g.rqw), job.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+                for (int i = 0; i < NRQ; ++i) {
+                    const int r = warp + i * nw;
+                    if (r < FRPS / 2)
+                        tma_load_1d(smem_u32(st + rq_base + r * g.rqw), job.RQ + size_t(j0 / 2 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
+                }
             }
         }
         // reconverge here: without it lane 0 runs the following row on its own, up to the first warp
@@ -557,7 +660,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         // when every legal candidate scores exactly 0 too, which the merge recognises (winner outside the image
         // -> first legal candidate, cv::minMaxLoc's first maximum).  So NCC never needs the explicit selects
         // for border positions, and SSD only for R > 5.
-        const int mode = (partial_lane || (pos_invalid && !NCC && R > FFREE_MASK_R)) ? 3 : (lane_invalid ? 2 : 1);
+        // Float operands (OPF): no key headroom and scores may be negative, so illegal positions always take the selects.
+        const int mode = (partial_lane || (pos_invalid && (OPF || (!NCC && R > FFREE_MASK_R)))) ? 3 : (lane_invalid ? 2 : 1);
         const int mmin = job.dmin - dlo - FM * ll;                        // mmin <= m <= mmax are inside [dmin, dmax]
         int mmax = job.dmax - dlo - FM * ll;
         if (mmin > FM - 1) mmax = -1;                                     // the whole lane lies below dmin: dead, like one above dmax
@@ -586,16 +690,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                 for (int j = jlo; j < jhi; ++j) {
                     const int r = j - sj * FRPS;
                     const int* lp_row = st + r * g.lpw + lp_off;
-                    const int* rq_row = st + lp_stage + (r >> 1) * g.rqw + rq_off;
-                    const int* e2_row = st + lp_stage + rq_stage + r * g.e2w + rq_off;
+                    const int* rq_row = st + rq_base + (OPF ? r : (r >> 1)) * g.rqw + rq_off;
+                    const int* e2_row = st + e2_base + r * g.e2w + rq_off;
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
                     const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
-#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic)
-#define SB_ROWF(P_, M_) fast_row<R, K, P_, M_, COST, HS, true>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
-                                                          st + lp_stage + rq_stage + e2_stage + r * g.elw + lp_off, tail, \
-                                                          part2 + size_t(j - (g.rb - g.base_y)) * g.wpart, x2base)
-                    if (j < jreg)       { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
+#define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS, false, OPF>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
+                                                          nullptr, nullptr, nullptr, 0, lp_row + lp_stage, rq_row + rq_stage)
+#define SB_ROWF(P_, M_) fast_row<R, K, P_, M_, COST, HS, true, OPF>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
+                                                          st + el_base + r * g.elw + lp_off, tail, \
+                                                          part2 + size_t(j - (g.rb - g.base_y)) * g.wpart, x2base, lp_row + lp_stage, rq_row + rq_stage)
+                    if constexpr (OPF) {          // one row per operand row: no byte-pair parity
+                        if (j < jreg) SB_ROW(0, 0);
+                        else if constexpr (FUSED) { if (mode == 1) SB_ROWF(0, 1); else if (mode == 2) SB_ROWF(0, 2); else SB_ROWF(0, 3); }
+                        else { if (mode == 1) SB_ROW(0, 1); else if (mode == 2) SB_ROW(0, 2); else SB_ROW(0, 3); }
+                    }
+                    else if (j < jreg)  { if (par) SB_ROW(1, 0); else SB_ROW(0, 0); }
+                    else if constexpr (FUSED && !GEN) { if (par) SB_ROWF(1, 1); else SB_ROWF(0, 1); }   // the host vouches for mode 1
                     else if constexpr (FUSED) {
                         if (mode == 1)      { if (par) SB_ROWF(1, 1); else SB_ROWF(0, 1); }
                         else if (mode == 2) { if (par) SB_ROWF(1, 2); else SB_ROWF(0, 2); }
@@ -626,17 +737,34 @@ SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(1
 #undef SB_DECL_PART
 // Fused pair kernels (SSD): parts 16..25 (fast_inst.cu).
 constexpr int FAST_FUSED_PARTS = 10;
-#define SB_DECL_FPART(n) fast_kernel_fn fast_pick_fused_part##n(int R, int hs);
+#define SB_DECL_FPART(n) fast_kernel_fn fast_pick_fused_part##n(int R, int hs, int gen);
 SB_DECL_FPART(16) SB_DECL_FPART(17) SB_DECL_FPART(18) SB_DECL_FPART(19) SB_DECL_FPART(20)
 SB_DECL_FPART(21) SB_DECL_FPART(22) SB_DECL_FPART(23) SB_DECL_FPART(24) SB_DECL_FPART(25)
 #undef SB_DECL_FPART
-static inline fast_kernel_fn fast_pick_fused(int R, int hs) {
-    typedef fast_kernel_fn (*part_fn)(int, int);
+// gen = 0: the launch's blocks are all MODE 1 (fast_fused_all_mode1); 1: any launch
+static inline fast_kernel_fn fast_pick_fused(int R, int hs, int gen) {
+    typedef fast_kernel_fn (*part_fn)(int, int, int);
     static const part_fn parts[FAST_FUSED_PARTS] = {fast_pick_fused_part16, fast_pick_fused_part17, fast_pick_fused_part18, fast_pick_fused_part19,
                                                     fast_pick_fused_part20, fast_pick_fused_part21, fast_pick_fused_part22, fast_pick_fused_part23,
                                                     fast_pick_fused_part24, fast_pick_fused_part25};
     for (int i = 0; i < FAST_FUSED_PARTS; ++i)
-        if (fast_kernel_fn fn = parts[i](R, hs)) return fn;
+        if (fast_kernel_fn fn = parts[i](R, hs, gen)) return fn;
+    return nullptr;
+}
+// Float-operand kernels: parts 26..37 = kind * 4 + radius subset; kind 0 = SSD, 1 = SSD fused pair, 2 = NCC.
+constexpr int FAST_OPF_PARTS = 12;
+enum { OPF_SSD = 0, OPF_SSD_FUSED = 1, OPF_NCC = 2 };
+#define SB_DECL_OPART(n) fast_kernel_fn fast_pick_opf_part##n(int R, int kind);
+SB_DECL_OPART(26) SB_DECL_OPART(27) SB_DECL_OPART(28) SB_DECL_OPART(29) SB_DECL_OPART(30) SB_DECL_OPART(31)
+SB_DECL_OPART(32) SB_DECL_OPART(33) SB_DECL_OPART(34) SB_DECL_OPART(35) SB_DECL_OPART(36) SB_DECL_OPART(37)
+#undef SB_DECL_OPART
+static inline fast_kernel_fn fast_pick_opf(int R, int kind) {
+    typedef fast_kernel_fn (*part_fn)(int, int);
+    static const part_fn parts[FAST_OPF_PARTS] = {fast_pick_opf_part26, fast_pick_opf_part27, fast_pick_opf_part28, fast_pick_opf_part29,
+                                                  fast_pick_opf_part30, fast_pick_opf_part31, fast_pick_opf_part32, fast_pick_opf_part33,
+                                                  fast_pick_opf_part34, fast_pick_opf_part35, fast_pick_opf_part36, fast_pick_opf_part37};
+    for (int i = 0; i < FAST_OPF_PARTS; ++i)
+        if (fast_kernel_fn fn = parts[i](R, kind)) return fn;
     return nullptr;
 }
 static inline fast_kernel_fn fast_pick(int cost, int R, int hs) {

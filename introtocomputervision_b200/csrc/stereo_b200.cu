@@ -129,22 +129,64 @@ static int run_exact(stereo_ctx* ctx, const Problem& p, cudaStream_t st) {
 
 // ---- path selection -------------------------------------------------------------------------------
 
-// Enqueues one direction.  For f32 inputs the "is this image really 8-bit" flag has to reach the
-// host to choose the kernel family: one 4-byte read-back and a stream synchronize.
+static bool fused_layout(const stereo_ctx* ctx, const Problem* ps, int n);
+
+// Float images: which kernel family applies (decided from the device-side classification, see classify_convert_kernel).
+enum { CLS_U8 = 0, CLS_F32_FAST = 1, CLS_EXACT = 2 };
+
+static Problem as_u8(Problem p) { p.ref.type = PixType::U8; p.tgt.type = PixType::U8; return p; }
+
+// Scratch for a float problem whose kernel family is only known after the classification: the larger of the three
+// families' needs plus the u8 copies of both images.  `dirs` = directions that share one launch sequence.
+static size_t f32_scratch_bytes(stereo_ctx* ctx, const Problem& p, int dirs) {
+    size_t need = exact_scratch_bytes(p);
+    const size_t f = size_t(dirs) * fast_scratch_bytes(ctx, p), u = size_t(dirs) * fast_scratch_bytes(ctx, as_u8(p));
+    if (f > need) need = f;
+    if (u > need) need = u;
+    return need + 2 * align256(size_t(p.rows) * align256(p.cols)) + 4096;
+}
+
+// Converts both float images to u8 copies while classifying them, reads the verdict back (one 16-byte copy and a stream
+// synchronize: the kernel family is a host decision) and says which family serves this image pair.
+static int classify_images(stereo_ctx* ctx, const Problem& p, cudaStream_t st, uint8_t* a8, uint8_t* b8, size_t pitch, int* cls) {
+    SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), st));
+    dim3 cb(32, 8), cg(div_round_up(p.cols, 32), div_round_up(p.rows, 8));
+    classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, a8, pitch, ctx->d_flag);
+    classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, b8, pitch, ctx->d_flag);
+    ctx->last_launches += 2;
+    SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    const unsigned* hf = reinterpret_cast<const unsigned*>(ctx->h_flag);
+    if (hf[0] == 0 && ctx->force_path != STEREO_PATH_FAST_F32) { *cls = CLS_U8; return STEREO_OK; }
+    *cls = CLS_EXACT;
+    if (hf[0] & 2u) return STEREO_OK;                                  // a pixel that is not finite
+    if (ctx->force_path == STEREO_PATH_FAST_U8) return STEREO_OK;      // (reported as "not applicable" by the caller)
+    // value range: [0, 255] for the blocks without a non-8-bit pixel, the tracked extremes for the others
+    double lo = 0.0, hi = 255.0;
+    if (hf[1]) { const double v = -double(f32_from_ordered(hf[1])); if (v < lo) lo = v; }
+    if (hf[2]) { const double v = double(f32_from_ordered(hf[2])); if (v > hi) hi = v; }
+    const double range = (hi - lo) * (1.0 + 1e-6), wnd = double(2 * p.R + 1) * (2 * p.R + 1);
+    bool ok;
+    if (p.cost == STEREO_COST_SSD)
+        // per element: round((l - r)^2) + 0.5 < 2^23 (mantissa trick of ssd_q_bits); per window: 128 * SSD + position < 2^32 - 1
+        ok = range * range + 1.0 < 8388607.0 && wnd * (range * range + 1.0) < 33554432.0 - 8193.0;
+    else
+        ok = -lo < 1.0e6 && hi < 1.0e6;                                // float32 sums of products stay far from overflow
+    if (ok) *cls = CLS_F32_FAST;
+    return STEREO_OK;
+}
+
+// Enqueues one direction.
 static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_arena = true) {
-    const size_t min_ref = size_t(p.cols) * (p.ref.type == PixType::F32 ? 4 : 1);
-    const size_t min_tgt = size_t(p.cols) * (p.tgt.type == PixType::F32 ? 4 : 1);
-    int rc = validate(p, min_ref, min_tgt);
+    const bool is_f32 = p.ref.type == PixType::F32;
+    const size_t min_step = size_t(p.cols) * (is_f32 ? 4 : 1);
+    int rc = validate(p, min_step, min_step);
     if (rc != STEREO_OK) return rc;
+    if (p.ref.type != p.tgt.type) { set_error("mixed pixel types (internal)"); return STEREO_ERR_INVALID_ARG; }
 
     const bool fast_ok = fast_supported(p) && ctx->force_path != STEREO_PATH_EXACT_F32;
     size_t need = exact_scratch_bytes(p);
-    size_t u8_bytes = 0;
-    if (fast_ok) {
-        need = need > fast_scratch_bytes(ctx, p) ? need : fast_scratch_bytes(ctx, p);
-        u8_bytes = 2 * align256(size_t(p.rows) * align256(p.cols));
-        need += u8_bytes;
-    }
+    if (fast_ok) need = is_f32 ? f32_scratch_bytes(ctx, p, 1) : (need > fast_scratch_bytes(ctx, p) ? need : fast_scratch_bytes(ctx, p));
     if (need > ctx->arena.cap) {
         rc = quiesce(ctx, st);
         if (rc != STEREO_OK) return rc;
@@ -153,41 +195,71 @@ static int run_problem(stereo_ctx* ctx, Problem p, cudaStream_t st, bool reset_a
     }
     if (reset_arena) ctx->arena.reset();
 
-    bool use_fast = fast_ok;
-    if (fast_ok && (p.ref.type == PixType::F32 || p.tgt.type == PixType::F32)) {
-        // classify + convert both images to u8 copies
+    int cls = is_f32 ? CLS_EXACT : CLS_U8;
+    if (fast_ok && is_f32) {
         const size_t pitch = align256(p.cols);
         uint8_t* a8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
         uint8_t* b8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
         if (!a8 || !b8) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
-        SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
-        dim3 cb(32, 8), cg(div_round_up(p.cols, 32), div_round_up(p.rows, 8));
-        Problem q = p;
-        if (p.ref.type == PixType::F32) {
-            classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, a8, pitch, ctx->d_flag);
-            q.ref = ImageView{a8, pitch, PixType::U8};
-            ctx->last_launches++;
-        }
-        if (p.tgt.type == PixType::F32) {
-            classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, b8, pitch, ctx->d_flag);
-            q.tgt = ImageView{b8, pitch, PixType::U8};
-            ctx->last_launches++;
-        }
-        SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        use_fast = (*ctx->h_flag == 0);
-        if (use_fast) p = q;
+        rc = classify_images(ctx, p, st, a8, b8, pitch, &cls);
+        if (rc != STEREO_OK) return rc;
+        if (cls == CLS_U8) { p.ref = ImageView{a8, pitch, PixType::U8}; p.tgt = ImageView{b8, pitch, PixType::U8}; }
     }
-    if (use_fast) {
-        ctx->last_path = STEREO_PATH_FAST_U8;
+    if (fast_ok && cls != CLS_EXACT) {
+        ctx->last_path = cls == CLS_U8 ? STEREO_PATH_FAST_U8 : STEREO_PATH_FAST_F32;
         return run_fast(ctx, p, st);
     }
-    if (ctx->force_path == STEREO_PATH_FAST_U8) {
-        set_error("fast u8 path forced but not applicable (non-8-bit input or unsupported window/range)");
+    if (ctx->force_path == STEREO_PATH_FAST_U8 || ctx->force_path == STEREO_PATH_FAST_F32) {
+        set_error("fast path forced but not applicable (pixel values or window/range outside what the running-sum kernels cover)");
         return STEREO_ERR_UNSUPPORTED;
     }
     ctx->last_path = STEREO_PATH_EXACT_F32;
     return run_exact(ctx, p, st);
+}
+
+// Both directions of ONE pair of float images (ps[0] left-referenced, ps[1] right-referenced, the same two device images):
+// classified once, then both maps from one launch sequence - one cost volume where the pair is fusable.
+static int run_pair_f32(stereo_ctx* ctx, Problem* ps, cudaStream_t st) {
+    const Problem& p = ps[0];
+    const size_t min_step = size_t(p.cols) * 4;
+    int rc = STEREO_OK;
+    for (int d = 0; d < 2 && rc == STEREO_OK; ++d) rc = validate(ps[d], min_step, min_step);
+    if (rc != STEREO_OK) return rc;
+    const size_t need = f32_scratch_bytes(ctx, p, 2);
+    if (need > ctx->arena.cap) {
+        rc = quiesce(ctx, st);
+        if (rc != STEREO_OK) return rc;
+        rc = ctx->arena.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->arena.reset();
+    const size_t pitch = align256(p.cols);
+    uint8_t* a8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
+    uint8_t* b8 = static_cast<uint8_t*>(ctx->arena.take(size_t(p.rows) * pitch));
+    if (!a8 || !b8) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    int cls = CLS_EXACT;
+    rc = classify_images(ctx, p, st, a8, b8, pitch, &cls);
+    if (rc != STEREO_OK) return rc;
+    if (cls == CLS_EXACT) {
+        if (ctx->force_path == STEREO_PATH_FAST_U8 || ctx->force_path == STEREO_PATH_FAST_F32) {
+            set_error("fast path forced but not applicable (pixel values outside what the running-sum kernels cover)");
+            return STEREO_ERR_UNSUPPORTED;
+        }
+        ctx->last_path = STEREO_PATH_EXACT_F32;
+        for (int d = 0; d < 2; ++d) {
+            ctx->arena.reset();
+            rc = run_exact(ctx, ps[d], st);
+            if (rc != STEREO_OK) return rc;
+        }
+        return STEREO_OK;
+    }
+    if (cls == CLS_U8) {
+        // ps[0]: ref = left, tgt = right; ps[1] the other way round
+        ps[0].ref = ImageView{a8, pitch, PixType::U8}; ps[0].tgt = ImageView{b8, pitch, PixType::U8};
+        ps[1].ref = ImageView{b8, pitch, PixType::U8}; ps[1].tgt = ImageView{a8, pitch, PixType::U8};
+    }
+    ctx->last_path = cls == CLS_U8 ? STEREO_PATH_FAST_U8 : STEREO_PATH_FAST_F32;
+    return run_fast_batch(ctx, ps, 2, st, fused_layout(ctx, ps, 2) ? 1 : 0);
 }
 
 // Enqueues `n` u8 problems that all take the packed path, several directions per launch sequence where they
@@ -366,9 +438,28 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
     return rc;
 }
 
+// A few pixels of a host float image: false as soon as one is not an integer in 0..255.  Noisy / contrast-scaled images
+// (main.cpp:140-153,191-193) fail on the first samples, so they skip the optimistic 8-bit pipeline instead of running
+// it, finding the flag set and being computed a second time by the float kernels.
+static bool host_sample_is_8bit(const void* img, size_t step, int rows, int cols) {
+    const int ny = rows < 8 ? rows : 8, nx = cols < 16 ? cols : 16;
+    for (int iy = 0; iy < ny; ++iy) {
+        const float* row = reinterpret_cast<const float*>(static_cast<const char*>(img) + size_t((long long)iy * (rows - 1) / (ny > 1 ? ny - 1 : 1)) * step);
+        for (int ix = 0; ix < nx; ++ix) {
+            const float v = row[(long long)ix * (cols - 1) / (nx > 1 ? nx - 1 : 1)];
+            if (!(v >= 0.f && v <= 255.f && v == float(int(v)))) return false;
+        }
+    }
+    return true;
+}
+
 static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
                                      const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
-    if (ctx->force_path == STEREO_PATH_EXACT_F32) return PIPE_NOT_APPLICABLE;
+    if (ctx->force_path == STEREO_PATH_EXACT_F32 || ctx->force_path == STEREO_PATH_FAST_F32) return PIPE_NOT_APPLICABLE;
+    if (type == PixType::F32)
+        for (int i = 0; i < n_pairs; ++i)
+            if (!host_sample_is_8bit(in[i].left, in[i].left_step, rows, cols) || !host_sample_is_8bit(in[i].right, in[i].right_step, rows, cols))
+                return PIPE_NOT_8BIT;
     const size_t px = type == PixType::F32 ? 4 : 1;
     const size_t in_pitch = align256(cols * px), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
     // validate each direction on a full-image problem (pointers only need to be non-null here)
@@ -733,7 +824,7 @@ float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measure
 int stereo_ctx_last_hot_jobs(const stereo_ctx* ctx) { return ctx ? ctx->hot_jobs : 0; }
 
 int stereo_ctx_force_path(stereo_ctx* ctx, int path) {
-    if (!ctx || path < 0 || path > STEREO_PATH_FAST_U8) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }
+    if (!ctx || path < 0 || path > STEREO_PATH_FAST_F32) { set_error("bad force_path argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->force_path = path;
     return STEREO_OK;
 }
@@ -965,6 +1056,8 @@ static int pair_device(stereo_ctx* ctx, int cost, PixType type, const void* left
         }
         return run_fast_jobs(ctx, p, 2, st);
     }
+    if (type == PixType::F32 && fast_supported(p[0]) && fast_supported(p[1]) && ctx->force_path != STEREO_PATH_EXACT_F32)
+        return run_pair_f32(ctx, p, st);
     int rc = run_problem(ctx, p[0], st);
     if (rc != STEREO_OK) return rc;
     return run_problem(ctx, p[1], st);
@@ -1038,6 +1131,20 @@ int stereo_disparity_pair_u8_device(stereo_ctx* ctx, int cost, const uint8_t* le
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
     begin_call(ctx, st);
     rc = pair_device(ctx, cost, PixType::U8, left, left_step, right, right_step, rows, cols, window_rad,
+                     disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes, st);
+    end_call(ctx, st);
+    return rc;
+}
+
+int stereo_disparity_pair_f32_device(stereo_ctx* ctx, int cost, const float* left, size_t left_step, const float* right,
+                                     size_t right_step, int rows, int cols, int window_rad, int disparity_range,
+                                     void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes,
+                                     void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    begin_call(ctx, st);
+    rc = pair_device(ctx, cost, PixType::F32, left, left_step, right, right_step, rows, cols, window_rad,
                      disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes, st);
     end_call(ctx, st);
     return rc;

@@ -110,7 +110,7 @@ def test_ssd_noisy_contrast_variants_vs_oracle(ctx):
     for Lf, Rf in ((synth.noisy_variant(L, 12), synth.noisy_variant(Rt, 13)),
                    (synth.contrast_variant(L), Rt.astype(np.float32))):
         dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(7, 95), ctx=ctx)
-        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert ctx.last_path == sb.PATH_FAST_F32 and ctx.last_fused_pairs == 1
         assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 7, -95, 0)))
         assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 7, 0, 95)))
 
@@ -324,8 +324,8 @@ def test_host_batch_chunked_items_vs_oracle(ctx, n, kind):
                 assert float(np.mean(br[i] == oracle.ncorr_fast(Rf, Lf, R, 0, rng))) >= NCC_DISP_AGREE
 
 
-def test_host_batch_f32_non_8bit_pair_falls_back_to_exact(ctx):
-    # one noisy pair in a CV_32FC1 batch: the whole batch is redone pair by pair, the noisy one on the exact kernels
+def test_host_batch_f32_non_8bit_pair_takes_float_kernels(ctx):
+    # one noisy pair in a CV_32FC1 batch: the batch goes pair by pair, the noisy one on the float running-sum kernels
     n, rows, cols, R, rng = 5, 30, 110, 2, 17
     Ls, Rs = [], []
     for i in range(n):
@@ -472,21 +472,21 @@ def test_fused_pair_with_costs_matches_single_calls(ctx):
     assert np.array_equal(cl, ol)
 
 
-def test_pipelined_host_non_8bit_falls_back_to_exact(ctx):
-    # the 8-bit flag is only known after the pipelined pass: a noisy image must be redone on the exact path
+def test_pipelined_host_non_8bit_is_redone_on_float_kernels(ctx):
+    # the 8-bit flag is only known after the pipelined pass: a noisy image must be redone by the float kernels
     L, Rt, _ = synth.make_pair(60, 200, 30, 31)
     Lf, Rf = synth.noisy_variant(L, 1), synth.noisy_variant(Rt, 2)
     Lf[-1, -1] += 0.25                                          # ... even when only the very last pixel is non-integer
     try:
         ctx.set_pipe_bands(3)
         dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(3, 29), ctx=ctx)
-        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert ctx.last_path == sb.PATH_FAST_F32
         assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 3, -29, 0)))
         assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 3, 0, 29)))
         Li = L.astype(np.float32)
         Li[-1, -1] += 0.5
         d = ctx.disparity(sb.COST_SSD, Li, Rt.astype(np.float32), 3, -29, 0, dtype=np.int16)
-        assert ctx.last_path == sb.PATH_EXACT_F32
+        assert ctx.last_path == sb.PATH_FAST_F32
         assert np.array_equal(d, oracle.ssd_fast(Li, Rt.astype(np.float32), 3, -29, 0))
     finally:
         ctx.set_pipe_bands(0)
@@ -758,3 +758,133 @@ def test_config4_full_size_fused_pair_and_ncc(ctx):
     d, s = ctx.disparity(sb.COST_NCORR, L, Rt, 5, -255, 0, dtype=np.int16, return_best=True)
     assert ctx.last_path == sb.PATH_FAST_U8
     assert_ncc_close(d, s, d_ref, s_ref)
+
+
+# ---- the float running-sum kernels (general float32 images) ------------------------------------------
+# SSD: q = (int)round(f32((l - r)^2)) per element (DisparitySSD.cpp:49-51) is an int, so int32 column / horizontal running
+# sums are exact: bit-exact disparities AND costs.  NCC: float32 running sums, north-star tolerance.
+
+def _float_variants(L, Rt, seed):
+    """The three input families of the ps2 executable: noise on both images (main.cpp:140-153), contrast on the left
+    image only (main.cpp:191-193), and both."""
+    yield "noisy", synth.noisy_variant(L, seed), synth.noisy_variant(Rt, seed + 1)
+    yield "contrast", synth.contrast_variant(L), Rt.astype(np.float32)
+    yield "noisy+contrast", synth.noisy_variant(L, seed) * np.float32(1.1), synth.noisy_variant(Rt, seed + 1)
+
+
+F32_SHAPES = [
+    # rows, cols, R, dmin, dmax
+    (24, 140, 7, -95, 0), (24, 140, 7, 0, 95), (30, 200, 6, -80, 0), (17, 90, 5, -20, 15), (40, 333, 4, -127, 0),
+    (12, 64, 0, 0, 7), (9, 300, 3, 0, 200), (21, 77, 2, -300, -100), (15, 500, 1, -130, 0), (33, 129, 7, 5, 40),
+]
+
+
+@pytest.mark.parametrize("rows,cols,R,dmin,dmax", F32_SHAPES)
+def test_ssd_float_kernels_vs_oracle(ctx, rows, cols, R, dmin, dmax):
+    L, Rt, _ = synth.make_pair(rows, cols, max(2, min(abs(dmin), abs(dmax), cols // 2)), 41000 + rows + cols)
+    for name, Lf, Rf in _float_variants(L, Rt, rows):
+        d_ref, c_ref = oracle.ssd_fast(Lf, Rf, R, dmin, dmax, return_cost=True)
+        d, c = ctx.disparity(sb.COST_SSD, Lf, Rf, R, dmin, dmax, dtype=np.int32, return_best=True)
+        assert ctx.last_path == sb.PATH_FAST_F32, name
+        bad = np.argwhere(d != d_ref)
+        assert bad.size == 0, f"{name}: disparity differs at {bad[:5].tolist()} (of {len(bad)})"
+        assert np.array_equal(c, c_ref), name
+
+
+@pytest.mark.parametrize("rows,cols,R,rng", [(24, 140, 7, 95), (30, 200, 6, 80), (16, 128, 6, 3), (19, 260, 5, 127),
+                                               (11, 90, 3, 40), (14, 700, 4, 255), (8, 40, 7, 95), (27, 641, 2, 63)])
+def test_ssd_float_fused_pairs_vs_oracle(ctx, rows, cols, R, rng):
+    L, Rt, _ = synth.make_pair(rows, cols, min(rng + 1, max(2, cols // 2)), 42000 + rows + cols)
+    for name, Lf, Rf in _float_variants(L, Rt, cols):
+        ref_l, ref_r = oracle.ssd_fast(Lf, Rf, R, -rng, 0), oracle.ssd_fast(Rf, Lf, R, 0, rng)
+        fl, fr = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, R, rng, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_FAST_F32 and ctx.last_fused_pairs == 1, name
+        bad = np.argwhere(fl != ref_l)
+        assert bad.size == 0, f"{name}: fused L->R differs at {bad[:5].tolist()} (of {len(bad)})"
+        bad = np.argwhere(fr != ref_r)
+        assert bad.size == 0, f"{name}: fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
+        ctx.set_fuse_pairs(False)
+        try:
+            ul, ur = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, R, rng, dtype=np.int16)
+            assert ctx.last_path == sb.PATH_FAST_F32 and ctx.last_fused_pairs == 0
+        finally:
+            ctx.set_fuse_pairs(True)
+        assert np.array_equal(ul, ref_l) and np.array_equal(ur, ref_r), name
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_ssd_float_kernels_random(ctx, seed):
+    rng = np.random.default_rng(43000 + seed)
+    rows, cols = int(rng.integers(1, 50)), int(rng.integers(4, 400))
+    R = int(rng.integers(0, 8))
+    a, b = sorted(int(v) for v in rng.integers(-150, 151, 2))
+    L, Rt, _ = synth.make_pair(rows, cols, 30, 43100 + seed)
+    gain = np.float32(rng.choice([1.0, 1.1, 0.37]))
+    Lf = (synth.noisy_variant(L, seed, sigma=float(rng.choice([0.3, 10.0, 25.0]))) * gain).astype(np.float32)
+    Rf = synth.noisy_variant(Rt, seed + 1)
+    if seed % 4 == 0:                         # half-integer pixel values: round-half-away ties in every element
+        Lf, Rf = np.round(Lf * 2) / np.float32(2), np.round(Rf * 2) / np.float32(2)
+    d_ref, c_ref = (oracle.ssd if seed < 4 else oracle.ssd_fast)(Lf, Rf, R, a, b, return_cost=True)
+    d, c = ctx.disparity(sb.COST_SSD, Lf, Rf, R, a, b, dtype=np.int32, return_best=True)
+    assert ctx.last_path == sb.PATH_FAST_F32
+    assert np.array_equal(d, d_ref), (rows, cols, R, a, b)
+    assert np.array_equal(c, c_ref), (rows, cols, R, a, b)
+
+
+def test_float_kernels_on_8bit_images_equal_packed_kernels(ctx):
+    # the same 8-bit-valued CV_32FC1 pair through both running-sum families
+    L, Rt, _ = synth.make_pair(40, 300, 64, 77)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    dl8, dr8 = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, 5, 100, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    n8, s8 = ctx.disparity(sb.COST_NCORR, Lf, Rf, 5, -100, 0, dtype=np.int16, return_best=True)
+    try:
+        ctx.force_path(sb.PATH_FAST_F32)
+        dlf, drf = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, 5, 100, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_FAST_F32
+        nf, sf = ctx.disparity(sb.COST_NCORR, Lf, Rf, 5, -100, 0, dtype=np.int16, return_best=True)
+        assert ctx.last_path == sb.PATH_FAST_F32
+    finally:
+        ctx.force_path(0)
+    assert np.array_equal(dl8, dlf) and np.array_equal(dr8, drf)
+    assert_ncc_close(nf, sf, n8, s8)
+
+
+def test_float_kernels_hand_wide_value_ranges_to_the_exact_path(ctx):
+    # pixel ranges beyond what the 32-bit keys / the 2^23 mantissa trick hold: exact per-element kernels, same results
+    L, Rt, _ = synth.make_pair(14, 80, 12, 5)
+    Lf, Rf = synth.noisy_variant(L, 1) * np.float32(40), synth.noisy_variant(Rt, 2) * np.float32(40)
+    d = ctx.disparity(sb.COST_SSD, Lf, Rf, 7, -20, 0, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_EXACT_F32
+    assert np.array_equal(d, oracle.ssd(Lf, Rf, 7, -20, 0))
+    Lf[3, 3] = np.inf
+    d = ctx.disparity(sb.COST_NCORR, Lf, Rf, 2, -20, 0, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_EXACT_F32
+
+
+@pytest.mark.parametrize("rows,cols,R,dmin,dmax", [(24, 140, 7, -95, 0), (24, 140, 7, 0, 95), (30, 200, 6, 0, 80),
+                                                    (17, 90, 5, -20, 15), (20, 333, 4, -127, 0), (9, 300, 3, 0, 200)])
+def test_ncc_float_kernels_vs_oracle(ctx, rows, cols, R, dmin, dmax):
+    L, Rt, _ = synth.make_pair(rows, cols, max(2, min(abs(dmin) + abs(dmax), cols // 2)), 44000 + rows + cols)
+    for name, Lf, Rf in _float_variants(L, Rt, rows):
+        d_ref, s_ref = oracle.ncorr_fast(Lf, Rf, R, dmin, dmax, return_score=True)
+        d, s = ctx.disparity(sb.COST_NCORR, Lf, Rf, R, dmin, dmax, dtype=np.int32, return_best=True)
+        assert ctx.last_path == sb.PATH_FAST_F32, name
+        assert_ncc_close(d, s, d_ref, s_ref)
+
+
+def test_ps2_problem_shapes_full_size_noisy_and_contrast(ctx):
+    """Problems 3 and 4 of the reference executable at their real size (config/ps2.yaml:29-36, main.cpp:140-153,191-193):
+    511x640, R = 7, range 95; Gaussian noise sigma 10 on both images, x1.1 contrast on the left one."""
+    L, Rt, _ = synth.make_pair(511, 640, 96, 11)
+    for name, Lf, Rf in (("noisy", synth.noisy_variant(L, 12), synth.noisy_variant(Rt, 13)),
+                         ("contrast", synth.contrast_variant(L), Rt.astype(np.float32))):
+        dl, dr = sb.disparitySSDPair(Lf, Rf, sb.DisparityConfig(7, 95), ctx=ctx)
+        assert ctx.last_path == sb.PATH_FAST_F32 and ctx.last_fused_pairs == 1, name
+        assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 7, -95, 0))), name
+        assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 7, 0, 95))), name
+        for ref, tgt, lo, hi in ((Lf, Rf, -95, 0), (Rf, Lf, 0, 95)):
+            d_ref, s_ref = oracle.ncorr_fast(ref, tgt, 7, lo, hi, return_score=True)
+            d, s = ctx.disparity(sb.COST_NCORR, ref, tgt, 7, lo, hi, dtype=np.int16, return_best=True)
+            assert ctx.last_path == sb.PATH_FAST_F32, name
+            assert_ncc_close(d, s, d_ref, s_ref)
