@@ -8,7 +8,10 @@ from pathlib import Path
 import os
 
 # STEREO_B200_LIB overrides the library file (kernel-variant experiments); the default is the in-tree build.
-LIB_PATH = Path(os.environ.get("STEREO_B200_LIB") or (Path(__file__).resolve().parent / "libstereo_b200.so"))
+# STEREO_LIB_TAG=<tag> loads an experiment build (libstereo_b200_<tag>.so, see build.py)
+_TAG = os.environ.get("STEREO_LIB_TAG", "")
+LIB_PATH = Path(os.environ.get("STEREO_B200_LIB") or
+                (Path(__file__).resolve().parent / ("libstereo_b200" + (f"_{_TAG}" if _TAG else "") + ".so")))
 
 STEREO_OK = 0
 ERR_INVALID_ARG, ERR_INVALID_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6

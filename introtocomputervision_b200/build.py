@@ -13,13 +13,15 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OBJ = CSRC / "_build"
-LIB = PKG / "libstereo_b200.so"
+# Experiment builds: STEREO_BUILD_TAG=<tag> compiles into csrc/_build_<tag>/ and links libstereo_b200_<tag>.so (loaded with
+# STEREO_LIB_TAG=<tag>, _capi.py); SB_* environment variables become -DSB_*=<value> tuning macros of the kernels.
+TAG = os.environ.get("STEREO_BUILD_TAG", "")
+OBJ = CSRC / ("_build" + (f"_{TAG}" if TAG else ""))
+LIB = PKG / ("libstereo_b200" + (f"_{TAG}" if TAG else "") + ".so")
 FAST_PARTS = 38          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused pair parts + 3 x 4 float-operand parts
 
 NVCC_FLAGS = [
-    *([f"-DSB_FK_FUSED={os.environ['SB_FK_FUSED']}"] if os.environ.get("SB_FK_FUSED") else []),
-    *([f"-DSB_FK_DEFAULT={os.environ['SB_FK_DEFAULT']}"] if os.environ.get("SB_FK_DEFAULT") else []),
+    *[f"-D{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SB_") and v != ""],
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -41,6 +43,10 @@ def units():
     return u
 
 
+def _mkdirs():
+    OBJ.mkdir(exist_ok=True)
+
+
 def _deps(src: Path):
     """Files a translation unit is rebuilt for: the hot-kernel parts only include fast_kernel.cuh / common.cuh."""
     api = list((PKG.parent / "include").glob("*.h"))
@@ -54,6 +60,8 @@ def sources():
 
 
 def needs_build() -> bool:
+    if TAG:
+        return True
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
@@ -67,9 +75,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
+    # experiment builds may recompile only some hot-kernel parts (STEREO_BUILD_PARTS="18,22") and borrow the other objects
+    # from the default build - such a library is only valid for the configurations those parts serve
+    only = os.environ.get("STEREO_BUILD_PARTS", "")
+    borrowed = set()
+    if TAG and only:
+        keep = {f"fast_inst_{int(i)}.o" for i in only.split(",")} | {"stereo_b200.o"}
+        for name, _, _ in units():
+            if name not in keep:
+                src_obj = CSRC / "_build" / name
+                if not src_obj.exists():
+                    raise RuntimeError(f"{src_obj} missing: build the default library first")
+                shutil.copy2(src_obj, OBJ / name)
+                borrowed.add(name)
 
     def compile_one(unit):
         name, src, extra = unit
+        if name in borrowed:
+            return ""
         obj = OBJ / name
         if not force and obj.exists() and all(d.stat().st_mtime <= obj.stat().st_mtime for d in _deps(src)):
             return ""

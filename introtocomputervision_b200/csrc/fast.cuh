@@ -365,11 +365,13 @@ __global__ void __launch_bounds__(128) prep_scale_pair_kernel(const __grid_const
         for (int x = 0; x < x1; ++x) { const float v = rs[x]; if (v > 0.f && (rsmin == 0.f || v < rsmin)) rsmin = v; }
         if (rsmin > 0.f) {
             // smallest power of two strictly above sqrt(elmax) * (1 + 2^-20); 1/rs is sqrt(E) to within 2^-23 relative
-            const float bound = float((1.0 / double(rsmin)) * (1.0 + 1.0 / 1048576.0));
+            // (float operands: 2^-10 of slack for the float32 running sums)
+            const float bound = float((1.0 / double(rsmin)) * (1.0 + (g.opf ? 1.0 / 1024.0 : 1.0 / 1048576.0)));
             int e; frexpf(bound, &e);
             magic = ldexpf(1.f, e);
         }
     }
+    if (g.opf) magic *= 3.f;        // C may be negative: keys live in [2 * 2^e, 4 * 2^e) (prep_scale_f_kernel)
     SC[size_t(strip) * g.nrows + yy] = magic;
 }
 
@@ -446,18 +448,38 @@ __global__ void __launch_bounds__(128) prep_e2f_kernel(const __grid_constant__ F
         job.E2[o] = valid ? q2 : int(KEY_INVALID);
         return;
     }
-    const int y = g.base_y + j;
+    job.RS[o] = 0.f;      // (NCC rows come from prep_rsf_kernel)
+}
+
+// NCC, float path: RS[j][q2] = 1 / sqrt(window energy of the extended target image at centre q2), separably: a block owns one
+// operand row and 256 - 2R centres; every thread sums the squares of ONE extended column over the 2R+1 window rows in
+// double (like OpenCV's double integral images), the centres then add 2R+1 neighbouring column sums from shared memory.
+__global__ void __launch_bounds__(256) prep_rsf_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    __shared__ double vs[256];
+    const int R = g.R, ts = 256 - 2 * R;
+    const int t = threadIdx.x;
+    const int j = blockIdx.y, y = g.base_y + j;
+    const int q20 = blockIdx.x * ts;
+    const bool row_ok = y >= g.rb && y < g.re;
+    double v = 0;
+    if (row_ok) {
+        const int e = q20 - job.eoff + R + t;              // extended column of this thread
+        for (int wy = -R; wy <= R; ++wy) { const double b = bextf(job.B, job.b_step, g.rows, g.cols, R, y + wy, e, g.ar0, g.ar1); v += b * b; }
+    }
+    vs[t] = v;
+    __syncthreads();
+    const int q2 = q20 + t;
+    if (t >= ts || q2 >= g.e2_pitch) return;
+    const int uc = q2 - job.eoff;
     float rs = 0.f;
-    if (valid && y >= g.rb && y < g.re) {
+    if (row_ok && uc >= job.cmin && uc <= job.cmax) {
         double er = 0;
-        for (int wy = -g.R; wy <= g.R; ++wy)
-            for (int t = 0; t <= 2 * g.R; ++t) {
-                const double b = bextf(job.B, job.b_step, g.rows, g.cols, g.R, y + wy, uc + g.R + t, g.ar0, g.ar1);
-                er += b * b;
-            }
+        for (int tt = 0; tt <= 2 * R; ++tt) er += vs[t + tt];
         rs = er > 0 ? float(1.0 / sqrt(er)) : 0.f;
     }
-    job.RS[o] = rs;
+    job.RS[size_t(j) * g.e2_pitch + q2] = rs;
 }
 
 // NCC, float path: window energies of the reference image per pixel (replicate padding, double sums) ...
@@ -670,48 +692,44 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
 // of the reference image and the 3R extended target columns of each window row in registers - and merged into the
 // same partial-key map (RED.MIN) with the key the hot kernel would have produced: BIAS + 128*(ER - 2C) + pos.
 template <int R>
-__global__ void __launch_bounds__(128) fused_border_kernel(const __grid_constant__ FastKernelParams P) {
-    constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1;
+__global__ void __launch_bounds__(32 * (R > 0 ? R : 1)) fused_border_kernel(const __grid_constant__ FastKernelParams P) {
+    // one thread per (pixel x', candidate c): threadIdx.x = pixel within the block, threadIdx.y = c
+    constexpr int W = 2 * R + 1;
     const FastGeom& g = P.g;
     const FastJob& job = P.job[g.npairs + blockIdx.z];          // the right-referenced direction: A = right image, B = left image
     const int range = job.dmax;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = threadIdx.y;
     const int xp = g.cols - 1 - idx;                            // the pixel x'
     const int yy = blockIdx.y, y = g.rb + yy;
     if (idx >= range || xp < 0) return;
     const int ncand = min(xp + range, g.cols - 1 + R) - g.cols + 1;
-    if (ncand <= 0) return;
+    if (c >= ncand) return;
     const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
-    int ssd[NCAND], eref = 0;
-#pragma unroll
-    for (int c = 0; c < NCAND; ++c) ssd[c] = 0;
+    int ssd = 0, eref = 0;
     // the 3R extended target columns right of unpadded column cols-R-1 are: R image columns, R times the replicated
-    // last column, R times the aliased first column of the next padded row (zero past the last padded row) - bext()
+    // last column, R times the aliased first column of the next padded row (zero past the last padded row) - bext();
+    // candidate c reads W of them from offset c
 #pragma unroll 1
     for (int wy = -R; wy <= R; ++wy) {
         const int ra = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
         const uint8_t* arow = A + size_t(ra) * job.a_step;
         const uint8_t* brow = B + size_t(ra) * job.b_step;
-        int a[W], b[NB];
-#pragma unroll
-        for (int i = 0; i < W; ++i) { a[i] = arow[clampi(xp - R + i, 0, g.cols - 1)]; eref += a[i] * a[i]; }
         const int edge = brow[g.cols - 1];
         const int wrap = bext(B, job.b_step, g.rows, g.cols, R, y + wy, g.cols + 4 * R, g.ar0, g.ar1);     // padded column cols + 3R >= Wp
 #pragma unroll
-        for (int i = 0; i < R; ++i) { b[i] = brow[max(g.cols - R + i, 0)]; b[R + i] = edge; b[2 * R + i] = wrap; }
-#pragma unroll
-        for (int c = 0; c < R; ++c)
-#pragma unroll
-            for (int i = 0; i < W; ++i) { const int d = a[i] - b[c + i]; ssd[c] += d * d; }
+        for (int i = 0; i < W; ++i) {
+            const int a = arow[clampi(xp - R + i, 0, g.cols - 1)];
+            const int t = c + i;                                  // index into the 3R extended columns
+            const int bv = t < R ? int(brow[max(g.cols - R + t, 0)]) : (t < 2 * R ? edge : wrap);
+            const int d = a - bv;
+            ssd += d * d; eref += a * a;
+        }
     }
     uint32_t* __restrict__ PART2 = reinterpret_cast<uint32_t*>(job.PART);
-#pragma unroll
-    for (int c = 0; c < R; ++c) {
-        if (c >= ncand) break;
-        const int pos = g.cols + c;
-        const uint32_t key = key_bias(R) + (uint32_t(ssd[c] - eref) << FKEY_BITS) + uint32_t(pos);
-        atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
-    }
+    const int pos = g.cols + c;
+    const uint32_t key = key_bias(R) + (uint32_t(ssd - eref) << FKEY_BITS) + uint32_t(pos);
+    atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
 }
 
 typedef void (*fused_border_fn)(const FastKernelParams);
@@ -1003,9 +1021,14 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         // float operand rows straight from the images (padding, row-wrap aliasing), position / energy rows
         prep_af_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), unsigned(lp_rows), nwalk), 256, 0, st>>>(kp);
         prep_bf_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), unsigned(rq_rows), nwalk), 256, 0, st>>>(kp);
-        prep_e2f_kernel<<<dim3(div_round_up(g.e2_pitch, 128), g.J, nz), 128, 0, st>>>(kp);
+        if (!ncc) prep_e2f_kernel<<<dim3(div_round_up(g.e2_pitch, 128), g.J, nz), 128, 0, st>>>(kp);
+        else prep_rsf_kernel<<<dim3(div_round_up(g.e2_pitch, 256 - 2 * g.R), g.J, nz), 256, 0, st>>>(kp);
         ctx->last_launches += 3;
-        if (ncc) {
+        if (ncc && fast_launch_is_pairs(ps, n)) {
+            // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
+            prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
+            ctx->last_launches += 1;
+        } else if (ncc) {
             prep_elf_kernel<<<dim3(div_round_up(g.cols, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
             prep_scale_f_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
             ctx->last_launches += 2;
@@ -1045,8 +1068,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
         if (g.border) {
             if (fused_border_fn bf = fused_border_pick(g.R)) {
-                const int bt = -ps[0].dmin <= 64 ? 64 : 128;          // one thread per pixel of the last `range` columns
-                bf<<<dim3(div_round_up(-ps[0].dmin, bt), g.nrows, unsigned(fused_pairs)), bt, 0, st>>>(kp);
+                // one thread per (pixel of the last `range` columns, candidate centred in the padding)
+                bf<<<dim3(div_round_up(-ps[0].dmin, 32), g.nrows, unsigned(fused_pairs)), dim3(32, g.R), 0, st>>>(kp);
                 ctx->last_launches += 1;
             }
         }

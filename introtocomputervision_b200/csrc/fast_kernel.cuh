@@ -68,7 +68,10 @@ constexpr int FKEY_BITS = 7;    // log2(FGROUP): low bits of a key order candida
 constexpr int FRPS = 8;         // operand rows per pipeline stage
 constexpr int FNST_MAX = 8;     // pipeline stages (fewer when the tile rows are wide, FastGeom::nst)
 constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kernel may use
-constexpr int FWARPS = 8;       // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers).  4-warp CTAs (narrower
+#ifndef SB_FWARPS
+#define SB_FWARPS 8
+#endif
+constexpr int FWARPS = SB_FWARPS; // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers).  4-warp CTAs (narrower
                                 // tiles for small images) were measured: one warp per scheduler cannot hide the row code's
                                 // latencies (511x640/96 fused pair: 91 us against 54 us with 8 warps)
 constexpr int FMAXJOBS = 8;     // directions (jobs) one launch sequence can carry
