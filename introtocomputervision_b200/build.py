@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 # Experiment builds: STEREO_BUILD_TAG=<tag> compiles into csrc/_build_<tag>/ and links libstereo_b200_<tag>.so (loaded with
 # STEREO_LIB_TAG=<tag>, _capi.py); SB_* environment variables become -DSB_*=<value> tuning macros of the kernels.
 TAG = os.environ.get("STEREO_BUILD_TAG", "")
-OBJ = CSRC / ("_build" + (f"_{TAG}" if TAG else ""))
+OBJ = (Path("/tmp") / f"sb_build_{TAG}") if TAG else CSRC / "_build"        # experiment objects stay out of the tree
 LIB = PKG / ("libstereo_b200" + (f"_{TAG}" if TAG else "") + ".so")
 FAST_PARTS = 38          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused pair parts + 3 x 4 float-operand parts
 

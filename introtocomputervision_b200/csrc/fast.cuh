@@ -892,7 +892,31 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
         spt = (g.nrows + seg_L - 1) / seg_L;
         t_seg = double(seg_L) + w * 0.5;
     }
-    if (t_seg < t_lin) {
+    g.sched = 0; g.ntiles = int(ntiles); g.nbands = 1;
+    // Many tiles (large images): row-band-major items, strided over the CTAs (FastGeom::sched) when some band count up to 16
+    // fills the waves to within 2 % of the linear split - the price of the L2 locality is one more warm-up per band.
+    static const int sched_env = [] { const char* e = getenv("STEREO_FAST_SCHED"); return e ? atoi(e) : -1; }();
+    int best_nb = 0; double t_band = 1e30;
+    if (ntiles >= ctx->sm_count && sched_env != 0) {
+        for (int nb = 1; nb <= 16; ++nb) {
+            const int Lb = (g.nrows + nb - 1) / nb;
+            if (Lb < 8 * w) break;
+            const long long items = ntiles * ((g.nrows + Lb - 1) / Lb);
+            const long long waves = (items + ctx->sm_count - 1) / ctx->sm_count;
+            const double t = double(waves) * (Lb + w * 0.5);
+            if (t < t_band) { t_band = t; best_nb = nb; }
+        }
+    }
+    if (best_nb > 0 && (t_band <= 1.02 * t_lin || sched_env == 1)) {
+        const int Lb = (g.nrows + best_nb - 1) / best_nb;
+        g.sched = 1;
+        g.L = Lb;
+        g.nbands = (g.nrows + Lb - 1) / Lb;
+        g.nrl = g.nrows;
+        g.total = ntiles * g.nrows;
+        const long long items = ntiles * g.nbands;
+        g.ctas = int(items < ctx->sm_count ? items : ctx->sm_count);
+    } else if (t_seg < t_lin) {
         g.L = seg_L;
         g.nrl = spt * seg_L;
         g.total = ntiles * g.nrl;

@@ -127,6 +127,11 @@ struct FastGeom {
                            // multiple of L when there are fewer tiles than SMs (then no CTA straddles two tiles)
     long long total;       // tiles x nrl (all jobs)
     long long L;           // linear rows per CTA
+    int sched;             // 0: CTA b owns the contiguous linear range [b*L, (b+1)*L);  1: row-band-major items (band, tile) of
+                           // L rows, CTA b owns items b, b + ctas, ... - the CTAs of a wave walk the SAME rows of neighbouring
+                           // tiles at the same time, so the target-side operand rows neighbouring tiles share (a tile is 80
+                           // pixels wide, its search range 256) are fetched from HBM once and then hit in L2
+    int ntiles, nbands;    // sched 1: tiles of the launch (all jobs), row bands per tile
 };
 
 // One direction of one image pair inside a launch.  All jobs of a launch share FastGeom; what depends
@@ -235,6 +240,12 @@ struct RowShape {
 // conversion instruction; larger windows convert with I2F and fold the magic add into the FFMA.
 #ifndef SB_KEY_LEA_MASK
 #define SB_KEY_LEA_MASK 0
+#endif
+#ifndef SB_KEY_LEA_FUSED
+#define SB_KEY_LEA_FUSED 0
+#endif
+#ifndef SB_KEY2_LEA
+#define SB_KEY2_LEA 0
 #endif
 constexpr int NCC_BIAS_MAX_R = 5;
 constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
@@ -359,6 +370,23 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
         const int4 v = lds128(e2_row + 4 * i);
         e2v[4 * i] = v.x; e2v[4 * i + 1] = v.y; e2v[4 * i + 2] = v.z; e2v[4 * i + 3] = v.w;
     }
+    // MODE 3: the selects are turned into masks once per row - per position (K + 3 of them, each used by up to four
+    // candidates) and per m - so that a candidate pays ONE three-input LOP3: key | inv[k + m] | mmask[m] (SSD: all-ones =
+    // KEY_INVALID loses every min) or key & ok[k + m] & mmask[m] (NCC: 0 = NCC_KEY_NONE loses every max).
+    uint32_t pmask[MODE == 3 ? S::NE : 1];
+    uint32_t mmask[MODE == 3 ? FM : 1];
+    if (MODE == 3) {
+#pragma unroll
+        for (int p = 0; p < S::NE; ++p) {
+            if (!NCC) pmask[MODE == 3 ? p : 0] = uint32_t(e2v[p]) == KEY_INVALID ? KEY_INVALID : 0u;
+            else pmask[MODE == 3 ? p : 0] = unsigned(cbase + p) < unsigned(cols) ? 0xFFFFFFFFu : 0u;
+        }
+#pragma unroll
+        for (int m = 0; m < FM; ++m) {
+            const bool out = m > mmax || m < mmin;
+            mmask[MODE == 3 ? m : 0] = NCC ? (out ? 0u : 0xFFFFFFFFu) : (out ? KEY_INVALID : 0u);
+        }
+    }
     int s[FM];                   // horizontal window sums: int (packed, OPF SSD) or float bits (OPF NCC)
     int sbias = 0;
     // opaque to the compiler: a literal would be re-associated out of the running sums and re-added per use
@@ -378,6 +406,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     uint32_t res[4];
     uint32_t acc[FM];            // FUSED: running minima of the diagonals k + 4*ll + m
     int elv[4];
+    uint32_t einv[4] = {0u, 0u, 0u, 0u};
     if (FUSED) {
 #pragma unroll
         for (int m = 0; m < FM; ++m) acc[m] = KEY_INVALID;
@@ -396,6 +425,10 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 #pragma unroll
                 for (int i = 0; i < 4; ++i) elv[i] = int(uint32_t(elv[i]) | lane_or);
             }
+            if (MODE == 3) {      // pixels the partner cannot centre a window on: one mask per pixel, shared by its four candidates
+#pragma unroll
+                for (int i = 0; i < 4; ++i) einv[i] = uint32_t(elv[i]) == KEY_INVALID ? KEY_INVALID : 0u;
+            }
         }
         uint32_t key[FM];
 #pragma unroll
@@ -413,19 +446,23 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 // literal multiplier: ptxas emits the immediate-form IMAD / LEA (2 register reads; the
                 // register file delivers ~2 operands per cycle per SMSP, tools/microbench/rf.cu)
                 uint32_t kv;
-                if (!OPF && (SB_KEY_LEA_MASK & (1 << m))) {      // shift-add on the ALU pipe
+                // (shift-add variants of either key were measured on the fused 4K/256 kernel: 3.51 .. 3.69 ms against 3.57 ms,
+                // i.e. inside the spread different register allocations of the same code produce - profiles/r2_hot_variants.md)
+                if (!OPF && ((FUSED ? SB_KEY_LEA_FUSED : SB_KEY_LEA_MASK) & (1 << m))) {      // shift-add on the ALU pipe
                     asm("{.reg .b32 t; shl.b32 t, %1, 8; add.s32 %0, t, %2;}" : "=r"(kv) : "r"(s[m]), "r"(e2v[k + m]));
                 } else {                                // IMAD (immediate) on the FMA-heavy pipe
                     kv = uint32_t(e2v[k + m]) + uint32_t(s[m]) * KEYMUL;
                 }
-                if (MODE == 3) kv = (uint32_t(e2v[k + m]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : kv;
+                if (MODE == 3) kv = kv | pmask[MODE == 3 ? k + m : 0] | mmask[MODE == 3 ? m : 0];
                 key[m] = kv;
                 if (FUSED) {
                     // the partner direction's key of the same cross term: BIAS + 128*(EL(x) - 2C) + x; pixels x beyond its
                     // legal centres (x > cols-1+R) carry EL2 = KEY_INVALID and lose like illegal search positions do (R <= 5;
                     // wider windows and float operands take the explicit selects of MODE 3 in the blocks that hold such pixels)
-                    uint32_t k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * KEYMUL;
-                    if (MODE == 3) k2 = (uint32_t(elv[k & 3]) == KEY_INVALID || m > mmax || m < mmin) ? KEY_INVALID : k2;
+                    uint32_t k2;
+                    if (!OPF && (SB_KEY2_LEA & (1 << m))) asm("{.reg .b32 t; shl.b32 t, %1, 8; add.s32 %0, t, %2;}" : "=r"(k2) : "r"(s[m]), "r"(elv[k & 3]));
+                    else k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * KEYMUL;
+                    if (MODE == 3) k2 = k2 | einv[k & 3] | mmask[MODE == 3 ? m : 0];
                     if (MODE == 2 && (R > FFREE_MASK_R || OPF)) k2 |= lane_or;
                     acc[m] = min(acc[m], k2);
                 }
@@ -438,7 +475,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                                        : __fmaf_rn(OPF ? __int_as_float(s[m]) : __int2float_rn(s[m]), rs, magic);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
                 uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
-                if (MODE == 3) kv = (unsigned(cbase + k + m) >= unsigned(cols) || m > mmax || m < mmin) ? NCC_KEY_NONE : kv;
+                if (MODE == 3) kv = kv & pmask[MODE == 3 ? k + m : 0] & mmask[MODE == 3 ? m : 0];
                 key[m] = kv;
             }
         }
@@ -538,15 +575,25 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
     // ---- this CTA's share of the (job, tile, row) space ----------------------------------------------
     // Linear index = tile * nrl + row with nrl >= nrows (rows nrows..nrl-1 of a tile are padding: when the launch has fewer
     // tiles than SMs, nrl is a multiple of L and every CTA's share lies inside one tile).
-    const long long lin_begin = (long long)blockIdx.x * g.L;
+    long long lin_begin = (long long)blockIdx.x * g.L;
     long long lin_end = lin_begin + g.L;
     if (lin_end > g.total) lin_end = g.total;
+    if (g.sched == 1) { lin_begin = blockIdx.x; lin_end = (long long)g.ntiles * g.nbands; }     // item indices, stride gridDim.x
     if (lin_begin >= lin_end) return;
     const int w = 2 * R + 1;
     const int tpj = g.tilesX * g.gblocks;        // tiles per job
     const int npair = FUSED ? g.npairs : 0;      // the partner of job jb is job jb + npair
     // next non-empty segment [r0, r1) of one tile at or after `lin`; false when the share is exhausted
     auto next_segment = [&](long long& lin, int& tile, int& r0, int& r1) -> bool {
+        if (g.sched == 1) {
+            if (lin >= lin_end) return false;
+            const int band = int(lin / g.ntiles);
+            tile = int(lin - (long long)band * g.ntiles);
+            r0 = band * int(g.L);
+            r1 = min(r0 + int(g.L), g.nrows);
+            lin += gridDim.x;
+            return true;
+        }
         while (lin < lin_end) {
             tile = int(lin / g.nrl);
             r0 = int(lin % g.nrl);
@@ -654,7 +701,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         const int js = y0 - w - g.base_y, je = y1 - g.base_y, jreg = y0 - g.base_y;
         // which flavour of candidate masking this warp's (HS x K pixels x DG disparities) block needs
         const int dlo = job.dlo0 + DG * grp;                              // first disparity of the group
-        bool pos_invalid = (x0w + dlo < job.cmin) || (x0w + HS * K - 1 + dlo + DG - 1 > job.cmax);
+        // (only the disparities of the group that lie inside [dmin, dmax] can name a position)
+        bool pos_invalid = (x0w + max(dlo, job.dmin) < job.cmin) || (x0w + HS * K - 1 + min(dlo + DG - 1, job.dmax) > job.cmax);
         if (FUSED) pos_invalid = pos_invalid || (x0w + HS * K - 1 > P.job[jb + npair].cmax);   // pixels the partner cannot centre a window on
         const bool hi_invalid = dlo + DG - 1 > job.dmax, lo_invalid = dlo < job.dmin;
         const bool lane_invalid = hi_invalid || lo_invalid;
