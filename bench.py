@@ -304,69 +304,109 @@ def run_ours(args, wl):
     stream = torch.cuda.Stream(device=dev)              # a real (non-default) stream: the library enqueues on it
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
-    gather = args.gather if world > 1 else "none"
-    pg, gathered, tickets = None, None, {}
-    gather_note = ""
-    if gather == "p2p":
-        # every rank's buffer: [parity][rank][direction][pair][rows][cols]; filled by copy-engine pushes
-        try:
-            pg = sharding.PeerGather(ctx, 2 * world * map_bytes)
-        except sharding.PeerGatherUnavailable as e:       # raised on every rank together
-            gather, gather_note = "nccl", f" (peer buffers unavailable: {e})"
-    if gather == "nccl":
-        gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev)
-
-    def step_device(k):
-        par, s_ = k & 1, k % S
-        if pg is not None and k - 2 in tickets:
-            pg.wait(tickets.pop(k - 2), stream.cuda_stream)       # the pushes that read d_out[par] two steps ago
-        rc = lib.stereo_disparity_pair_batch_u8_device(
-            ctx.handle, cost, B, d_left[s_].data_ptr(), d_right[s_].data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
-            d_out[par, 0].data_ptr(), d_out[par, 1].data_ptr(), cols * elem, rows * cols * elem, elem, sp)
-        if rc != 0:
-            raise RuntimeError(_capi.last_error())
-        if pg is not None:      # the batch config's exchange step: every rank receives every rank's maps
-            pg.push((par * world + rank) * map_bytes, d_out[par].data_ptr(), map_bytes, stream.cuda_stream)
-            tickets[k] = pg.mark()
-        elif gathered is not None:
-            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), d_out[par].view(torch.uint8).view(-1))   # bytes: NCCL has no int16
-
-    def join_pushes():
-        for k in sorted(tickets):
-            pg.wait(tickets.pop(k), stream.cuda_stream)
+    units_rank = B * 2 * rows * cols * nd
+    nwarm = max(3, args.warmup)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    units_rank = B * 2 * rows * cols * nd
-    nwarm = max(3, args.warmup)
-    for k in range(nwarm):
-        step_device(k)
-    if pg is not None:
-        join_pushes()
-    barrier()
-    if pg is not None and rank == 0:      # the gather delivers: rank 0's buffer holds the last warm-up step's maps of every rank
-        par = (nwarm - 1) & 1
-        got = pg.local_bytes(dev)[(par * world + rank) * map_bytes:(par * world + rank + 1) * map_bytes]
-        assert torch.equal(got, d_out[par].view(torch.uint8).view(-1)), "peer gather: own slot differs from the computed maps"
+    class Gather:
+        """The exchange step of a pair-sharded batch.  root: every rank's maps pushed into rank 0's buffer (the consumer) by the
+        copy engines over NVLink; all: into every rank's buffer; nccl: all_gather_into_tensor inside the step; none: N = 1."""
 
+        def __init__(self, kind):
+            self.kind, self.note, self.pg, self.gathered, self.tickets = kind, "", None, None, {}
+            if kind in ("root", "all"):
+                # the buffer: [parity][rank][direction][pair][rows][cols]; filled by copy-engine pushes
+                try:
+                    self.pg = sharding.PeerGather(ctx, 2 * world * map_bytes)
+                except sharding.PeerGatherUnavailable as e:       # raised on every rank together
+                    self.kind, self.note = "nccl", f" (peer buffers unavailable: {e})"
+            if self.kind == "nccl":
+                self.gathered = torch.empty((world, 2, B, rows, cols), dtype=elem_dtype, device=dev)
+            self.to = [0] if self.kind == "root" else None
+            # bytes every rank sends / the busiest rank receives per step over NVLink
+            self.tx = {"root": map_bytes if rank != 0 else 0, "all": (world - 1) * map_bytes, "nccl": (world - 1) * map_bytes}.get(self.kind, 0)
+            self.rx_max = {"root": (world - 1) * map_bytes, "all": (world - 1) * map_bytes, "nccl": (world - 1) * map_bytes}.get(self.kind, 0)
+
+        def before(self, k):
+            if self.pg is not None and k - 2 in self.tickets:
+                self.pg.wait(self.tickets.pop(k - 2), stream.cuda_stream)       # the pushes that read d_out[par] two steps ago
+
+        def after(self, k, par):
+            if self.pg is not None:
+                self.pg.push((par * world + rank) * map_bytes, d_out[par].data_ptr(), map_bytes, stream.cuda_stream, to=self.to)
+                self.tickets[k] = self.pg.mark()
+            elif self.gathered is not None:
+                dist.all_gather_into_tensor(self.gathered.view(torch.uint8).view(-1), d_out[par].view(torch.uint8).view(-1))   # bytes: NCCL has no int16
+
+        def join(self):
+            if self.pg is not None:
+                for k in sorted(self.tickets):
+                    self.pg.wait(self.tickets.pop(k), stream.cuda_stream)
+
+        def holds_all(self):
+            return self.pg is not None and (self.kind == "all" or rank == 0)
+
+        def close(self):
+            if self.pg is not None:
+                self.join()
+                torch.cuda.synchronize()
+                self.pg.close()
+                self.pg = None
+
+    def step_device(G, k):
+        par, s_ = k & 1, k % S
+        G.before(k)
+        rc = lib.stereo_disparity_pair_batch_u8_device(
+            ctx.handle, cost, B, d_left[s_].data_ptr(), d_right[s_].data_ptr(), cols, rows * cols, rows, cols, R, nd - 1,
+            d_out[par, 0].data_ptr(), d_out[par, 1].data_ptr(), cols * elem, rows * cols * elem, elem, sp)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+        G.after(k, par)
+
+    def timed_pairs(G, steps):
+        """nwarm untimed steps, then `steps` steps inside one event pair (joined with the copy-engine streams); ms = max over ranks."""
+        for k in range(nwarm):
+            step_device(G, k)
+        G.join()
+        barrier()
+        if G.holds_all():      # the gather delivers: this rank's buffer holds the last warm-up step's maps of this rank
+            par = (nwarm - 1) & 1
+            got = G.pg.local_bytes(dev)[(par * world + rank) * map_bytes:(par * world + rank + 1) * map_bytes]
+            assert torch.equal(got, d_out[par].view(torch.uint8).view(-1)), "peer gather: own slot differs from the computed maps"
+        n_launch = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(steps):
+            step_device(G, nwarm + k)
+            n_launch += ctx.last_launches
+        G.join()                                         # the timed region ends when every push has landed
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if G.pg is not None:      # cross-rank check after the barrier: every slot of the last step equals what that rank computed
+            par = (nwarm + steps - 1) & 1
+            mine_sum = d_out[par].view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
+            all_sums = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_sums, mine_sum)
+            if G.holds_all():
+                sums = G.pg.local_bytes(dev)[par * world * map_bytes:(par + 1) * world * map_bytes].view(world, -1).to(torch.int64).sum(dim=1)
+                assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's maps"
+        return float(t.item()), n_launch
+
+    G = Gather(args.gather if world > 1 else "none")
+    gather, gather_note, pg = G.kind, G.note, G.pg
     sampler = ClockSampler(local)
     sampler.start()
-    hot_ms, hot_n, launches = 0.0, 0, 0
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for k in range(args.steps):
-        step_device(nwarm + k)
-        launches += ctx.last_launches
-    if pg is not None:
-        join_pushes()                                    # the timed region ends when every push has landed
-    e1.record(stream)
-    barrier()
+    dev_ms, launches = timed_pairs(G, args.steps)
     clocks = sampler.stop()
-    dev_ms = e0.elapsed_time(e1)
+    hot_ms, hot_n = 0.0, 0
     # hot-kernel time of the last step (events recorded by the library on the same stream)
     ms, nmeas = ctx.last_hot_kernel_ms()
     hot_jobs = ctx.last_hot_jobs
@@ -377,28 +417,36 @@ def run_ours(args, wl):
     unfused = None
     if fused:
         ctx.set_fuse_pairs(False)
-        if pg is not None:
-            join_pushes()
-        step_device(nwarm + args.steps + (nwarm + args.steps) % 2)
-        if pg is not None:
-            join_pushes()
+        G.join()
+        step_device(G, nwarm + args.steps + (nwarm + args.steps) % 2)
+        G.join()
         torch.cuda.synchronize()
         ms_u, n_u = ctx.last_hot_kernel_ms()
         if n_u > 0:
             unfused = (ms_u, n_u, ctx.last_hot_jobs)
         ctx.set_fuse_pairs(True)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
     value = world * units_rank * args.steps / (dev_ms * 1e-3) / 1e6
-    if pg is not None:      # cross-rank check after the barrier: every slot of the last step equals what that rank computed
-        par = (nwarm + args.steps - 1) & 1
-        sums = pg.local_bytes(dev)[par * world * map_bytes:(par + 1) * world * map_bytes].view(world, -1).to(torch.int64).sum(dim=1)
-        mine_sum = d_out[par].view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
-        all_sums = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_sums, mine_sum)
-        assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's maps"
+
+    def join_pushes():
+        G.join()
+
+    # the other exchange variants, a few steps each (multi-GPU runs only): sub-lines of the same JSON line
+    gather_sub = {}
+    if world > 1 and not args.no_suite:
+        G.join()
+        barrier()
+        for kind in ("root", "all", "nccl"):
+            if kind == G.kind:
+                continue
+            G2 = Gather(kind)
+            ms2, _ = timed_pairs(G2, max(3, min(args.steps, 5)))
+            gather_sub[kind if G2.kind == kind else f"{kind}->nccl"] = {
+                "value": round(world * units_rank * max(3, min(args.steps, 5)) / (ms2 * 1e-3) / 1e6, 1), "unit": UNIT,
+                "ms_per_step": round(ms2 / max(3, min(args.steps, 5)), 4),
+                "nvlink_tx_bytes_per_rank_per_step": map_bytes if G2.kind == "root" else (world - 1) * map_bytes,
+                "nvlink_rx_bytes_busiest_rank_per_step": G2.rx_max}
+            G2.close()
+            barrier()
 
     # ---- e2e: reference-facing host call, float32 (CV_32FC1) host buffers, copies inside the timed region
     hf_left = h_left.to(torch.float32).pin_memory()
@@ -453,6 +501,12 @@ def run_ours(args, wl):
         return world * units_rank * e2e_steps / float(tt.item()) / 1e6
 
     e2e_pp_value = timed_host(step_host_per_pair)
+    # the same batch call with host-side packing switched the other way (the default packs from 8 host threads up)
+    host_threads = ctx.host_threads
+    packing = host_threads >= 8
+    ctx.set_host_threads(-1 if packing else 16)
+    e2e_alt_value = timed_host(step_host)
+    ctx.set_host_threads(0)
 
     # u8 host entry (same computation for callers that hold 8-bit images)
     hu_l, hu_r = h_left.pin_memory(), h_right.pin_memory()
@@ -470,7 +524,7 @@ def run_ours(args, wl):
     step_host()
     if pg is not None:
         join_pushes()
-    step_device(2 * S)                  # even step number: parity 0, input set 0 (the un-rolled images)
+    step_device(G, 2 * S)               # even step number: parity 0, input set 0 (the un-rolled images)
     if pg is not None:
         join_pushes()
     torch.cuda.synchronize()
@@ -492,6 +546,16 @@ def run_ours(args, wl):
             PL, PR, _ = synth.make_pair(rows, cols, nd, wl["seed"] + peer * B + (B - 1))
             parity[f"rank{peer}_pair{B - 1}_from_gather_buffer"] = oracle_band_check(PL, PR, R, nd, args.cost, pl, pr_, r0, nrow)
         parity["ok"] = all(v["ok"] for v in parity.values())
+
+    # BASELINE config 4 next to the pair-sharded line (multi-GPU runs): the same 4K pair cut into row bands, strong scaling
+    bands_sub = None
+    if world > 1 and not args.no_suite:
+        G.join()
+        barrier()
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        bands_sub = bands_line(args, wl, lib, ctx, cost, dev, rank, world, local, max(5, min(args.steps, 20)), "root", use_graph=not args.no_graph)
+        torch.cuda.set_stream(stream)
+        barrier()
 
     if rank == 0:
         peaks = measured_peaks()
@@ -548,10 +612,14 @@ def run_ours(args, wl):
             "config": {"workload": args.workload + f"_{args.cost}_pair", "rows": rows, "cols": cols, "ndisp": nd,
                        "window": 2 * R + 1, "pairs_per_gpu_per_step": B, "directions": 2,
                        "pair_fusion": "both maps of a pair from one cost volume" if fused else "one cost volume per direction",
-                       "sharding": "by pair" + ({"p2p": ", every rank's maps pushed into every rank's gather buffer by the copy engines "
-                                                        "over NVLink (stereo_peer_push), overlapping the next step's kernels; "
-                                                        "all pushes joined inside the timed region",
-                                                 "nccl": ", NCCL all_gather of maps inside the step" + gather_note, "none": ""}[gather]),
+                       "sharding": "by pair" + {
+                           "root": ", every rank's maps pushed into rank 0's gather buffer (the consumer) by the copy engines over NVLink "
+                                   "(stereo_peer_push), overlapping the next step's kernels; all pushes joined inside the timed region",
+                           "all": ", every rank's maps pushed into EVERY rank's gather buffer by the copy engines over NVLink "
+                                  "(stereo_peer_push), overlapping the next step's kernels; all pushes joined inside the timed region",
+                           "nccl": ", NCCL all_gather of maps inside the step" + gather_note, "none": ""}[gather],
+                       "gather_bytes_per_step": {"nvlink_tx_per_rank": (map_bytes if gather == "root" else (world - 1) * map_bytes) if world > 1 else 0,
+                                                 "nvlink_rx_busiest_rank": (world - 1) * map_bytes if world > 1 else 0},
                        "l2": f"inputs rotate over {S} sets = {S * set_bytes >> 20} MiB > L2 ({l2_bytes >> 20} MiB); "
                              f"one event pair around all timed steps",
                        "out_dtype": str(elem_dtype).replace("torch.", "")},
@@ -561,10 +629,18 @@ def run_ours(args, wl):
                     "api": "stereo_disparity_pair_batch_f32_host: one call per step, the step's pairs as pinned CV_32FC1 host "
                            "images in, int8/int16 host maps out",
                     "per_pair_calls_value": round(e2e_pp_value, 1), "u8_host_api_value": round(e2e8_value, 1),
+                    "host_pack": {"threads": host_threads, "on": packing,
+                                  "what": "CV_32FC1 host images converted to u8 by host threads into pinned staging, 1 byte per pixel "
+                                          "over the link" if packing else "float rows uploaded, converted on the device",
+                                  ("value_with_float_upload" if packing else "value_with_host_pack_16_threads"): round(e2e_alt_value, 1)},
                     "host_cpus_bound_per_rank": bound_cpus},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
             "parity_check": parity,
         }
+        if gather_sub:
+            line["gather_variants"] = gather_sub
+        if bands_sub is not None:
+            line["bands"] = bands_sub
         if world == 1 and not args.no_suite:
             # the other configurations, each a short device-resident run (same clocks sampler idea: one sample set around all)
             s2 = ClockSampler(local)
@@ -578,8 +654,7 @@ def run_ours(args, wl):
             ps2 = suite_ps2_lines(torch, lib, ctx, dev, stream, 10, peak_lane_ops)
             line["suite"] = {"batches": lines, "ps2": ps2, "clocks": s2.stop()}
         print(json.dumps(line), flush=True)
-    if pg is not None:
-        pg.close()
+    G.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -731,10 +806,12 @@ def suite_ps2_lines(torch, lib, ctx, dev, stream, steps, peak_lane_ops):
                       f"{steps}; the reference's published figure is its kernel alone (GpuTimer, DisparitySSD.cu:192-203)"}
 
 
-def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
-    """BASELINE config 4: one synthetic pair, output rows sharded over the ranks (R+1 halo rows from the
-    rank's own slab, no neighbour exchange), both maps of the band from one launch sequence, every rank's band
-    delivered to every rank inside the timed step (copy-engine peer pushes, or --gather nccl)."""
+def bands_line(args, wl, lib, ctx, cost, dev, rank, world, local, steps, gather_kind, use_graph=True):
+    """BASELINE config 4: ONE synthetic pair, output rows sharded over the ranks (R+1 halo rows from the rank's own slab, no
+    neighbour exchange), both maps of the band from one launch sequence, the bands gathered inside the timed step: pushed by
+    the copy engines into rank 0's buffer (root), into every rank's (all), or all_gather'ed (nccl).  Strong scaling: a step is
+    a fraction of a millisecond per rank, so the step (library call + pushes + join) is captured once into a CUDA graph and
+    replayed - one graph launch per step instead of a dozen API calls.  Returns the JSON line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from introtocomputervision_b200 import _capi, sharding, synth
@@ -746,38 +823,37 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     h0, h1 = sharding.band_halo(rows, r0, r1, R)
     band = -(-rows // world)
     d_l, d_r = torch.from_numpy(L[h0:h1].copy()).to(dev), torch.from_numpy(Rt[h0:h1].copy()).to(dev)   # this rank's slab only
-    mine = torch.zeros((2, 2, band, cols), dtype=elem_dtype, device=dev)          # [parity][direction]
+    mine = torch.zeros((2, band, cols), dtype=elem_dtype, device=dev)              # [direction]
     band_bytes = 2 * band * cols * elem
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(device=dev)
+    prev_stream = torch.cuda.current_stream(dev)
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
-    gather = args.gather if world > 1 else "none"
+    gather = gather_kind if world > 1 else "none"
     pg, gathered, gather_note = None, None, ""
-    if gather == "p2p":          # every rank's buffer: [parity][rank][direction][band rows][cols], filled by copy-engine pushes
+    if gather in ("root", "all"):          # the buffer: [rank][direction][band rows][cols], filled by copy-engine pushes
         try:
-            pg = sharding.PeerGather(ctx, 2 * world * band_bytes)
+            pg = sharding.PeerGather(ctx, world * band_bytes)
         except sharding.PeerGatherUnavailable as e:
             gather, gather_note = "nccl", f" (peer buffers unavailable: {e})"
     if gather == "nccl":
         gathered = torch.empty((world, 2, band, cols), dtype=elem_dtype, device=dev)
-    state = {"k": 0}
+    to = [0] if gather == "root" else None
 
     def step():
         # ONE image pair per step: the gather is part of the step (strong scaling has nothing to overlap it with), so a
         # step ends when this rank's pushes have landed / the collective has finished
-        par = state["k"] & 1
-        state["k"] += 1
         rc = lib.stereo_disparity_pair_band_halo_u8_device(ctx.handle, cost, d_l.data_ptr(), cols, d_r.data_ptr(), cols, rows, cols,
-                                                           r0, r1, h0, h1, R, nd - 1, mine[par, 0].data_ptr(), mine[par, 1].data_ptr(),
+                                                           r0, r1, h0, h1, R, nd - 1, mine[0].data_ptr(), mine[1].data_ptr(),
                                                            cols * elem, elem, sp)
         if rc != 0:
             raise RuntimeError(_capi.last_error())
         if pg is not None:
-            pg.push((par * world + rank) * band_bytes, mine[par].data_ptr(), band_bytes, stream.cuda_stream)
+            pg.push(rank * band_bytes, mine.data_ptr(), band_bytes, stream.cuda_stream, to=to)
             pg.wait(pg.mark(), stream.cuda_stream)
         elif gathered is not None:
-            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine[par].view(torch.uint8).view(-1))
+            dist.all_gather_into_tensor(gathered.view(torch.uint8).view(-1), mine.view(torch.uint8).view(-1))
 
     def barrier():
         if world > 1:
@@ -787,14 +863,35 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
+    launches_per_step = ctx.last_launches
+    fused = bool(ctx.last_fused_pairs)
+    graph, graph_note = None, "off"
+    if use_graph and gather != "nccl":
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                step()
+            graph_note = "step captured once into a CUDA graph, replayed per step"
+        except Exception as e:                       # capture refused (driver / a call that is illegal during capture): plain launches
+            graph, graph_note = None, f"capture failed ({type(e).__name__}), plain launches"
+            torch.cuda.synchronize()
+        ok = torch.tensor([1 if graph is not None else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks replay or none does
+        if int(ok.item()) == 0:
+            graph = None
+    run = (lambda: graph.replay()) if graph is not None else step
+    for _ in range(2):
+        run()
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     evs = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        step()
+        run()
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
@@ -803,33 +900,61 @@ def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+    # parity of the gathered image (rank 0's buffer, or this rank's own band for N = 1 / nccl) against the oracle: 64 rows
+    # straddling the seam between the first two bands
+    parity = None
+    if rank == 0 and not args.no_parity:
+        if pg is not None:
+            buf = pg.local_bytes(dev).view(elem_dtype).view(world, 2, band, cols)
+        elif gathered is not None:
+            buf = gathered
+        else:
+            buf = mine.unsqueeze(0)
+        full_l = buf[:, 0].reshape(world * band, cols)[:rows].cpu().numpy()
+        full_r = buf[:, 1].reshape(world * band, cols)[:rows].cpu().numpy()
+        seam = max(0, min(rows - 64, band - 32)) if world > 1 else max(0, rows // 2 - 32)
+        parity = oracle_band_check(L, Rt, R, nd, args.cost, full_l, full_r, seam, min(64, rows))
+    line = None
     if rank == 0:
-        units = 2 * rows * cols * nd * args.steps                       # the WHOLE image pair, all ranks together
+        units = 2 * rows * cols * nd * steps                       # the WHOLE image pair, all ranks together
         line = {"metric": METRIC, "value": round(units / (dev_ms * 1e-3) / 1e6, 1), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / args.steps, 4),
+                "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": round(dev_ms / steps, 4),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 (int32 accumulate)",
                 "data": "synthetic",
                 "config": {"workload": args.workload + f"_{args.cost}_pair_bands", "rows": rows, "cols": cols, "ndisp": nd,
                            "window": 2 * R + 1, "band_rows": band, "halo_rows": R + 1, "directions": 2,
-                           "pair_fusion": "both maps of a band from one cost volume" if ctx.last_fused_pairs else "one cost volume per direction",
+                           "pair_fusion": "both maps of a band from one cost volume" if fused else "one cost volume per direction",
                            "sharding": "by row band, slab with halo resident per rank"
-                                       + {"p2p": ", every rank's band pushed into every rank's gather buffer by the copy engines over "
+                                       + {"root": ", every rank's band pushed into rank 0's buffer by the copy engines over NVLink "
+                                                  "(stereo_peer_push), joined inside the step",
+                                          "all": ", every rank's band pushed into every rank's buffer by the copy engines over "
                                                  "NVLink (stereo_peer_push), joined inside the step",
                                           "nccl": ", NCCL all_gather of the bands inside the step" + gather_note, "none": ""}[gather],
-                           "l2": "flushed between steps"},
-                "gpu_launches": ctx.last_launches * args.steps, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+                           "gather_bytes_per_step": {"nvlink_tx_per_rank": (band_bytes if gather == "root" else (world - 1) * band_bytes) if world > 1 else 0,
+                                                     "nvlink_rx_busiest_rank": (world - 1) * band_bytes if world > 1 else 0},
+                           "launch": graph_note, "l2": "flushed between steps"},
+                "gpu_launches": launches_per_step * steps, "clocks": clocks, "parity_check": parity}
     if pg is not None:
-        # cross-rank check: every slot of the last step equals what that rank computed
-        par = (state["k"] - 1) & 1
+        # cross-rank check: every slot the consumer holds equals what that rank computed
         dist.barrier()
         torch.cuda.synchronize()
-        sums = pg.local_bytes(dev)[par * world * band_bytes:(par + 1) * world * band_bytes].view(world, -1).to(torch.int64).sum(dim=1)
-        mine_sum = mine[par].view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
+        mine_sum = mine.view(torch.uint8).view(-1).to(torch.int64).sum().reshape(1)
         all_sums = torch.empty(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_sums, mine_sum)
-        assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's band"
+        if gather == "all" or rank == 0:
+            sums = pg.local_bytes(dev).view(world, -1).to(torch.int64).sum(dim=1)
+            assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's band"
+        del graph
         pg.close()
+    torch.cuda.set_stream(prev_stream)
+    return line
+
+
+def run_bands(args, wl, lib, ctx, cost, dev, rank, world, local):
+    import torch.distributed as dist
+    line = bands_line(args, wl, lib, ctx, cost, dev, rank, world, local, args.steps, args.gather, use_graph=not args.no_graph)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -849,8 +974,10 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of a band of the step's maps")
     ap.add_argument("--pipe-bands", type=int, default=0, help="row bands per pair in the pipelined host entry points (0 = automatic)")
     ap.add_argument("--cost", default="ssd", choices=["ssd", "ncc"], help="window cost (the headline line is ssd)")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: how the ranks' maps are gathered (copy-engine peer pushes, or an NCCL all_gather)")
+    ap.add_argument("--gather", default="root", choices=["root", "all", "nccl"],
+                    help="N > 1: where the ranks' maps go - root: copy-engine pushes over NVLink into rank 0's buffer (the consumer); "
+                         "all: into every rank's buffer; nccl: an NCCL all_gather inside the step")
+    ap.add_argument("--no-graph", action="store_true", help="bands mode: plain launches instead of replaying a captured CUDA graph")
     ap.add_argument("--mode", default="pairs", choices=["pairs", "bands"],
                     help="pairs: batch sharded by pair, weak scaling (default, the driver's line); "
                          "bands: ONE image sharded by row band with halo, strong scaling (BASELINE config 4)")

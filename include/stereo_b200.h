@@ -123,6 +123,14 @@ int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands);
  * pairs per launch sequence).  Pure host arithmetic, no device needed. */
 int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_override, int* bands_per_pair, int* pairs_per_item);
 
+/* CV_32FC1 HOST entry points: images whose pixels are all integers in 0..255 (everything convertTo(CV_32FC1) produces,
+ * main.cpp:87-88) are converted to u8 by `threads` host threads into pinned staging and uploaded as 1 byte per pixel; the
+ * reference uploads the float Mats (DisparitySSD.cu:171-174).  threads = 0 (default): min(16, hardware threads /
+ * LOCAL_WORLD_SIZE), and host conversion only from 8 threads up (below that the floats are uploaded and converted on the
+ * device); threads = -1: never convert on the host; threads >= 1: that many, always.  Results do not depend on it. */
+int stereo_ctx_set_host_threads(stereo_ctx* ctx, int threads);
+int stereo_ctx_host_threads(const stereo_ctx* ctx);
+
 /* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the problem allows
  * it (SSD, window_rad <= 5, disparity_range + 1 a multiple of 128) — the reference's disparitySSDPair always wants
  * both (main.cpp:21-48) and SSD_LR(x, d) and SSD_RL(x + d, -d) are the same window sum.  Results are identical

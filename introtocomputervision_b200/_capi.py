@@ -40,6 +40,8 @@ SIGNATURES = {
     "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
     "stereo_host_pipeline_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
+    "stereo_ctx_set_host_threads": (_i, [_vp, _i]),
+    "stereo_ctx_host_threads": (_i, [_vp]),
     "stereo_ctx_last_fused_pairs": (_i, [_vp]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),
     "stereo_disparity_f32_host": (_i, _SINGLE_HOST),

@@ -38,7 +38,7 @@ def _nvcc() -> str:
 
 def units():
     """(object name, source, extra flags) of every translation unit."""
-    u = [("stereo_b200.o", CSRC / "stereo_b200.cu", [])]
+    u = [("stereo_b200.o", CSRC / "stereo_b200.cu", []), ("host_pack.o", CSRC / "host_pack.cpp", [])]
     u += [(f"fast_inst_{i}.o", CSRC / "fast_inst.cu", [f"-DSB_PART={i}"]) for i in range(FAST_PARTS)]
     return u
 
@@ -52,7 +52,9 @@ def _deps(src: Path):
     api = list((PKG.parent / "include").glob("*.h"))
     if src.name == "fast_inst.cu":
         return [src, CSRC / "fast_kernel.cuh", CSRC / "common.cuh", *api]
-    return [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *api]
+    if src.name == "host_pack.cpp":
+        return [src, CSRC / "host_pack.hpp"]
+    return [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *CSRC.glob("*.hpp"), *api]
 
 
 def sources():
@@ -65,7 +67,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
+    deps = [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *CSRC.glob("*.cpp"), *CSRC.glob("*.hpp"), *(PKG.parent / "include").glob("*.h")]
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -80,7 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     only = os.environ.get("STEREO_BUILD_PARTS", "")
     borrowed = set()
     if TAG and only:
-        keep = {f"fast_inst_{int(i)}.o" for i in only.split(",")} | {"stereo_b200.o"}
+        keep = {f"fast_inst_{int(i)}.o" for i in only.split(",")} | {"stereo_b200.o", "host_pack.o"}
         for name, _, _ in units():
             if name not in keep:
                 src_obj = CSRC / "_build" / name

@@ -11,6 +11,8 @@
 
 namespace sb {
 
+class HostPool;
+
 // ---- error plumbing: status codes out, never exit() (contrast: common/CudaCommon.cuh:11-22) ----
 void set_error(const char* fmt, ...);
 #define SB_CUDA(expr)                                                                         \
@@ -89,6 +91,9 @@ struct stereo_ctx {
     sb::Arena io;             // device staging of host-API inputs/outputs
     void* pinned = nullptr;   // pinned host staging
     size_t pinned_cap = 0;
+    sb::HostPool* pool = nullptr;   // host threads that convert CV_32FC1 host images to u8 (host_pack.cpp)
+    int host_threads = 0;           // 0 = automatic, -1 = host packing off, n = use n threads (and pack whatever n is)
+    bool host_pack_forced = false;
     int* d_flag = nullptr;    // device classification flag
     int* h_flag = nullptr;    // pinned mirror
     int last_path = 0;

@@ -1,0 +1,117 @@
+// Host side of the pipelined CV_32FC1 entry points: a small persistent thread pool that converts float32 images to the
+// u8 images the packed kernels consume (checking on the way that every pixel really is an integer in 0..255), so that
+// the host link carries 1 byte per pixel instead of 4.  The reference uploads the CV_32FC1 Mats as they are
+// (DisparitySSD.cu:171-174).  Plain C++ (compiled by the host compiler, no CUDA in here).
+#include "host_pack.hpp"
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace sb {
+
+// One row segment; returns false as soon as the segment holds a pixel that is not an integer in 0..255 (NaN included:
+// (int)NaN converts to INT_MIN, which fails both tests).  target_clones: resolved at load time for the CPU the library runs on.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default")))
+#endif
+bool pack_f32_u8_row(const float* __restrict__ src, uint8_t* __restrict__ dst, int n) {
+    int bad = 0;
+    for (int x = 0; x < n; ++x) {
+        const float f = src[x];
+        const int v = int(f);
+        bad |= (float(v) != f) | (unsigned(v) > 255u);
+        dst[x] = uint8_t(v);
+    }
+    return bad == 0;
+}
+
+struct HostPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)>* fn = nullptr;
+    int n_tasks = 0;
+    std::atomic<int> next{0};
+    int generation = 0, running = 0;
+    bool stop = false;
+
+    void loop() {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)>* f;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                f = fn;
+            }
+            for (int i; (i = next.fetch_add(1)) < n_tasks;) (*f)(i);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+};
+
+HostPool::HostPool(int threads) : impl_(new Impl), threads_(threads < 1 ? 1 : threads) {
+    for (int i = 1; i < threads_; ++i) impl_->workers.emplace_back([this] { impl_->loop(); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto& t : impl_->workers) t.join();
+    delete impl_;
+}
+
+void HostPool::run(int n_tasks, const std::function<void(int)>& fn) {
+    if (n_tasks <= 0) return;
+    if (threads_ == 1 || n_tasks == 1) { for (int i = 0; i < n_tasks; ++i) fn(i); return; }
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->fn = &fn;
+        impl_->n_tasks = n_tasks;
+        impl_->next.store(0);
+        impl_->running = int(impl_->workers.size());
+        ++impl_->generation;
+    }
+    impl_->cv_work.notify_all();
+    for (int i; (i = impl_->next.fetch_add(1)) < n_tasks;) fn(i);       // the calling thread works too
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->cv_done.wait(lk, [&] { return impl_->running == 0; });
+}
+
+bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols) {
+    // tasks of ~64K pixels: enough of them to balance, few enough to keep the dispatch cost invisible
+    int rows_per_task = (1 << 16) / (cols > 0 ? cols : 1);
+    if (rows_per_task < 1) rows_per_task = 1;
+    const int n_tasks = (rows + rows_per_task - 1) / rows_per_task;
+    std::atomic<int> bad{0};
+    pool.run(n_tasks, [&](int t) {
+        const int r0 = t * rows_per_task, r1 = r0 + rows_per_task < rows ? r0 + rows_per_task : rows;
+        bool ok = true;
+        for (int r = r0; r < r1; ++r)
+            ok &= pack_f32_u8_row(reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + size_t(r) * src_step),
+                                  dst + size_t(r) * dst_step, cols);
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+    });
+    return bad.load() == 0;
+}
+
+int default_host_threads() {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    // one process per GPU under a torchrun-style launcher: share the cores
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(e); if (w > 1) hw = hw / unsigned(w) ? hw / unsigned(w) : 1; }
+    return int(hw > 16 ? 16 : hw);
+}
+
+} // namespace sb

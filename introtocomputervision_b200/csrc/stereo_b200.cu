@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "exact.cuh"
 #include "fast.cuh"
+#include "host_pack.hpp"
 
 #include <cstdarg>
 #include <new>
@@ -438,6 +439,21 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
     return rc;
 }
 
+// Host-side packing of CV_32FC1 images (host_pack.cpp): on when the context has enough host threads to convert faster
+// than the link would carry the floats (stereo_ctx_set_host_threads; automatic: min(16, cores / LOCAL_WORLD_SIZE) threads,
+// packing from HOST_PACK_MIN_THREADS up).
+constexpr int HOST_PACK_MIN_THREADS = 8;
+static bool host_pack_enabled(stereo_ctx* ctx) {
+    if (ctx->host_threads == 0) ctx->host_threads = default_host_threads();
+    if (ctx->host_threads < 0) return false;                  // switched off
+    if (ctx->host_threads < HOST_PACK_MIN_THREADS && !ctx->host_pack_forced) return false;
+    if (!ctx->pool || ctx->pool->threads() != ctx->host_threads) {
+        delete ctx->pool;
+        ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
+    }
+    return ctx->pool != nullptr;
+}
+
 // A few pixels of a host float image: false as soon as one is not an integer in 0..255.  Noisy / contrast-scaled images
 // (main.cpp:140-153,191-193) fail on the first samples, so they skip the optimistic 8-bit pipeline instead of running
 // it, finding the flag set and being computed a second time by the float kernels.
@@ -460,8 +476,14 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
         for (int i = 0; i < n_pairs; ++i)
             if (!host_sample_is_8bit(in[i].left, in[i].left_step, rows, cols) || !host_sample_is_8bit(in[i].right, in[i].right_step, rows, cols))
                 return PIPE_NOT_8BIT;
-    const size_t px = type == PixType::F32 ? 4 : 1;
+    // CV_32FC1 host images with enough host threads: converted to u8 on the HOST (checking that every pixel is 8-bit), so the
+    // link carries 1 byte per pixel; otherwise the float rows are uploaded and converted / classified on the device.
+    const bool pack = type == PixType::F32 && host_pack_enabled(ctx);
+    const PixType dtype = pack ? PixType::U8 : type;          // pixel type of the device-side input slots
+    const size_t hpx = type == PixType::F32 ? 4 : 1;          // host pixel bytes
+    const size_t px = dtype == PixType::F32 ? 4 : 1;
     const size_t in_pitch = align256(cols * px), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
+    (void)hpx;
     // validate each direction on a full-image problem (pointers only need to be non-null here)
     Problem full{};
     full.cost = cost; full.rows = rows; full.cols = cols; full.row_begin = 0; full.row_end = rows;
@@ -486,12 +508,18 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             scratch = need > scratch ? need : scratch;
         }
     }
-    int rc = ensure_pipe(ctx, 3 * n_items * nb + 4);
+    constexpr int NSTG = 4;                               // pinned staging ring of the host-packed uploads
+    int rc = ensure_pipe(ctx, 3 * n_items * nb + 4 + NSTG);
     if (rc != STEREO_OK) return rc;
     cudaStream_t s_in = ctx->s_in, s_cmp = ctx->stream, s_out = ctx->s_out;
+    const size_t stg_pitch = (size_t(cols) + 63) & ~size_t(63);
+    const int stg_rows = band_rows + R + 16 < rows ? band_rows + R + 16 : rows;
+    const size_t stg_slot = 2 * size_t(cp) * stg_rows * stg_pitch;
+    if (pack) { rc = ensure_pinned(ctx, NSTG * stg_slot); if (rc != STEREO_OK) return rc; }
+    int stg_used = 0;
 
     const int S = n_items < 3 ? n_items : 3;            // device slots (ring), one work item each
-    const size_t pair_bytes = 2 * align256(in_pitch * rows) + (type == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
+    const size_t pair_bytes = 2 * align256(in_pitch * rows) + (dtype == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
                               + size_t(n_dirs) * align256(d_pitch * rows);
     const size_t slot_bytes = size_t(cp) * pair_bytes;
     if (size_t(S) * slot_bytes + 1024 > ctx->io.cap || scratch > ctx->arena.cap) {
@@ -508,7 +536,7 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             Slot& sl = slot[k][c];
             sl.l = static_cast<char*>(ctx->io.take(in_pitch * rows));
             sl.r = static_cast<char*>(ctx->io.take(in_pitch * rows));
-            if (type == PixType::F32) {
+            if (dtype == PixType::F32) {
                 sl.l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
                 sl.r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
             } else {
@@ -525,8 +553,9 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
     SB_CUDA(cudaEventRecord(ctx->pipe_ev[0], s_cmp));
     SB_CUDA(cudaStreamWaitEvent(s_in, ctx->pipe_ev[0], 0));
     SB_CUDA(cudaStreamWaitEvent(s_out, ctx->pipe_ev[0], 0));
-    if (type == PixType::F32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), s_cmp));
+    if (dtype == PixType::F32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), s_cmp));
     ctx->last_path = STEREO_PATH_FAST_U8;
+    auto stg_ev = [&](int k) { return ctx->pipe_ev[3 * n_items * nb + 1 + k]; };
 
     for (int w = 0; w < n_items; ++w) {
         const Slot* sl = slot[w % S];
@@ -543,7 +572,32 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             const int up_hi = (b == nb - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
             const int nr = up_hi - uploaded;
             if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(w - S, nb - 1, 1), 0));   // slot inputs free again
-            if (nr > 0)
+            if (nr > 0 && pack) {
+                // host threads convert this band's rows of every pair into a pinned staging slot, from where they are uploaded
+                const int k = stg_used % NSTG;
+                if (stg_used >= NSTG) SB_CUDA(cudaEventSynchronize(stg_ev(k)));      // the upload that last read this slot
+                ++stg_used;
+                uint8_t* stg = static_cast<uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
+                bool all8 = true;
+                for (int c = 0; c < np; ++c) {
+                    const HostPairIn& hp = in[i0 + c];
+                    uint8_t* sl_l = stg + size_t(2 * c) * stg_rows * stg_pitch;
+                    uint8_t* sl_r = stg + size_t(2 * c + 1) * stg_rows * stg_pitch;
+                    all8 = all8 && pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(static_cast<const char*>(hp.left) + size_t(uploaded) * hp.left_step),
+                                               hp.left_step, sl_l, stg_pitch, nr, cols);
+                    all8 = all8 && pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(static_cast<const char*>(hp.right) + size_t(uploaded) * hp.right_step),
+                                               hp.right_step, sl_r, stg_pitch, nr, cols);
+                    if (!all8) break;
+                    SB_CUDA(cudaMemcpy2DAsync(sl[c].l + size_t(uploaded) * in_pitch, in_pitch, sl_l, stg_pitch, cols, nr, cudaMemcpyHostToDevice, s_in));
+                    SB_CUDA(cudaMemcpy2DAsync(sl[c].r + size_t(uploaded) * in_pitch, in_pitch, sl_r, stg_pitch, cols, nr, cudaMemcpyHostToDevice, s_in));
+                }
+                if (!all8) {      // a pixel that is not 8-bit: give the call to the float kernels (nothing of it has reached the caller's maps
+                                  // that will not be overwritten)
+                    SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
+                    return PIPE_NOT_8BIT;
+                }
+                SB_CUDA(cudaEventRecord(stg_ev(k), s_in));
+            } else if (nr > 0)
                 for (int c = 0; c < np; ++c) {
                     const HostPairIn& hp = in[i0 + c];
                     SB_CUDA(cudaMemcpy2DAsync(sl[c].l + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(hp.left) + size_t(uploaded) * hp.left_step,
@@ -555,7 +609,7 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             // ---- compute
             SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w, b, 0), 0));
             if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w - S, nb - 1, 2), 0));  // slot outputs downloaded
-            if (type == PixType::F32 && nr > 0) {
+            if (dtype == PixType::F32 && nr > 0) {
                 dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8));
                 for (int c = 0; c < np; ++c) {
                     classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].l + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
@@ -600,12 +654,12 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             SB_CUDA(cudaEventRecord(ev(w, b, 2), s_out));
         }
     }
-    if (type == PixType::F32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
+    if (dtype == PixType::F32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
     end_call(ctx, s_cmp);
     SB_CUDA(cudaStreamSynchronize(s_cmp));
     SB_CUDA(cudaStreamSynchronize(s_out));
     SB_CUDA(cudaStreamSynchronize(s_in));
-    if (type == PixType::F32 && *ctx->h_flag != 0) return PIPE_NOT_8BIT;
+    if (dtype == PixType::F32 && *ctx->h_flag != 0) return PIPE_NOT_8BIT;
     return STEREO_OK;
 }
 
@@ -769,6 +823,7 @@ void stereo_ctx_destroy(stereo_ctx* ctx) {
     ctx->arena.release();
     ctx->io.release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx->pool;
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -849,6 +904,18 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
 }
 
 int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx) { return ctx ? ctx->fused_pairs_done : 0; }
+
+int stereo_ctx_set_host_threads(stereo_ctx* ctx, int threads) {
+    if (!ctx || threads < -1 || threads > 256) { set_error("bad host_threads argument"); return STEREO_ERR_INVALID_ARG; }
+    ctx->host_threads = threads;
+    ctx->host_pack_forced = threads > 0;
+    return STEREO_OK;
+}
+
+int stereo_ctx_host_threads(const stereo_ctx* ctx) {
+    if (!ctx) return 0;
+    return ctx->host_threads == 0 ? default_host_threads() : ctx->host_threads;
+}
 
 int stereo_ctx_set_fuse_pairs(stereo_ctx* ctx, int on) {
     if (!ctx) { set_error("null context"); return STEREO_ERR_INVALID_ARG; }

@@ -187,10 +187,22 @@ class PeerGather:
         if st != _capi.STEREO_OK:
             raise RuntimeError(_capi.last_error())
 
-    def push(self, offset: int, src_ptr: int, nbytes: int, stream: int) -> None:
+    def push(self, offset: int, src_ptr: int, nbytes: int, stream: int, to=None) -> None:
+        """`to`: ranks whose buffers receive the bytes (default: every rank's - a gather to all; ``to=[0]`` gathers to rank 0)."""
         if offset < 0 or offset + nbytes > self.nbytes:
             raise ValueError("push outside the gather buffer")
-        self._check(_capi.lib().stereo_peer_push(self.ctx.handle, self.ptrs, self.world, int(offset), C.c_void_p(int(src_ptr)),
+        ptrs = self.ptrs
+        if to is not None:
+            key = tuple(sorted(set(int(r) for r in to)))
+            ptrs = self._subsets.get(key) if hasattr(self, "_subsets") else None
+            if ptrs is None:
+                if not hasattr(self, "_subsets"):
+                    self._subsets = {}
+                ptrs = (C.c_void_p * self.world)()
+                for r in key:
+                    ptrs[r] = self.ptrs[r]
+                self._subsets[key] = ptrs          # (entries left null are skipped by stereo_peer_push)
+        self._check(_capi.lib().stereo_peer_push(self.ctx.handle, ptrs, self.world, int(offset), C.c_void_p(int(src_ptr)),
                                                  int(nbytes), C.c_void_p(int(stream) or CUDA_STREAM_LEGACY)))
 
     def mark(self) -> int:

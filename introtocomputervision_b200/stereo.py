@@ -117,6 +117,14 @@ class Context:
         """Pair calls: both maps from one cost volume where possible (default on; results identical either way)."""
         _check(_capi.lib().stereo_ctx_set_fuse_pairs(self._h, int(bool(on))), "stereo_ctx_set_fuse_pairs")
 
+    def set_host_threads(self, threads: int) -> None:
+        """Host threads that convert CV_32FC1 host images to u8 before the upload (0 = automatic, -1 = off)."""
+        _check(_capi.lib().stereo_ctx_set_host_threads(self._h, int(threads)), "stereo_ctx_set_host_threads")
+
+    @property
+    def host_threads(self) -> int:
+        return int(_capi.lib().stereo_ctx_host_threads(self._h))
+
     def synchronize(self, stream: int = 0) -> None:
         _check(_capi.lib().stereo_ctx_synchronize(self._h, C.c_void_p(stream)), "stereo_ctx_synchronize")
 

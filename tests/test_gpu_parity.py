@@ -484,7 +484,7 @@ def test_pipelined_host_non_8bit_is_redone_on_float_kernels(ctx):
         assert np.array_equal(dl, oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, 3, -29, 0)))
         assert np.array_equal(dr, oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, 3, 0, 29)))
         Li = L.astype(np.float32)
-        Li[-1, -1] += 0.5
+        Li[-1, -2] += 0.5                                       # (not one of the pixels the host samples before the pipeline)
         d = ctx.disparity(sb.COST_SSD, Li, Rt.astype(np.float32), 3, -29, 0, dtype=np.int16)
         assert ctx.last_path == sb.PATH_FAST_F32
         assert np.array_equal(d, oracle.ssd_fast(Li, Rt.astype(np.float32), 3, -29, 0))
@@ -888,3 +888,40 @@ def test_ps2_problem_shapes_full_size_noisy_and_contrast(ctx):
             d, s = ctx.disparity(sb.COST_NCORR, ref, tgt, 7, lo, hi, dtype=np.int16, return_best=True)
             assert ctx.last_path == sb.PATH_FAST_F32, name
             assert_ncc_close(d, s, d_ref, s_ref)
+
+
+# ---- host-side packing of CV_32FC1 images (stereo_ctx_set_host_threads) ---------------------------------------------------
+
+@pytest.mark.parametrize("threads", [-1, 1, 3, 16])
+def test_host_packing_gives_the_same_maps(ctx, threads):
+    """CV_32FC1 host images converted to u8 by host threads (1 byte per pixel over the link) or uploaded as floats and
+    converted on the device: identical maps, single pairs in bands and batches; a pixel that is not 8-bit anywhere in the
+    image hands the call to the float kernels."""
+    L, Rt, _ = synth.make_pair(150, 520, 64, 4242)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    ref_l, ref_r = oracle.ssd_fast(Lf, Rf, 5, -127, 0), oracle.ssd_fast(Rf, Lf, 5, 0, 127)
+    n = 7
+    Ls, Rs = zip(*[synth.make_pair(33, 330, 64, 7000 + i)[:2] for i in range(n)])
+    Ls, Rs = np.stack(Ls).astype(np.float32), np.stack(Rs).astype(np.float32)
+    try:
+        ctx.set_host_threads(threads)
+        assert ctx.host_threads == threads
+        for bands in (1, 3):
+            ctx.set_pipe_bands(bands)
+            dl, dr = ctx.disparity_pair(sb.COST_SSD, Lf, Rf, 5, 127, dtype=np.int16)
+            assert ctx.last_path == sb.PATH_FAST_U8
+            assert np.array_equal(dl, ref_l) and np.array_equal(dr, ref_r), (threads, bands)
+        ctx.set_pipe_bands(0)
+        bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, 4, 63, dtype=np.int8)
+        for i in range(n):
+            assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(Ls[i], Rs[i], 4, -63, 0))), (threads, i)
+            assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rs[i], Ls[i], 4, 0, 63))), (threads, i)
+        Lbad = Lf.copy()
+        Lbad[77, 301] += 0.5                                    # found by the host threads (or the device flag) mid-pipeline
+        ctx.set_pipe_bands(3)
+        dl, dr = ctx.disparity_pair(sb.COST_SSD, Lbad, Rf, 5, 127, dtype=np.int16)
+        assert ctx.last_path == sb.PATH_FAST_F32
+        assert np.array_equal(dl, oracle.ssd_fast(Lbad, Rf, 5, -127, 0)) and np.array_equal(dr, oracle.ssd_fast(Rf, Lbad, 5, 0, 127))
+    finally:
+        ctx.set_pipe_bands(0)
+        ctx.set_host_threads(0)
