@@ -13,8 +13,12 @@
 //
 // Differences, all deliberate: `use_gpu_disparity: false` is an error (this build has no CPU path — the
 // reference's serial:: functions are the *oracle* here, not product code); optional keys `device`
-// (GPU ordinal, default 0), `noise_seed` (cv::RNG state, default OpenCV's 0xffffffff) and
-// `opencv_gray_shift` (14 = the RGB2GRAY coefficients of OpenCV 3.4.1, the default; 15 = OpenCV >= 3.4.2).
+// (GPU ordinal, default 0), `noise_seed` (cv::RNG state, default OpenCV's 0xffffffff),
+// `opencv_gray_shift` (14 = the RGB2GRAY coefficients of OpenCV 3.4.1, the default; 15 = OpenCV >= 3.4.2) and
+// `gpus` (default 1 = the reference's behaviour; N > 1: every pair's output rows are sharded over the first N B200s in
+// row bands with halo, stereo_mgpu_*, same maps).
+// Both maps of a pair come from ONE library call (one upload of the pair; SSD pairs from one cost volume), so each of the
+// two "... execution took" lines the reference prints per pair reports half of that call's device time.
 #include "imgproc.hpp"
 #include "yaml_subset.hpp"
 
@@ -24,6 +28,7 @@
 #include <cstdarg>
 #include <ctime>
 #include <functional>
+#include <memory>
 
 namespace {
 
@@ -55,6 +60,7 @@ struct Config {
     DisparityParams p[6];
     uint64_t noise_seed = 0xffffffffu;
     int device = 0;
+    int gpus = 1;                                            // > 1: row-band sharding over the first `gpus` devices
     int gray_shift = 14;                                     // OpenCV 3.4.1's RGB2GRAY coefficients (15: OpenCV >= 3.4.2)
 };
 
@@ -94,23 +100,33 @@ Config load_config(const std::string& path) {
     }
     if (y.has("noise_seed")) cfg.noise_seed = uint64_t(y.integer("noise_seed"));
     if (y.has("device")) cfg.device = int(y.integer("device"));
+    if (y.has("gpus")) cfg.gpus = int(y.integer("gpus"));
     if (y.has("opencv_gray_shift")) cfg.gray_shift = int(y.integer("opencv_gray_shift")) == 15 ? 15 : 14;
     return cfg;
 }
 
 // disparitySSDPair / disparityNCorrPair (main.cpp:21-78): left-referenced over [-range, 0], then
 // right-referenced (images swapped) over [0, +range].
-using CostFn = void (*)(const sb::Mat&, const sb::Mat&, size_t, int, int, sb::Mat&);
-void disparity_pair(CostFn fn, const char* kernel_name, const sb::Mat& left, const sb::Mat& right, const DisparityParams& p,
+sb::MultiGpu* g_mgpu = nullptr;
+void disparity_pair(int cost, const char* kernel_name, const sb::Mat& left, const sb::Mat& right, const DisparityParams& p,
                     sb::Mat& left_disp, sb::Mat& right_disp) {
-    for (int dir = 0; dir < 2; ++dir) {
-        file_info("Setting up CUDA kernel execution...");                                  // DisparitySSD.cu:157-158,191,203
-        file_info("Original image: rows=%d cols=%d", left.rows, left.cols);
-        file_info("Launching %s", kernel_name);
-        if (dir == 0) fn(left, right, p.window_radius, -p.disparity_range, 0, left_disp);
-        else fn(right, left, p.window_radius, 0, p.disparity_range, right_disp);
-        file_info("%s execution took %g ms", kernel_name, double(sb::lastKernelMs()));
+    file_info("Setting up CUDA kernel execution...");                                  // DisparitySSD.cu:157-158,191,203
+    file_info("Original image: rows=%d cols=%d", left.rows, left.cols);
+    file_info("Launching %s", kernel_name);
+    double ms;
+    if (g_mgpu) {
+        g_mgpu->disparityPairBands(cost, left, right, p.window_radius, p.disparity_range, left_disp, right_disp);
+        ms = 0;
+        for (int k = 0; k < g_mgpu->deviceCount(); ++k) { const double t = stereo_ctx_last_kernel_ms(stereo_mgpu_ctx(g_mgpu->handle(), k)); if (t > ms) ms = t; }
+    } else {
+        sb::run_pair(cost, left, right, p.window_radius, p.disparity_range, left_disp, right_disp, sb::S8C1, nullptr);
+        ms = double(sb::lastKernelMs());
     }
+    file_info("%s execution took %g ms", kernel_name, ms / 2);
+    file_info("Setting up CUDA kernel execution...");
+    file_info("Original image: rows=%d cols=%d", left.rows, left.cols);
+    file_info("Launching %s", kernel_name);
+    file_info("%s execution took %g ms", kernel_name, ms / 2);
 }
 
 void write_maps(const Config& cfg, const std::string& stem, sb::Mat& left_disp, sb::Mat& right_disp, bool with_inverted) {
@@ -124,7 +140,7 @@ void write_maps(const Config& cfg, const std::string& stem, sb::Mat& left_disp, 
 struct Variant { char part; enum Kind { Clean, Noisy, Contrast } kind; };
 
 // One problem = one image pair, one cost, and a list of input variants (main.cpp:80-327).
-void run_problem(const Config& cfg, ps2::CvRng& rng, int number, const char* pair, bool gray_from_colour, CostFn fn, const char* kernel_name,
+void run_problem(const Config& cfg, ps2::CvRng& rng, int number, const char* pair, bool gray_from_colour, int fn, const char* kernel_name,
                  std::initializer_list<Variant> variants, bool with_inverted) {
     info("Problem %d begins", number);
     const auto start = std::chrono::high_resolution_clock::now();
@@ -161,18 +177,28 @@ int main(int argc, char** argv) {
             return -1;
         }
         if (cfg.device != 0) setenv("STEREO_B200_DEVICE", std::to_string(cfg.device).c_str(), 1);
-        sb::default_ctx();                                       // context creation = common::warmup() (main.cpp:346-349)
+        std::unique_ptr<sb::MultiGpu> mgpu;
+        if (cfg.gpus > 1) {
+            std::vector<int> devs;
+            for (int k = 0; k < cfg.gpus; ++k) devs.push_back(cfg.device + k);
+            mgpu.reset(new sb::MultiGpu(devs));
+            g_mgpu = mgpu.get();
+            info("Sharding every pair over %d GPUs in row bands", mgpu->deviceCount());
+        } else {
+            sb::default_ctx();                                   // context creation = common::warmup() (main.cpp:346-349)
+        }
         file_info("GPU warmup done");
         ps2::CvRng rng(cfg.noise_seed);
         const auto start = std::chrono::high_resolution_clock::now();
         using V = Variant;
-        run_problem(cfg, rng, 1, "pair0", false, cuda::disparitySSD, "disparitySSDKernel", {{'a', V::Clean}}, false);
-        run_problem(cfg, rng, 2, "pair1", true, cuda::disparitySSD, "disparitySSDKernel", {{'a', V::Clean}}, true);
-        run_problem(cfg, rng, 3, "pair1", true, cuda::disparitySSD, "disparitySSDKernel", {{'a', V::Noisy}, {'b', V::Contrast}}, true);
-        run_problem(cfg, rng, 4, "pair1", true, cuda::disparityNCorr, "disparityNCorrKernel", {{'a', V::Clean}, {'b', V::Noisy}, {'c', V::Contrast}}, true);
-        run_problem(cfg, rng, 5, "pair2", true, cuda::disparityNCorr, "disparityNCorrKernel", {{'a', V::Clean}}, true);
+        run_problem(cfg, rng, 1, "pair0", false, STEREO_COST_SSD, "disparitySSDKernel", {{'a', V::Clean}}, false);
+        run_problem(cfg, rng, 2, "pair1", true, STEREO_COST_SSD, "disparitySSDKernel", {{'a', V::Clean}}, true);
+        run_problem(cfg, rng, 3, "pair1", true, STEREO_COST_SSD, "disparitySSDKernel", {{'a', V::Noisy}, {'b', V::Contrast}}, true);
+        run_problem(cfg, rng, 4, "pair1", true, STEREO_COST_NCORR, "disparityNCorrKernel", {{'a', V::Clean}, {'b', V::Noisy}, {'c', V::Contrast}}, true);
+        run_problem(cfg, rng, 5, "pair2", true, STEREO_COST_NCORR, "disparityNCorrKernel", {{'a', V::Clean}}, true);
         const std::chrono::duration<double, std::milli> runtime = std::chrono::high_resolution_clock::now() - start;
         info("Total runtime: %g ms", runtime.count());
+        g_mgpu = nullptr;
     } catch (const std::exception& e) {
         error("%s", e.what());
         error("Configuration load failed!");

@@ -397,7 +397,8 @@ def run_ours(args, wl):
             dist.all_gather_into_tensor(all_sums, mine_sum)
             if G.holds_all():
                 sums = G.pg.local_bytes(dev)[par * world * map_bytes:(par + 1) * world * map_bytes].view(world, -1).to(torch.int64).sum(dim=1)
-                assert torch.equal(sums, all_sums), "peer gather: a rank's slot does not match that rank's maps"
+                assert torch.equal(sums, all_sums), f"peer gather ({G.kind}): slots {sums.tolist()} != ranks' maps {all_sums.tolist()} (parity {par})"
+            barrier()             # nobody pushes the next step into a slot the consumer is still checking
         return float(t.item()), n_launch
 
     G = Gather(args.gather if world > 1 else "none")
@@ -527,7 +528,7 @@ def run_ours(args, wl):
     step_device(G, 2 * S)               # even step number: parity 0, input set 0 (the un-rolled images)
     if pg is not None:
         join_pushes()
-    torch.cuda.synchronize()
+    barrier()                            # every rank's pushes of that step have landed in the consumer's buffer
     assert torch.equal(d_out[0, 0].cpu(), h_dl) and torch.equal(d_out[0, 1].cpu(), h_dr), "host and device entry points disagree"
 
     # parity check outside every timed region (rank 0): a 64-row band of the step's maps - and, in multi-GPU runs, of a

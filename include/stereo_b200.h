@@ -293,6 +293,56 @@ int stereo_peer_push(stereo_ctx* ctx, void* const* dst_ptrs, int n_dst, size_t d
 int stereo_peer_mark(stereo_ctx* ctx, int* ticket_out);
 int stereo_peer_wait(stereo_ctx* ctx, int ticket, void* cuda_stream);
 
+/* ---- one row band of a pair, HOST images (a device's share of a row-band sharded pair) -------------- */
+/* left / right: FULL-image host origins (cv::Mat data pointers); only the slab of rows the band [row_begin, row_end) needs -
+ * window halo plus the row of the SSD flat-index wrap, stereo_band_halo_rows - is uploaded.  disp_left / disp_right point
+ * at the band's first output row.  Synchronous.  The f32 form converts the slab to u8 on the host; images that are not
+ * 8-bit-valued return STEREO_ERR_UNSUPPORTED (callers take a whole-image call then). */
+int stereo_disparity_pair_band_u8_host(stereo_ctx* ctx, int cost,
+                                       const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step,
+                                       int rows, int cols, int row_begin, int row_end, int window_rad, int disparity_range,
+                                       void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+int stereo_disparity_pair_band_f32_host(stereo_ctx* ctx, int cost,
+                                        const float* left, size_t left_step, const float* right, size_t right_step,
+                                        int rows, int cols, int row_begin, int row_end, int window_rad, int disparity_range,
+                                        void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+
+/* ---- several GPUs in ONE process (SURVEY.md §8b "context create/destroy taking a device list", §8e) ---------- */
+/*
+ * The reference is single-GPU (lib/DisparitySSD.cu:143-207).  A stereo_mgpu owns one stereo_ctx per listed device
+ * (devices = NULL: every visible sm_100 device) and one host thread per device during a call.  The path has no exchange
+ * inside the computation: batches are sharded by pair (contiguous blocks), one pair by row bands with halo; every device
+ * uploads only its share and downloads its maps straight into the caller's host arrays - results are bit-identical to the
+ * single-GPU calls.  A device ordinal may be listed more than once (several contexts on one GPU).
+ */
+typedef struct stereo_mgpu stereo_mgpu;
+int stereo_mgpu_create(const int* devices, int n_devices, stereo_mgpu** out);
+void stereo_mgpu_destroy(stereo_mgpu* mg);
+int stereo_mgpu_device_count(const stereo_mgpu* mg);
+/* The context of the index-th listed device (for stereo_ctx_set_* knobs); owned by the stereo_mgpu. */
+stereo_ctx* stereo_mgpu_ctx(stereo_mgpu* mg, int index);
+/* Batches (BASELINE config 5): same arguments as stereo_disparity_pair_batch_{u8,f32}_host. */
+int stereo_mgpu_disparity_pair_batch_u8_host(stereo_mgpu* mg, int cost, int n_pairs,
+                                             const uint8_t* left, const uint8_t* right, size_t img_step, size_t pair_stride,
+                                             int rows, int cols, int window_rad, int disparity_range,
+                                             void* disp_left, void* disp_right, size_t disp_step, size_t disp_pair_stride,
+                                             int disp_elem_bytes);
+int stereo_mgpu_disparity_pair_batch_f32_host(stereo_mgpu* mg, int cost, int n_pairs,
+                                              const float* left, const float* right, size_t img_step, size_t pair_stride,
+                                              int rows, int cols, int window_rad, int disparity_range,
+                                              void* disp_left, void* disp_right, size_t disp_step, size_t disp_pair_stride,
+                                              int disp_elem_bytes);
+/* One pair in row bands (BASELINE config 4): same arguments as stereo_disparity_pair_{u8,f32}_host.  Float images that are
+ * not 8-bit-valued are computed whole on the first device. */
+int stereo_mgpu_disparity_pair_bands_u8_host(stereo_mgpu* mg, int cost,
+                                             const uint8_t* left, size_t left_step, const uint8_t* right, size_t right_step,
+                                             int rows, int cols, int window_rad, int disparity_range,
+                                             void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+int stereo_mgpu_disparity_pair_bands_f32_host(stereo_mgpu* mg, int cost,
+                                              const float* left, size_t left_step, const float* right, size_t right_step,
+                                              int rows, int cols, int window_rad, int disparity_range,
+                                              void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes);
+
 /* Blocks until everything enqueued on `cuda_stream` (NULL = the context's stream) has finished and
  * returns any asynchronous error. */
 int stereo_ctx_synchronize(stereo_ctx* ctx, void* cuda_stream);

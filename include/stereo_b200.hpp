@@ -192,4 +192,60 @@ inline void disparityNCorr(const sb::MatT& left, const sb::MatT& right, const si
 }
 } // namespace cuda
 
+// The reference's CPU twins (DisparitySSD.h:38-43, DisparityNCorr.h:39-44; selected by `use_gpu_disparity: false`,
+// main.cpp:31-37).  Their results are this library's parity target, so the same GPU path serves both names.
+namespace serial {
+inline void disparitySSD(const sb::MatT& left, const sb::MatT& right, const size_t windowRad, const int minDisparity,
+                         const int maxDisparity, sb::MatT& disparity) {
+    cuda::disparitySSD(left, right, windowRad, minDisparity, maxDisparity, disparity);
+}
+inline void disparityNCorr(const sb::MatT& left, const sb::MatT& right, const size_t windowRad, const int minDisparity,
+                           const int maxDisparity, sb::MatT& disparity) {
+    cuda::disparityNCorr(left, right, windowRad, minDisparity, maxDisparity, disparity);
+}
+} // namespace serial
+
+namespace sb {
+
+// Several B200s in one process (stereo_mgpu_*): one pair in row bands with halo, batches by pair.
+class MultiGpu {
+public:
+    explicit MultiGpu(const std::vector<int>& devices = {}) {
+        check(stereo_mgpu_create(devices.empty() ? nullptr : devices.data(), int(devices.size()), &mg_), "stereo_mgpu_create");
+    }
+    ~MultiGpu() { stereo_mgpu_destroy(mg_); }
+    MultiGpu(const MultiGpu&) = delete;
+    MultiGpu& operator=(const MultiGpu&) = delete;
+    int deviceCount() const { return stereo_mgpu_device_count(mg_); }
+    stereo_mgpu* handle() { return mg_; }
+
+    // disparitySSDPair / disparityNCorrPair (main.cpp:21-78) with the output rows sharded over the devices
+    void disparityPairBands(int cost, const MatT& left, const MatT& right, size_t windowRad, int disparityRange, MatT& disparityLeft,
+                            MatT& disparityRight, bool wide = false) {
+        if (left.rows != right.rows || left.cols != right.cols || left.type() != right.type())
+            check(STEREO_ERR_INVALID_ARG, "disparity pair: left/right differ in size or type (main.cpp:27-28)");
+        const int out_type = wide ? S16C1 : S8C1, elem = wide ? 2 : 1;
+        disparityLeft.create(left.rows, left.cols, out_type);
+        disparityRight.create(left.rows, left.cols, out_type);
+        int st;
+        if (left.type() == F32C1)
+            st = stereo_mgpu_disparity_pair_bands_f32_host(mg_, cost, reinterpret_cast<const float*>(left.data), left.step,
+                                                           reinterpret_cast<const float*>(right.data), right.step, left.rows, left.cols,
+                                                           int(windowRad), disparityRange, disparityLeft.data, disparityRight.data,
+                                                           disparityLeft.step, elem);
+        else if (left.type() == U8C1)
+            st = stereo_mgpu_disparity_pair_bands_u8_host(mg_, cost, left.data, left.step, right.data, right.step, left.rows, left.cols,
+                                                          int(windowRad), disparityRange, disparityLeft.data, disparityRight.data,
+                                                          disparityLeft.step, elem);
+        else
+            st = STEREO_ERR_INVALID_ARG;
+        check(st, "MultiGpu::disparityPairBands");
+    }
+
+private:
+    stereo_mgpu* mg_ = nullptr;
+};
+
+} // namespace sb
+
 #endif // STEREO_B200_HPP_

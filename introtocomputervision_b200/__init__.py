@@ -6,11 +6,11 @@ The compute lives in ``libstereo_b200.so`` (hand-written CUDA behind the C ABI d
 """
 from ._capi import (COST_NCORR, COST_SSD, PATH_EXACT_F32, PATH_FAST_F32, PATH_FAST_U8, PATH_NONE,  # noqa: F401
                     StereoLibraryMissing)
-from .stereo import (Context, DisparityConfig, StereoError, default_context, disparityNCorr,  # noqa: F401
+from .stereo import (Context, DisparityConfig, MultiGpu, StereoError, default_context, disparityNCorr,  # noqa: F401
                      disparityNCorrPair, disparitySSD, disparitySSDPair)
 
 __all__ = [
-    "COST_SSD", "COST_NCORR", "PATH_NONE", "PATH_EXACT_F32", "PATH_FAST_U8", "PATH_FAST_F32", "Context", "DisparityConfig",
+    "COST_SSD", "COST_NCORR", "PATH_NONE", "PATH_EXACT_F32", "PATH_FAST_U8", "PATH_FAST_F32", "Context", "MultiGpu", "DisparityConfig",
     "StereoError", "StereoLibraryMissing", "default_context", "disparitySSD", "disparityNCorr",
     "disparitySSDPair", "disparityNCorrPair",
 ]

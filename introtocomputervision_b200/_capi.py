@@ -65,6 +65,16 @@ SIGNATURES = {
     "stereo_peer_push": (_i, [_vp, C.POINTER(_vp), _i, _sz, _vp, _sz, _vp]),
     "stereo_peer_mark": (_i, [_vp, C.POINTER(_i)]),
     "stereo_peer_wait": (_i, [_vp, _i, _vp]),
+    "stereo_disparity_pair_band_u8_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i]),
+    "stereo_disparity_pair_band_f32_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i]),
+    "stereo_mgpu_create": (_i, [C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "stereo_mgpu_destroy": (None, [_vp]),
+    "stereo_mgpu_device_count": (_i, [_vp]),
+    "stereo_mgpu_ctx": (_vp, [_vp, _i]),
+    "stereo_mgpu_disparity_pair_batch_u8_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
+    "stereo_mgpu_disparity_pair_batch_f32_host": (_i, [_vp, _i, _i, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _vp, _vp, _sz, _sz, _i]),
+    "stereo_mgpu_disparity_pair_bands_u8_host": (_i, _PAIR_HOST),
+    "stereo_mgpu_disparity_pair_bands_f32_host": (_i, _PAIR_HOST),
     "stereo_disparity_band_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
 }
 

@@ -38,7 +38,8 @@ def _nvcc() -> str:
 
 def units():
     """(object name, source, extra flags) of every translation unit."""
-    u = [("stereo_b200.o", CSRC / "stereo_b200.cu", []), ("host_pack.o", CSRC / "host_pack.cpp", [])]
+    u = [("stereo_b200.o", CSRC / "stereo_b200.cu", []), ("host_pack.o", CSRC / "host_pack.cpp", []),
+         ("mgpu.o", CSRC / "mgpu.cpp", [])]
     u += [(f"fast_inst_{i}.o", CSRC / "fast_inst.cu", [f"-DSB_PART={i}"]) for i in range(FAST_PARTS)]
     return u
 
@@ -54,6 +55,8 @@ def _deps(src: Path):
         return [src, CSRC / "fast_kernel.cuh", CSRC / "common.cuh", *api]
     if src.name == "host_pack.cpp":
         return [src, CSRC / "host_pack.hpp"]
+    if src.name == "mgpu.cpp":
+        return [src, *api]
     return [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *CSRC.glob("*.hpp"), *api]
 
 
@@ -82,7 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     only = os.environ.get("STEREO_BUILD_PARTS", "")
     borrowed = set()
     if TAG and only:
-        keep = {f"fast_inst_{int(i)}.o" for i in only.split(",")} | {"stereo_b200.o", "host_pack.o"}
+        keep = {f"fast_inst_{int(i)}.o" for i in only.split(",")} | {"stereo_b200.o", "host_pack.o", "mgpu.o"}
         for name, _, _ in units():
             if name not in keep:
                 src_obj = CSRC / "_build" / name

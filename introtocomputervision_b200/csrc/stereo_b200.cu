@@ -1247,6 +1247,89 @@ int stereo_disparity_pair_band_halo_u8_device(stereo_ctx* ctx, int cost, const u
     return rc;
 }
 
+// ---- one row band of a pair from HOST images (a device's share of a row-band sharded pair) ------------------------------
+// Uploads only the slab of rows the band needs (window halo + the row of the SSD flat-index wrap), computes both maps of
+// the band in one launch sequence and downloads them into the caller's band rows.  CV_32FC1 images are converted to u8 on
+// the host while the slab is staged; an image that is not 8-bit-valued makes the call return STEREO_ERR_UNSUPPORTED (the
+// band entry points are 8-bit only; callers then take a whole-image call).
+static int pair_band_host(stereo_ctx* ctx, int cost, PixType type, const void* left, size_t left_step, const void* right,
+                          size_t right_step, int rows, int cols, int row_begin, int row_end, int R, int range,
+                          void* disp_left, void* disp_right, size_t disp_step, int elem) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!left || !right || !disp_left || !disp_right) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768) { set_error("bad image size %d x %d", rows, cols); return STEREO_ERR_INVALID_ARG; }
+    if (row_begin < 0 || row_end > rows || row_begin >= row_end) { set_error("bad row band [%d, %d)", row_begin, row_end); return STEREO_ERR_INVALID_ARG; }
+    if (elem != 1 && elem != 2 && elem != 4) { set_error("disp_elem_bytes must be 1, 2 or 4"); return STEREO_ERR_INVALID_ARG; }
+    const size_t px = type == PixType::F32 ? 4 : 1;
+    if (left_step < cols * px || right_step < cols * px || disp_step < size_t(cols) * elem) { set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG; }
+    if (R < 0 || range < 0) { set_error("window_rad and disparity_range must be >= 0"); return STEREO_ERR_INVALID_ARG; }
+    int h0 = 0, h1 = 0;
+    rc = stereo_band_halo_rows(rows, row_begin, row_end, R, &h0, &h1);
+    if (rc != STEREO_OK) return rc;
+    const int nh = h1 - h0, nb = row_end - row_begin;
+    cudaStream_t st = ctx->stream;
+    const size_t u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
+    const size_t need = 2 * u8_pitch * nh + 2 * d_pitch * nb + 1024;
+    if (need > ctx->io.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        rc = ctx->io.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->io.reset();
+    uint8_t* d_l = static_cast<uint8_t*>(ctx->io.take(u8_pitch * nh));
+    uint8_t* d_r = static_cast<uint8_t*>(ctx->io.take(u8_pitch * nh));
+    char* d_dl = static_cast<char*>(ctx->io.take(d_pitch * nb));
+    char* d_dr = static_cast<char*>(ctx->io.take(d_pitch * nb));
+    if (!d_l || !d_r || !d_dl || !d_dr) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
+    const char* hl = static_cast<const char*>(left) + size_t(h0) * left_step;
+    const char* hr = static_cast<const char*>(right) + size_t(h0) * right_step;
+    if (type == PixType::F32) {
+        const size_t stg_pitch = (size_t(cols) + 63) & ~size_t(63);
+        SB_CUDA(cudaStreamSynchronize(st));                     // (the staging may still feed an earlier upload)
+        rc = ensure_pinned(ctx, 2 * stg_pitch * nh);
+        if (rc != STEREO_OK) return rc;
+        if (ctx->host_threads == 0) ctx->host_threads = default_host_threads();
+        const int nt = ctx->host_threads > 0 ? ctx->host_threads : 1;
+        if (!ctx->pool || ctx->pool->threads() != nt) { delete ctx->pool; ctx->pool = new (std::nothrow) HostPool(nt); }
+        if (!ctx->pool) { set_error("out of host memory"); return STEREO_ERR_ALLOC; }
+        uint8_t* sl = static_cast<uint8_t*>(ctx->pinned);
+        uint8_t* sr = sl + stg_pitch * nh;
+        const bool ok = pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(hl), left_step, sl, stg_pitch, nh, cols) &&
+                        pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(hr), right_step, sr, stg_pitch, nh, cols);
+        if (!ok) { set_error("row-band entry points take 8-bit-valued images only"); return STEREO_ERR_UNSUPPORTED; }
+        SB_CUDA(cudaMemcpy2DAsync(d_l, u8_pitch, sl, stg_pitch, cols, nh, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpy2DAsync(d_r, u8_pitch, sr, stg_pitch, cols, nh, cudaMemcpyHostToDevice, st));
+    } else {
+        SB_CUDA(cudaMemcpy2DAsync(d_l, u8_pitch, hl, left_step, cols, nh, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpy2DAsync(d_r, u8_pitch, hr, right_step, cols, nh, cudaMemcpyHostToDevice, st));
+    }
+    rc = stereo_disparity_pair_band_halo_u8_device(ctx, cost, d_l, u8_pitch, d_r, u8_pitch, rows, cols, row_begin, row_end, h0, h1, R, range,
+                                                   d_dl, d_dr, d_pitch, elem, st);
+    if (rc == STEREO_OK) {
+        cudaError_t e = cudaMemcpy2DAsync(disp_left, disp_step, d_dl, d_pitch, size_t(cols) * elem, nb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(disp_right, disp_step, d_dr, d_pitch, size_t(cols) * elem, nb, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { set_error("download failed: %s", cudaGetErrorString(e)); rc = STEREO_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);                  // also on errors: nothing may still touch the caller's buffers
+    if (rc == STEREO_OK && e != cudaSuccess) { set_error("band call failed: %s", cudaGetErrorString(e)); rc = STEREO_ERR_CUDA; }
+    return rc;
+}
+
+int stereo_disparity_pair_band_u8_host(stereo_ctx* ctx, int cost, const uint8_t* left, size_t left_step, const uint8_t* right,
+                                       size_t right_step, int rows, int cols, int row_begin, int row_end, int window_rad,
+                                       int disparity_range, void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes) {
+    return pair_band_host(ctx, cost, PixType::U8, left, left_step, right, right_step, rows, cols, row_begin, row_end, window_rad,
+                          disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes);
+}
+
+int stereo_disparity_pair_band_f32_host(stereo_ctx* ctx, int cost, const float* left, size_t left_step, const float* right,
+                                        size_t right_step, int rows, int cols, int row_begin, int row_end, int window_rad,
+                                        int disparity_range, void* disp_left, void* disp_right, size_t disp_step, int disp_elem_bytes) {
+    return pair_band_host(ctx, cost, PixType::F32, left, left_step, right, right_step, rows, cols, row_begin, row_end, window_rad,
+                          disparity_range, disp_left, disp_right, disp_step, disp_elem_bytes);
+}
+
 int stereo_disparity_pair_batch_u8_device(stereo_ctx* ctx, int cost, int n_pairs, const uint8_t* left,
                                           const uint8_t* right, size_t img_step, size_t pair_stride, int rows,
                                           int cols, int window_rad, int disparity_range, void* disp_left,

@@ -202,6 +202,73 @@ def _prep_pair(a: np.ndarray, b: np.ndarray, f32_name: str, u8_name: str):
     return a, b, getattr(_capi.lib(), name)
 
 
+class MultiGpu:
+    """Several B200s in one process (``stereo_mgpu_*``): batches sharded by pair, one pair by row bands; host arrays in,
+    host arrays out.  ``devices=None``: every visible sm_100 device; an ordinal may repeat (several contexts on one GPU)."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            st = _capi.lib().stereo_mgpu_create(None, 0, C.byref(self._h))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            st = _capi.lib().stereo_mgpu_create(arr, len(devices), C.byref(self._h))
+        _check(st, "stereo_mgpu_create")
+
+    @property
+    def device_count(self) -> int:
+        return int(_capi.lib().stereo_mgpu_device_count(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            _capi.lib().stereo_mgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def disparity_pair_bands(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, disparity_range: int,
+                             dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
+        left, right, fn = _prep_pair(left, right, "stereo_mgpu_disparity_pair_bands_f32_host", "stereo_mgpu_disparity_pair_bands_u8_host")
+        rows, cols = left.shape
+        dt = np.dtype(dtype)
+        dl, dr = np.empty((rows, cols), dt), np.empty((rows, cols), dt)
+        st = fn(self._h, int(cost), left.ctypes.data, left.strides[0], right.ctypes.data, right.strides[0], rows, cols,
+                int(window_rad), int(disparity_range), dl.ctypes.data, dr.ctypes.data, dl.strides[0], _ELEM[dt])
+        _check(st, fn.__name__)
+        return dl, dr
+
+    def disparity_pair_batch(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, disparity_range: int,
+                             dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
+        left, right = np.asarray(left), np.asarray(right)
+        if left.dtype == np.float32 and right.dtype == np.float32:
+            kind, name = np.float32, "stereo_mgpu_disparity_pair_batch_f32_host"
+        elif left.dtype == np.uint8 and right.dtype == np.uint8:
+            kind, name = np.uint8, "stereo_mgpu_disparity_pair_batch_u8_host"
+        else:
+            raise TypeError("batch images must both be float32 (CV_32FC1) or both uint8")
+        left, right = np.ascontiguousarray(left, kind), np.ascontiguousarray(right, kind)
+        if left.ndim != 3 or left.shape != right.shape:
+            raise ValueError("batch inputs must be (n, rows, cols) arrays of equal shape")
+        n, rows, cols = left.shape
+        dt = np.dtype(dtype)
+        dl, dr = np.empty((n, rows, cols), dt), np.empty((n, rows, cols), dt)
+        st = getattr(_capi.lib(), name)(
+            self._h, int(cost), n, left.ctypes.data, right.ctypes.data, left.strides[1], left.strides[0], rows, cols,
+            int(window_rad), int(disparity_range), dl.ctypes.data, dr.ctypes.data, dl.strides[1], dl.strides[0], _ELEM[dt])
+        _check(st, name)
+        return dl, dr
+
+
 _default: Optional[Context] = None
 
 
