@@ -114,6 +114,27 @@ def ncorr_fast(ref, tgt, window_rad, min_disp, max_disp, return_score=False):
     return _run("oracle_disparity_ncorr_fast", ref, tgt, window_rad, min_disp, max_disp, return_score, np.float32)
 
 
+def refgpu(cost, ref, tgt, window_rad, min_disp, max_disp, return_best=False):
+    """What the reference's GPU kernels compute (DisparitySSD.cu:27-141 / DisparityNCorr.cu:28-175):
+    cost 0 = SSD, 1 = NCC; int32 disparities (-1 where nothing won) and, on request, the kernels' running-best map."""
+    lib = _load()
+    ref, tgt = _f32(ref), _f32(tgt)
+    if ref.shape != tgt.shape:
+        raise OracleError("shape mismatch")
+    rows, cols = ref.shape
+    disp = np.empty((rows, cols), np.int32)
+    best = np.empty((rows, cols), np.float32)
+    fn = lib.oracle_disparity_refgpu
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_float), C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                   C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    st = fn(int(cost), _fp(ref), cols, _fp(tgt), cols, rows, cols, int(window_rad), int(min_disp), int(max_disp),
+            disp.ctypes.data_as(C.POINTER(C.c_int32)), best.ctypes.data_as(C.POINTER(C.c_float)))
+    if st != 0:
+        raise OracleError(f"oracle_disparity_refgpu failed with status {st}")
+    return (disp, best) if return_best else disp
+
+
 def narrow_i8(disp):
     """The reference's ``disparity.at<char>(...) = int`` store (DisparitySSD.cpp:59)."""
     return (np.asarray(disp).astype(np.int64) & 0xFF).astype(np.uint8).view(np.int8)
