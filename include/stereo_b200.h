@@ -72,6 +72,7 @@ typedef enum stereo_path {
     STEREO_PATH_NONE = 0,
     STEREO_PATH_EXACT_F32 = 1,  /* any float input, window and range: per-element reference arithmetic, no running sums */
     STEREO_PATH_FAST_U8 = 2,    /* integer-valued 0..255 inputs: packed dot-product running sums */
+    STEREO_PATH_REFGPU = 4,     /* stereo_disparity_refgpu_*: the function the reference's GPU kernels compute */
     STEREO_PATH_FAST_F32 = 3    /* general float inputs of bounded range (noise / contrast variants, main.cpp:140-153,191-193):
                                    per-element round((l-r)^2) as exact int32 running sums (SSD), float32 running sums (NCC) */
 } stereo_path;
@@ -292,6 +293,25 @@ int stereo_peer_push(stereo_ctx* ctx, void* const* dst_ptrs, int n_dst, size_t d
                      void* after_stream);
 int stereo_peer_mark(stereo_ctx* ctx, int* ticket_out);
 int stereo_peer_wait(stereo_ctx* ctx, int ticket, void* cuda_stream);
+
+/* ---- reference-GPU-semantics mode ------------------------------------------------- */
+/*
+ * Everything above reproduces the reference's CPU functions (the parity target).  Its GTX-1080 kernels compute a
+ * different function: a (2R+1) x 2R window, clamp-to-edge addressing, every d in [min_disp, max_disp], float32 rolling
+ * column sums restarted every 40 rows, SSD accepted only below 5e6 and NCC only above 0, -1 where nothing won
+ * (lib/DisparitySSD.cu:16,27-141,177; lib/DisparityNCorr.cu:16,28-175,211).  These two entry points compute THAT function,
+ * every float operation in the kernels' order, so maps the reference's GPU build produced can be reproduced.
+ * disp_out: int8 (the kernels store `char`); best_out (nullable): the kernels' running best SSD / score map.
+ * The range must fit the kernels' `char` loop variable.  Checked bit for bit against oracle_disparity_refgpu. */
+int stereo_disparity_refgpu_f32_host(stereo_ctx* ctx, int cost,
+                                     const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                                     int rows, int cols, int window_rad, int min_disp, int max_disp,
+                                     int8_t* disp_out, size_t disp_step, float* best_out, size_t best_step);
+int stereo_disparity_refgpu_f32_device(stereo_ctx* ctx, int cost,
+                                       const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                                       int rows, int cols, int window_rad, int min_disp, int max_disp,
+                                       int8_t* disp_out, size_t disp_step, float* best_out, size_t best_step,
+                                       void* cuda_stream);
 
 /* ---- one row band of a pair, HOST images (a device's share of a row-band sharded pair) -------------- */
 /* left / right: FULL-image host origins (cv::Mat data pointers); only the slab of rows the band [row_begin, row_end) needs -

@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("STEREO_B200_LIB") or
 STEREO_OK = 0
 ERR_INVALID_ARG, ERR_INVALID_RANGE, ERR_NO_DEVICE, ERR_CUDA, ERR_ALLOC, ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 COST_SSD, COST_NCORR = 0, 1
-PATH_NONE, PATH_EXACT_F32, PATH_FAST_U8, PATH_FAST_F32 = 0, 1, 2, 3
+PATH_NONE, PATH_EXACT_F32, PATH_FAST_U8, PATH_FAST_F32, PATH_REFGPU = 0, 1, 2, 3, 4
 
 _vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
 
@@ -65,6 +65,8 @@ SIGNATURES = {
     "stereo_peer_push": (_i, [_vp, C.POINTER(_vp), _i, _sz, _vp, _sz, _vp]),
     "stereo_peer_mark": (_i, [_vp, C.POINTER(_i)]),
     "stereo_peer_wait": (_i, [_vp, _i, _vp]),
+    "stereo_disparity_refgpu_f32_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz]),
+    "stereo_disparity_refgpu_f32_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "stereo_disparity_pair_band_u8_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i]),
     "stereo_disparity_pair_band_f32_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i]),
     "stereo_mgpu_create": (_i, [C.POINTER(_i), _i, C.POINTER(_vp)]),

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "exact.cuh"
 #include "fast.cuh"
+#include "compat.cuh"
 #include "host_pack.hpp"
 
 #include <cstdarg>
@@ -1032,6 +1033,73 @@ int stereo_disparity_u8_host(stereo_ctx* ctx, int cost, const uint8_t* ref, size
                              void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out, size_t best_step) {
     return host_single(ctx, cost, PixType::U8, ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp,
                        max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step);
+}
+
+// ---- reference-GPU-semantics mode (compat.cuh) ------------------------------------------------------------------------------
+int stereo_disparity_refgpu_f32_device(stereo_ctx* ctx, int cost, const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                                       int rows, int cols, int window_rad, int min_disp, int max_disp, int8_t* disp_out,
+                                       size_t disp_step, float* best_out, size_t best_step, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!ref || !tgt || !disp_out) { set_error("null pointer"); return STEREO_ERR_INVALID_ARG; }
+    if (rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768) { set_error("bad image size %d x %d", rows, cols); return STEREO_ERR_INVALID_ARG; }
+    if (cost != STEREO_COST_SSD && cost != STEREO_COST_NCORR) { set_error("unknown cost %d", cost); return STEREO_ERR_INVALID_ARG; }
+    if (ref_step < size_t(cols) * 4 || tgt_step < size_t(cols) * 4 || disp_step < size_t(cols) || (best_out && best_step < size_t(cols) * 4)) {
+        set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG;
+    }
+    if (window_rad < 0 || window_rad > 64) { set_error("window_rad must be in [0, 64]"); return STEREO_ERR_INVALID_ARG; }
+    if (min_disp > max_disp) { set_error("min_disp (%d) > max_disp (%d)", min_disp, max_disp); return STEREO_ERR_INVALID_RANGE; }
+    // the reference's loop variable is a `char` (DisparitySSD.cu:41,56): ranges beyond int8 never terminate there
+    if (min_disp < -128 || max_disp > 126) { set_error("the reference's GPU kernels index disparities with a char: range must lie in [-128, 126]"); return STEREO_ERR_INVALID_RANGE; }
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    begin_call(ctx, st);
+    const dim3 grid(div_round_up(cols, CG_TILE), div_round_up(rows, CG_ROWS));
+    const int threads = CG_TILE + 2 * window_rad;
+    const size_t smem = size_t(3) * threads * sizeof(float);
+    if (cost == STEREO_COST_SSD)
+        refgpu_kernel<STEREO_COST_SSD><<<grid, threads, smem, st>>>(ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp, max_disp, disp_out, disp_step, best_out, best_step);
+    else
+        refgpu_kernel<STEREO_COST_NCORR><<<grid, threads, smem, st>>>(ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp, max_disp, disp_out, disp_step, best_out, best_step);
+    ctx->last_launches += 1;
+    ctx->last_path = STEREO_PATH_REFGPU;
+    end_call(ctx, st);
+    SB_CUDA(cudaGetLastError());
+    return STEREO_OK;
+}
+
+int stereo_disparity_refgpu_f32_host(stereo_ctx* ctx, int cost, const float* ref, size_t ref_step, const float* tgt, size_t tgt_step,
+                                     int rows, int cols, int window_rad, int min_disp, int max_disp, int8_t* disp_out,
+                                     size_t disp_step, float* best_out, size_t best_step) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!ref || !tgt || !disp_out || rows <= 0 || cols <= 0 || rows > 32768 || cols > 32768) { set_error("bad arguments"); return STEREO_ERR_INVALID_ARG; }
+    if (ref_step < size_t(cols) * 4 || tgt_step < size_t(cols) * 4) { set_error("a step is smaller than its row"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t st = ctx->stream;
+    const size_t in_pitch = align256(size_t(cols) * 4), d_pitch = align256(cols);
+    const size_t need = 3 * in_pitch * rows + d_pitch * rows + 1024;
+    if (need > ctx->io.cap) {
+        SB_CUDA(cudaStreamSynchronize(st));
+        rc = ctx->io.reserve(need);
+        if (rc != STEREO_OK) return rc;
+    }
+    ctx->io.reset();
+    char* d_ref = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_tgt = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_best = static_cast<char*>(ctx->io.take(in_pitch * rows));
+    char* d_disp = static_cast<char*>(ctx->io.take(d_pitch * rows));
+    SB_CUDA(cudaMemcpy2DAsync(d_ref, in_pitch, ref, ref_step, size_t(cols) * 4, rows, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpy2DAsync(d_tgt, in_pitch, tgt, tgt_step, size_t(cols) * 4, rows, cudaMemcpyHostToDevice, st));
+    rc = stereo_disparity_refgpu_f32_device(ctx, cost, reinterpret_cast<const float*>(d_ref), in_pitch, reinterpret_cast<const float*>(d_tgt), in_pitch,
+                                            rows, cols, window_rad, min_disp, max_disp, reinterpret_cast<int8_t*>(d_disp), d_pitch,
+                                            best_out ? reinterpret_cast<float*>(d_best) : nullptr, in_pitch, st);
+    if (rc == STEREO_OK) {
+        cudaError_t e = cudaMemcpy2DAsync(disp_out, disp_step, d_disp, d_pitch, cols, rows, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && best_out) e = cudaMemcpy2DAsync(best_out, best_step, d_best, in_pitch, size_t(cols) * 4, rows, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) { set_error("download failed: %s", cudaGetErrorString(e)); rc = STEREO_ERR_CUDA; }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == STEREO_OK && e != cudaSuccess) { set_error("compat call failed: %s", cudaGetErrorString(e)); rc = STEREO_ERR_CUDA; }
+    return rc;
 }
 
 int stereo_disparity_f32_device(stereo_ctx* ctx, int cost, const float* ref, size_t ref_step, const float* tgt,

@@ -142,6 +142,23 @@ class Context:
         _check(st, fn.__name__)
         return (disp, best) if return_best else disp
 
+    def disparity_refgpu(self, cost: int, ref: np.ndarray, tgt: np.ndarray, window_rad: int, min_disp: int, max_disp: int,
+                         return_best: bool = False):
+        """The function the reference's GPU kernels compute (``stereo_disparity_refgpu_f32_host``): int8 map,
+        -1 where no candidate passed the kernels' threshold."""
+        ref, tgt = np.ascontiguousarray(ref, np.float32), np.ascontiguousarray(tgt, np.float32)
+        if ref.ndim != 2 or ref.shape != tgt.shape:
+            raise ValueError("left/right must be 2-D arrays of equal shape")
+        rows, cols = ref.shape
+        disp = np.empty((rows, cols), np.int8)
+        best = np.empty((rows, cols), np.float32) if return_best else None
+        st = _capi.lib().stereo_disparity_refgpu_f32_host(
+            self._h, int(cost), ref.ctypes.data, ref.strides[0], tgt.ctypes.data, tgt.strides[0], rows, cols, int(window_rad),
+            int(min_disp), int(max_disp), disp.ctypes.data, disp.strides[0], best.ctypes.data if return_best else None,
+            best.strides[0] if return_best else 0)
+        _check(st, "stereo_disparity_refgpu_f32_host")
+        return (disp, best) if return_best else disp
+
     def disparity_pair(self, cost: int, left: np.ndarray, right: np.ndarray, window_rad: int, disparity_range: int,
                        dtype=np.int8) -> Tuple[np.ndarray, np.ndarray]:
         left, right, fn = _prep_pair(left, right, "stereo_disparity_pair_f32_host", "stereo_disparity_pair_u8_host")

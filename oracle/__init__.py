@@ -14,6 +14,7 @@ from .oracle import (  # noqa: F401
     ncorr_fast,
     ref_ncorr,
     ref_ssd,
+    refgpu,
     set_num_threads,
     num_threads,
     ssd,
