@@ -139,6 +139,37 @@ void write_maps(const Config& cfg, const std::string& stem, sb::Mat& left_disp, 
 
 struct Variant { char part; enum Kind { Clean, Noisy, Contrast } kind; };
 
+// ---- device images (stereo_dev_* / stereo_image_*): a pair is uploaded once, as 8-bit pixels, and its grey float images
+//      stay on the device for both directions and for every problem that uses the pair ------------------------------------
+struct DevImage {
+    void* p = nullptr; size_t step = 0; int rows = 0, cols = 0;
+    DevImage() = default;
+    DevImage(int r, int c, size_t elem) : rows(r), cols(c) {
+        step = (size_t(c) * elem + 255) & ~size_t(255);
+        sb::check(stereo_dev_alloc(sb::default_ctx(), step * r, &p), "stereo_dev_alloc");
+    }
+    DevImage(DevImage&& o) noexcept { *this = std::move(o); }
+    DevImage& operator=(DevImage&& o) noexcept { std::swap(p, o.p); step = o.step; rows = o.rows; cols = o.cols; return *this; }
+    DevImage(const DevImage&) = delete;
+    DevImage& operator=(const DevImage&) = delete;
+    ~DevImage() { if (p) stereo_dev_free(sb::default_ctx(), p); }
+    float* f32() const { return static_cast<float*>(p); }
+};
+std::map<std::string, DevImage> g_gray;             // image key -> CV_32FC1 grey image on the device
+
+const DevImage& device_gray(const Config& cfg, const std::string& key, bool gray_from_colour) {
+    auto it = g_gray.find(key);
+    if (it != g_gray.end()) return it->second;
+    const ps2::Image8& img = cfg.images.at(key);
+    if (!gray_from_colour && img.channels != 1) throw std::runtime_error("expected a single-channel image (the reference asserts CV_32FC1, main.cpp:27)");
+    stereo_ctx* ctx = sb::default_ctx();
+    DevImage raw(img.rows, img.cols * img.channels, 1), gray(img.rows, img.cols, 4);
+    sb::check(stereo_dev_upload(ctx, raw.p, raw.step, img.data.data(), size_t(img.cols) * img.channels, size_t(img.cols) * img.channels, img.rows), "stereo_dev_upload");
+    sb::check(stereo_image_gray_f32_device(ctx, static_cast<const uint8_t*>(raw.p), raw.step, img.rows, img.cols, img.channels, cfg.gray_shift,
+                                           gray.f32(), gray.step, nullptr), "stereo_image_gray_f32_device");
+    return g_gray.emplace(key, std::move(gray)).first->second;
+}
+
 // One problem = one image pair, one cost, and a list of input variants (main.cpp:80-327).
 void run_problem(const Config& cfg, ps2::CvRng& rng, int number, const char* pair, bool gray_from_colour, int fn, const char* kernel_name,
                  std::initializer_list<Variant> variants, bool with_inverted) {
@@ -146,16 +177,59 @@ void run_problem(const Config& cfg, ps2::CvRng& rng, int number, const char* pai
     const auto start = std::chrono::high_resolution_clock::now();
     const ps2::Image8& li = cfg.images.at(std::string(pair) + "-L");
     const ps2::Image8& ri = cfg.images.at(std::string(pair) + "-R");
-    const sb::Mat left = gray_from_colour ? ps2::rgb2gray_on_bgr_as_float(li, cfg.gray_shift) : ps2::to_float(li);
-    const sb::Mat right = gray_from_colour ? ps2::rgb2gray_on_bgr_as_float(ri, cfg.gray_shift) : ps2::to_float(ri);
-    if (left.rows != right.rows || left.cols != right.cols) throw std::runtime_error("left/right image sizes differ (main.cpp:28)");
+    if (li.rows != ri.rows || li.cols != ri.cols) throw std::runtime_error("left/right image sizes differ (main.cpp:28)");
     sb::Mat ld, rd;
-    for (const Variant& v : variants) {
-        sb::Mat l = left, r = right;
-        if (v.kind == Variant::Noisy) ps2::add_noise(rng, left, right, 0.f, 10.f, l, r);   // main.cpp:169
-        if (v.kind == Variant::Contrast) { l = ps2::scaled(left, 1.1f); r = ps2::scaled(right, 1.1f); }   // main.cpp:191-193
-        disparity_pair(fn, kernel_name, l, r, cfg.p[number], ld, rd);
-        write_maps(cfg, "ps2-" + std::to_string(number) + "-" + v.part, ld, rd, with_inverted);
+    if (g_mgpu) {         // several GPUs: host images, output rows sharded (stereo_mgpu_*)
+        const sb::Mat left = gray_from_colour ? ps2::rgb2gray_on_bgr_as_float(li, cfg.gray_shift) : ps2::to_float(li);
+        const sb::Mat right = gray_from_colour ? ps2::rgb2gray_on_bgr_as_float(ri, cfg.gray_shift) : ps2::to_float(ri);
+        for (const Variant& v : variants) {
+            sb::Mat l = left, r = right;
+            if (v.kind == Variant::Noisy) ps2::add_noise(rng, left, right, 0.f, 10.f, l, r);   // main.cpp:169
+            if (v.kind == Variant::Contrast) { l = ps2::scaled(left, 1.1f); r = ps2::scaled(right, 1.1f); }   // main.cpp:191-193
+            disparity_pair(fn, kernel_name, l, r, cfg.p[number], ld, rd);
+            write_maps(cfg, "ps2-" + std::to_string(number) + "-" + v.part, ld, rd, with_inverted);
+        }
+    } else {
+        stereo_ctx* ctx = sb::default_ctx();
+        const DevImage& gl = device_gray(cfg, std::string(pair) + "-L", gray_from_colour);
+        const DevImage& gr = device_gray(cfg, std::string(pair) + "-R", gray_from_colour);
+        const int rows = gl.rows, cols = gl.cols;
+        DevImage vl(rows, cols, 4), vr(rows, cols, 4), nz(rows, cols, 4), dl(rows, cols, 1), dr(rows, cols, 1);
+        for (const Variant& v : variants) {
+            const float* l = gl.f32(); const float* r = gr.f32();
+            if (v.kind == Variant::Noisy) {               // addNoise (main.cpp:140-153): cv::randn's stream on the host, the add on the device
+                sb::Mat noise(rows, cols, sb::F32C1);
+                const DevImage* src[2] = {&gl, &gr}; DevImage* dst[2] = {&vl, &vr};
+                for (int k = 0; k < 2; ++k) {
+                    rng.fill_normal(noise, 0.f, 10.f);
+                    sb::check(stereo_dev_upload(ctx, nz.p, nz.step, noise.data, noise.step, size_t(cols) * 4, rows), "stereo_dev_upload");
+                    sb::check(stereo_image_scale_add_f32_device(ctx, src[k]->f32(), src[k]->step, nz.f32(), nz.step, 1.f, rows, cols, dst[k]->f32(), dst[k]->step, nullptr),
+                              "stereo_image_scale_add_f32_device");
+                    sb::check(stereo_ctx_synchronize(ctx, nullptr), "stereo_ctx_synchronize");     // nz is reused for the second image
+                }
+                l = vl.f32(); r = vr.f32();
+            } else if (v.kind == Variant::Contrast) {     // main.cpp:191-193
+                sb::check(stereo_image_scale_add_f32_device(ctx, gl.f32(), gl.step, nullptr, 0, 1.1f, rows, cols, vl.f32(), vl.step, nullptr), "scale");
+                sb::check(stereo_image_scale_add_f32_device(ctx, gr.f32(), gr.step, nullptr, 0, 1.1f, rows, cols, vr.f32(), vr.step, nullptr), "scale");
+                l = vl.f32(); r = vr.f32();
+            }
+            const size_t step = v.kind == Variant::Clean ? gl.step : vl.step;
+            file_info("Setting up CUDA kernel execution...");                                  // DisparitySSD.cu:157-158,191,203
+            file_info("Original image: rows=%d cols=%d", rows, cols);
+            file_info("Launching %s", kernel_name);
+            sb::check(stereo_disparity_pair_f32_device(ctx, fn, l, step, r, step, rows, cols, int(cfg.p[number].window_radius), cfg.p[number].disparity_range,
+                                                       dl.p, dr.p, dl.step, 1, nullptr), kernel_name);
+            ld.create(rows, cols, sb::S8C1); rd.create(rows, cols, sb::S8C1);
+            sb::check(stereo_dev_download(ctx, ld.data, ld.step, dl.p, dl.step, size_t(cols), rows), "stereo_dev_download");
+            sb::check(stereo_dev_download(ctx, rd.data, rd.step, dr.p, dr.step, size_t(cols), rows), "stereo_dev_download");
+            const double ms = double(sb::lastKernelMs());
+            file_info("%s execution took %g ms", kernel_name, ms / 2);
+            file_info("Setting up CUDA kernel execution...");
+            file_info("Original image: rows=%d cols=%d", rows, cols);
+            file_info("Launching %s", kernel_name);
+            file_info("%s execution took %g ms", kernel_name, ms / 2);
+            write_maps(cfg, "ps2-" + std::to_string(number) + "-" + v.part, ld, rd, with_inverted);
+        }
     }
     const std::chrono::duration<double, std::milli> runtime = std::chrono::high_resolution_clock::now() - start;
     info("Problem %d runtime = %g ms", number, runtime.count());
@@ -199,6 +273,7 @@ int main(int argc, char** argv) {
         const std::chrono::duration<double, std::milli> runtime = std::chrono::high_resolution_clock::now() - start;
         info("Total runtime: %g ms", runtime.count());
         g_mgpu = nullptr;
+        g_gray.clear();
     } catch (const std::exception& e) {
         error("%s", e.what());
         error("Configuration load failed!");

@@ -294,6 +294,27 @@ int stereo_peer_push(stereo_ctx* ctx, void* const* dst_ptrs, int n_dst, size_t d
 int stereo_peer_mark(stereo_ctx* ctx, int* ticket_out);
 int stereo_peer_wait(stereo_ctx* ctx, int ticket, void* cuda_stream);
 
+/* ---- device images and preprocessing ----------------------------------------------------- */
+/*
+ * What the ps2 executable does to an image between imread and the disparity call, on the device, so that an image pair
+ * is uploaded ONCE (as 8-bit pixels) and serves both directions and every problem that uses it; the reference uploads
+ * both float Mats again for every direction (DisparitySSD.cu:171-174).
+ *   stereo_dev_alloc/free/upload/download : plain device buffers for callers without the CUDA runtime (synchronous copies)
+ *   gray   : channels == 1: Mat::convertTo(CV_32FC1) unscaled (main.cpp:87-88); 3 or 4: cvtColor(COLOR_RGB2GRAY) on the
+ *            interleaved data as loaded (BGR from imread, main.cpp:114-117) with OpenCV's fixed-point coefficients
+ *            (shift 14 = OpenCV 3.4.1, 15 = later), then convertTo
+ *   scale_add : out = a * scale (+ add, nullable): `left * 1.1f` (main.cpp:191-193) and `first + noise` (main.cpp:146-152),
+ *            separately rounded float32 operations.  The noise field itself is cv::randn's sequential stream: host.
+ */
+int stereo_dev_alloc(stereo_ctx* ctx, size_t bytes, void** ptr);
+int stereo_dev_free(stereo_ctx* ctx, void* ptr);
+int stereo_dev_upload(stereo_ctx* ctx, void* dst, size_t dst_step, const void* src, size_t src_step, size_t row_bytes, int rows);
+int stereo_dev_download(stereo_ctx* ctx, void* dst, size_t dst_step, const void* src, size_t src_step, size_t row_bytes, int rows);
+int stereo_image_gray_f32_device(stereo_ctx* ctx, const uint8_t* img, size_t step, int rows, int cols, int channels, int shift,
+                                 float* out, size_t out_step, void* cuda_stream);
+int stereo_image_scale_add_f32_device(stereo_ctx* ctx, const float* a, size_t a_step, const float* add, size_t add_step, float scale,
+                                      int rows, int cols, float* out, size_t out_step, void* cuda_stream);
+
 /* ---- reference-GPU-semantics mode ------------------------------------------------- */
 /*
  * Everything above reproduces the reference's CPU functions (the parity target).  Its GTX-1080 kernels compute a

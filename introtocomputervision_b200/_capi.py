@@ -65,6 +65,12 @@ SIGNATURES = {
     "stereo_peer_push": (_i, [_vp, C.POINTER(_vp), _i, _sz, _vp, _sz, _vp]),
     "stereo_peer_mark": (_i, [_vp, C.POINTER(_i)]),
     "stereo_peer_wait": (_i, [_vp, _i, _vp]),
+    "stereo_dev_alloc": (_i, [_vp, _sz, C.POINTER(_vp)]),
+    "stereo_dev_free": (_i, [_vp, _vp]),
+    "stereo_dev_upload": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i]),
+    "stereo_dev_download": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _i]),
+    "stereo_image_gray_f32_device": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "stereo_image_scale_add_f32_device": (_i, [_vp, _vp, _sz, _vp, _sz, C.c_float, _i, _i, _vp, _sz, _vp]),
     "stereo_disparity_refgpu_f32_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz]),
     "stereo_disparity_refgpu_f32_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "stereo_disparity_pair_band_u8_host": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _i]),

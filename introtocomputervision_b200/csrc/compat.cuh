@@ -9,7 +9,7 @@
 //     sum / sqrtf(a_t * a_i), wins if > the best so far, which starts at 0 (DisparityNCorr.cu:16,104-111); NaN never wins
 //   * pixels nothing won keep -1 (:177); disparities are stored as `char`
 // Every float operation happens in the reference's order, so the results are the ones its kernels produce (bit for bit
-// against the C restatement in oracle/stereo_oracle.c; the reference's own outputs are Git-LFS stubs and its .cu files need
+// against the C restatement the tests hold; the reference's own outputs are Git-LFS stubs and its .cu files need
 // texture references that CUDA 12 no longer has).  One CTA = 64 + 2R threads, one shared-memory column sum each; the first
 // 64 also own an output column.  No textures, no per-disparity read-modify-write of global memory.
 #pragma once

@@ -4,6 +4,7 @@
 #include "exact.cuh"
 #include "fast.cuh"
 #include "compat.cuh"
+#include "imgproc.cuh"
 #include "host_pack.hpp"
 
 #include <cstdarg>
@@ -1033,6 +1034,65 @@ int stereo_disparity_u8_host(stereo_ctx* ctx, int cost, const uint8_t* ref, size
                              void* disp_out, size_t disp_step, int disp_elem_bytes, void* best_out, size_t best_step) {
     return host_single(ctx, cost, PixType::U8, ref, ref_step, tgt, tgt_step, rows, cols, window_rad, min_disp,
                        max_disp, disp_out, disp_step, disp_elem_bytes, best_out, best_step);
+}
+
+// ---- device images and preprocessing (imgproc.cuh) ---------------------------------------------------------------------------
+int stereo_dev_alloc(stereo_ctx* ctx, size_t bytes, void** ptr) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!ptr || bytes == 0) { set_error("bad allocation arguments"); return STEREO_ERR_INVALID_ARG; }
+    if (cudaMalloc(ptr, bytes) != cudaSuccess) { (void)cudaGetLastError(); *ptr = nullptr; set_error("device allocation of %zu bytes failed", bytes); return STEREO_ERR_ALLOC; }
+    return STEREO_OK;
+}
+
+int stereo_dev_free(stereo_ctx* ctx, void* ptr) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (ptr) { SB_CUDA(cudaStreamSynchronize(ctx->stream)); SB_CUDA(cudaFree(ptr)); }
+    return STEREO_OK;
+}
+
+int stereo_dev_upload(stereo_ctx* ctx, void* dst, size_t dst_step, const void* src, size_t src_step, size_t row_bytes, int rows) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!dst || !src || rows <= 0 || row_bytes == 0 || dst_step < row_bytes || src_step < row_bytes) { set_error("bad upload arguments"); return STEREO_ERR_INVALID_ARG; }
+    SB_CUDA(cudaMemcpy2DAsync(dst, dst_step, src, src_step, row_bytes, rows, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));          // the host buffer is the caller's again
+    return STEREO_OK;
+}
+
+int stereo_dev_download(stereo_ctx* ctx, void* dst, size_t dst_step, const void* src, size_t src_step, size_t row_bytes, int rows) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!dst || !src || rows <= 0 || row_bytes == 0 || dst_step < row_bytes || src_step < row_bytes) { set_error("bad download arguments"); return STEREO_ERR_INVALID_ARG; }
+    SB_CUDA(cudaMemcpy2DAsync(dst, dst_step, src, src_step, row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return STEREO_OK;
+}
+
+int stereo_image_gray_f32_device(stereo_ctx* ctx, const uint8_t* img, size_t step, int rows, int cols, int channels, int shift,
+                                 float* out, size_t out_step, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!img || !out || rows <= 0 || cols <= 0 || (channels != 1 && channels != 3 && channels != 4) || (shift != 14 && shift != 15) ||
+        step < size_t(cols) * channels || out_step < size_t(cols) * 4) { set_error("bad gray conversion arguments"); return STEREO_ERR_INVALID_ARG; }
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    gray_f32_kernel<<<dim3(div_round_up(cols, 256), rows), 256, 0, st>>>(img, step, rows, cols, channels, shift, out, out_step);
+    SB_CUDA(cudaGetLastError());
+    return STEREO_OK;
+}
+
+int stereo_image_scale_add_f32_device(stereo_ctx* ctx, const float* a, size_t a_step, const float* add, size_t add_step, float scale,
+                                      int rows, int cols, float* out, size_t out_step, void* cuda_stream) {
+    int rc = check_ctx(ctx);
+    if (rc != STEREO_OK) return rc;
+    if (!a || !out || rows <= 0 || cols <= 0 || a_step < size_t(cols) * 4 || out_step < size_t(cols) * 4 || (add && add_step < size_t(cols) * 4)) {
+        set_error("bad scale/add arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    scale_add_f32_kernel<<<dim3(div_round_up(cols, 256), rows), 256, 0, st>>>(a, a_step, add, add_step, scale, rows, cols, out, out_step);
+    SB_CUDA(cudaGetLastError());
+    return STEREO_OK;
 }
 
 // ---- reference-GPU-semantics mode (compat.cuh) ------------------------------------------------------------------------------
