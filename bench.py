@@ -505,7 +505,8 @@ def run_ours(args, wl):
     # the same batch call with host-side packing switched the other way (the default packs from 8 host threads up)
     host_threads = ctx.host_threads
     packing = host_threads >= 8
-    ctx.set_host_threads(-1 if packing else 16)
+    alt_threads = -1 if packing else max(2, host_threads)      # forced on with the threads this rank would get
+    ctx.set_host_threads(alt_threads)
     e2e_alt_value = timed_host(step_host)
     ctx.set_host_threads(0)
 
@@ -633,7 +634,7 @@ def run_ours(args, wl):
                     "host_pack": {"threads": host_threads, "on": packing,
                                   "what": "CV_32FC1 host images converted to u8 by host threads into pinned staging, 1 byte per pixel "
                                           "over the link" if packing else "float rows uploaded, converted on the device",
-                                  ("value_with_float_upload" if packing else "value_with_host_pack_16_threads"): round(e2e_alt_value, 1)},
+                                  ("value_with_float_upload" if packing else f"value_with_host_pack_forced_{alt_threads}_threads"): round(e2e_alt_value, 1)},
                     "host_cpus_bound_per_rank": bound_cpus},
             "gpu_launches": launches, "e2e_gpu_launches": e2e_launches, "clocks": clocks,
             "parity_check": parity,

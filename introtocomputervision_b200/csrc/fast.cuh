@@ -451,35 +451,49 @@ __global__ void __launch_bounds__(128) prep_e2f_kernel(const __grid_constant__ F
     job.RS[o] = 0.f;      // (NCC rows come from prep_rsf_kernel)
 }
 
-// NCC, float path: RS[j][q2] = 1 / sqrt(window energy of the extended target image at centre q2), separably: a block owns one
-// operand row and 256 - 2R centres; every thread sums the squares of ONE extended column over the 2R+1 window rows in
-// double (like OpenCV's double integral images), the centres then add 2R+1 neighbouring column sums from shared memory.
+// NCC, float path: RS[j][q2] = 1 / sqrt(window energy of the extended target image at centre q2), separably: a block owns
+// RSF_ROWS consecutive operand rows and 256 - 2R centres; every thread keeps the sum of squares of ONE extended column over
+// the 2R+1 window rows in double (like OpenCV's double integral images; squares of floats are exact in double) and slides it
+// down the block's rows, the centres then add 2R+1 neighbouring column sums from shared memory.
+constexpr int RSF_ROWS = 8;
 __global__ void __launch_bounds__(256) prep_rsf_kernel(const __grid_constant__ FastKernelParams P) {
     const FastGeom& g = P.g;
     const FastJob& job = P.job[blockIdx.z];
-    __shared__ double vs[256];
+    __shared__ double vs[RSF_ROWS][256];
     const int R = g.R, ts = 256 - 2 * R;
     const int t = threadIdx.x;
-    const int j = blockIdx.y, y = g.base_y + j;
+    const int j0 = blockIdx.y * RSF_ROWS;
     const int q20 = blockIdx.x * ts;
-    const bool row_ok = y >= g.rb && y < g.re;
+    const int e = q20 - job.eoff + R + t;                  // extended column of this thread
+    auto sq = [&](int i) -> double { const double b = bextf(job.B, job.b_step, g.rows, g.cols, R, i, e, g.ar0, g.ar1); return b * b; };
     double v = 0;
-    if (row_ok) {
-        const int e = q20 - job.eoff + R + t;              // extended column of this thread
-        for (int wy = -R; wy <= R; ++wy) { const double b = bextf(job.B, job.b_step, g.rows, g.cols, R, y + wy, e, g.ar0, g.ar1); v += b * b; }
+    {
+        const int y = g.base_y + j0;
+        for (int wy = -R; wy <= R; ++wy) v += sq(y + wy);
     }
-    vs[t] = v;
+#pragma unroll 1
+    for (int r = 0; r < RSF_ROWS; ++r) {
+        const int y = g.base_y + j0 + r;
+        if (r > 0) v += sq(y + R) - sq(y - R - 1);
+        vs[r][t] = v;
+    }
     __syncthreads();
     const int q2 = q20 + t;
     if (t >= ts || q2 >= g.e2_pitch) return;
     const int uc = q2 - job.eoff;
-    float rs = 0.f;
-    if (row_ok && uc >= job.cmin && uc <= job.cmax) {
-        double er = 0;
-        for (int tt = 0; tt <= 2 * R; ++tt) er += vs[t + tt];
-        rs = er > 0 ? float(1.0 / sqrt(er)) : 0.f;
+    const bool col_ok = uc >= job.cmin && uc <= job.cmax;
+#pragma unroll 1
+    for (int r = 0; r < RSF_ROWS; ++r) {
+        const int j = j0 + r, y = g.base_y + j;
+        if (j >= g.J) break;
+        float rs = 0.f;
+        if (col_ok && y >= g.rb && y < g.re) {
+            double er = 0;
+            for (int tt = 0; tt <= 2 * R; ++tt) er += vs[r][t + tt];
+            rs = er > 0 ? float(1.0 / sqrt(er)) : 0.f;
+        }
+        job.RS[size_t(j) * g.e2_pitch + q2] = rs;
     }
-    job.RS[size_t(j) * g.e2_pitch + q2] = rs;
 }
 
 // NCC, float path: window energies of the reference image per pixel (replicate padding, double sums) ...
@@ -732,7 +746,61 @@ __global__ void __launch_bounds__(32 * (R > 0 ? R : 1)) fused_border_kernel(cons
     atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
 }
 
+// The same with one thread per PIXEL, the window of the reference image and the 3R extended target columns of each window
+// row in registers, all R candidates per thread: fewer loads in total - the better kernel when the launch has many such
+// pixels (720 rows x 63 columns x 4 pairs: 13 us against 39 us), the worse one when it has few (511 x 95 x 1: 20 us against 4).
+template <int R>
+__global__ void __launch_bounds__(128) fused_border_px_kernel(const __grid_constant__ FastKernelParams P) {
+    constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1;
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[g.npairs + blockIdx.z];
+    const int range = job.dmax;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xp = g.cols - 1 - idx;
+    const int yy = blockIdx.y, y = g.rb + yy;
+    if (idx >= range || xp < 0) return;
+    const int ncand = min(xp + range, g.cols - 1 + R) - g.cols + 1;
+    if (ncand <= 0) return;
+    const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
+    int ssd[NCAND], eref = 0;
+#pragma unroll
+    for (int c = 0; c < NCAND; ++c) ssd[c] = 0;
+#pragma unroll 1
+    for (int wy = -R; wy <= R; ++wy) {
+        const int ra = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+        const uint8_t* arow = A + size_t(ra) * job.a_step;
+        const uint8_t* brow = B + size_t(ra) * job.b_step;
+        int a[W], b[NB];
+#pragma unroll
+        for (int i = 0; i < W; ++i) { a[i] = arow[clampi(xp - R + i, 0, g.cols - 1)]; eref += a[i] * a[i]; }
+        const int edge = brow[g.cols - 1];
+        const int wrap = bext(B, job.b_step, g.rows, g.cols, R, y + wy, g.cols + 4 * R, g.ar0, g.ar1);
+#pragma unroll
+        for (int i = 0; i < R; ++i) { b[i] = brow[max(g.cols - R + i, 0)]; b[R + i] = edge; b[2 * R + i] = wrap; }
+#pragma unroll
+        for (int c = 0; c < R; ++c)
+#pragma unroll
+            for (int i = 0; i < W; ++i) { const int d = a[i] - b[c + i]; ssd[c] += d * d; }
+    }
+    uint32_t* __restrict__ PART2 = reinterpret_cast<uint32_t*>(job.PART);
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+        if (c >= ncand) break;
+        const int pos = g.cols + c;
+        const uint32_t key = key_bias(R) + (uint32_t(ssd[c] - eref) << FKEY_BITS) + uint32_t(pos);
+        atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
+    }
+}
+
 typedef void (*fused_border_fn)(const FastKernelParams);
+static inline fused_border_fn fused_border_px_pick(int R) {
+    switch (R) {
+        case 1: return fused_border_px_kernel<1>; case 2: return fused_border_px_kernel<2>; case 3: return fused_border_px_kernel<3>;
+        case 4: return fused_border_px_kernel<4>; case 5: return fused_border_px_kernel<5>; case 6: return fused_border_px_kernel<6>;
+        case 7: return fused_border_px_kernel<7>;
+    }
+    return nullptr;
+}
 static inline fused_border_fn fused_border_pick(int R) {
     switch (R) {
         case 1: return fused_border_kernel<1>; case 2: return fused_border_kernel<2>; case 3: return fused_border_kernel<3>;
@@ -1046,7 +1114,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         prep_af_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), unsigned(lp_rows), nwalk), 256, 0, st>>>(kp);
         prep_bf_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), unsigned(rq_rows), nwalk), 256, 0, st>>>(kp);
         if (!ncc) prep_e2f_kernel<<<dim3(div_round_up(g.e2_pitch, 128), g.J, nz), 128, 0, st>>>(kp);
-        else prep_rsf_kernel<<<dim3(div_round_up(g.e2_pitch, 256 - 2 * g.R), g.J, nz), 256, 0, st>>>(kp);
+        else prep_rsf_kernel<<<dim3(div_round_up(g.e2_pitch, 256 - 2 * g.R), div_round_up(g.J, RSF_ROWS), nz), 256, 0, st>>>(kp);
         ctx->last_launches += 3;
         if (ncc && fast_launch_is_pairs(ps, n)) {
             // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
@@ -1091,8 +1159,15 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     if (!fn) { set_error("no hot kernel for R=%d hs=%d opf=%d (internal)", g.R, g.hs, g.opf); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
         if (g.border) {
-            if (fused_border_fn bf = fused_border_pick(g.R)) {
-                // one thread per (pixel of the last `range` columns, candidate centred in the padding)
+            const long long px = (long long)(-ps[0].dmin) * g.nrows * fused_pairs;      // pixels with candidates in the padding
+            if (px >= 65536) {          // many: one thread per pixel
+                if (fused_border_fn bf = fused_border_px_pick(g.R)) {
+                    const int bt = -ps[0].dmin <= 64 ? 64 : 128;
+                    bf<<<dim3(div_round_up(-ps[0].dmin, bt), g.nrows, unsigned(fused_pairs)), bt, 0, st>>>(kp);
+                    ctx->last_launches += 1;
+                }
+            } else if (fused_border_fn bf = fused_border_pick(g.R)) {
+                // few: one thread per (pixel of the last `range` columns, candidate centred in the padding)
                 bf<<<dim3(div_round_up(-ps[0].dmin, 32), g.nrows, unsigned(fused_pairs)), dim3(32, g.R), 0, st>>>(kp);
                 ctx->last_launches += 1;
             }
