@@ -149,10 +149,21 @@ def bind_to_gpu_cpus(index: int):
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 1) + 63) // 64)
         cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus and cpus != os.sched_getaffinity(0):
+        avail = os.sched_getaffinity(0)
+        cpus &= avail
+        if cpus and cpus != avail:
             os.sched_setaffinity(0, cpus)
             return len(cpus)
+        # every GPU reports the same CPUs (one NUMA node, a VM): give each rank its own slice so that the ranks' host
+        # threads do not migrate over each other
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        order = sorted(avail)
+        per = len(order) // max(world, 1)
+        if world > 1 and per >= 2:
+            mine = set(order[local * per:(local + 1) * per])
+            os.sched_setaffinity(0, mine)
+            return len(mine)
     except Exception:
         pass
     return None

@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 TAG = os.environ.get("STEREO_BUILD_TAG", "")
 OBJ = (Path("/tmp") / f"sb_build_{TAG}") if TAG else CSRC / "_build"        # experiment objects stay out of the tree
 LIB = PKG / ("libstereo_b200" + (f"_{TAG}" if TAG else "") + ".so")
-FAST_PARTS = 38          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused pair parts + 3 x 4 float-operand parts
+FAST_PARTS = 48          # 16 cost x radius x strips-per-warp parts + 2 x 5 fused SSD parts + 3 x 4 float-operand parts + 2 x 5 fused NCC parts
 
 NVCC_FLAGS = [
     *[f"-D{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("SB_") and v != ""],

@@ -845,7 +845,9 @@ static inline bool fast_pair_fusable(const Problem& a, const Problem& b) {
     static const bool off = [] { const char* e = getenv("STEREO_FUSE_PAIRS"); return e && atoi(e) == 0; }();
     if (off || !fast_batchable(a, b)) return false;
     const int range = -a.dmin;
-    return a.cost == STEREO_COST_SSD && a.R <= FMAXR && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
+    static const bool ncc_off = [] { const char* e = getenv("STEREO_FUSE_NCC"); return e && atoi(e) == 0; }();
+    const bool cost_ok = a.cost == STEREO_COST_SSD || (a.cost == STEREO_COST_NCORR && a.ref.type == PixType::U8 && !ncc_off);
+    return cost_ok && a.R <= FMAXR && a.dmax == 0 && range > 0 && b.dmin == 0 && b.dmax == range &&
            a.ref.ptr == b.tgt.ptr && a.tgt.ptr == b.ref.ptr && a.ref.step == b.tgt.step && a.tgt.step == b.ref.step;
 }
 
@@ -885,7 +887,7 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
     g.hs = g.opf ? 1 : fast_pick_hs(g.D);
     const int w = 2 * p.R + 1;
     for (;;) {
-        g.K = g.opf ? fast_kf(p.R) : fast_k(p.R, fused_pairs > 0, g.hs);
+        g.K = g.opf ? fast_kf(p.R) : ((fused_pairs > 0 && p.cost == STEREO_COST_NCORR) ? FK_FUSED_NCC : fast_k(p.R, fused_pairs > 0, g.hs));
         g.dg = FGROUP / g.hs;
         g.G = (g.D + g.dg - 1) / g.dg;
         g.gc = (g.hs == 1 && g.G % 2 == 0) ? 2 : 1;
@@ -904,7 +906,7 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
     // fused: the strips also cover the R columns of right padding the partner direction may centre a window on -
     // unless that costs a whole tile of a narrow image (>= 1/8 more work); then fused_border_kernel takes them
     g.nstrips = (p.cols + g.K - 1) / g.K;
-    if (fused_pairs > 0 && p.R > 0) {
+    if (fused_pairs > 0 && p.R > 0 && p.cost == STEREO_COST_SSD) {      // (NCC candidates never centre in the padding)
         const int ext_strips = (p.cols + p.R + g.K - 1) / g.K;
         const int t0 = (g.nstrips + g.spc - 1) / g.spc, t1 = (ext_strips + g.spc - 1) / g.spc;
         if (t1 > t0 && t0 <= 8 && !g.opf) g.border = 1;      // (the border kernel is 8-bit only)
@@ -1016,7 +1018,7 @@ static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 
 static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
     size_t best = 0;
     for (int fused = 0; fused <= 1; ++fused) {
-        if (fused && p.cost != STEREO_COST_SSD) break;
+        if (fused && p.cost != STEREO_COST_SSD && p.ref.type != PixType::U8) break;
       {
         FastGeom g; FastJob jb{};
         fast_geometry(ctx, &p, 1, g, &jb, fused);
@@ -1055,6 +1057,13 @@ static inline int fast_ctx_init(stereo_ctx*) {
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
     }
     for (int R = 0; R <= FMAXR; ++R)
+        for (int hs = 1; hs <= 2; ++hs) {
+            fast_kernel_fn fn = fast_pick_fused_ncc(R, hs);
+            if (!fn) { set_error("fused NCC pair kernel (R %d, hs %d) missing from the build", R, hs); return STEREO_ERR_UNSUPPORTED; }
+            cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM_BUDGET);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return STEREO_ERR_CUDA; }
+        }
+    for (int R = 0; R <= FMAXR; ++R)
         for (int kind = 0; kind < 3; ++kind) {
             fast_kernel_fn fn = fast_pick_opf(R, kind);
             if (!fn) { set_error("float-operand kernel (R %d, kind %d) missing from the build", R, kind); return STEREO_ERR_UNSUPPORTED; }
@@ -1087,10 +1096,11 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         const bool partner = fused_pairs > 0 && i >= fused_pairs;      // only its energy rows and partial keys exist
         if (partner) {
             jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
+            jb.RS = reinterpret_cast<float*>(jb.E2);                  // NCC: the same rows hold 1/sqrt(energy)
             jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
             if (!jb.E2 || !jb.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
-            // every strip merges into the partner's partial keys with RED.MIN: start from "no candidate"
-            SB_CUDA(cudaMemsetAsync(jb.PART, 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
+            // every strip merges into the partner's partial keys with RED.MIN (NCC: RED.MAX): start from "no candidate"
+            SB_CUDA(cudaMemsetAsync(jb.PART, ncc ? 0x00 : 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
             continue;
         }
         jb.LP = static_cast<int32_t*>(ctx->arena.take(lp_rows * g.lp_pitch * 4));
@@ -1145,7 +1155,9 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
             prep_e2_kernel<<<dim3(div_round_up(g.e2_pitch, PE_COLS), div_round_up(g.nrows, PE_ROWS), nz), PE_COLS, pe_smem, st>>>(kp, vpitch);
             ctx->last_launches += 3;
         }
-        if (ncc && (!legacy_prep) && fast_launch_is_pairs(ps, n)) {
+        if (ncc && fused_pairs) {
+            // fused NCC pairs scale every key per pixel, from the other direction's RS rows inside the hot kernel
+        } else if (ncc && (!legacy_prep) && fast_launch_is_pairs(ps, n)) {
             // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
             prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
             ctx->last_launches += 1;
@@ -1154,7 +1166,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
             prep_scale_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, vpitch);
             ctx->last_launches += 2;
         }
-        fn = fused_pairs ? fast_pick_fused(g.R, g.hs, fast_fused_all_mode1(g) ? 0 : 1) : fast_pick(ps[0].cost, g.R, g.hs);
+        fn = fused_pairs ? (ncc ? fast_pick_fused_ncc(g.R, g.hs) : fast_pick_fused(g.R, g.hs, fast_fused_all_mode1(g) ? 0 : 1)) : fast_pick(ps[0].cost, g.R, g.hs);
     }
     if (!fn) { set_error("no hot kernel for R=%d hs=%d opf=%d (internal)", g.R, g.hs, g.opf); return STEREO_ERR_UNSUPPORTED; }
     if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)

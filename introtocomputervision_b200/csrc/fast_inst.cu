@@ -5,10 +5,11 @@
 //   16..20 one strip per warp, radius subsets {0,1,2,3}, {4}, {5}, {6}, {7};  21..25 two strips per warp, same subsets.
 //   SB_PART = 26..37: the float-operand kernels (OPF): kind * 4 + radius subset {0,1,2,3}, {4}, {5}, {6,7};
 //   kind 0 = SSD, 1 = SSD fused pair, 2 = NCC.
+//   SB_PART = 38..47: the fused NCC pair kernels (packed operands), laid out like 16..25.
 #include "fast_kernel.cuh"
 
 #ifndef SB_PART
-#error "compile with -DSB_PART=0..37"
+#error "compile with -DSB_PART=0..47"
 #endif
 
 namespace sb {
@@ -16,7 +17,28 @@ namespace sb {
 #define SB_CAT2(a, b) a##b
 #define SB_CAT(a, b) SB_CAT2(a, b)
 
-#if SB_PART >= 26
+#if SB_PART >= 38
+// fused NCC pair kernels: 38..42 one strip per warp, radius subsets {0,1,2,3}, {4}, {5}, {6}, {7}; 43..47 two strips per warp
+#define SB_FUSED_NCC_KERNEL(R_, HS_) fast_cost_kernel<R_, FK_FUSED_NCC, FWARPS, STEREO_COST_NCORR, HS_, true, true>
+fast_kernel_fn SB_CAT(fast_pick_fused_part, SB_PART)(int R, int hs, int gen) {
+    constexpr int HS = (SB_PART - 38) / 5 + 1;
+    constexpr int SUB = (SB_PART - 38) % 5;
+    (void)gen;
+    if (hs != HS) return nullptr;
+    if constexpr (SUB == 0) {
+        switch (R) {
+        case 0: return SB_FUSED_NCC_KERNEL(0, HS);
+        case 1: return SB_FUSED_NCC_KERNEL(1, HS);
+        case 2: return SB_FUSED_NCC_KERNEL(2, HS);
+        case 3: return SB_FUSED_NCC_KERNEL(3, HS);
+        }
+    } else {
+        constexpr int RR = SUB + 3;       // 4, 5, 6, 7
+        if (R == RR) return SB_FUSED_NCC_KERNEL(RR, HS);
+    }
+    return nullptr;
+}
+#elif SB_PART >= 26
 // float-operand kernels (general float32 images): kind 0 = SSD, 1 = SSD fused pair, 2 = NCC
 #define SB_OPF_KERNEL(R_) fast_cost_kernel<R_, fast_kf(R_), FWARPS, (KIND == OPF_NCC ? STEREO_COST_NCORR : STEREO_COST_SSD), 1, KIND == OPF_SSD_FUSED, true, true>
 fast_kernel_fn SB_CAT(fast_pick_opf_part, SB_PART)(int R, int kind) {

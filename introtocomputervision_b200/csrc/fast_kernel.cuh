@@ -57,6 +57,10 @@ constexpr int FK_FUSED = SB_FK_FUSED, FK_FUSED2 = SB_FK_FUSED2;
 #define SB_FK_FUSED_WIDE 16
 #endif
 constexpr int FK_WIDE_R = 6;    // first radius that takes the narrower strips
+#ifndef SB_FK_FUSED_NCC
+#define SB_FK_FUSED_NCC 16
+#endif
+constexpr int FK_FUSED_NCC = SB_FK_FUSED_NCC;   // fused NCC pairs: the per-position scales take the registers four more pixels would
 // float-operand kernels (OPF): K + 2R <= 30 column sums per disparity next to the operand words in flight
 __host__ __device__ constexpr int fast_kf(int R) { return R <= 3 ? 24 : (R <= 5 ? 20 : 16); }
 __host__ __device__ constexpr int fast_k(int R, bool fused, int hs) {
@@ -409,10 +413,28 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     uint32_t einv[4] = {0u, 0u, 0u, 0u};
     if (FUSED) {
 #pragma unroll
-        for (int m = 0; m < FM; ++m) acc[m] = KEY_INVALID;
+        for (int m = 0; m < FM; ++m) acc[m] = NCC ? NCC_KEY_NONE : KEY_INVALID;      // running minima (SSD) / maxima (NCC)
     }
     constexpr int LSF = 32 / HS;                                          // lanes per strip
     const uint32_t top_or = (FUSED && ll == LSF - 1) ? KEY_INVALID : 0u;  // the top lane of a strip opens a fresh diagonal every step
+    // FUSED NCC.  Both maps order candidates by C * rs with rs = 1/sqrt(energy of the OTHER image's window): the own pixel
+    // x by rs_R[pos] (e2v), the partner pixel x' = pos by rs_L[x] (elv, the partner direction's RS row).  The fixed-point
+    // scale of a key must be common to all candidates of ONE pixel and bound their scores: C * rs_R[pos] <= sqrt(EL(x)) =
+    // 1 / rs_L[x] and C * rs_L[x] <= sqrt(ER(pos)) = 1 / rs_R[pos] (Cauchy-Schwarz), so the scale of either map is a power of
+    // two read off the exponent of the OTHER map's rs - per PIXEL (the unfused kernels share one scale per strip row, which
+    // costs mantissa bits where a dark window sits next to a bright one): 2^(127 - E) or 2^(128 - E) > 1/rs for rs = 2^(E-127) * 1.m.
+    // rs = 0 (empty or illegal window) gives the scale inf, every key of that pixel then has value bits 0 and the position
+    // bits alone decide - the first candidate, which is what an all-zero score row gives the oracle.
+    // (the mantissa add carries into the exponent when rs is at least 2^-19 above a power of two: then 2^(127 - E) already
+    // exceeds 1/rs by the slack the rounding of the sums needs, one more key bit than 2^(128 - E))
+    auto scale_of = [](int rs_bits) -> float { return __int_as_float(0x7F800000 - ((rs_bits + 0x007FFFF0) & 0x7F800000)); };
+    float own_scale[4];                                   // FUSED NCC: scale of the pixels k .. k+3
+    float pos_scale[FUSED && NCC ? S::NE : 1];            // FUSED NCC: scale of the partner pixels (positions) of this lane
+    const uint32_t lane_or2 = (uint32_t(FGROUP - 32 / HS * FM + FM * ll) << 2) | 3u;   // partner: reversed index of candidate (m = 0) in ITS group
+    if (FUSED && NCC) {
+#pragma unroll
+        for (int p = 0; p < S::NE; ++p) pos_scale[FUSED && NCC ? p : 0] = scale_of(e2v[p]);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {                 // [pixel-loop-begin] (tests/test_capi.py checks that nothing spills in here)
         update(k + 2 * R);
@@ -421,13 +443,17 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             elv[0] = v.x; elv[1] = v.y; elv[2] = v.z; elv[3] = v.w;
             // a lane outside [dmin, dmax] contributes to neither map; for R <= 5 the partner's key of such a lane loses
             // through its energy term alone (KEY_INVALID - 256*C stays above every valid key), one OR per pixel
-            if (MODE == 2 && R <= FFREE_MASK_R && !OPF) {
+            if (MODE == 2 && R <= FFREE_MASK_R && !OPF && !NCC) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) elv[i] = int(uint32_t(elv[i]) | lane_or);
             }
-            if (MODE == 3) {      // pixels the partner cannot centre a window on: one mask per pixel, shared by its four candidates
+            if (MODE == 3 && !NCC) {      // pixels the partner cannot centre a window on: one mask per pixel, shared by its four candidates
 #pragma unroll
                 for (int i = 0; i < 4; ++i) einv[i] = uint32_t(elv[i]) == KEY_INVALID ? KEY_INVALID : 0u;
+            }
+            if (NCC) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) own_scale[i] = scale_of(elv[i]);
             }
         }
         uint32_t key[FM];
@@ -468,15 +494,27 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 }
             } else {
                 const float rs = __int_as_float(e2v[k + m]);
+                const float mg = FUSED ? own_scale[k & 3] : magic;
                 // BIASED: s is the float 2^23 + C, so C*rs + magic = fma(s, rs, magic - 2^23*rs); the addend is exact
-                // (Sterbenz / common-ulp argument: 2^23*rs >= 2990 > magic/2 for R <= 5), i.e. ONE rounding
+                // (Sterbenz / common-ulp argument: 2^23*rs >= 2990 > magic/2 for R <= 5), i.e. ONE rounding (the per-pixel
+                // scales of fused launches may be twice as large: the addend then rounds, by at most half a key unit)
                 // OPF: `magic` arrives as 3 * 2^e (C may be negative): r lies in [2*2^e, 4*2^e)
-                const float r = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, magic))
-                                       : __fmaf_rn(OPF ? __int_as_float(s[m]) : __int2float_rn(s[m]), rs, magic);
+                const float cf = BIASED ? 0.f : (OPF ? __int_as_float(s[m]) : __int2float_rn(s[m]));
+                const float r = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, mg)) : __fmaf_rn(cf, rs, mg);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
                 uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
                 if (MODE == 3) kv = kv & pmask[MODE == 3 ? k + m : 0] & mmask[MODE == 3 ? m : 0];
                 key[m] = kv;
+                if (FUSED) {
+                    // the partner's key of the same cross term: its candidate is THIS pixel (rs_L[x] = elv), its scale the one of
+                    // position k + m, its candidate index inside its group runs against this lane's (d' = -d)
+                    const float rs2 = __int_as_float(elv[k & 3]), mg2 = pos_scale[FUSED && NCC ? k + m : 0];
+                    const float r2 = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs2, __fmaf_rn(rs2, -8388608.0f, mg2)) : __fmaf_rn(cf, rs2, mg2);
+                    uint32_t k2 = (uint32_t(__float_as_int(r2)) << NCC_KEY_SHIFT) + (lane_or2 + 4u * m);
+                    if (MODE == 3) k2 = k2 & mmask[MODE == 3 ? m : 0];
+                    if (MODE == 2) k2 = mmax < 0 ? NCC_KEY_NONE : k2;
+                    acc[m] = max(acc[m], k2);
+                }
             }
         }
         uint32_t best;
@@ -506,30 +544,33 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             // the lane's other three diagonals move down one slot and the slot on top takes over lane ll+1's
             const uint32_t done = acc[0];
             uint32_t in;
-            if (HS == 1) { in = __shfl_down_sync(0xffffffffu, done, 1) | top_or; if (ll == 0) tail[k] = done; }
-            else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF) | top_or; if (ll == 0) tail[32 * sub + k] = done; }
+            // (a fresh diagonal starts at "no candidate": all ones for the SSD minima, zero for the NCC maxima)
+            if (HS == 1) { in = __shfl_down_sync(0xffffffffu, done, 1); if (ll == 0) tail[k] = done; }
+            else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF); if (ll == 0) tail[32 * sub + k] = done; }
+            in = NCC ? (in & ~top_or) : (in | top_or);
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
         }
     }                                             // [pixel-loop-end]
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
+        auto merge = [&](uint32_t* p, uint32_t v) { if (NCC) atomicMax(p, v); else atomicMin(p, v); };
         if (HS == 1) {
-            const uint32_t tv = (ll < K) ? tail[ll] : KEY_INVALID;
+            const uint32_t tv = (ll < K) ? tail[ll] : (NCC ? NCC_KEY_NONE : KEY_INVALID);
             const int xt = x2base + ll;
-            if (ll < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tv);
+            if (ll < K && unsigned(xt) < unsigned(cols)) merge(part2_row + xt, tv);
         } else {
             const int lane = sub * LSF + ll;
 #pragma unroll
             for (int h = 0; h < HS; ++h) {               // strip h of the warp: its tail, one entry per lane
                 const int xt = x2base + (h - sub) * K + lane;
-                if (lane < K && unsigned(xt) < unsigned(cols)) atomicMin(part2_row + xt, tail[32 * h + lane]);
+                if (lane < K && unsigned(xt) < unsigned(cols)) merge(part2_row + xt, tail[32 * h + lane]);
             }
         }
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             const int xa = x2base + K + FM * ll + m;
-            if (unsigned(xa) < unsigned(cols)) atomicMin(part2_row + xa, acc[m]);
+            if (unsigned(xa) < unsigned(cols)) merge(part2_row + xa, acc[m]);
         }
         __syncwarp();             // the next row overwrites the tail
     }
@@ -542,7 +583,8 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 // stage stages the entering AND the leaving rows of both images.
 template <int R, int K, int NW, int COST, int HS, bool FUSED = false, bool GEN = true, bool OPF = false>
 __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_constant__ FastKernelParams P) {
-    static_assert(!FUSED || (COST == STEREO_COST_SSD && K % 4 == 0 && K <= 32), "fused pair kernel: SSD, strips of 4k <= 32 pixels");
+    static_assert(!FUSED || (K % 4 == 0 && K <= 32), "fused pair kernel: strips of 4k <= 32 pixels");
+    static_assert(!FUSED || COST == STEREO_COST_SSD || !OPF, "fused NCC pairs: packed operands only");
     static_assert(!OPF || (HS == 1 && GEN && K % 4 == 0), "float operands: one strip per warp, general masks");
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr int LS = 32 / HS;                 // lanes per strip
@@ -657,8 +699,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                         tma_load_1d(smem_u32(st + rq_base + rq_stage + r * g.rqw), job.RQ + size_t(j0 + r) * g.rq_pitch + q0, uint32_t(g.rqw) * 4u, bar);
                     }
                     tma_load_1d(smem_u32(st + e2_base + r * g.e2w), e2src + size_t(j0 + r) * g.e2_pitch + q20, uint32_t(g.e2w) * 4u, bar);
-                    if (FUSED)      // the partner's energy rows: E2'[j][x], x = pixel column (its eoff is 0)
-                        tma_load_1d(smem_u32(st + el_base + r * g.elw), P.job[jb + npair].E2 + size_t(j0 + r) * g.e2_pitch + p0,
+                    if (FUSED)      // the partner's energy rows: E2'[j][x] (NCC: RS'[j][x]), x = pixel column (its eoff is 0)
+                        tma_load_1d(smem_u32(st + el_base + r * g.elw),
+                                    (NCC ? reinterpret_cast<const int32_t*>(P.job[jb + npair].RS) : P.job[jb + npair].E2) + size_t(j0 + r) * g.e2_pitch + p0,
                                     uint32_t(g.elw) * 4u, bar);
                 }
             }
@@ -718,7 +761,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
         if (mmin > FM - 1) mmax = -1;                                     // the whole lane lies below dmin: dead, like one above dmax
         // SSD: OR-mask that invalidates a whole lane; NCC: reversed position of the lane's first candidate
         const uint32_t lane_or = NCC ? (uint32_t(FGROUP - 1 - FM * ll) << 2 | 3u) : (mmax < 0 ? KEY_INVALID : 0u);
-        const float* sc_row = NCC ? job.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
+        const float* sc_row = (NCC && !FUSED) ? job.SC + size_t(strip) * g.nrows - (g.rb - g.base_y) : nullptr;   // indexed by operand row j
         const int cbase = x0 + dlo + FM * ll;                             // centre column of candidate (k=0, m=0)
         const int lp_off = (wstrip + sub) * K;
         const int rq_off = lp_off + DG * (warp % g.gc) + FM * ll;
@@ -745,7 +788,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fast_cost_kernel(const __grid_cons
                     const int* e2_row = st + e2_base + r * g.e2w + rq_off;
                     int32_t* out_row = part + size_t(j - (g.rb - g.base_y)) * g.wpart;
                     const int par = j & 1;
-                    const float magic = (NCC && j >= jreg) ? __ldg(sc_row + j) : 0.f;
+                    const float magic = (NCC && !FUSED && j >= jreg) ? __ldg(sc_row + j) : 0.f;
 #define SB_ROW(P_, M_) fast_row<R, K, P_, M_, COST, HS, false, OPF>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
                                                           nullptr, nullptr, nullptr, 0, lp_row + lp_stage, rq_row + rq_stage)
 #define SB_ROWF(P_, M_) fast_row<R, K, P_, M_, COST, HS, true, OPF>(col, lp_row, rq_row, e2_row, out_row, mmin, mmax, lane_or, ll, sub, cbase, g.cols, magic, \
@@ -786,12 +829,23 @@ constexpr int FAST_PARTS = 16;
 SB_DECL_PART(0) SB_DECL_PART(1) SB_DECL_PART(2) SB_DECL_PART(3) SB_DECL_PART(4) SB_DECL_PART(5) SB_DECL_PART(6) SB_DECL_PART(7)
 SB_DECL_PART(8) SB_DECL_PART(9) SB_DECL_PART(10) SB_DECL_PART(11) SB_DECL_PART(12) SB_DECL_PART(13) SB_DECL_PART(14) SB_DECL_PART(15)
 #undef SB_DECL_PART
-// Fused pair kernels (SSD): parts 16..25 (fast_inst.cu).
+// Fused pair kernels: SSD parts 16..25, NCC parts 38..47 (fast_inst.cu).
 constexpr int FAST_FUSED_PARTS = 10;
 #define SB_DECL_FPART(n) fast_kernel_fn fast_pick_fused_part##n(int R, int hs, int gen);
 SB_DECL_FPART(16) SB_DECL_FPART(17) SB_DECL_FPART(18) SB_DECL_FPART(19) SB_DECL_FPART(20)
 SB_DECL_FPART(21) SB_DECL_FPART(22) SB_DECL_FPART(23) SB_DECL_FPART(24) SB_DECL_FPART(25)
+SB_DECL_FPART(38) SB_DECL_FPART(39) SB_DECL_FPART(40) SB_DECL_FPART(41) SB_DECL_FPART(42)
+SB_DECL_FPART(43) SB_DECL_FPART(44) SB_DECL_FPART(45) SB_DECL_FPART(46) SB_DECL_FPART(47)
 #undef SB_DECL_FPART
+static inline fast_kernel_fn fast_pick_fused_ncc(int R, int hs) {
+    typedef fast_kernel_fn (*part_fn)(int, int, int);
+    static const part_fn parts[FAST_FUSED_PARTS] = {fast_pick_fused_part38, fast_pick_fused_part39, fast_pick_fused_part40, fast_pick_fused_part41,
+                                                    fast_pick_fused_part42, fast_pick_fused_part43, fast_pick_fused_part44, fast_pick_fused_part45,
+                                                    fast_pick_fused_part46, fast_pick_fused_part47};
+    for (int i = 0; i < FAST_FUSED_PARTS; ++i)
+        if (fast_kernel_fn fn = parts[i](R, hs, 1)) return fn;
+    return nullptr;
+}
 // gen = 0: the launch's blocks are all MODE 1 (fast_fused_all_mode1); 1: any launch
 static inline fast_kernel_fn fast_pick_fused(int R, int hs, int gen) {
     typedef fast_kernel_fn (*part_fn)(int, int, int);

@@ -14,4 +14,4 @@ timeout 600 python bench.py --mode bands > gpurun_out/${T}_bench_n1_bands.json 2
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-suite --no-parity > gpurun_out/${T}_launches_bench.log 2>&1; echo "ncu bench launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fast_cost_kernel -s 2 -c 1 -o gpurun_out/${T}_fused_4k python tools/probe_hot.py 2160,3840,256,5,ssd,4 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 python tools/probe_hot.py 511,640,96,7,ssd,1,f32 511,640,96,7,ssd,1,noisy 511,640,96,7,ncc,1,f32 511,640,96,7,ncc,1,noisy 720,1280,64,4,ssd,4 2160,3840,256,5,ssd,1,noisy > gpurun_out/${T}_probe.jsonl 2> gpurun_out/${T}_probe.err; cat gpurun_out/${T}_probe.jsonl
-tail -2 gpurun_out/${T}_err*.log
+for f in gpurun_out/${T}_err*.log; do tail -n 2 "$f"; done; true
