@@ -129,7 +129,7 @@ def test_docs_name_only_real_entry_points():
         text = (ROOT / doc).read_text()
         for m in re.finditer(r"\bstereo_[a-z0-9_{},*]+", text):
             tok = m.group(0).rstrip(",")
-            if tok in ("stereo_ctx", "stereo_b200", "stereo_cost", "stereo_oracle", "stereo_b200_") or tok.startswith(("stereo_b200.", "stereo_oracle.")):
+            if tok in ("stereo_ctx", "stereo_b200", "stereo_cost", "stereo_path", "stereo_mgpu", "stereo_status", "stereo_oracle", "stereo_b200_") or tok.startswith(("stereo_b200.", "stereo_oracle.")):
                 continue
             if "{" in tok:                     # e.g. stereo_disparity_pair_batch_{u8,f32}_{host,device}
                 parts = re.split(r"[{}]", tok)
