@@ -5,6 +5,7 @@
 #include "host_pack.hpp"
 
 #include <atomic>
+#include <cstdint>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -27,6 +28,47 @@ bool pack_f32_u8_row(const float* __restrict__ src, uint8_t* __restrict__ dst, i
     }
     return bad == 0;
 }
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#include <immintrin.h>
+// AVX-512 row: 64 pixels per iteration, non-temporal stores into the (64-byte aligned) pinned staging - the staged bytes are
+// read next by the DMA engine, not by a core, so they should not displace the source image from the caches nor cost a
+// read-for-ownership of the destination lines.
+__attribute__((target("avx512f,avx512bw")))
+static bool pack_row_avx512(const float* __restrict__ src, uint8_t* __restrict__ dst, int n) {
+    __m512i bad = _mm512_setzero_si512();
+    __mmask16 ne = 0;
+    int x = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 63) == 0;
+    for (; x + 64 <= n; x += 64) {
+        const __m512 f0 = _mm512_loadu_ps(src + x), f1 = _mm512_loadu_ps(src + x + 16), f2 = _mm512_loadu_ps(src + x + 32), f3 = _mm512_loadu_ps(src + x + 48);
+        const __m512i i0 = _mm512_cvttps_epi32(f0), i1 = _mm512_cvttps_epi32(f1), i2 = _mm512_cvttps_epi32(f2), i3 = _mm512_cvttps_epi32(f3);
+        ne |= _mm512_cmp_ps_mask(_mm512_cvtepi32_ps(i0), f0, _CMP_NEQ_UQ) | _mm512_cmp_ps_mask(_mm512_cvtepi32_ps(i1), f1, _CMP_NEQ_UQ) |
+              _mm512_cmp_ps_mask(_mm512_cvtepi32_ps(i2), f2, _CMP_NEQ_UQ) | _mm512_cmp_ps_mask(_mm512_cvtepi32_ps(i3), f3, _CMP_NEQ_UQ);
+        bad = _mm512_or_si512(bad, _mm512_or_si512(_mm512_or_si512(i0, i1), _mm512_or_si512(i2, i3)));
+        const __m128i b0 = _mm512_cvtepi32_epi8(i0), b1 = _mm512_cvtepi32_epi8(i1), b2 = _mm512_cvtepi32_epi8(i2), b3 = _mm512_cvtepi32_epi8(i3);
+        __m512i out = _mm512_castsi128_si512(b0);
+        out = _mm512_inserti32x4(out, b1, 1);
+        out = _mm512_inserti32x4(out, b2, 2);
+        out = _mm512_inserti32x4(out, b3, 3);
+        if (aligned) _mm512_stream_si512(reinterpret_cast<__m512i*>(dst + x), out);
+        else _mm512_storeu_si512(dst + x, out);
+    }
+    // any bit above the low 8 set in any lane <=> some value outside 0..255 (negative values have the sign bits set)
+    int oob = _mm512_test_epi32_mask(bad, _mm512_set1_epi32(~0xFF)) != 0;
+    for (; x < n; ++x) {
+        const float f = src[x];
+        const int v = int(f);
+        oob |= (float(v) != f) | (unsigned(v) > 255u);
+        dst[x] = uint8_t(v);
+    }
+    return !oob && ne == 0;
+}
+static const bool g_have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+#else
+static const bool g_have_avx512 = false;
+static bool pack_row_avx512(const float*, uint8_t*, int) { return false; }
+#endif
 
 struct HostPool::Impl {
     std::vector<std::thread> workers;
@@ -98,9 +140,13 @@ bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst
     pool.run(n_tasks, [&](int t) {
         const int r0 = t * rows_per_task, r1 = r0 + rows_per_task < rows ? r0 + rows_per_task : rows;
         bool ok = true;
-        for (int r = r0; r < r1; ++r)
-            ok &= pack_f32_u8_row(reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + size_t(r) * src_step),
-                                  dst + size_t(r) * dst_step, cols);
+        for (int r = r0; r < r1; ++r) {
+            const float* s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + size_t(r) * src_step);
+            ok &= g_have_avx512 ? pack_row_avx512(s, dst + size_t(r) * dst_step, cols) : pack_f32_u8_row(s, dst + size_t(r) * dst_step, cols);
+        }
+#if defined(__x86_64__) && defined(__GNUC__)
+        if (g_have_avx512) __builtin_ia32_sfence();       // the non-temporal stores are visible before the upload is enqueued
+#endif
         if (!ok) bad.store(1, std::memory_order_relaxed);
     });
     return bad.load() == 0;
