@@ -513,9 +513,9 @@ def run_ours(args, wl):
         return world * units_rank * e2e_steps / float(tt.item()) / 1e6
 
     e2e_pp_value = timed_host(step_host_per_pair)
-    # the same batch call with host-side packing switched the other way (the default packs from 4 host threads up)
+    # the same batch call with host-side packing switched the other way (the default packs from 8 host threads up)
     host_threads = ctx.host_threads
-    packing = host_threads >= 4
+    packing = host_threads >= 8
     alt_threads = -1 if packing else max(2, host_threads)      # forced on with the threads this rank would get
     ctx.set_host_threads(alt_threads)
     e2e_alt_value = timed_host(step_host)

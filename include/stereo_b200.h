@@ -127,7 +127,7 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
 /* CV_32FC1 HOST entry points: images whose pixels are all integers in 0..255 (everything convertTo(CV_32FC1) produces,
  * main.cpp:87-88) are converted to u8 by `threads` host threads into pinned staging and uploaded as 1 byte per pixel; the
  * reference uploads the float Mats (DisparitySSD.cu:171-174).  threads = 0 (default): min(16, hardware threads /
- * LOCAL_WORLD_SIZE), and host conversion only from 4 threads up (below that the floats are uploaded and converted on the
+ * LOCAL_WORLD_SIZE), and host conversion only from 8 threads up (below that the floats are uploaded and converted on the
  * device); threads = -1: never convert on the host; threads >= 1: that many, always.  Results do not depend on it. */
 int stereo_ctx_set_host_threads(stereo_ctx* ctx, int threads);
 int stereo_ctx_host_threads(const stereo_ctx* ctx);

@@ -444,7 +444,7 @@ static int pairs_host_pipelined(stereo_ctx* ctx, int cost, PixType type, int n_p
 // Host-side packing of CV_32FC1 images (host_pack.cpp): on when the context has enough host threads to convert faster
 // than the link would carry the floats (stereo_ctx_set_host_threads; automatic: min(16, cores / LOCAL_WORLD_SIZE) threads,
 // packing from HOST_PACK_MIN_THREADS up).
-constexpr int HOST_PACK_MIN_THREADS = 4;
+constexpr int HOST_PACK_MIN_THREADS = 8;
 static bool host_pack_enabled(stereo_ctx* ctx) {
     if (ctx->host_threads == 0) ctx->host_threads = default_host_threads();
     if (ctx->host_threads < 0) return false;                  // switched off
