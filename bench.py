@@ -192,13 +192,14 @@ def cpu_reference_sample(wl, rows_per_thread: int, threads: int, cost: str = "ss
     def work(i):
         a = np.ascontiguousarray(Lf[i * band:(i + 1) * band])
         b = np.ascontiguousarray(Rf[i * band:(i + 1) * band])
-        fn(a, b, R, -(nd - 1), 0)
+        fn(a, b, R, -(nd - 1), 0)          # disparitySSDPair / disparityNCorrPair (main.cpp:21-78): left-referenced map ...
+        fn(b, a, R, 0, nd - 1)             # ... then the images swapped over [0, +range]
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(work, range(threads)))
     dt = time.perf_counter() - t0
-    units = threads * band * wl["cols"] * nd          # every row of every band is computed
+    units = 2 * threads * band * wl["cols"] * nd      # every row of every band is computed, both directions
     what = {("ssd", "reference"): "reference serial::disparitySSD compiled -O2 from /root/reference (oracle/_ref)",
             ("ssd", "port"): "C port of serial::disparitySSD (oracle/stereo_oracle.c)",
             ("ncc", "reference"): "reference serial::disparityNCorr compiled -O2 from /root/reference (oracle/_ref) over the "
@@ -206,7 +207,7 @@ def cpu_reference_sample(wl, rows_per_thread: int, threads: int, cost: str = "ss
             ("ncc", "port"): "C port of serial::disparityNCorr (oracle/stereo_oracle.c)"}[(cost, kind)]
     desc = {"kind": kind, "cores": threads,
             "sample": f"{threads} threads x {band}-row full-width bands ({wl['cols']} cols, {nd} disparities, "
-                      f"{2 * R + 1}x{2 * R + 1} window), L->R {cost.upper()}, " + what}
+                      f"{2 * R + 1}x{2 * R + 1} window), both directions of the pair, {cost.upper()}, " + what}
     return units / dt / 1e6, dt, desc
 
 
@@ -228,8 +229,8 @@ def run_reference_arm(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32->int32" if args.cost == "ssd" else "f32 (f64 window energies)", "data": "synthetic",
-        "config": {"workload": args.workload + f"_{args.cost}", **{k: wl[k] for k in ("rows", "cols", "ndisp")},
-                   "window": 2 * wl["R"] + 1, "sample_rows_per_thread": args.ref_rows},
+        "config": {"workload": args.workload + f"_{args.cost}_pair", **{k: wl[k] for k in ("rows", "cols", "ndisp")},
+                   "window": 2 * wl["R"] + 1, "directions": 2, "sample_rows_per_thread": args.ref_rows},
         "cpu_baseline": {**desc, "value": round(value, 3), "unit": UNIT},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -251,6 +251,9 @@ struct RowShape {
 #ifndef SB_KEY2_LEA
 #define SB_KEY2_LEA 0
 #endif
+#ifndef SB_TAIL_BATCH
+#define SB_TAIL_BATCH 0
+#endif
 constexpr int NCC_BIAS_MAX_R = 5;
 constexpr int NCC_FLOAT_BIAS = 0x4B000000;        // bit pattern of 8388608.0f
 constexpr int NCC_KEY_SHIFT = 9;                  // mantissa -> bits 9..31
@@ -411,6 +414,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     uint32_t acc[FM];            // FUSED: running minima of the diagonals k + 4*ll + m
     int elv[4];
     uint32_t einv[4] = {0u, 0u, 0u, 0u};
+    uint32_t ret4[4] = {0u, 0u, 0u, 0u};
     if (FUSED) {
 #pragma unroll
         for (int m = 0; m < FM; ++m) acc[m] = NCC ? NCC_KEY_NONE : KEY_INVALID;      // running minima (SSD) / maxima (NCC)
@@ -545,8 +549,15 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             const uint32_t done = acc[0];
             uint32_t in;
             // (a fresh diagonal starts at "no candidate": all ones for the SSD minima, zero for the NCC maxima)
+#if SB_TAIL_BATCH
+            // lane 0's retired diagonals go to the tail four at a time (one STS.128 per four pixels instead of four STS)
+            ret4[k & 3] = done;
+            if (HS == 1) { in = __shfl_down_sync(0xffffffffu, done, 1); if ((k & 3) == 3 && ll == 0) *reinterpret_cast<uint4*>(tail + k - 3) = make_uint4(ret4[0], ret4[1], ret4[2], ret4[3]); }
+            else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF); if ((k & 3) == 3 && ll == 0) *reinterpret_cast<uint4*>(tail + 32 * sub + k - 3) = make_uint4(ret4[0], ret4[1], ret4[2], ret4[3]); }
+#else
             if (HS == 1) { in = __shfl_down_sync(0xffffffffu, done, 1); if (ll == 0) tail[k] = done; }
             else { in = __shfl_down_sync(0xffffffffu, done, 1, LSF); if (ll == 0) tail[32 * sub + k] = done; }
+#endif
             in = NCC ? (in & ~top_or) : (in | top_or);
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
         }

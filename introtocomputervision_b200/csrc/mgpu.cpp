@@ -117,11 +117,13 @@ int stereo_mgpu_create(const int* devices, int n_devices, stereo_mgpu** out) {
         stereo_ctx* c = nullptr;
         const int rc = stereo_ctx_create(d, &c);
         if (rc != STEREO_OK) { stereo_mgpu_destroy(mg); return rc; }
-        // the devices' host threads share the cores
-        stereo_ctx_set_host_threads(c, 0);
         mg->ctx.push_back(c);
         mg->device.push_back(d);
     }
+    // the devices' host threads share the cores: each context packs CV_32FC1 images with its share of them, or (fewer
+    // than the packing threshold of 8 each) uploads the floats and converts on the device
+    const int share = stereo_ctx_host_threads(mg->ctx[0]) / int(mg->ctx.size());
+    for (stereo_ctx* c : mg->ctx) stereo_ctx_set_host_threads(c, share >= 8 ? share : -1);
     *out = mg;
     return STEREO_OK;
 }
