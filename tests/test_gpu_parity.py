@@ -1011,3 +1011,22 @@ def test_ncc_fused_pairs_full_size_and_batches(ctx):
         a, b = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
         assert float(np.mean(bl[i] == oracle.narrow_i8(oracle.ncorr_fast(a, b, 4, -63, 0)))) >= NCC_DISP_AGREE, i
         assert float(np.mean(br[i] == oracle.narrow_i8(oracle.ncorr_fast(b, a, 4, 0, 63)))) >= NCC_DISP_AGREE, i
+
+
+def test_config4_full_size_ncc_pair_and_noisy_float_pair(ctx):
+    """3840x2160, 256 disparities, 11x11 at full size through the two kernel families added in round 2: the NCC pair from one
+    cost volume (both maps within the north-star tolerance) and a noisy CV_32FC1 SSD pair on the float running-sum kernels
+    (both maps bit-exact)."""
+    L, Rt, _ = synth.make_pair(2160, 3840, 256, 1002)
+    Lf, Rf = L.astype(np.float32), Rt.astype(np.float32)
+    dl, dr = ctx.disparity_pair(sb.COST_NCORR, L, Rt, 5, 255, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_U8 and ctx.last_fused_pairs >= 1
+    assert float(np.mean(dl == oracle.ncorr_fast(Lf, Rf, 5, -255, 0))) >= NCC_DISP_AGREE
+    assert float(np.mean(dr == oracle.ncorr_fast(Rf, Lf, 5, 0, 255))) >= NCC_DISP_AGREE
+    Ln, Rn = synth.noisy_variant(L, 21), synth.noisy_variant(Rt, 22)
+    fl, fr = ctx.disparity_pair(sb.COST_SSD, Ln, Rn, 5, 255, dtype=np.int16)
+    assert ctx.last_path == sb.PATH_FAST_F32 and ctx.last_fused_pairs >= 1
+    bad = np.argwhere(fl != oracle.ssd_fast(Ln, Rn, 5, -255, 0))
+    assert bad.size == 0, f"4K noisy fused L->R differs at {bad[:5].tolist()} (of {len(bad)})"
+    bad = np.argwhere(fr != oracle.ssd_fast(Rn, Ln, 5, 0, 255))
+    assert bad.size == 0, f"4K noisy fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
