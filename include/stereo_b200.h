@@ -131,6 +131,10 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
  * device); threads = -1: never convert on the host; threads >= 1: that many, always.  Results do not depend on it. */
 int stereo_ctx_set_host_threads(stereo_ctx* ctx, int threads);
 int stereo_ctx_host_threads(const stereo_ctx* ctx);
+/* The conversion itself, on `threads` host threads (pure host code, no device needed): rows x cols float32 -> u8;
+ * *all_8bit = 1 when every pixel is an integer in 0..255 (otherwise the u8 image is meaningless). */
+int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
+                            int* all_8bit);
 
 /* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the problem allows
  * it (SSD, window_rad <= 5, disparity_range + 1 a multiple of 128) — the reference's disparitySSDPair always wants

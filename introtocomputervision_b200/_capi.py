@@ -42,6 +42,7 @@ SIGNATURES = {
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
     "stereo_ctx_set_host_threads": (_i, [_vp, _i]),
     "stereo_ctx_host_threads": (_i, [_vp]),
+    "stereo_host_pack_f32_u8": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, C.POINTER(_i)]),
     "stereo_ctx_last_fused_pairs": (_i, [_vp]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),
     "stereo_disparity_f32_host": (_i, _SINGLE_HOST),

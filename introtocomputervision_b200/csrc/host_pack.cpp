@@ -64,7 +64,7 @@ static bool pack_row_avx512(const float* __restrict__ src, uint8_t* __restrict__
     }
     return !oob && ne == 0;
 }
-static const bool g_have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+static const bool g_have_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("STEREO_NO_AVX512");
 #else
 static const bool g_have_avx512 = false;
 static bool pack_row_avx512(const float*, uint8_t*, int) { return false; }

@@ -907,6 +907,16 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
 
 int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx) { return ctx ? ctx->fused_pairs_done : 0; }
 
+// Pure host code (no device): the conversion the pipelined CV_32FC1 entry points run on their host threads.
+int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads, int* all_8bit) {
+    if (!src || !dst || !all_8bit || rows <= 0 || cols <= 0 || src_step < size_t(cols) * 4 || dst_step < size_t(cols) || threads < 1 || threads > 256) {
+        set_error("bad pack arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    HostPool pool(threads);
+    *all_8bit = pack_f32_u8(pool, src, src_step, dst, dst_step, rows, cols) ? 1 : 0;
+    return STEREO_OK;
+}
+
 int stereo_ctx_set_host_threads(stereo_ctx* ctx, int threads) {
     if (!ctx || threads < -1 || threads > 256) { set_error("bad host_threads argument"); return STEREO_ERR_INVALID_ARG; }
     ctx->host_threads = threads;
