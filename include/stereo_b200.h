@@ -136,10 +136,12 @@ int stereo_ctx_host_threads(const stereo_ctx* ctx);
 int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
                             int* all_8bit);
 
-/* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the problem allows
- * it (SSD, window_rad <= 5, disparity_range + 1 a multiple of 128) — the reference's disparitySSDPair always wants
- * both (main.cpp:21-48) and SSD_LR(x, d) and SSD_RL(x + d, -d) are the same window sum.  Results are identical
- * either way; on (the default) is faster.  0 switches back to one cost volume per direction. */
+/* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the kernels allow it -
+ * SSD with any disparity_range and window_rad <= 7 on 8-bit-valued or float images, NCC on 8-bit-valued images - the
+ * reference's disparitySSDPair / disparityNCorrPair always want both (main.cpp:21-78) and the window cost of (x, d) in
+ * one direction IS the window cost of (x + d, -d) in the other.  SSD results are identical either way (bit-exact), NCC
+ * results agree like any two evaluations of the same scores (per-pixel instead of per-strip key scales); on (the default)
+ * is faster.  0 switches back to one cost volume per direction. */
 int stereo_ctx_set_fuse_pairs(stereo_ctx* ctx, int on);
 /* Image pairs of the last call whose two maps came out of one cost volume. */
 int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx);

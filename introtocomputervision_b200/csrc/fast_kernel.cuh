@@ -1,4 +1,4 @@
-// Packed u8 path: the hot kernels of the library (sm_100a).
+// The hot kernels of the library (sm_100a): packed 8-bit operands (below) and float operands (OPF, see fast_row).
 //
 // For images that are exactly 8-bit the window cost is an integer and
 //     SSD(x,d) = EL(x) + ER(x+d) - 2*C(x,d),   C = sum over the window of l*r,
@@ -21,7 +21,11 @@
 //
 // Pair launches (FUSED): the same cross terms also give the map of the OTHER direction of the image pair
 // (C(x, d) is candidate -d of the partner pixel x + d), kept as running minima along the diagonals of the
-// (x, x + d) plane - see fast_row.  Strips are 20 (16) pixels wide there instead of 24.
+// (x, x + d) plane - see fast_row.  Strips are 20 (16) pixels wide there instead of 24.  SSD for any candidate count, every
+// radius up to 7 and either operand type; NCC (diagonal maxima, per-pixel key scales) for packed operands.
+//
+// Float operands (OPF): general float32 images (noise / contrast variants) on the same running sums - SSD with the
+// per-element round((l-r)^2) as exact int32 sums, NCC in float32 - from rows of the padded float images themselves.
 //
 // Reference semantics reproduced: replicate padding, the clamped candidate
 // range in padded coordinates, the flat-index row wrap of the SSD target reads (realised by building
@@ -264,15 +268,17 @@ constexpr uint32_t NCC_KEY_NONE = 0u;             // "no legal candidate" (loses
 // own K-pixel strip; `sub` is the lane's sub-warp, `ll` its lane index inside it.  The per-pixel warp
 // reduction then runs once per sub-warp over the full warp with the other lanes neutralised.
 //
-// FUSED (SSD, D a multiple of the 128 / HS disparities of a group, R <= 5): the R->L map of the same image pair comes out of
-// the same cross terms.  C(x, d) serves the L->R pixel x AND the R->L pixel x' = x + d, whose
-// candidate -d it is (main.cpp:33,43: the second call swaps the images and mirrors the range).  A lane's four
-// candidates at pixel step k lie on the diagonals t = k + 4*lane + m of the (x, x') plane (t = x' - x0 - dlo), so
-// the warp keeps the running minimum of 128 live diagonals in registers, 4 per lane: every step each lane merges
-// its four keys  key2 = EL2[x] + 256*s  (EL2 = the partner direction's energy/position term for candidate x), hands
-// the diagonal it will not touch again to the lane below (one SHFL) and lane 0 retires one finished diagonal into
-// a 24-word shared-memory tail.  At the end of the row the tail and the 128 live diagonals are merged into the
-// partner's partial-key map with RED.MIN (several strips contribute to one x').
+// FUSED: the R->L map of the same image pair comes out of the same cross terms.  C(x, d) serves the L->R
+// pixel x AND the R->L pixel x' = x + d, whose candidate -d it is (main.cpp:33,43: the second call swaps the images and mirrors
+// the range).  A lane's four candidates at pixel step k lie on the diagonals t = k + 4*lane + m of the (x, x') plane
+// (t = x' - x0 - dlo), so the warp keeps the running minimum (NCC: maximum) of 128 live diagonals in registers, 4 per lane: every
+// step each lane merges its four keys  key2 = EL2[x] + 256*s  (EL2 = the partner direction's energy/position term for
+// candidate x), hands the diagonal it will not touch again to the lane below (one SHFL) and lane 0 retires one finished diagonal
+// into a shared-memory tail.  At the end of the row the tail and the 128 live diagonals are merged into the partner's
+// partial-key map with RED.MIN / RED.MAX (several strips contribute to one x').  Any candidate count: the walked direction's
+// groups are aligned to the TOP of its range (FastJob::dlo0) so that the partner's groups are these groups reversed, the
+// candidates below dmin are masked in both maps (MODE 2 / 3).  R = 6, 7 and float operands take MODE 3 where a block holds
+// illegal positions of either direction.
 // OPF (float operands): the images are general float32 (noise / contrast variants, main.cpp:140-153,191-193), the
 // operand rows are rows of the replicate-padded (extended) float images themselves - entering row and leaving row
 // of the reference image (lp_row / lp_old) and of the target image (rq_row / rq_old) - and
