@@ -136,6 +136,28 @@ int stereo_ctx_host_threads(const stereo_ctx* ctx);
 int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
                             int* all_8bit);
 
+/* How the hot kernel of a batch of `n_pairs` (<= 4) equally shaped pair problems would be launched on a device with
+ * `sm_count` SMs (pure host arithmetic, no device needed; tests pin the scheduling decisions with it).
+ * schedule: 0 = linear split of the (tile, row) space, 1 = equal row segments per tile (fewer tiles than SMs),
+ * 2 = row-band-major items strided over the CTAs (many tiles: neighbouring tiles walk the same rows together). */
+typedef struct stereo_launch_plan_t {
+    int fused;            /* both maps from one cost volume */
+    int strip_px;         /* pixels per thread (K) */
+    int strips_per_warp;  /* 1, or 2 for searches of at most 64 candidates */
+    int groups;           /* 128- (64-) disparity groups */
+    int tile_px;          /* pixels per CTA tile */
+    int tiles;            /* tiles of the launch */
+    int ctas;             /* grid size */
+    int schedule;
+    int rows_per_item;    /* rows per CTA share (schedule 0, 1) or per band (2) */
+    int bands;            /* schedule 2: row bands per tile */
+    int stages;           /* TMA pipeline stages */
+    int smem_bytes;
+    int border_kernel;    /* fused SSD: candidates centred in the right padding come from fused_border_kernel */
+} stereo_launch_plan_t;
+int stereo_launch_plan(int cost, int float_operands, int n_pairs, int rows, int cols, int window_rad, int disparity_range, int fuse,
+                       int sm_count, stereo_launch_plan_t* plan);
+
 /* Pair calls (stereo_disparity_pair_*): compute BOTH maps of a pair from one cost volume where the kernels allow it -
  * SSD with any disparity_range and window_rad <= 7 on 8-bit-valued or float images, NCC on 8-bit-valued images - the
  * reference's disparitySSDPair / disparityNCorrPair always want both (main.cpp:21-78) and the window cost of (x, d) in

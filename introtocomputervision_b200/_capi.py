@@ -42,6 +42,7 @@ SIGNATURES = {
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
     "stereo_ctx_set_host_threads": (_i, [_vp, _i]),
     "stereo_ctx_host_threads": (_i, [_vp]),
+    "stereo_launch_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "stereo_host_pack_f32_u8": (_i, [_vp, _sz, _vp, _sz, _i, _i, _i, C.POINTER(_i)]),
     "stereo_ctx_last_fused_pairs": (_i, [_vp]),
     "stereo_ctx_synchronize": (_i, [_vp, _vp]),
@@ -86,6 +87,11 @@ SIGNATURES = {
     "stereo_mgpu_disparity_pair_bands_f32_host": (_i, _PAIR_HOST),
     "stereo_disparity_band_u8_device": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
 }
+
+class LaunchPlan(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("fused", "strip_px", "strips_per_warp", "groups", "tile_px", "tiles", "ctas", "schedule",
+                                       "rows_per_item", "bands", "stages", "smem_bytes", "border_kernel")]
+
 
 _lib = None
 

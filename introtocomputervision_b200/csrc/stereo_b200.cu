@@ -905,6 +905,42 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
     return STEREO_OK;
 }
 
+// Pure host arithmetic (no device): the geometry of the hot-kernel launch a batch of `n_pairs` pair problems would get.
+int stereo_launch_plan(int cost, int float_operands, int n_pairs, int rows, int cols, int window_rad, int disparity_range, int fuse,
+                       int sm_count, stereo_launch_plan_t* plan) {
+    if (!plan || n_pairs < 1 || 2 * n_pairs > FMAXJOBS || rows <= 0 || cols <= 0 || window_rad < 0 || window_rad > FMAXR || disparity_range < 0 ||
+        sm_count < 1 || (cost != STEREO_COST_SSD && cost != STEREO_COST_NCORR)) {
+        set_error("bad launch plan arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    stereo_ctx tmp;
+    tmp.sm_count = sm_count;
+    Problem ps[FMAXJOBS];
+    static const char dummy_l = 0, dummy_r = 0;
+    for (int k = 0; k < n_pairs; ++k) {
+        Problem two[2];
+        const PixType t = float_operands ? PixType::F32 : PixType::U8;
+        two[0] = Problem{};
+        two[0].cost = cost; two[0].rows = rows; two[0].cols = cols; two[0].row_begin = 0; two[0].row_end = rows;
+        two[0].avail_begin = 0; two[0].avail_end = rows; two[0].R = window_rad;
+        two[1] = two[0];
+        two[0].ref = ImageView{&dummy_l + k, size_t(cols), t}; two[0].tgt = ImageView{&dummy_r + k, size_t(cols), t};
+        two[0].dmin = -disparity_range; two[0].dmax = 0;
+        two[1].ref = two[0].tgt; two[1].tgt = two[0].ref; two[1].dmin = 0; two[1].dmax = disparity_range;
+        ps[k] = two[0]; ps[n_pairs + k] = two[1];
+    }
+    if (!fast_supported(ps[0])) { set_error("outside what the running-sum kernels cover"); return STEREO_ERR_UNSUPPORTED; }
+    tmp.fuse_pairs = fuse ? 1 : 0;
+    const bool fused = fused_layout(&tmp, ps, 2 * n_pairs);
+    FastKernelParams kp{};
+    fast_geometry(&tmp, ps, 2 * n_pairs, kp.g, kp.job, fused ? n_pairs : 0);
+    const FastGeom& g = kp.g;
+    plan->fused = fused ? 1 : 0;
+    plan->strip_px = g.K; plan->strips_per_warp = g.hs; plan->groups = g.G; plan->tile_px = g.spc * g.K; plan->tiles = g.ntiles;
+    plan->ctas = g.ctas; plan->schedule = g.sched == 1 ? 2 : (g.nrl != g.nrows ? 1 : 0); plan->rows_per_item = int(g.L);
+    plan->bands = g.sched == 1 ? g.nbands : 0; plan->stages = g.nst; plan->smem_bytes = int(fast_smem_bytes(g)); plan->border_kernel = g.border;
+    return STEREO_OK;
+}
+
 int stereo_ctx_last_fused_pairs(const stereo_ctx* ctx) { return ctx ? ctx->fused_pairs_done : 0; }
 
 // Pure host code (no device): the conversion the pipelined CV_32FC1 entry points run on their host threads.

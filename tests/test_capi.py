@@ -141,3 +141,38 @@ def test_docs_name_only_real_entry_points():
                 assert any(n.startswith(tok.rstrip("*")) for n in names), f"{doc}: no entry point starts with {tok}"
             else:
                 assert tok in names or any(n.startswith(tok) for n in names), f"{doc}: {tok} is not declared in the header"
+
+
+def test_launch_plan_pins_the_scheduling_decisions():
+    """stereo_launch_plan (pure host arithmetic): which kernel flavour and which cut of the (tile, row) space a launch gets on a
+    148-SM device.  Pins the decisions DESIGN.md §4.2 / §4.4 describe."""
+    lib = _capi.lib()
+
+    def plan(cost, f32, n, rows, cols, R, rng, fuse=1, sms=148):
+        p = _capi.LaunchPlan()
+        assert lib.stereo_launch_plan(cost, f32, n, rows, cols, R, rng, fuse, sms, C.byref(p)) == 0, _capi.last_error()
+        return p
+
+    SSD, NCC = 0, 1
+    p = plan(SSD, 0, 4, 2160, 3840, 5, 255)              # the headline launch: many tiles -> row-band-major items, full waves
+    assert (p.fused, p.strip_px, p.groups, p.schedule, p.bands, p.ctas) == (1, 20, 2, 2, 3, 148)
+    assert (p.tiles * p.bands) % 148 <= 148 and -(-p.tiles * p.bands // 148) * 148 - p.tiles * p.bands <= 4
+    p = plan(SSD, 0, 4, 1080, 1920, 4, 127)              # 52 tiles: linear split over all SMs
+    assert (p.fused, p.schedule, p.ctas) == (1, 0, 148)
+    p = plan(SSD, 0, 1, 511, 640, 7, 95)                 # the reference's own problem 2: few tiles -> equal segments, every SM busy
+    assert (p.fused, p.strip_px, p.schedule, p.border_kernel) == (1, 16, 1, 1) and p.ctas >= 140 and p.rows_per_item >= 8
+    p = plan(SSD, 0, 1, 511, 640, 7, 95, fuse=0)
+    assert (p.fused, p.strip_px) == (0, 20)              # unfused wide windows: 20-pixel strips (24 spilled)
+    p = plan(SSD, 1, 1, 511, 640, 7, 95)                 # noisy / contrast variants: float operands, fused, no 8-bit border kernel
+    assert (p.fused, p.strip_px, p.border_kernel) == (1, 16, 0) and p.ctas >= 140
+    p = plan(NCC, 0, 1, 511, 640, 7, 95)
+    assert (p.fused, p.strip_px) == (1, 16)              # NCC pairs from one cost volume
+    p = plan(NCC, 1, 1, 511, 640, 7, 95)
+    assert p.fused == 0                                  # ... not for float operands
+    p = plan(SSD, 0, 4, 720, 1280, 4, 63)                # config 5: two strips per warp, border kernel instead of a sixth tile
+    assert (p.fused, p.strips_per_warp, p.strip_px, p.border_kernel) == (1, 2, 16, 1)
+    for q in (plan(SSD, 0, 1, 128, 128, 6, 3), plan(SSD, 0, 2, 97, 3000, 2, 300), plan(NCC, 0, 3, 2000, 64, 0, 1)):
+        assert 1 <= q.ctas <= 148 and q.stages >= 2 and q.smem_bytes <= 227 * 1024
+    bad = _capi.LaunchPlan()
+    assert lib.stereo_launch_plan(SSD, 0, 5, 10, 10, 1, 1, 1, 148, C.byref(bad)) != 0     # more pairs than one launch carries
+    assert lib.stereo_launch_plan(SSD, 0, 1, 10, 10, 9, 1, 1, 148, C.byref(bad)) != 0     # radius beyond the running-sum kernels
