@@ -1030,3 +1030,26 @@ def test_config4_full_size_ncc_pair_and_noisy_float_pair(ctx):
     assert bad.size == 0, f"4K noisy fused L->R differs at {bad[:5].tolist()} (of {len(bad)})"
     bad = np.argwhere(fr != oracle.ssd_fast(Rn, Ln, 5, 0, 255))
     assert bad.size == 0, f"4K noisy fused R->L differs at {bad[:5].tolist()} (of {len(bad)})"
+
+
+# ---- size-independent properties at the full BASELINE sizes --------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows,cols,nd,R", [(2160, 3840, 256, 5), (1080, 1920, 128, 4), (720, 1280, 64, 4)])
+def test_known_shift_at_full_size(ctx, rows, cols, nd, R):
+    """right(x) = left(x + k): away from the borders every window has an exact match at disparity -k (L->R) / +k (R->L), for SSD
+    and NCC, whatever the image size (SURVEY.md §8c's behavioural known-answer test, at configs 3, 4 and 5's sizes)."""
+    rng = np.random.default_rng(rows + nd)
+    left = rng.integers(1, 256, (rows, cols + nd), dtype=np.uint8)
+    k = nd // 3 + 1
+    L, Rt = np.ascontiguousarray(left[:, :cols]), np.ascontiguousarray(left[:, k:k + cols])
+    dt = np.int16 if nd > 128 else np.int8
+    for cost in (sb.COST_SSD, sb.COST_NCORR):
+        dl, dr = ctx.disparity_pair(cost, L, Rt, R, nd - 1, dtype=dt)
+        assert ctx.last_fused_pairs >= 1
+        # L->R: pixel x of the left image shows up at x - k in the right one; R->L the other way round
+        assert np.all(dl[R:-R, k + R + 1:-R - 1] == -k), (cost, "L->R")
+        assert np.all(dr[R:-R, R + 1:cols - k - R - 1] == k), (cost, "R->L")
+    # idempotence of the pair call and agreement of the u8 and the CV_32FC1 entry points on the same data
+    d2l, d2r = ctx.disparity_pair(sb.COST_SSD, L.astype(np.float32), Rt.astype(np.float32), R, nd - 1, dtype=dt)
+    d3l, d3r = ctx.disparity_pair(sb.COST_SSD, L, Rt, R, nd - 1, dtype=dt)
+    assert np.array_equal(d2l, d3l) and np.array_equal(d2r, d3r)
