@@ -99,7 +99,8 @@ int stereo_ctx_last_path(const stereo_ctx* ctx);
  * reference logs the same quantity, DisparitySSD.cu:192-203).  <0 if unavailable.  For the pipelined
  * HOST entry points the pair brackets the compute stream, which waits for every band's upload: the
  * figure then includes upload time the kernels were blocked on (stereo_ctx_last_hot_kernel_ms is
- * kernels only). */
+ * kernels only).  CV_32FC1 DEVICE calls: the time the device idles while the host reads the classification
+ * verdict is left out (classification kernels + the kernels of the chosen family). */
 float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
 /* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels; one launch
  * covers up to 8 directions of equally shaped problems), summed over the launches that were measured

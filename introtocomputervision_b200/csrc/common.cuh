@@ -84,6 +84,8 @@ struct stereo_ctx {
     cudaEvent_t* pipe_ev = nullptr;                 // pool of timing-free events for the pipeline
     int pipe_ev_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_gap0 = nullptr, ev_gap1 = nullptr;   // float device calls: the device idles between these two while the host reads
+    bool gap_recorded = false;                          // the classification verdict; last_kernel_ms leaves that gap out
     bool timing_pending = false;
     bool have_prev_call = false;                    // ev1 marks the end of the previous call ...
     cudaStream_t prev_stream = nullptr;             // ... which was enqueued on this stream

@@ -158,7 +158,10 @@ static int classify_images(stereo_ctx* ctx, const Problem& p, cudaStream_t st, u
     classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, b8, pitch, ctx->d_flag);
     ctx->last_launches += 2;
     SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaEventRecord(ctx->ev_gap0, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    SB_CUDA(cudaEventRecord(ctx->ev_gap1, st));          // (the kernels chosen below follow this mark)
+    ctx->gap_recorded = true;
     const unsigned* hf = reinterpret_cast<const unsigned*>(ctx->h_flag);
     if (hf[0] == 0 && ctx->force_path != STEREO_PATH_FAST_F32) { *cls = CLS_U8; return STEREO_OK; }
     *cls = CLS_EXACT;
@@ -329,6 +332,7 @@ static void begin_call(stereo_ctx* ctx, cudaStream_t st) {
     ctx->hot_total = 0;
     ctx->hot_jobs = 0;
     ctx->fused_pairs_done = 0;
+    ctx->gap_recorded = false;
     cudaEventRecord(ctx->ev0, st);
 }
 static void end_call(stereo_ctx* ctx, cudaStream_t st) {
@@ -801,6 +805,8 @@ int stereo_ctx_create(int device, stereo_ctx** ctx_out) {
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_gap0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_gap1);
     for (int i = 0; i < stereo_ctx::HOT_EVENTS && e == cudaSuccess; ++i) {
         e = cudaEventCreate(&c->hot0[i]);
         if (e == cudaSuccess) e = cudaEventCreate(&c->hot1[i]);
@@ -830,6 +836,8 @@ void stereo_ctx_destroy(stereo_ctx* ctx) {
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_gap0) cudaEventDestroy(ctx->ev_gap0);
+    if (ctx->ev_gap1) cudaEventDestroy(ctx->ev_gap1);
     for (int i = 0; i < stereo_ctx::HOT_EVENTS; ++i) {
         if (ctx->hot0[i]) cudaEventDestroy(ctx->hot0[i]);
         if (ctx->hot1[i]) cudaEventDestroy(ctx->hot1[i]);
@@ -853,7 +861,11 @@ float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx) {
     stereo_ctx* c = const_cast<stereo_ctx*>(ctx);
     if (c->timing_pending) {
         float ms = -1.f;
-        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
+            float gap = 0.f;      // float device calls: the host round trip of the classification verdict is not kernel time
+            if (c->gap_recorded && cudaEventElapsedTime(&gap, c->ev_gap0, c->ev_gap1) == cudaSuccess && gap > 0.f && gap < ms) ms -= gap;
+            c->last_ms = ms;
+        }
         else (void)cudaGetLastError();
         c->timing_pending = false;
     }
