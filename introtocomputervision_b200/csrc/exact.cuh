@@ -140,8 +140,13 @@ static inline float f32_from_ordered(unsigned u) {
     const unsigned b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
     float f; memcpy(&f, &b, 4); return f;
 }
-__global__ void classify_convert_kernel(const float* __restrict__ img, size_t step, int rows, int cols,
-                                        uint8_t* __restrict__ out, size_t out_step, int* flag) {
+// blockIdx.z selects the image: both images of a pair go through one launch.
+__global__ void classify_convert_kernel(const float* __restrict__ img0, size_t step0, uint8_t* __restrict__ out0,
+                                        const float* __restrict__ img1, size_t step1, uint8_t* __restrict__ out1,
+                                        int rows, int cols, size_t out_step, int* flag) {
+    const float* __restrict__ img = blockIdx.z ? img1 : img0;
+    const size_t step = blockIdx.z ? step1 : step0;
+    uint8_t* __restrict__ out = blockIdx.z ? out1 : out0;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     bool bad = false, nonfinite = false;

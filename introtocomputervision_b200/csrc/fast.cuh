@@ -31,39 +31,89 @@ __device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One launch for the stages that feed the hot kernel
+// ---------------------------------------------------------------------------------------------------
+// A 511x640 pair spends 4-8 us in each of these stages and ~3 us between two dependent launches - as much as in its hot
+// kernel - and the stages do not depend on each other: their grids are laid end to end along blockIdx.x of ONE launch
+// (the longest-running stage first).
+struct PrepStages {
+    unsigned gx[3], gy[3], gz[3];     // grid of stage i (gx = 0: absent)
+    unsigned first[4];                // first flat CTA index of stage i; first[3] = CTAs of the launch
+    int rows_per_cta;                 // prep_tgt stage (float launches: rows of the AF / BF arrays)
+    int border_ppr_log2;              // fused_border stage: log2(pixels per row of a CTA)
+};
+static inline void prep_stage_set(PrepStages& s, int i, unsigned gx, unsigned gy, unsigned gz) { s.gx[i] = gx; s.gy[i] = gy; s.gz[i] = gz; }
+// STEREO_PREP_SPLIT=1 (profiling knob): every stage as its own launch of the same kernel, so a launch list times them apart.
+template <typename Fn>
+static inline int prep_launch(Fn fn, const FastKernelParams& kp, PrepStages& stg, cudaStream_t st);
+static inline unsigned prep_stage_finish(PrepStages& s) {
+    unsigned at = 0;
+    for (int i = 0; i < 3; ++i) { s.first[i] = at; at += s.gx[i] * s.gy[i] * s.gz[i]; }
+    s.first[3] = at;
+    return at;
+}
+template <typename Fn>
+static inline int prep_launch(Fn fn, const FastKernelParams& kp, PrepStages& stg, cudaStream_t st) {
+    static const bool split = [] { const char* e = getenv("STEREO_PREP_SPLIT"); return e && atoi(e) != 0; }();
+    if (!split) { fn<<<prep_stage_finish(stg), 256, 0, st>>>(kp, stg); return 1; }
+    int launches = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (!stg.gx[i]) continue;
+        PrepStages one = stg;
+        for (int k = 0; k < 3; ++k) if (k != i) one.gx[k] = one.gy[k] = one.gz[k] = 0;
+        fn<<<prep_stage_finish(one), 256, 0, st>>>(kp, one);
+        ++launches;
+    }
+    return launches;
+}
+__device__ __forceinline__ uint3 prep_stage_block(const PrepStages& s, int i) {
+    const unsigned b = blockIdx.x - s.first[i];
+    return make_uint3(b % s.gx[i], (b / s.gx[i]) % s.gy[i], b / (s.gx[i] * s.gy[i]));
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Prep kernels: operand rows in the layout the hot loop consumes
 // ---------------------------------------------------------------------------------------------------
-// LP[j][p]: 4 columns per thread, 16-byte stores.
-// Every prep / merge kernel takes the launch's parameter block; blockIdx.z selects the job.
-__global__ void __launch_bounds__(256) prep_lp_kernel(const __grid_constant__ FastKernelParams P) {
+// Every prep / merge kernel takes the launch's parameter block; the z index of its grid selects the job.  The stages that
+// do not depend on each other are bodies taking their block index as an argument: prep_u8_kernel / prep_f32_kernel below lay
+// their grids end to end in ONE launch.
+//
+// LP[j][p]: 4 columns per thread, 16-byte stores.  256 threads.
+constexpr int LP_ROWS = 8;            // operand rows per CTA
+__device__ __forceinline__ void prep_lp_body(const FastKernelParams& P, const uint3 bid) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
+    const FastJob& job = P.job[bid.z];
     const uint8_t* __restrict__ A = job.A; const size_t step = job.a_step;
     int32_t* __restrict__ LP = job.LP;
-    const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int j = blockIdx.y;
+    const int p4 = (bid.x * 256 + threadIdx.x) * 4;
     if (p4 >= g.lp_pitch) return;
-    const int y = g.base_y + j;
-    const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
-    const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
     // Fused pair launches: padded columns past the end of the row (the windows of the partner direction's candidates
     // centred in the right padding, DisparitySSD.cpp:39-40,50) alias the next padded row, exactly as in the
     // extended TARGET image of an unfused launch (bext).  The direction's own pixels never read those columns.
     const bool ext = g.npairs > 0 && p4 + 3 >= g.cols + 2 * g.R;
-    int v[4];
+    int col[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int col = clampi(p4 + t - g.R, 0, g.cols - 1);
-        int lnew = rnew[col], lold = rold[col];
-        if (ext) {
-            lnew = bext(A, step, g.rows, g.cols, g.R, y + g.R, p4 + t + g.R, g.ar0, g.ar1);
-            lold = bext(A, step, g.rows, g.cols, g.R, y - g.R - 1, p4 + t + g.R, g.ar0, g.ar1);
+    for (int t = 0; t < 4; ++t) col[t] = clampi(p4 + t - g.R, 0, g.cols - 1);
+    const int j0 = int(bid.y) * LP_ROWS, j1 = min(g.J, j0 + LP_ROWS);
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+        const int y = g.base_y + j;
+        const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+        const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+        int v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int lnew, lold;
+            if (ext) {
+                lnew = bext(A, step, g.rows, g.cols, g.R, y + g.R, p4 + t + g.R, g.ar0, g.ar1);
+                lold = bext(A, step, g.rows, g.cols, g.R, y - g.R - 1, p4 + t + g.R, g.ar0, g.ar1);
+            } else { lnew = rnew[col[t]]; lold = rold[col[t]]; }
+            // SSD: (-l_new, +l_old) so the running sums hold -C; NCC: (+l_new, -l_old), sums hold +C
+            const int a_new = g.cost == STEREO_COST_SSD ? -lnew : lnew, a_old = g.cost == STEREO_COST_SSD ? lold : -lold;
+            v[t] = int(uint32_t(uint16_t(int16_t(a_new))) | (uint32_t(uint16_t(int16_t(a_old))) << 16));
         }
-        // SSD: (-l_new, +l_old) so the running sums hold -C; NCC: (+l_new, -l_old), sums hold +C
-        const int a_new = g.cost == STEREO_COST_SSD ? -lnew : lnew, a_old = g.cost == STEREO_COST_SSD ? lold : -lold;
-        v[t] = int(uint32_t(uint16_t(int16_t(a_new))) | (uint32_t(uint16_t(int16_t(a_old))) << 16));
+        *reinterpret_cast<int4*>(LP + size_t(j) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<int4*>(LP + size_t(j) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
 }
 
 // RQ[jp][q]: 4 positions per thread, 16-byte stores.
@@ -172,7 +222,7 @@ constexpr int PT_VSTRIDE = PT_THREADS + 16;   // words per shared-memory row (sl
 __host__ __device__ constexpr int pt_ts(int R) { return (PT_THREADS - 2 * R) & ~3; }
 
 template <int R, bool INTERIOR>
-__device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& job, int rows_per_cta, int (&vs)[2][4][PT_VSTRIDE]) {
+__device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& job, const uint3 bid, int rows_per_cta, int (&vs)[2][4][PT_VSTRIDE]) {
     const uint8_t* __restrict__ B = job.B; const size_t step = job.b_step;
     uint32_t* __restrict__ RQ = job.RQ;
     constexpr int TS = pt_ts(R);
@@ -180,7 +230,7 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
     constexpr int NVEC = (NV + 3) / 4;
     const int t = threadIdx.x;
     const int delta = job.qoff - job.eoff + R;
-    const int x0 = -delta + int(blockIdx.x) * TS;          // first V column of this CTA (multiple of 4)
+    const int x0 = -delta + int(bid.x) * TS;               // first V column of this CTA (multiple of 4)
     const int x = x0 + t;
     // column mapping of bext(): which source column, and whether the flat index falls into a neighbouring row
     const int Wp = g.cols + 2 * R;
@@ -198,7 +248,7 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
         const int r = clampi(clampi(i + shift, 0, rows - 1), ar0, ar1 - 1);
         return Bc[size_t(r) * step];
     };
-    const int j0 = int(blockIdx.y) * rows_per_cta;
+    const int j0 = int(bid.y) * rows_per_cta;
     const int j1 = min(g.J, j0 + rows_per_cta);
     const bool ncc = g.cost != STEREO_COST_SSD;
     // vertical sum of squares of the row above the first one
@@ -294,26 +344,15 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
 }
 
 template <int R>
-__global__ void __launch_bounds__(PT_THREADS) prep_tgt_kernel(const __grid_constant__ FastKernelParams P, int rows_per_cta) {
+__device__ __forceinline__ void prep_tgt_stage(const FastKernelParams& P, const uint3 bid, int rows_per_cta, int (&vs)[2][4][PT_VSTRIDE]) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
-    __shared__ __align__(16) int vs[2][4][PT_VSTRIDE];
+    const FastJob& job = P.job[bid.z];
     // rows this CTA reads: base_y + j0 - R - 2 .. base_y + j1 + R (one more either side for the row-wrap columns)
-    const int j0 = int(blockIdx.y) * rows_per_cta, j1 = min(g.J, j0 + rows_per_cta);
+    const int j0 = int(bid.y) * rows_per_cta, j1 = min(g.J, j0 + rows_per_cta);
     const int ilo = g.base_y + j0 - R - 2, ihi = g.base_y + j1 + R;
     const bool interior = ilo >= max(0, g.ar0) && ihi <= min(g.rows, g.ar1) - 1;
-    if (interior) prep_tgt_body<R, true>(g, job, rows_per_cta, vs);
-    else prep_tgt_body<R, false>(g, job, rows_per_cta, vs);
-}
-
-typedef void (*prep_tgt_fn)(const FastKernelParams, int);
-static inline prep_tgt_fn prep_tgt_pick(int R) {
-    switch (R) {
-        case 0: return prep_tgt_kernel<0>; case 1: return prep_tgt_kernel<1>; case 2: return prep_tgt_kernel<2>;
-        case 3: return prep_tgt_kernel<3>; case 4: return prep_tgt_kernel<4>; case 5: return prep_tgt_kernel<5>;
-        case 6: return prep_tgt_kernel<6>; case 7: return prep_tgt_kernel<7>;
-    }
-    return nullptr;
+    if (interior) prep_tgt_body<R, true>(g, job, bid, rows_per_cta, vs);
+    else prep_tgt_body<R, false>(g, job, bid, rows_per_cta, vs);
 }
 
 // NCC: per strip (K pixels) and output row, the power of two just above sqrt(max EL) — the binade the
@@ -400,55 +439,62 @@ __device__ __forceinline__ float bextf(const uint8_t* __restrict__ B, size_t ste
 // AF[jj][p]: rows of the replicate-padded reference image, array row jj <-> image row base_y - R - 1 + jj, p = padded
 // column.  Operand row j of the hot kernel = (entering row AF[j + 2R + 1], leaving row AF[j]).  Fused pair launches: the
 // columns past the padded row alias the next padded row exactly like the extended target image does (see prep_lp_kernel).
-__global__ void __launch_bounds__(256) prep_af_kernel(const __grid_constant__ FastKernelParams P) {
+constexpr int FR_ROWS = 4;            // image rows per CTA of the two stages below
+__device__ __forceinline__ void prep_af_body(const FastKernelParams& P, const uint3 bid, const int nrows_total) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
-    const int p4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int jj = blockIdx.y;
+    const FastJob& job = P.job[bid.z];
+    const int p4 = (bid.x * 256 + threadIdx.x) * 4;
     if (p4 >= g.lp_pitch) return;
-    const int i = g.base_y - g.R - 1 + jj;
-    const float* row = reinterpret_cast<const float*>(job.A + size_t(clampi(clampi(i, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * job.a_step);
     const bool ext = g.npairs > 0 && p4 + 3 >= g.cols + 2 * g.R;
-    float v[4];
+    const int jj0 = int(bid.y) * FR_ROWS, jj1 = min(nrows_total, jj0 + FR_ROWS);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        v[t] = ext ? bextf(job.A, job.a_step, g.rows, g.cols, g.R, i, p4 + t + g.R, g.ar0, g.ar1)
-                   : row[clampi(p4 + t - g.R, 0, g.cols - 1)];
+    for (int jj = jj0; jj < jj1; ++jj) {
+        const int i = g.base_y - g.R - 1 + jj;
+        const float* row = reinterpret_cast<const float*>(job.A + size_t(clampi(clampi(i, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * job.a_step);
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            v[t] = ext ? bextf(job.A, job.a_step, g.rows, g.cols, g.R, i, p4 + t + g.R, g.ar0, g.ar1)
+                       : row[clampi(p4 + t - g.R, 0, g.cols - 1)];
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.LP) + size_t(jj) * g.lp_pitch + p4) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.LP) + size_t(jj) * g.lp_pitch + p4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // BF[jj][q]: rows of the extended target image, column q <-> extended column e = q - qoff.
-__global__ void __launch_bounds__(256) prep_bf_kernel(const __grid_constant__ FastKernelParams P) {
+__device__ __forceinline__ void prep_bf_body(const FastKernelParams& P, const uint3 bid, const int nrows_total) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
-    const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int jj = blockIdx.y;
+    const FastJob& job = P.job[bid.z];
+    const int q4 = (bid.x * 256 + threadIdx.x) * 4;
     if (q4 >= g.rq_pitch || !job.RQ) return;
-    const int i = g.base_y - g.R - 1 + jj;
-    float v[4];
+    const int jj0 = int(bid.y) * FR_ROWS, jj1 = min(nrows_total, jj0 + FR_ROWS);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] = bextf(job.B, job.b_step, g.rows, g.cols, g.R, i, q4 + t - job.qoff, g.ar0, g.ar1);
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.RQ) + size_t(jj) * g.rq_pitch + q4) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int jj = jj0; jj < jj1; ++jj) {
+        const int i = g.base_y - g.R - 1 + jj;
+        float v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = bextf(job.B, job.b_step, g.rows, g.cols, g.R, i, q4 + t - job.qoff, g.ar0, g.ar1);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(job.RQ) + size_t(jj) * g.rq_pitch + q4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
 }
 
 // Position / energy rows of the float path.  SSD: E2[j][q2] = q2 for a legal centre, KEY_INVALID otherwise (the key is
 // 128 * SSD + position, there is no energy term).  NCC: RS[j][q2] = 1 / sqrt(window energy of the extended target image),
 // summed in double like OpenCV's integral images (0 for an illegal centre or an empty window).
-__global__ void __launch_bounds__(128) prep_e2f_kernel(const __grid_constant__ FastKernelParams P) {
+// (SSD only; 4 positions per thread, 256 threads.)
+__device__ __forceinline__ void prep_e2f_body(const FastKernelParams& P, const uint3 bid) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
-    const int q2 = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (q2 >= g.e2_pitch) return;
-    const int uc = q2 - job.eoff;
-    const bool valid = uc >= job.cmin && uc <= job.cmax;
-    const size_t o = size_t(j) * g.e2_pitch + q2;
-    if (g.cost == STEREO_COST_SSD) {
-        job.E2[o] = valid ? q2 : int(KEY_INVALID);
-        return;
+    const FastJob& job = P.job[bid.z];
+    const int q2 = (bid.x * 256 + threadIdx.x) * 4;
+    const int j = bid.y;
+    if (q2 >= g.e2_pitch) return;                          // (e2_pitch is a multiple of 4)
+    int key[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int uc = q2 + k - job.eoff;
+        key[k] = (uc >= job.cmin && uc <= job.cmax) ? q2 + k : int(KEY_INVALID);
     }
-    job.RS[o] = 0.f;      // (NCC rows come from prep_rsf_kernel)
+    *reinterpret_cast<int4*>(job.E2 + size_t(j) * g.e2_pitch + q2) = make_int4(key[0], key[1], key[2], key[3]);
 }
 
 // NCC, float path: RS[j][q2] = 1 / sqrt(window energy of the extended target image at centre q2), separably: a block owns
@@ -456,14 +502,14 @@ __global__ void __launch_bounds__(128) prep_e2f_kernel(const __grid_constant__ F
 // the 2R+1 window rows in double (like OpenCV's double integral images; squares of floats are exact in double) and slides it
 // down the block's rows, the centres then add 2R+1 neighbouring column sums from shared memory.
 constexpr int RSF_ROWS = 8;
-__global__ void __launch_bounds__(256) prep_rsf_kernel(const __grid_constant__ FastKernelParams P) {
+__device__ __forceinline__ void prep_rsf_body(const FastKernelParams& P, const uint3 bid) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
+    const FastJob& job = P.job[bid.z];
     __shared__ double vs[RSF_ROWS][256];
     const int R = g.R, ts = 256 - 2 * R;
     const int t = threadIdx.x;
-    const int j0 = blockIdx.y * RSF_ROWS;
-    const int q20 = blockIdx.x * ts;
+    const int j0 = bid.y * RSF_ROWS;
+    const int q20 = bid.x * ts;
     const int e = q20 - job.eoff + R + t;                  // extended column of this thread
     auto sq = [&](int i) -> double { const double b = bextf(job.B, job.b_step, g.rows, g.cols, R, i, e, g.ar0, g.ar1); return b * b; };
     double v = 0;
@@ -494,6 +540,15 @@ __global__ void __launch_bounds__(256) prep_rsf_kernel(const __grid_constant__ F
         }
         job.RS[size_t(j) * g.e2_pitch + q2] = rs;
     }
+}
+
+// Float operands.  Stage 0: position rows (SSD) or 1/sqrt(energy) rows (NCC); 1: target rows; 2: reference rows.
+__global__ void __launch_bounds__(256) prep_f32_kernel(const __grid_constant__ FastKernelParams P, const __grid_constant__ PrepStages s) {
+    if (blockIdx.x < s.first[1]) {
+        if (P.g.cost == STEREO_COST_SSD) prep_e2f_body(P, prep_stage_block(s, 0));
+        else prep_rsf_body(P, prep_stage_block(s, 0));
+    } else if (blockIdx.x < s.first[2]) prep_bf_body(P, prep_stage_block(s, 1), s.rows_per_cta);
+    else prep_af_body(P, prep_stage_block(s, 2), s.rows_per_cta);
 }
 
 // NCC, float path: window energies of the reference image per pixel (replicate padding, double sums) ...
@@ -702,112 +757,118 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
 // [cols, min(x' + range, cols-1+R)], whose windows run past the end of the padded row and alias the next row through
 // the flat index (bext).  Normally the strips simply extend R columns (LP rows built with bext); when those R columns
 // would cost a whole extra tile (narrow images: 1280 columns = 4 tiles of 320, +4 columns = a fifth), the <= R
-// candidates of the last `range` pixels of every row are evaluated here instead - one thread per pixel, the window
-// of the reference image and the 3R extended target columns of each window row in registers - and merged into the
-// same partial-key map (RED.MIN) with the key the hot kernel would have produced: BIAS + 128*(ER - 2C) + pos.
+// candidates of the last `range` pixels of every row are evaluated here instead and merged into the same partial-key
+// map (RED.MIN) with the key the hot kernel would have produced: BIAS + 128*(ER - 2C) + pos.
+//
+// A CTA of 256 threads takes 2^k pixels (32..256, the smallest that covers `range`) of 256 / 2^k consecutive rows: the 3R
+// extended target columns of a window row - R image columns, R times the replicated last column, R times the aliased first
+// column of the next padded row (zero past the last padded row) - depend on the row alone, so the CTA packs every
+// candidate's W-byte window of every window row it touches into words in shared memory once (and sums their squares: ER);
+// a thread then packs its pixel's reference window rows the same way and takes 4 IDP.4A per (window row, candidate)
+// against broadcast LDS.128 reads.  (The first version read every byte of both windows per candidate: 45 us for 511 rows x
+// 95 pixels against 50 us for the whole cost volume.)
+constexpr int FB_THREADS = 256;
+constexpr int FB_MAXROWS = FB_THREADS / 32;
+static inline int fused_border_ppr_log2(int range) { int k = 5; while (k < 8 && (1 << k) < range) ++k; return k; }
 template <int R>
-__global__ void __launch_bounds__(32 * (R > 0 ? R : 1)) fused_border_kernel(const __grid_constant__ FastKernelParams P) {
-    // one thread per (pixel x', candidate c): threadIdx.x = pixel within the block, threadIdx.y = c
-    constexpr int W = 2 * R + 1;
+__device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, const uint3 bid, const int ppr_log2) {
+    constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1, NWORD = (W + 3) / 4;
+    constexpr int TR = W + FB_MAXROWS - 1;                     // window rows a CTA touches at most
+    __shared__ uint8_t bcol[TR][NB + 1];
+    __shared__ __align__(16) uint32_t bw[TR][NCAND][4];
+    __shared__ int er[FB_MAXROWS][NCAND];
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[g.npairs + blockIdx.z];          // the right-referenced direction: A = right image, B = left image
+    const FastJob& job = P.job[g.npairs + bid.z];               // the right-referenced direction: A = right image, B = left image
     const int range = job.dmax;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = threadIdx.y;
-    const int xp = g.cols - 1 - idx;                            // the pixel x'
-    const int yy = blockIdx.y, y = g.rb + yy;
-    if (idx >= range || xp < 0) return;
-    const int ncand = min(xp + range, g.cols - 1 + R) - g.cols + 1;
-    if (c >= ncand) return;
+    const int rpc = FB_THREADS >> ppr_log2, tr = W + rpc - 1;    // output rows of this CTA, window rows they touch
+    const int yy0 = int(bid.y) * rpc, y0 = g.rb + yy0;
     const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
-    int ssd = 0, eref = 0;
-    // the 3R extended target columns right of unpadded column cols-R-1 are: R image columns, R times the replicated
-    // last column, R times the aliased first column of the next padded row (zero past the last padded row) - bext();
-    // candidate c reads W of them from offset c
-#pragma unroll 1
-    for (int wy = -R; wy <= R; ++wy) {
-        const int ra = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
-        const uint8_t* arow = A + size_t(ra) * job.a_step;
+    for (int t = threadIdx.x; t < tr * NB; t += FB_THREADS) {
+        const int wr = t / NB, k = t % NB;
+        const int ra = clampi(clampi(y0 + wr - R, 0, g.rows - 1), g.ar0, g.ar1 - 1);
         const uint8_t* brow = B + size_t(ra) * job.b_step;
-        const int edge = brow[g.cols - 1];
-        const int wrap = bext(B, job.b_step, g.rows, g.cols, R, y + wy, g.cols + 4 * R, g.ar0, g.ar1);     // padded column cols + 3R >= Wp
+        bcol[wr][k] = k < R ? brow[max(g.cols - R + k, 0)] : k < 2 * R ? brow[g.cols - 1]
+                    : uint8_t(bext(B, job.b_step, g.rows, g.cols, R, y0 + wr - R, g.cols + 4 * R, g.ar0, g.ar1));   // padded column cols + 3R >= Wp
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tr * NCAND * 4; t += FB_THREADS) {
+        const int wr = t / (NCAND * 4), c = (t / 4) % NCAND, q = t % 4;
+        uint32_t word = 0;
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            const int a = arow[clampi(xp - R + i, 0, g.cols - 1)];
-            const int t = c + i;                                  // index into the 3R extended columns
-            const int bv = t < R ? int(brow[max(g.cols - R + t, 0)]) : (t < 2 * R ? edge : wrap);
-            const int d = a - bv;
-            ssd += d * d; eref += a * a;
+        for (int k = 0; k < 4; ++k) { const int i = 4 * q + k; if (i < W) word |= uint32_t(bcol[wr][c + i]) << (8 * k); }
+        bw[wr][c][q] = word;
+    }
+    __syncthreads();
+    if (threadIdx.x < rpc * NCAND) {
+        const int r = threadIdx.x / NCAND, c = threadIdx.x % NCAND;
+        uint32_t e = 0;
+        for (int wr = 0; wr < W; ++wr)
+#pragma unroll
+            for (int q = 0; q < NWORD; ++q) e = __dp4a(bw[r + wr][c][q], bw[r + wr][c][q], e);
+        er[r][c] = int(e);
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> ppr_log2;
+    const int idx = (int(bid.x) << ppr_log2) + (threadIdx.x & ((1 << ppr_log2) - 1));
+    const int xp = g.cols - 1 - idx;                            // the pixel x'
+    const int yy = yy0 + r, y = y0 + r;
+    if (yy >= g.nrows || idx >= range || xp < 0) return;
+    const int ncand = min(range - idx, R);                      // centres cols .. min(x' + range, cols-1+R)
+    uint32_t acc[NCAND];
+#pragma unroll
+    for (int c = 0; c < NCAND; ++c) acc[c] = 0;
+    const bool interior = xp - R >= 0 && xp + R <= g.cols - 1;
+#pragma unroll 2
+    for (int wr = 0; wr < W; ++wr) {
+        const int ra = clampi(clampi(y + wr - R, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+        const uint8_t* arow = A + size_t(ra) * job.a_step;
+        uint32_t aw[NWORD];
+#pragma unroll
+        for (int q = 0; q < NWORD; ++q) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * q + k;
+                if (i < W) word |= uint32_t(arow[interior ? xp - R + i : clampi(xp - R + i, 0, g.cols - 1)]) << (8 * k);
+            }
+            aw[q] = word;
+        }
+#pragma unroll
+        for (int c = 0; c < NCAND; ++c) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bw[r + wr][c]);
+            const uint32_t bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int q = 0; q < NWORD; ++q) acc[c] = __dp4a(aw[q], bq[q], acc[c]);
         }
     }
     uint32_t* __restrict__ PART2 = reinterpret_cast<uint32_t*>(job.PART);
-    const int pos = g.cols + c;
-    const uint32_t key = key_bias(R) + (uint32_t(ssd - eref) << FKEY_BITS) + uint32_t(pos);
-    atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
-}
-
-// The same with one thread per PIXEL, the window of the reference image and the 3R extended target columns of each window
-// row in registers, all R candidates per thread: fewer loads in total - the better kernel when the launch has many such
-// pixels (720 rows x 63 columns x 4 pairs: 13 us against 39 us), the worse one when it has few (511 x 95 x 1: 20 us against 4).
-template <int R>
-__global__ void __launch_bounds__(128) fused_border_px_kernel(const __grid_constant__ FastKernelParams P) {
-    constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1;
-    const FastGeom& g = P.g;
-    const FastJob& job = P.job[g.npairs + blockIdx.z];
-    const int range = job.dmax;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int xp = g.cols - 1 - idx;
-    const int yy = blockIdx.y, y = g.rb + yy;
-    if (idx >= range || xp < 0) return;
-    const int ncand = min(xp + range, g.cols - 1 + R) - g.cols + 1;
-    if (ncand <= 0) return;
-    const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
-    int ssd[NCAND], eref = 0;
 #pragma unroll
-    for (int c = 0; c < NCAND; ++c) ssd[c] = 0;
-#pragma unroll 1
-    for (int wy = -R; wy <= R; ++wy) {
-        const int ra = clampi(clampi(y + wy, 0, g.rows - 1), g.ar0, g.ar1 - 1);
-        const uint8_t* arow = A + size_t(ra) * job.a_step;
-        const uint8_t* brow = B + size_t(ra) * job.b_step;
-        int a[W], b[NB];
-#pragma unroll
-        for (int i = 0; i < W; ++i) { a[i] = arow[clampi(xp - R + i, 0, g.cols - 1)]; eref += a[i] * a[i]; }
-        const int edge = brow[g.cols - 1];
-        const int wrap = bext(B, job.b_step, g.rows, g.cols, R, y + wy, g.cols + 4 * R, g.ar0, g.ar1);
-#pragma unroll
-        for (int i = 0; i < R; ++i) { b[i] = brow[max(g.cols - R + i, 0)]; b[R + i] = edge; b[2 * R + i] = wrap; }
-#pragma unroll
-        for (int c = 0; c < R; ++c)
-#pragma unroll
-            for (int i = 0; i < W; ++i) { const int d = a[i] - b[c + i]; ssd[c] += d * d; }
-    }
-    uint32_t* __restrict__ PART2 = reinterpret_cast<uint32_t*>(job.PART);
-#pragma unroll
-    for (int c = 0; c < R; ++c) {
+    for (int c = 0; c < NCAND; ++c) {
         if (c >= ncand) break;
         const int pos = g.cols + c;
-        const uint32_t key = key_bias(R) + (uint32_t(ssd[c] - eref) << FKEY_BITS) + uint32_t(pos);
+        const uint32_t key = key_bias(R) + ((uint32_t(er[r][c]) - 2u * acc[c]) << FKEY_BITS) + uint32_t(pos);
         atomicMin(PART2 + (size_t((pos - xp) / g.dg) * g.nrows + yy) * g.wpart + xp, key);
     }
 }
 
-typedef void (*fused_border_fn)(const FastKernelParams);
-static inline fused_border_fn fused_border_px_pick(int R) {
+// u8 operands.  Stage 0: target rows, energies / position keys (prep_tgt); 1: the partner's candidates in the right padding
+// (fused_border, fused pairs only - after the memset of the partners' partial keys); 2: reference rows (prep_lp).
+template <int R>
+__global__ void __launch_bounds__(256, R >= 6 ? 3 : 4) prep_u8_kernel(const __grid_constant__ FastKernelParams P, const __grid_constant__ PrepStages s) {
+    static_assert(PT_THREADS == 256 && FB_THREADS == 256, "the stages share one CTA shape");
+    __shared__ __align__(16) int vs[2][4][PT_VSTRIDE];
+    if (blockIdx.x < s.first[1]) prep_tgt_stage<R>(P, prep_stage_block(s, 0), s.rows_per_cta, vs);
+    else if (blockIdx.x < s.first[2]) { if constexpr (R > 0) fused_border_stage<R>(P, prep_stage_block(s, 1), s.border_ppr_log2); }
+    else prep_lp_body(P, prep_stage_block(s, 2));
+}
+typedef void (*prep_u8_fn)(const FastKernelParams, const PrepStages);
+static inline prep_u8_fn prep_u8_pick(int R) {
     switch (R) {
-        case 1: return fused_border_px_kernel<1>; case 2: return fused_border_px_kernel<2>; case 3: return fused_border_px_kernel<3>;
-        case 4: return fused_border_px_kernel<4>; case 5: return fused_border_px_kernel<5>; case 6: return fused_border_px_kernel<6>;
-        case 7: return fused_border_px_kernel<7>;
+        case 0: return prep_u8_kernel<0>; case 1: return prep_u8_kernel<1>; case 2: return prep_u8_kernel<2>;
+        case 3: return prep_u8_kernel<3>; case 4: return prep_u8_kernel<4>; case 5: return prep_u8_kernel<5>;
+        case 6: return prep_u8_kernel<6>; case 7: return prep_u8_kernel<7>;
     }
     return nullptr;
-}
-static inline fused_border_fn fused_border_pick(int R) {
-    switch (R) {
-        case 1: return fused_border_kernel<1>; case 2: return fused_border_kernel<2>; case 3: return fused_border_kernel<3>;
-        case 4: return fused_border_kernel<4>; case 5: return fused_border_kernel<5>; case 6: return fused_border_kernel<6>;
-        case 7: return fused_border_kernel<7>;
-    }
-    return nullptr;      // R = 0: the padding is empty
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1119,13 +1180,15 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     const unsigned nz = unsigned(n), nwalk = fused_pairs ? unsigned(fused_pairs) : nz;
     static const bool legacy_prep = [] { const char* e = getenv("STEREO_PREP_LEGACY"); return e && atoi(e) != 0; }();
     fast_kernel_fn fn = nullptr;
+    PrepStages stg{};
     if (opf) {
-        // float operand rows straight from the images (padding, row-wrap aliasing), position / energy rows
-        prep_af_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), unsigned(lp_rows), nwalk), 256, 0, st>>>(kp);
-        prep_bf_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), unsigned(rq_rows), nwalk), 256, 0, st>>>(kp);
-        if (!ncc) prep_e2f_kernel<<<dim3(div_round_up(g.e2_pitch, 128), g.J, nz), 128, 0, st>>>(kp);
-        else prep_rsf_kernel<<<dim3(div_round_up(g.e2_pitch, 256 - 2 * g.R), div_round_up(g.J, RSF_ROWS), nz), 256, 0, st>>>(kp);
-        ctx->last_launches += 3;
+        // float operand rows straight from the images (padding, row-wrap aliasing), position / energy rows: one launch
+        if (!ncc) prep_stage_set(stg, 0, unsigned(div_round_up(g.e2_pitch / 4, 256)), g.J, nz);
+        else prep_stage_set(stg, 0, unsigned(div_round_up(g.e2_pitch, 256 - 2 * g.R)), unsigned(div_round_up(g.J, RSF_ROWS)), nz);
+        stg.rows_per_cta = int(lp_rows);                 // (== rq_rows)
+        prep_stage_set(stg, 1, unsigned(div_round_up(g.rq_pitch / 4, 256)), unsigned(div_round_up(rq_rows, size_t(FR_ROWS))), nwalk);
+        prep_stage_set(stg, 2, unsigned(div_round_up(g.lp_pitch / 4, 256)), unsigned(div_round_up(lp_rows, size_t(FR_ROWS))), nwalk);
+        ctx->last_launches += prep_launch(prep_f32_kernel, kp, stg, st);
         if (ncc && fast_launch_is_pairs(ps, n)) {
             // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
             prep_scale_pair_kernel<<<dim3(div_round_up(g.tilesX * g.spc, 128), g.nrows, nz), 128, 0, st>>>(kp, n / 2);
@@ -1137,18 +1200,29 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         }
         fn = fast_pick_opf(g.R, ncc ? OPF_NCC : (fused_pairs ? OPF_SSD_FUSED : OPF_SSD));
     } else {
-        prep_lp_kernel<<<dim3(div_round_up(g.lp_pitch / 4, 256), g.J, nwalk), 256, 0, st>>>(kp);
-        ctx->last_launches += 1;
-        if (!legacy_prep || fused_pairs) {
+        // reference rows, target rows + energies and (fused pairs with a narrow last tile) the partner's candidates centred in
+        // the right padding: one launch.  (STEREO_PREP_LEGACY=1, unfused launches only: the target stage as three passes.)
+        const bool three_pass = legacy_prep && !fused_pairs;
+        if (!three_pass) {
             int delta_max = 0;
             for (int i = 0; i < n; ++i) { const int d = kp.job[i].qoff - kp.job[i].eoff + g.R; if (d > delta_max) delta_max = d; }
             const int span = g.rq_pitch > g.e2_pitch + delta_max ? g.rq_pitch : g.e2_pitch + delta_max;
             const int tiles = int(div_round_up(span, pt_ts(g.R)));
             int rpc = PT_ROWS;                          // fewer rows per CTA while the grid would leave SMs idle
             while (rpc > 16 && (long long)tiles * div_round_up(g.J, rpc) * n < 6LL * ctx->sm_count) rpc /= 2;
-            prep_tgt_pick(g.R)<<<dim3(tiles, div_round_up(g.J, rpc), nz), PT_THREADS, 0, st>>>(kp, rpc);
-            ctx->last_launches += 1;
-        } else {   // three-pass version (debug knob): RQ rows, vertical sums in HBM, horizontal sums
+            stg.rows_per_cta = rpc;
+            prep_stage_set(stg, 0, unsigned(tiles), unsigned(div_round_up(g.J, rpc)), nz);
+        }
+        if (fused_pairs && g.border && g.R > 0) {
+            const int range = -ps[0].dmin, k = fused_border_ppr_log2(range);
+            stg.border_ppr_log2 = k;
+            prep_stage_set(stg, 1, unsigned(div_round_up(range, 1 << k)), unsigned(div_round_up(g.nrows, FB_THREADS >> k)), unsigned(fused_pairs));
+        }
+        prep_stage_set(stg, 2, unsigned(div_round_up(g.lp_pitch / 4, 256)), unsigned(div_round_up(g.J, LP_ROWS)), nwalk);
+        prep_u8_fn pf = prep_u8_pick(g.R);
+        if (!pf) { set_error("no prep kernel for R=%d (internal)", g.R); return STEREO_ERR_UNSUPPORTED; }
+        ctx->last_launches += prep_launch(pf, kp, stg, st);
+        if (three_pass) {   // RQ rows, vertical sums in HBM, horizontal sums
             prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
             prep_v_kernel<<<dim3(div_round_up(vpitch, 128), div_round_up(g.nrows, PV_ROWS), nz), 128, 0, st>>>(kp, vpitch, 0);
             const size_t pe_smem = size_t(PE_ROWS) * (PE_COLS + 2 * g.R) * sizeof(int);
@@ -1169,23 +1243,7 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         fn = fused_pairs ? (ncc ? fast_pick_fused_ncc(g.R, g.hs) : fast_pick_fused(g.R, g.hs, fast_fused_all_mode1(g) ? 0 : 1)) : fast_pick(ps[0].cost, g.R, g.hs);
     }
     if (!fn) { set_error("no hot kernel for R=%d hs=%d opf=%d (internal)", g.R, g.hs, g.opf); return STEREO_ERR_UNSUPPORTED; }
-    if (fused_pairs) {                             // (the partners' memsets are not counted as kernel launches)
-        if (g.border) {
-            const long long px = (long long)(-ps[0].dmin) * g.nrows * fused_pairs;      // pixels with candidates in the padding
-            if (px >= 65536) {          // many: one thread per pixel
-                if (fused_border_fn bf = fused_border_px_pick(g.R)) {
-                    const int bt = -ps[0].dmin <= 64 ? 64 : 128;
-                    bf<<<dim3(div_round_up(-ps[0].dmin, bt), g.nrows, unsigned(fused_pairs)), bt, 0, st>>>(kp);
-                    ctx->last_launches += 1;
-                }
-            } else if (fused_border_fn bf = fused_border_pick(g.R)) {
-                // few: one thread per (pixel of the last `range` columns, candidate centred in the padding)
-                bf<<<dim3(div_round_up(-ps[0].dmin, 32), g.nrows, unsigned(fused_pairs)), dim3(32, g.R), 0, st>>>(kp);
-                ctx->last_launches += 1;
-            }
-        }
-        ctx->fused_pairs_done += fused_pairs;
-    }
+    if (fused_pairs) ctx->fused_pairs_done += fused_pairs;     // (the partners' memsets are not counted as kernel launches)
     const int hot = ctx->hot_used < stereo_ctx::HOT_EVENTS ? ctx->hot_used : -1;
     if (hot >= 0) cudaEventRecord(ctx->hot0[hot], st);
     fn<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);

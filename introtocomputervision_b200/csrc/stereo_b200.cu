@@ -153,10 +153,10 @@ static size_t f32_scratch_bytes(stereo_ctx* ctx, const Problem& p, int dirs) {
 // synchronize: the kernel family is a host decision) and says which family serves this image pair.
 static int classify_images(stereo_ctx* ctx, const Problem& p, cudaStream_t st, uint8_t* a8, uint8_t* b8, size_t pitch, int* cls) {
     SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), st));
-    dim3 cb(32, 8), cg(div_round_up(p.cols, 32), div_round_up(p.rows, 8));
-    classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, p.rows, p.cols, a8, pitch, ctx->d_flag);
-    classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.tgt.ptr), p.tgt.step, p.rows, p.cols, b8, pitch, ctx->d_flag);
-    ctx->last_launches += 2;
+    dim3 cb(32, 8), cg(div_round_up(p.cols, 32), div_round_up(p.rows, 8), 2);
+    classify_convert_kernel<<<cg, cb, 0, st>>>(static_cast<const float*>(p.ref.ptr), p.ref.step, a8, static_cast<const float*>(p.tgt.ptr), p.tgt.step, b8,
+                                               p.rows, p.cols, pitch, ctx->d_flag);
+    ctx->last_launches += 1;
     SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaEventRecord(ctx->ev_gap0, st));
     SB_CUDA(cudaStreamSynchronize(st));
@@ -616,13 +616,13 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w, b, 0), 0));
             if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w - S, nb - 1, 2), 0));  // slot outputs downloaded
             if (dtype == PixType::F32 && nr > 0) {
-                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8));
+                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8), 2);
                 for (int c = 0; c < np; ++c) {
-                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].l + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
-                                                                 sl[c].l8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
-                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].r + size_t(uploaded) * in_pitch), in_pitch, nr, cols,
-                                                                 sl[c].r8 + size_t(uploaded) * u8_pitch, u8_pitch, ctx->d_flag);
-                    ctx->last_launches += 2;
+                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].l + size_t(uploaded) * in_pitch), in_pitch,
+                                                                 sl[c].l8 + size_t(uploaded) * u8_pitch,
+                                                                 reinterpret_cast<const float*>(sl[c].r + size_t(uploaded) * in_pitch), in_pitch,
+                                                                 sl[c].r8 + size_t(uploaded) * u8_pitch, nr, cols, u8_pitch, ctx->d_flag);
+                    ctx->last_launches += 1;
                 }
             }
             if (nr > 0) uploaded = up_hi;

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Device-resident timing probe: whole-call and hot-kernel milliseconds for a list of problem shapes.
 
-    python tools/probe_hot.py rows,cols,ndisp,R,cost,pairs[,f32|noisy] ...   -> one JSON line per shape
+    python tools/probe_hot.py [--queued] rows,cols,ndisp,R,cost,pairs[,f32|noisy] ...   -> one JSON line per shape
+
+--queued times the call with its launches already queued behind a running kernel (device time without the host's
+launch cost); the default starts from an idle device, as a caller sees it.
 
 u8 shapes go through stereo_disparity_pair_batch_u8_device, f32 / noisy ones (CV_32FC1 device images, 8-bit-valued or
 with Gaussian noise) through stereo_disparity_pair_f32_device, pair by pair."""
@@ -28,7 +31,8 @@ def main():
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for spec in sys.argv[1:]:
+    queued = "--queued" in sys.argv        # leave the L2 flush in flight: the call's launches queue up behind it
+    for spec in [a for a in sys.argv[1:] if not a.startswith("--")]:
         parts = spec.split(",")
         rows, cols, nd, R = (int(v) for v in parts[:4])
         cost_name, B = parts[4], int(parts[5])
@@ -64,7 +68,10 @@ def main():
         ms_call, ms_hot = [], []
         for _ in range(15):
             flush.zero_()
-            torch.cuda.synchronize()
+            if queued:
+                flush.zero_()
+            else:
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             call()
