@@ -103,7 +103,7 @@ int stereo_ctx_last_path(const stereo_ctx* ctx);
  * verdict is left out (classification kernels + the kernels of the chosen family). */
 float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
 /* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels; one launch
- * covers up to 8 directions of equally shaped problems), summed over the launches that were measured
+ * covers up to 16 directions of equally shaped problems), summed over the launches that were measured
  * (at most 16 per call); *launches_measured (nullable) receives how many that was.  <0 if the call used
  * no hot kernel.  This is the number the roofline report divides by. */
 float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measured);

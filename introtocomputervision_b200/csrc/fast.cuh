@@ -79,7 +79,10 @@ __device__ __forceinline__ uint3 prep_stage_block(const PrepStages& s, int i) {
 // their grids end to end in ONE launch.
 //
 // LP[j][p]: 4 columns per thread, 16-byte stores.  256 threads.
-constexpr int LP_ROWS = 8;            // operand rows per CTA
+// A CTA takes LP_ROWS rows: every load of all of them is issued before the first store (a plain row loop waits for one
+// memory round trip per row - the stores keep the next row's loads from moving up - and one row per CTA keeps only 8 bytes
+// per thread in flight: 99 us for four 4K pairs where the bytes need 30).
+constexpr int LP_ROWS = 4;
 __device__ __forceinline__ void prep_lp_body(const FastKernelParams& P, const uint3 bid) {
     const FastGeom& g = P.g;
     const FastJob& job = P.job[bid.z];
@@ -94,25 +97,36 @@ __device__ __forceinline__ void prep_lp_body(const FastKernelParams& P, const ui
     int col[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) col[t] = clampi(p4 + t - g.R, 0, g.cols - 1);
-    const int j0 = int(bid.y) * LP_ROWS, j1 = min(g.J, j0 + LP_ROWS);
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-        const int y = g.base_y + j;
-        const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
-        const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+    const int j0 = int(bid.y) * LP_ROWS;
+    int lnew[LP_ROWS][4], lold[LP_ROWS][4];
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+        const int y = g.base_y + min(j0 + r, g.J - 1);
+        if (ext) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                lnew[r][t] = bext(A, step, g.rows, g.cols, g.R, y + g.R, p4 + t + g.R, g.ar0, g.ar1);
+                lold[r][t] = bext(A, step, g.rows, g.cols, g.R, y - g.R - 1, p4 + t + g.R, g.ar0, g.ar1);
+            }
+        } else {
+            const uint8_t* rnew = A + size_t(clampi(clampi(y + g.R, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+            const uint8_t* rold = A + size_t(clampi(clampi(y - g.R - 1, 0, g.rows - 1), g.ar0, g.ar1 - 1)) * step;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { lnew[r][t] = rnew[col[t]]; lold[r][t] = rold[col[t]]; }
+        }
+    }
+    const bool ssd = g.cost == STEREO_COST_SSD;
+#pragma unroll
+    for (int r = 0; r < LP_ROWS; ++r) {
+        if (j0 + r >= g.J) break;
         int v[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            int lnew, lold;
-            if (ext) {
-                lnew = bext(A, step, g.rows, g.cols, g.R, y + g.R, p4 + t + g.R, g.ar0, g.ar1);
-                lold = bext(A, step, g.rows, g.cols, g.R, y - g.R - 1, p4 + t + g.R, g.ar0, g.ar1);
-            } else { lnew = rnew[col[t]]; lold = rold[col[t]]; }
             // SSD: (-l_new, +l_old) so the running sums hold -C; NCC: (+l_new, -l_old), sums hold +C
-            const int a_new = g.cost == STEREO_COST_SSD ? -lnew : lnew, a_old = g.cost == STEREO_COST_SSD ? lold : -lold;
+            const int a_new = ssd ? -lnew[r][t] : lnew[r][t], a_old = ssd ? lold[r][t] : -lold[r][t];
             v[t] = int(uint32_t(uint16_t(int16_t(a_new))) | (uint32_t(uint16_t(int16_t(a_old))) << 16));
         }
-        *reinterpret_cast<int4*>(LP + size_t(j) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<int4*>(LP + size_t(j0 + r) * g.lp_pitch + p4) = make_int4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -272,28 +286,26 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
         pn = Bc + size_t(g.base_y + j0 + R + shift) * step;
         po = Bc + size_t(g.base_y + j0 - R - 1 + shift) * step;
     }
-    int nb[8];
-    auto fetch = [&](int jj) {
+    // two 4-row groups of source bytes are in flight ahead of the one being summed (16 bytes per thread: with one group
+    // the stage moved 1.4 TB/s - 32 warps x 32 lanes x 8 bytes per SM against ~0.8 us of latency)
+    int nb[8], nb2[8];
+    auto fetch = [&](int jj, int (&dst)[8]) {
         if (INTERIOR) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                nb[4 * h] = pn[0]; nb[4 * h + 2] = pn[step]; nb[4 * h + 1] = po[0]; nb[4 * h + 3] = po[step];
+                dst[4 * h] = pn[0]; dst[4 * h + 2] = pn[step]; dst[4 * h + 1] = po[0]; dst[4 * h + 3] = po[step];
                 pn += 2 * step; po += 2 * step;
             }
         } else {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int ye = g.base_y + jj + 2 * h;
-                nb[4 * h] = load(ye + R); nb[4 * h + 1] = load(ye - R - 1); nb[4 * h + 2] = load(ye + 1 + R); nb[4 * h + 3] = load(ye - R);
+                dst[4 * h] = load(ye + R); dst[4 * h + 1] = load(ye - R - 1); dst[4 * h + 2] = load(ye + 1 + R); dst[4 * h + 3] = load(ye - R);
             }
         }
     };
-    fetch(j0);
-    int buf = 0;
-    for (int jj = j0; jj < j1; jj += 4, buf ^= 1) {
-        int cb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cb[i] = nb[i];
+    // vertical stage of one 4-row group: RQ words, running sums of squares into the shared-memory tile
+    auto vertical = [&](const int jj, const int buf, const int (&cb)[8]) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int b0 = cb[4 * h], b1 = cb[4 * h + 1], b2 = cb[4 * h + 2], b3 = cb[4 * h + 3];
@@ -303,7 +315,18 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
             v += b2 * b2 - b3 * b3;
             vs[buf][2 * h + 1][t] = v;
         }
-        if (jj + 4 < j1) fetch(jj + 4);                     // in flight across the barrier and the horizontal stage
+    };
+    fetch(j0, nb);
+    if (j0 + 4 < j1) fetch(j0 + 4, nb2);
+    // two groups per trip, each with its own registers: a refill is issued as soon as its group has been summed and stays in
+    // flight across two barriers and horizontal stages (moving a group between register sets would wait for its loads)
+    for (int jj0 = j0; jj0 < j1; jj0 += 8) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int jj = jj0 + 4 * half, buf = half;
+        if (jj >= j1) break;
+        if (half == 0) { vertical(jj, buf, nb); if (jj + 8 < j1) fetch(jj + 8, nb); }
+        else           { vertical(jj, buf, nb2); if (jj + 8 < j1) fetch(jj + 8, nb2); }
         __syncthreads();
         const int y = g.base_y + jj + hr;
         if (h_ok && y >= g.rb && y < g.re) {
@@ -340,6 +363,7 @@ __device__ __forceinline__ void prep_tgt_body(const FastGeom& g, const FastJob& 
                 *reinterpret_cast<float4*>(job.RS + o) = make_float4(rs[0], rs[1], rs[2], rs[3]);
             }
         }
+      }
     }
 }
 
@@ -614,23 +638,21 @@ __device__ __forceinline__ void store_disp4(void* disp_out, size_t disp_step, in
     }
 }
 
-// 4 pixels per thread: 16-byte loads of the partial keys, vector stores of the disparities.
-__global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_constant__ FastKernelParams P) {
+// A thread takes MG_SUB blocks of 4 pixels, 512 columns apart: the 16-byte loads of the partial keys of all of them (first
+// MG_PRE groups) are issued before the first is used - 64 bytes per thread in flight; one block per thread left the launch
+// at 3.6 TB/s (188 us for four 4K pairs) - then vector stores of the disparities.
+constexpr int MG_SUB = 2, MG_PRE = 2, MG_THREADS = 128, MG_COLS = MG_THREADS * 4 * MG_SUB;
+__device__ __forceinline__ void merge_ssd_block(const FastKernelParams& P, const FastJob& job, const int yy, const int x4, const int4 (&pre)[MG_PRE]) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
     const int32_t* __restrict__ PART = job.PART;
     const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
     void* best_out = job.best; const size_t best_step = job.best_step;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int yy = blockIdx.y;
-    if (x4 >= g.cols) return;
     int bestc[4], bestd[4];
     bool found[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { bestc[k] = INT_MAX; bestd[k] = 0; found[k] = false; }
     const uint32_t thresh = g.opf ? KEY_INVALID : key_invalid_threshold(g.R), bias = key_bias(g.R);
-    for (int grp = 0; grp < g.G; ++grp) {
-        const int4 kv = *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4);
+    auto take = [&](const int grp, const int4 kv) {
         const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -643,7 +665,10 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
             const int c = g.opf ? int((key - q2) >> FKEY_BITS) : (int(key - q2 - bias) >> FKEY_BITS);
             if (!found[k] || c < bestc[k]) { bestc[k] = c; bestd[k] = int(q2) - job.eoff - x; found[k] = true; }
         }
-    }
+    };
+#pragma unroll
+    for (int i = 0; i < MG_PRE; ++i) if (i < g.G) take(i, pre[i]);
+    for (int grp = MG_PRE; grp < g.G; ++grp) take(grp, *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4));
     store_disp4(job.disp, job.disp_step, job.elem, yy, x4, g.cols, bestd);
     // EL(x), the window energy of the reference image (replicate padding), is only needed to report
     // the cost and to honour the 99999999 threshold (DisparitySSD.cpp:37); with (2R+1)^2 * 255^2 < 99999999
@@ -668,24 +693,38 @@ __global__ void __launch_bounds__(128) fast_merge_ssd_kernel(const __grid_consta
     }
 }
 
+__global__ void __launch_bounds__(MG_THREADS) fast_merge_ssd_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int yy = blockIdx.y;
+    int4 pre[MG_SUB][MG_PRE];
+#pragma unroll
+    for (int sblk = 0; sblk < MG_SUB; ++sblk) {
+        const int x4 = blockIdx.x * MG_COLS + sblk * (MG_THREADS * 4) + threadIdx.x * 4;
+#pragma unroll
+        for (int i = 0; i < MG_PRE; ++i)
+            if (x4 < g.cols && i < g.G) pre[sblk][i] = *reinterpret_cast<const int4*>(job.PART + (size_t(i) * g.nrows + yy) * g.wpart + x4);
+    }
+#pragma unroll
+    for (int sblk = 0; sblk < MG_SUB; ++sblk) {
+        const int x4 = blockIdx.x * MG_COLS + sblk * (MG_THREADS * 4) + threadIdx.x * 4;
+        if (x4 < g.cols) merge_ssd_block(P, job, yy, x4, pre[sblk]);
+    }
+}
+
 // NCC: winning key per group -> first maximum over the groups -> disparity with the reference's
 // alignment rule (DisparityNCorr.cpp:67) and, on request, the winning score recomputed exactly with
 // TM_CCORR_NORMED's arithmetic (float32 numerator, double energies; see ncorr_exact_kernel).
-__global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_constant__ FastKernelParams P) {
+__device__ __forceinline__ void merge_ncc_block(const FastKernelParams& P, const FastJob& job, const int yy, const int x4, const int4 (&pre)[MG_PRE]) {
     const FastGeom& g = P.g;
-    const FastJob& job = P.job[blockIdx.z];
     const int32_t* __restrict__ PART = job.PART;
     const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
     const uint8_t* __restrict__ B = job.B; const size_t b_step = job.b_step;
     void* best_out = job.best; const size_t best_step = job.best_step;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int yy = blockIdx.y;
-    if (x4 >= g.cols) return;
     long long bestv[4]; int bestd[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { bestv[k] = -1; bestd[k] = 0; }
-    for (int grp = 0; grp < g.G; ++grp) {
-        const int4 kv = *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4);
+    auto take = [&](const int grp, const int4 kv) {
         const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -694,7 +733,10 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
             const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
             if (v > bestv[k]) { bestv[k] = v; bestd[k] = job.dlo0 + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
         }
-    }
+    };
+#pragma unroll
+    for (int i = 0; i < MG_PRE; ++i) if (i < g.G) take(i, pre[i]);
+    for (int grp = MG_PRE; grp < g.G; ++grp) take(grp, *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4));
     const bool right_aligned = (job.dmin <= 0 && job.dmax <= 0);
     int disp[4], centre[4];
 #pragma unroll
@@ -749,6 +791,25 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
     }
 }
 
+__global__ void __launch_bounds__(MG_THREADS) fast_merge_ncc_kernel(const __grid_constant__ FastKernelParams P) {
+    const FastGeom& g = P.g;
+    const FastJob& job = P.job[blockIdx.z];
+    const int yy = blockIdx.y;
+    int4 pre[MG_SUB][MG_PRE];
+#pragma unroll
+    for (int sblk = 0; sblk < MG_SUB; ++sblk) {
+        const int x4 = blockIdx.x * MG_COLS + sblk * (MG_THREADS * 4) + threadIdx.x * 4;
+#pragma unroll
+        for (int i = 0; i < MG_PRE; ++i)
+            if (x4 < g.cols && i < g.G) pre[sblk][i] = *reinterpret_cast<const int4*>(job.PART + (size_t(i) * g.nrows + yy) * g.wpart + x4);
+    }
+#pragma unroll
+    for (int sblk = 0; sblk < MG_SUB; ++sblk) {
+        const int x4 = blockIdx.x * MG_COLS + sblk * (MG_THREADS * 4) + threadIdx.x * 4;
+        if (x4 < g.cols) merge_ncc_block(P, job, yy, x4, pre[sblk]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Fused pair launches: the partner's candidates centred in the right padding, evaluated directly
 // ---------------------------------------------------------------------------------------------------
@@ -760,16 +821,22 @@ __global__ void __launch_bounds__(128) fast_merge_ncc_kernel(const __grid_consta
 // candidates of the last `range` pixels of every row are evaluated here instead and merged into the same partial-key
 // map (RED.MIN) with the key the hot kernel would have produced: BIAS + 128*(ER - 2C) + pos.
 //
-// A CTA of 256 threads takes 2^k pixels (32..256, the smallest that covers `range`) of 256 / 2^k consecutive rows: the 3R
+// A CTA of 256 threads takes 2^k pixels (32..256, the smallest that covers `range`) of 256 / 2^k consecutive rows.  The 3R
 // extended target columns of a window row - R image columns, R times the replicated last column, R times the aliased first
-// column of the next padded row (zero past the last padded row) - depend on the row alone, so the CTA packs every
-// candidate's W-byte window of every window row it touches into words in shared memory once (and sums their squares: ER);
-// a thread then packs its pixel's reference window rows the same way and takes 4 IDP.4A per (window row, candidate)
-// against broadcast LDS.128 reads.  (The first version read every byte of both windows per candidate: 45 us for 511 rows x
-// 95 pixels against 50 us for the whole cost volume.)
+// column of the next padded row (zero past the last padded row) - depend on the row alone: the CTA packs every candidate's
+// W-byte window of every window row it touches into words in shared memory once (and sums their squares: ER).  The
+// reference-image patch under the CTA's windows is staged in shared memory by the same round of loads; a thread packs its
+// pixel's window rows from there and takes 4 IDP.4A per (window row, candidate) against broadcast LDS.128 reads.
+// (The first version read every byte of both windows from global memory per candidate: 45 us for 511 rows x 95 pixels
+// against 50 us for the whole cost volume.)
 constexpr int FB_THREADS = 256;
 constexpr int FB_MAXROWS = FB_THREADS / 32;
 static inline int fused_border_ppr_log2(int range) { int k = 5; while (k < 8 && (1 << k) < range) ++k; return k; }
+__host__ __device__ constexpr int fb_patch_bytes(int R) {          // largest patch over k = 5..8: (W + 256/2^k - 1) rows x (2^k + 2R + 1)
+    int best = 0;
+    for (int k = 5; k <= 8; ++k) { const int v = (2 * R + 1 + (256 >> k) - 1) * ((1 << k) + 2 * R + 1); if (v > best) best = v; }
+    return best;
+}
 template <int R>
 __device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, const uint3 bid, const int ppr_log2) {
     constexpr int W = 2 * R + 1, NB = 3 * R > 0 ? 3 * R : 1, NCAND = R > 0 ? R : 1, NWORD = (W + 3) / 4;
@@ -777,11 +844,15 @@ __device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, co
     __shared__ uint8_t bcol[TR][NB + 1];
     __shared__ __align__(16) uint32_t bw[TR][NCAND][4];
     __shared__ int er[FB_MAXROWS][NCAND];
+    __shared__ uint8_t apatch[fb_patch_bytes(R)];
     const FastGeom& g = P.g;
     const FastJob& job = P.job[g.npairs + bid.z];               // the right-referenced direction: A = right image, B = left image
     const int range = job.dmax;
-    const int rpc = FB_THREADS >> ppr_log2, tr = W + rpc - 1;    // output rows of this CTA, window rows they touch
+    const int ppr = 1 << ppr_log2, rpc = FB_THREADS >> ppr_log2; // pixels per row and output rows of this CTA
+    const int tr = W + rpc - 1;                                  // window rows it touches
     const int yy0 = int(bid.y) * rpc, y0 = g.rb + yy0;
+    const int xr = g.cols - 1 - (int(bid.x) << ppr_log2);        // its rightmost pixel; pixel il is x' = xr - il
+    const int pw = ppr + 2 * R, pitch = pw + 1, xlo = xr - ppr + 1 - R;   // patch column pc <-> image column xlo + pc
     const uint8_t* __restrict__ A = job.A; const uint8_t* __restrict__ B = job.B;
     for (int t = threadIdx.x; t < tr * NB; t += FB_THREADS) {
         const int wr = t / NB, k = t % NB;
@@ -789,6 +860,11 @@ __device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, co
         const uint8_t* brow = B + size_t(ra) * job.b_step;
         bcol[wr][k] = k < R ? brow[max(g.cols - R + k, 0)] : k < 2 * R ? brow[g.cols - 1]
                     : uint8_t(bext(B, job.b_step, g.rows, g.cols, R, y0 + wr - R, g.cols + 4 * R, g.ar0, g.ar1));   // padded column cols + 3R >= Wp
+    }
+    for (int pr = threadIdx.x >> 5; pr < tr; pr += FB_THREADS / 32) {
+        const int ra = clampi(clampi(y0 + pr - R, 0, g.rows - 1), g.ar0, g.ar1 - 1);
+        const uint8_t* arow = A + size_t(ra) * job.a_step;
+        for (int pc = threadIdx.x & 31; pc < pw; pc += 32) apatch[pr * pitch + pc] = arow[clampi(xlo + pc, 0, g.cols - 1)];
     }
     __syncthreads();
     for (int t = threadIdx.x; t < tr * NCAND * 4; t += FB_THREADS) {
@@ -808,29 +884,24 @@ __device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, co
         er[r][c] = int(e);
     }
     __syncthreads();
-    const int r = threadIdx.x >> ppr_log2;
-    const int idx = (int(bid.x) << ppr_log2) + (threadIdx.x & ((1 << ppr_log2) - 1));
-    const int xp = g.cols - 1 - idx;                            // the pixel x'
-    const int yy = yy0 + r, y = y0 + r;
+    const int r = threadIdx.x >> ppr_log2, il = threadIdx.x & (ppr - 1);
+    const int idx = (int(bid.x) << ppr_log2) + il;
+    const int xp = xr - il;                                     // the pixel x'
+    const int yy = yy0 + r;
     if (yy >= g.nrows || idx >= range || xp < 0) return;
     const int ncand = min(range - idx, R);                      // centres cols .. min(x' + range, cols-1+R)
     uint32_t acc[NCAND];
 #pragma unroll
     for (int c = 0; c < NCAND; ++c) acc[c] = 0;
-    const bool interior = xp - R >= 0 && xp + R <= g.cols - 1;
-#pragma unroll 2
-    for (int wr = 0; wr < W; ++wr) {
-        const int ra = clampi(clampi(y + wr - R, 0, g.rows - 1), g.ar0, g.ar1 - 1);
-        const uint8_t* arow = A + size_t(ra) * job.a_step;
+    const uint8_t* ap = apatch + r * pitch + (ppr - 1 - il);    // window element i of window row wr: ap[wr * pitch + i]
+#pragma unroll 3
+    for (int wr = 0; wr < W; ++wr, ap += pitch) {
         uint32_t aw[NWORD];
 #pragma unroll
         for (int q = 0; q < NWORD; ++q) {
             uint32_t word = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = 4 * q + k;
-                if (i < W) word |= uint32_t(arow[interior ? xp - R + i : clampi(xp - R + i, 0, g.cols - 1)]) << (8 * k);
-            }
+            for (int k = 0; k < 4; ++k) { const int i = 4 * q + k; if (i < W) word |= uint32_t(ap[i]) << (8 * k); }
             aw[q] = word;
         }
 #pragma unroll
@@ -1249,8 +1320,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     fn<<<g.ctas, g.nw * 32, fast_smem_bytes(g), st>>>(kp);
     if (hot >= 0) { cudaEventRecord(ctx->hot1[hot], st); ctx->hot_used++; ctx->hot_jobs += n; }
     ctx->hot_total++;
-    if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
-    else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, 512), g.nrows, nz), 128, 0, st>>>(kp);
+    if (ncc) fast_merge_ncc_kernel<<<dim3(div_round_up(g.cols, MG_COLS), g.nrows, nz), MG_THREADS, 0, st>>>(kp);
+    else     fast_merge_ssd_kernel<<<dim3(div_round_up(g.cols, MG_COLS), g.nrows, nz), MG_THREADS, 0, st>>>(kp);
     ctx->last_launches += 2;
     SB_CUDA(cudaGetLastError());
     return STEREO_OK;

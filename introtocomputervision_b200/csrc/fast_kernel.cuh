@@ -82,7 +82,7 @@ constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kern
 constexpr int FWARPS = SB_FWARPS; // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers).  4-warp CTAs (narrower
                                 // tiles for small images) were measured: one warp per scheduler cannot hide the row code's
                                 // latencies (511x640/96 fused pair: 91 us against 54 us with 8 warps)
-constexpr int FMAXJOBS = 8;     // directions (jobs) one launch sequence can carry
+constexpr int FMAXJOBS = 16;    // directions (jobs) one launch sequence can carry (8 pairs; the parameter block stays below 4 KB)
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone

@@ -417,13 +417,16 @@ static int pipe_bands(const stereo_ctx* ctx, int n_pairs, int rows) {
 }
 
 // Pairs per work item of the pipeline.  Small images (BASELINE config 5: 1280x720, 64 disparities) ride several
-// pairs per item so that one launch sequence carries up to FMAXJOBS directions, as the device batch entry point
-// does; large images stay one pair (or one band of a pair) per item.
+// pairs per item so that one launch sequence carries several pairs, as the device batch entry point does (which takes
+// up to FMAXJOBS / 2; items stay at PIPE_CPMAX so that uploads, kernels and downloads of different items overlap); large
+// images stay one pair (or one band of a pair) per item.
+constexpr int PIPE_CPMAX = 4;
+static_assert(2 * PIPE_CPMAX <= FMAXJOBS, "a pipeline item is one launch sequence");
 static int pipe_chunk_pairs(int n_pairs, int nb, int rows, int cols) {
     if (nb > 1) return 1;
     const long long px = (long long)rows * cols;
     long long cp = ((4ll << 20) + px - 1) / px;           // ~4 Mpix of reference image per item
-    if (cp > FMAXJOBS / 2) cp = FMAXJOBS / 2;
+    if (cp > PIPE_CPMAX) cp = PIPE_CPMAX;
     if (cp > n_pairs / 3) cp = n_pairs / 3;               // keep at least three items in flight
     return cp < 1 ? 1 : int(cp);
 }
@@ -535,7 +538,7 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
     }
     ctx->io.reset();
     struct Slot { char* l; char* r; uint8_t* l8; uint8_t* r8; char* out[2]; };
-    constexpr int CPMAX = FMAXJOBS / 2;
+    constexpr int CPMAX = PIPE_CPMAX;
     Slot slot[3][CPMAX] = {};
     for (int k = 0; k < S; ++k)
         for (int c = 0; c < cp; ++c) {
