@@ -36,31 +36,32 @@ __device__ __forceinline__ int bext(const uint8_t* __restrict__ B, size_t step, 
 // A 511x640 pair spends 4-8 us in each of these stages and ~3 us between two dependent launches - as much as in its hot
 // kernel - and the stages do not depend on each other: their grids are laid end to end along blockIdx.x of ONE launch
 // (the longest-running stage first).
+constexpr int PREP_STAGES = 4;
 struct PrepStages {
-    unsigned gx[3], gy[3], gz[3];     // grid of stage i (gx = 0: absent)
-    unsigned first[4];                // first flat CTA index of stage i; first[3] = CTAs of the launch
+    unsigned gx[PREP_STAGES], gy[PREP_STAGES], gz[PREP_STAGES];   // grid of stage i (gx = 0: absent)
+    unsigned first[PREP_STAGES + 1];  // first flat CTA index of stage i; first[PREP_STAGES] = CTAs of the launch
     int rows_per_cta;                 // prep_tgt stage (float launches: rows of the AF / BF arrays)
     int border_ppr_log2;              // fused_border stage: log2(pixels per row of a CTA)
+    unsigned fill_words;              // fill stage: 16-byte words of one partner's partial-key map
+    int fill_value;                   // ... and the word they are set to
 };
 static inline void prep_stage_set(PrepStages& s, int i, unsigned gx, unsigned gy, unsigned gz) { s.gx[i] = gx; s.gy[i] = gy; s.gz[i] = gz; }
-// STEREO_PREP_SPLIT=1 (profiling knob): every stage as its own launch of the same kernel, so a launch list times them apart.
-template <typename Fn>
-static inline int prep_launch(Fn fn, const FastKernelParams& kp, PrepStages& stg, cudaStream_t st);
 static inline unsigned prep_stage_finish(PrepStages& s) {
     unsigned at = 0;
-    for (int i = 0; i < 3; ++i) { s.first[i] = at; at += s.gx[i] * s.gy[i] * s.gz[i]; }
-    s.first[3] = at;
+    for (int i = 0; i < PREP_STAGES; ++i) { s.first[i] = at; at += s.gx[i] * s.gy[i] * s.gz[i]; }
+    s.first[PREP_STAGES] = at;
     return at;
 }
+// STEREO_PREP_SPLIT=1 (profiling knob): every stage as its own launch of the same kernel, so a launch list times them apart.
 template <typename Fn>
 static inline int prep_launch(Fn fn, const FastKernelParams& kp, PrepStages& stg, cudaStream_t st) {
     static const bool split = [] { const char* e = getenv("STEREO_PREP_SPLIT"); return e && atoi(e) != 0; }();
     if (!split) { fn<<<prep_stage_finish(stg), 256, 0, st>>>(kp, stg); return 1; }
     int launches = 0;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < PREP_STAGES; ++i) {
         if (!stg.gx[i]) continue;
         PrepStages one = stg;
-        for (int k = 0; k < 3; ++k) if (k != i) one.gx[k] = one.gy[k] = one.gz[k] = 0;
+        for (int k = 0; k < PREP_STAGES; ++k) if (k != i) one.gx[k] = one.gy[k] = one.gz[k] = 0;
         fn<<<prep_stage_finish(one), 256, 0, st>>>(kp, one);
         ++launches;
     }
@@ -79,10 +80,25 @@ __device__ __forceinline__ uint3 prep_stage_block(const PrepStages& s, int i) {
 // their grids end to end in ONE launch.
 //
 // LP[j][p]: 4 columns per thread, 16-byte stores.  256 threads.
+// Fused pairs: every strip merges into the partner's partial keys with RED.MIN (NCC: RED.MAX), which therefore start from
+// "no candidate".  As a stage of the prep launch the stores ride under the other stages' latency (a memset in front of the
+// launch: 270 MB = 45 us for four 4K pairs).  A CTA sets 256 x 4 16-byte words of partner bid.z's map.
+constexpr unsigned FILL_WORDS_PER_CTA = 256 * 4;
+__device__ __forceinline__ void prep_fill_body(const FastKernelParams& P, const uint3 bid, const PrepStages& s) {
+    int4* __restrict__ dst = reinterpret_cast<int4*>(P.job[P.g.npairs + bid.z].PART);
+    const int4 v = make_int4(s.fill_value, s.fill_value, s.fill_value, s.fill_value);
+    const unsigned w0 = bid.x * FILL_WORDS_PER_CTA + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const unsigned w = w0 + i * 256; if (w < s.fill_words) dst[w] = v; }
+}
+
 // A CTA takes LP_ROWS rows: every load of all of them is issued before the first store (a plain row loop waits for one
 // memory round trip per row - the stores keep the next row's loads from moving up - and one row per CTA keeps only 8 bytes
 // per thread in flight: 99 us for four 4K pairs where the bytes need 30).
-constexpr int LP_ROWS = 4;
+#ifndef SB_LP_ROWS
+#define SB_LP_ROWS 4
+#endif
+constexpr int LP_ROWS = SB_LP_ROWS;
 __device__ __forceinline__ void prep_lp_body(const FastKernelParams& P, const uint3 bid) {
     const FastGeom& g = P.g;
     const FastJob& job = P.job[bid.z];
@@ -566,13 +582,14 @@ __device__ __forceinline__ void prep_rsf_body(const FastKernelParams& P, const u
     }
 }
 
-// Float operands.  Stage 0: position rows (SSD) or 1/sqrt(energy) rows (NCC); 1: target rows; 2: reference rows.
+// Float operands.  Stage 0: position rows (SSD) or 1/sqrt(energy) rows (NCC); 1: target rows; 2: reference rows; 3: prep_fill.
 __global__ void __launch_bounds__(256) prep_f32_kernel(const __grid_constant__ FastKernelParams P, const __grid_constant__ PrepStages s) {
     if (blockIdx.x < s.first[1]) {
         if (P.g.cost == STEREO_COST_SSD) prep_e2f_body(P, prep_stage_block(s, 0));
         else prep_rsf_body(P, prep_stage_block(s, 0));
     } else if (blockIdx.x < s.first[2]) prep_bf_body(P, prep_stage_block(s, 1), s.rows_per_cta);
-    else prep_af_body(P, prep_stage_block(s, 2), s.rows_per_cta);
+    else if (blockIdx.x < s.first[3]) prep_af_body(P, prep_stage_block(s, 2), s.rows_per_cta);
+    else prep_fill_body(P, prep_stage_block(s, 3), s);
 }
 
 // NCC, float path: window energies of the reference image per pixel (replicate padding, double sums) ...
@@ -641,7 +658,10 @@ __device__ __forceinline__ void store_disp4(void* disp_out, size_t disp_step, in
 // A thread takes MG_SUB blocks of 4 pixels, 512 columns apart: the 16-byte loads of the partial keys of all of them (first
 // MG_PRE groups) are issued before the first is used - 64 bytes per thread in flight; one block per thread left the launch
 // at 3.6 TB/s (188 us for four 4K pairs) - then vector stores of the disparities.
-constexpr int MG_SUB = 2, MG_PRE = 2, MG_THREADS = 128, MG_COLS = MG_THREADS * 4 * MG_SUB;
+#ifndef SB_MG_SUB
+#define SB_MG_SUB 2
+#endif
+constexpr int MG_SUB = SB_MG_SUB, MG_PRE = 2, MG_THREADS = 128, MG_COLS = MG_THREADS * 4 * MG_SUB;
 __device__ __forceinline__ void merge_ssd_block(const FastKernelParams& P, const FastJob& job, const int yy, const int x4, const int4 (&pre)[MG_PRE]) {
     const FastGeom& g = P.g;
     const int32_t* __restrict__ PART = job.PART;
@@ -923,14 +943,16 @@ __device__ __forceinline__ void fused_border_stage(const FastKernelParams& P, co
 }
 
 // u8 operands.  Stage 0: target rows, energies / position keys (prep_tgt); 1: the partner's candidates in the right padding
-// (fused_border, fused pairs only - after the memset of the partners' partial keys); 2: reference rows (prep_lp).
+// (fused_border, fused pairs only - after a memset of the partners' partial keys); 2: reference rows (prep_lp); 3: fused pairs
+// without a border stage: the partners' partial keys start from "no candidate" (prep_fill).
 template <int R>
 __global__ void __launch_bounds__(256, R >= 6 ? 3 : 4) prep_u8_kernel(const __grid_constant__ FastKernelParams P, const __grid_constant__ PrepStages s) {
     static_assert(PT_THREADS == 256 && FB_THREADS == 256, "the stages share one CTA shape");
     __shared__ __align__(16) int vs[2][4][PT_VSTRIDE];
     if (blockIdx.x < s.first[1]) prep_tgt_stage<R>(P, prep_stage_block(s, 0), s.rows_per_cta, vs);
     else if (blockIdx.x < s.first[2]) { if constexpr (R > 0) fused_border_stage<R>(P, prep_stage_block(s, 1), s.border_ppr_log2); }
-    else prep_lp_body(P, prep_stage_block(s, 2));
+    else if (blockIdx.x < s.first[3]) prep_lp_body(P, prep_stage_block(s, 2));
+    else prep_fill_body(P, prep_stage_block(s, 3), s);
 }
 typedef void (*prep_u8_fn)(const FastKernelParams, const PrepStages);
 static inline prep_u8_fn prep_u8_pick(int R) {
@@ -1218,6 +1240,8 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
     const int vpitch = fast_vpitch(g);
     const int w = 2 * g.R + 1;
     const size_t lp_rows = opf ? size_t(g.J + w) : size_t(g.J), rq_rows = opf ? size_t(g.J + w) : size_t(g.J / 2);
+    const size_t part_words = size_t(g.G) * g.nrows * g.wpart / 4;                       // (wpart is a multiple of 4)
+    const bool fill_by_memset = (fused_pairs && g.border && g.R > 0) || part_words > 0xFFFFFFFFull - FILL_WORDS_PER_CTA;
     for (int i = 0; i < n; ++i) {
         FastJob& jb = kp.job[i];
         const Problem& p = ps[i];
@@ -1231,8 +1255,9 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
             jb.RS = reinterpret_cast<float*>(jb.E2);                  // NCC: the same rows hold 1/sqrt(energy)
             jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
             if (!jb.E2 || !jb.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
-            // every strip merges into the partner's partial keys with RED.MIN (NCC: RED.MAX): start from "no candidate"
-            SB_CUDA(cudaMemsetAsync(jb.PART, ncc ? 0x00 : 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
+            // every strip merges into the partner's partial keys with RED.MIN (NCC: RED.MAX): start from "no candidate" -
+            // a stage of the prep launch, or (the border stage merges into them inside that launch) a memset in front of it
+            if (fill_by_memset) SB_CUDA(cudaMemsetAsync(jb.PART, ncc ? 0x00 : 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));
             continue;
         }
         jb.LP = static_cast<int32_t*>(ctx->arena.take(lp_rows * g.lp_pitch * 4));
@@ -1259,6 +1284,10 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         stg.rows_per_cta = int(lp_rows);                 // (== rq_rows)
         prep_stage_set(stg, 1, unsigned(div_round_up(g.rq_pitch / 4, 256)), unsigned(div_round_up(rq_rows, size_t(FR_ROWS))), nwalk);
         prep_stage_set(stg, 2, unsigned(div_round_up(g.lp_pitch / 4, 256)), unsigned(div_round_up(lp_rows, size_t(FR_ROWS))), nwalk);
+        if (fused_pairs && !fill_by_memset) {
+            stg.fill_words = unsigned(part_words); stg.fill_value = ncc ? 0 : -1;
+            prep_stage_set(stg, 3, unsigned(div_round_up((long long)part_words, FILL_WORDS_PER_CTA)), 1, unsigned(fused_pairs));
+        }
         ctx->last_launches += prep_launch(prep_f32_kernel, kp, stg, st);
         if (ncc && fast_launch_is_pairs(ps, n)) {
             // both directions of every pair are in the launch: the reference-image energies are the partner's RS rows
@@ -1292,6 +1321,10 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         prep_stage_set(stg, 2, unsigned(div_round_up(g.lp_pitch / 4, 256)), unsigned(div_round_up(g.J, LP_ROWS)), nwalk);
         prep_u8_fn pf = prep_u8_pick(g.R);
         if (!pf) { set_error("no prep kernel for R=%d (internal)", g.R); return STEREO_ERR_UNSUPPORTED; }
+        if (fused_pairs && !fill_by_memset) {
+            stg.fill_words = unsigned(part_words); stg.fill_value = ncc ? 0 : -1;
+            prep_stage_set(stg, 3, unsigned(div_round_up((long long)part_words, FILL_WORDS_PER_CTA)), 1, unsigned(fused_pairs));
+        }
         ctx->last_launches += prep_launch(pf, kp, stg, st);
         if (three_pass) {   // RQ rows, vertical sums in HBM, horizontal sums
             prep_rq_kernel<<<dim3(div_round_up(g.rq_pitch / 4, 256), g.J / 2, nz), 256, 0, st>>>(kp);
