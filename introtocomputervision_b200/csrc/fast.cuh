@@ -1183,7 +1183,7 @@ static inline size_t fast_scratch_bytes(stereo_ctx* ctx, const Problem& p) {
         if (g.opf) { add(size_t(g.J + 2 * g.R + 1) * g.lp_pitch * 4); add(size_t(g.J + 2 * g.R + 1) * g.rq_pitch * 4); }
         else { add(size_t(g.J) * g.lp_pitch * 4); add(size_t(g.J / 2) * g.rq_pitch * 4); }
         add(size_t(g.J) * g.e2_pitch * 4);
-        add(size_t(g.G) * g.nrows * g.wpart * 4);
+        add((size_t(g.G) * g.nrows * g.wpart + 2 * fused_part_pad_words(g.G)) * 4);
         add(size_t(g.nrows) * fast_vpitch(g) * 4);
         if (p.cost == STEREO_COST_NCORR) { add(size_t(g.J) * g.e2_pitch * 4); add(size_t(g.tilesX) * g.spc * g.nrows * 4); }
         if (b > best) best = b;
@@ -1253,8 +1253,10 @@ static inline int run_fast_batch(stereo_ctx* ctx, const Problem* ps, int n, cuda
         if (partner) {
             jb.E2 = static_cast<int32_t*>(ctx->arena.take(size_t(g.J) * g.e2_pitch * 4));
             jb.RS = reinterpret_cast<float*>(jb.E2);                  // NCC: the same rows hold 1/sqrt(energy)
-            jb.PART = static_cast<int32_t*>(ctx->arena.take(size_t(g.G) * g.nrows * g.wpart * 4));
+            const size_t pad = fused_part_pad_words(g.G);             // (a multiple of 64 words: the map stays 256-byte aligned)
+            jb.PART = static_cast<int32_t*>(ctx->arena.take((size_t(g.G) * g.nrows * g.wpart + 2 * pad) * 4));
             if (!jb.E2 || !jb.PART) { set_error("scratch arena too small (internal)"); return STEREO_ERR_ALLOC; }
+            jb.PART += pad;
             // every strip merges into the partner's partial keys with RED.MIN (NCC: RED.MAX): start from "no candidate" -
             // a stage of the prep launch, or (the border stage merges into them inside that launch) a memset in front of it
             if (fill_by_memset) SB_CUDA(cudaMemsetAsync(jb.PART, ncc ? 0x00 : 0xFF, size_t(g.G) * g.nrows * g.wpart * 4, st));

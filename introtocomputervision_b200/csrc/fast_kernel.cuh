@@ -82,6 +82,10 @@ constexpr int FSMEM_BUDGET = 220 * 1024;   // dynamic shared memory the hot kern
 constexpr int FWARPS = SB_FWARPS; // warps per CTA (K=24 pixels x 4 disparities per thread: ~254 registers).  4-warp CTAs (narrower
                                 // tiles for small images) were measured: one warp per scheduler cannot hide the row code's
                                 // latencies (511x640/96 fused pair: 91 us against 54 us with 8 warps)
+// Fused pair launches: words of slack either side of a partner's partial-key map (see the row epilogue of fast_row): the
+// merges of lanes whose partner pixel lies outside the image land at most one disparity range + a strip before the first
+// row or behind the last one.
+static inline size_t fused_part_pad_words(int G) { return size_t(G) * 128 + 512; }
 constexpr int FMAXJOBS = 16;    // directions (jobs) one launch sequence can carry (8 pairs; the parameter block stays below 4 KB)
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
@@ -179,7 +183,6 @@ __device__ __forceinline__ int dp2a_hi(int a, unsigned b, int c) {
     int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -570,23 +573,30 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
-        auto merge = [&](uint32_t* p, uint32_t v) { if (NCC) atomicMax(p, v); else atomicMin(p, v); };
+        // Unconditional REDs: a lane whose partner pixel lies outside the image sends the neutral key instead of skipping the
+        // merge (its address may fall into a neighbouring row or into the FUSED_PART_PAD words either side of the partner's
+        // map, where a neutral key changes nothing).  As `if (in range) atomicMin(...)` every one of the five merges of a row
+        // became its own divergence region (BSSY / BRA / R2UR x2 / REDG / BSYNC - ptxas does the same to a predicated `red`), and
+        // the row epilogue took 20 % of the kernel's stall samples with 9 % of its instructions.
+        auto merge = [&](uint32_t* row, int x, uint32_t v, bool ok) {
+            const uint32_t vv = ok ? v : (NCC ? NCC_KEY_NONE : KEY_INVALID);
+            if (NCC) atomicMax(row + x, vv); else atomicMin(row + x, vv);
+        };
         if (HS == 1) {
             const uint32_t tv = (ll < K) ? tail[ll] : (NCC ? NCC_KEY_NONE : KEY_INVALID);
             const int xt = x2base + ll;
-            if (ll < K && unsigned(xt) < unsigned(cols)) merge(part2_row + xt, tv);
+            merge(part2_row, xt, tv, unsigned(xt) < unsigned(cols));          // (tv is already neutral for ll >= K)
         } else {
-            const int lane = sub * LSF + ll;
-#pragma unroll
-            for (int h = 0; h < HS; ++h) {               // strip h of the warp: its tail, one entry per lane
-                const int xt = x2base + (h - sub) * K + lane;
-                if (lane < K && unsigned(xt) < unsigned(cols)) merge(part2_row + xt, tail[32 * h + lane]);
-            }
+            // every half-warp merges the tail of its own strip, one entry per lane (K <= lanes per strip)
+            static_assert(!FUSED || HS == 1 || K <= 32 / HS, "two-strip warps: a strip's tail fits its half-warp");
+            const uint32_t tv = (ll < K) ? tail[32 * sub + ll] : (NCC ? NCC_KEY_NONE : KEY_INVALID);
+            const int xt = x2base + ll;
+            merge(part2_row, xt, tv, unsigned(xt) < unsigned(cols));
         }
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             const int xa = x2base + K + FM * ll + m;
-            if (unsigned(xa) < unsigned(cols)) merge(part2_row + xa, acc[m]);
+            merge(part2_row, xa, acc[m], unsigned(xa) < unsigned(cols));
         }
         __syncwarp();             // the next row overwrites the tail
     }
