@@ -1051,7 +1051,7 @@ static inline void fast_geometry_nw(const stereo_ctx* ctx, const Problem* ps, in
         g.rqw = round_up(tile_px + 2 * p.R + g.dg * g.gc + FM, 4);
         g.e2w = round_up(tile_px + g.dg * g.gc + FM, 4);
         g.elw = fused_pairs > 0 ? tile_px : 0;
-        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16 - (fused_pairs > 0 ? FWARPS * 256 : 0)) / fast_stage_bytes(g));
+        g.nst = int((FSMEM_BUDGET - 2 * FNST_MAX * 8 - 16 - FWARPS * 32 - (fused_pairs > 0 ? FWARPS * 256 : 0)) / fast_stage_bytes(g));
         if (g.nst > FNST_MAX) g.nst = FNST_MAX;
         if (g.nst >= 4 || g.hs == 1) break;
         g.hs = 1;                                  // tile rows too wide for a useful pipeline: single-strip kernels
@@ -1162,7 +1162,7 @@ static inline void fast_geometry(const stereo_ctx* ctx, const Problem* ps, int n
 static inline bool fast_fused_all_mode1(const FastGeom& g) { return g.R <= FFREE_MASK_R && g.D % g.dg == 0; }
 
 static inline size_t fast_smem_bytes(const FastGeom& g) {
-    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + (g.elw ? FWARPS * 256 : 0);
+    return size_t(g.nst) * fast_stage_bytes(g) + 2 * FNST_MAX * 8 + 16 + FWARPS * 32 + (g.elw ? FWARPS * 256 : 0);      // stages, barriers, producer caches, tails
 }
 
 static inline int fast_vpitch(const FastGeom& g) { return round_up(g.e2_pitch + 2 * g.R + PE_COLS, 64); }
