@@ -124,6 +124,11 @@ int stereo_ctx_set_pipe_bands(stereo_ctx* ctx, int bands);
  * (bands_override = stereo_ctx_set_pipe_bands' value, 0 = automatic) and pairs per item (small images ride several
  * pairs per launch sequence).  Pure host arithmetic, no device needed. */
 int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_override, int* bands_per_pair, int* pairs_per_item);
+/* The row bands of work item `item` of such a call: writes the ascending boundaries (first 0, last rows) to bounds[0 .. n-1]
+ * and returns n (negative: error; cap = room in bounds).  With automatic bands, 4K-sized images are cut unevenly: the
+ * first item of a call begins and the last item ends with a band of an eighth of the image - the first upload and the last
+ * download are the only copies no kernel overlaps - and the items in between go as whole images. */
+int stereo_host_pipeline_item_bands(int n_pairs, int rows, int cols, int bands_override, int item, int* bounds, int cap);
 
 /* CV_32FC1 HOST entry points: images whose pixels are all integers in 0..255 (everything convertTo(CV_32FC1) produces,
  * main.cpp:87-88) are converted to u8 by `threads` host threads into pinned staging and uploaded as 1 byte per pixel; the

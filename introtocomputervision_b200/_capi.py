@@ -39,6 +39,7 @@ SIGNATURES = {
     "stereo_ctx_force_path": (_i, [_vp, _i]),
     "stereo_ctx_set_pipe_bands": (_i, [_vp, _i]),
     "stereo_host_pipeline_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "stereo_host_pipeline_item_bands": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), _i]),
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
     "stereo_ctx_set_host_threads": (_i, [_vp, _i]),
     "stereo_ctx_host_threads": (_i, [_vp]),

@@ -5,6 +5,7 @@
 #include "host_pack.hpp"
 
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <condition_variable>
 #include <mutex>
@@ -70,32 +71,51 @@ static const bool g_have_avx512 = false;
 static bool pack_row_avx512(const float*, uint8_t*, int) { return false; }
 #endif
 
+// Workers and the caller poll for a bounded time before they block: inside one pipelined call the conversions follow each
+// other within microseconds (one per work item), and a condition-variable wake-up of 15 threads costs about as much as
+// converting a quarter of a 4K band.  After HOST_POOL_SPIN_US without work a worker sleeps on the condition variable, so an
+// idle context costs nothing.
+constexpr int HOST_POOL_SPIN_US = 250;
+
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
 struct HostPool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work;
     const std::function<void(int)>* fn = nullptr;
     int n_tasks = 0;
     std::atomic<int> next{0};
-    int generation = 0, running = 0;
-    bool stop = false;
+    std::atomic<int> generation{0};     // bumped by run() after fn / n_tasks / next / pending are in place
+    std::atomic<int> pending{0};        // workers that have not finished the current generation yet
+    std::atomic<bool> stop{false};
 
     void loop() {
         int seen = 0;
         for (;;) {
-            const std::function<void(int)>* f;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_work.wait(lk, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
-                f = fn;
+            auto t0 = std::chrono::steady_clock::now();
+            int g, polls = 0;
+            while ((g = generation.load(std::memory_order_acquire)) == seen && !stop.load(std::memory_order_relaxed)) {
+                cpu_relax();
+                if ((++polls & 63) == 0 &&
+                    std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > HOST_POOL_SPIN_US) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_work.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+                    t0 = std::chrono::steady_clock::now();
+                }
             }
-            for (int i; (i = next.fetch_add(1)) < n_tasks;) (*f)(i);
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--running == 0) cv_done.notify_all();
-            }
+            if (stop.load()) return;
+            seen = g;
+            const std::function<void(int)>* f = fn;
+            const int n = n_tasks;
+            for (int i; (i = next.fetch_add(1, std::memory_order_relaxed)) < n;) (*f)(i);
+            pending.fetch_sub(1, std::memory_order_release);
         }
     }
 };
@@ -107,7 +127,7 @@ HostPool::HostPool(int threads) : impl_(new Impl), threads_(threads < 1 ? 1 : th
 HostPool::~HostPool() {
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
-        impl_->stop = true;
+        impl_->stop.store(true);
     }
     impl_->cv_work.notify_all();
     for (auto& t : impl_->workers) t.join();
@@ -117,32 +137,47 @@ HostPool::~HostPool() {
 void HostPool::run(int n_tasks, const std::function<void(int)>& fn) {
     if (n_tasks <= 0) return;
     if (threads_ == 1 || n_tasks == 1) { for (int i = 0; i < n_tasks; ++i) fn(i); return; }
-    {
-        std::lock_guard<std::mutex> lk(impl_->mu);
-        impl_->fn = &fn;
-        impl_->n_tasks = n_tasks;
-        impl_->next.store(0);
-        impl_->running = int(impl_->workers.size());
-        ++impl_->generation;
-    }
+    impl_->fn = &fn;
+    impl_->n_tasks = n_tasks;
+    impl_->next.store(0, std::memory_order_relaxed);
+    impl_->pending.store(int(impl_->workers.size()), std::memory_order_relaxed);
+    impl_->generation.fetch_add(1, std::memory_order_seq_cst);
+    { std::lock_guard<std::mutex> lk(impl_->mu); }          // orders the bump against a worker that is about to sleep
     impl_->cv_work.notify_all();
-    for (int i; (i = impl_->next.fetch_add(1)) < n_tasks;) fn(i);       // the calling thread works too
-    std::unique_lock<std::mutex> lk(impl_->mu);
-    impl_->cv_done.wait(lk, [&] { return impl_->running == 0; });
+    for (int i; (i = impl_->next.fetch_add(1, std::memory_order_relaxed)) < n_tasks;) fn(i);       // the calling thread works too
+    // every worker has to pass through this generation (it reads fn / n_tasks) before the next run() may change them
+    for (int polls = 0; impl_->pending.load(std::memory_order_acquire) != 0;) {
+        cpu_relax();
+        if ((++polls & 1023) == 0) std::this_thread::yield();
+    }
 }
 
-bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols) {
-    // tasks of ~64K pixels: enough of them to balance, few enough to keep the dispatch cost invisible
-    int rows_per_task = (1 << 16) / (cols > 0 ? cols : 1);
-    if (rows_per_task < 1) rows_per_task = 1;
-    const int n_tasks = (rows + rows_per_task - 1) / rows_per_task;
+bool pack_f32_u8_jobs(HostPool& pool, const PackJob* jobs, int n_jobs) {
+    // tasks of ~64K pixels: enough of them to balance, few enough to keep the dispatch cost invisible; the tasks of all
+    // images of one work item (left and right of every pair riding it) go out in ONE dispatch
+    constexpr int MAXJ = 16;
+    if (n_jobs > MAXJ) {
+        bool ok = true;
+        for (int j = 0; j < n_jobs; j += MAXJ) ok = pack_f32_u8_jobs(pool, jobs + j, n_jobs - j < MAXJ ? n_jobs - j : MAXJ) && ok;
+        return ok;
+    }
+    int first[MAXJ + 1], rpt[MAXJ];
+    first[0] = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        rpt[j] = (1 << 16) / (jobs[j].cols > 0 ? jobs[j].cols : 1);
+        if (rpt[j] < 1) rpt[j] = 1;
+        first[j + 1] = first[j] + (jobs[j].rows > 0 ? (jobs[j].rows + rpt[j] - 1) / rpt[j] : 0);
+    }
     std::atomic<int> bad{0};
-    pool.run(n_tasks, [&](int t) {
-        const int r0 = t * rows_per_task, r1 = r0 + rows_per_task < rows ? r0 + rows_per_task : rows;
+    pool.run(first[n_jobs], [&](int t) {
+        int j = 0;
+        while (t >= first[j + 1]) ++j;
+        const PackJob& J = jobs[j];
+        const int r0 = (t - first[j]) * rpt[j], r1 = r0 + rpt[j] < J.rows ? r0 + rpt[j] : J.rows;
         bool ok = true;
         for (int r = r0; r < r1; ++r) {
-            const float* s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + size_t(r) * src_step);
-            ok &= g_have_avx512 ? pack_row_avx512(s, dst + size_t(r) * dst_step, cols) : pack_f32_u8_row(s, dst + size_t(r) * dst_step, cols);
+            const float* s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(J.src) + size_t(r) * J.src_step);
+            ok &= g_have_avx512 ? pack_row_avx512(s, J.dst + size_t(r) * J.dst_step, J.cols) : pack_f32_u8_row(s, J.dst + size_t(r) * J.dst_step, J.cols);
         }
 #if defined(__x86_64__) && defined(__GNUC__)
         if (g_have_avx512) __builtin_ia32_sfence();       // the non-temporal stores are visible before the upload is enqueued
@@ -150,6 +185,11 @@ bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst
         if (!ok) bad.store(1, std::memory_order_relaxed);
     });
     return bad.load() == 0;
+}
+
+bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols) {
+    const PackJob job{src, src_step, dst, dst_step, rows, cols};
+    return pack_f32_u8_jobs(pool, &job, 1);
 }
 
 int default_host_threads() {

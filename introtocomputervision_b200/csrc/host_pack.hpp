@@ -24,6 +24,9 @@ private:
 // rows x cols float32 (row stride src_step bytes) -> u8 (row stride dst_step bytes).  false: some pixel is not an integer
 // in 0..255 (the u8 image is then meaningless).
 bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols);
+// several images in one dispatch of the pool (the images of one work item of the host pipeline)
+struct PackJob { const float* src; size_t src_step; uint8_t* dst; size_t dst_step; int rows, cols; };
+bool pack_f32_u8_jobs(HostPool& pool, const PackJob* jobs, int n_jobs);
 
 // min(16, hardware threads / LOCAL_WORLD_SIZE)
 int default_host_threads();

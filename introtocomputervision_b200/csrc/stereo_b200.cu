@@ -7,6 +7,7 @@
 #include "imgproc.cuh"
 #include "host_pack.hpp"
 
+#include <chrono>
 #include <cstdarg>
 #include <new>
 #include <vector>
@@ -384,6 +385,13 @@ struct HostPairIn { const void* left; size_t left_step; const void* right; size_
 
 enum { PIPE_NOT_APPLICABLE = 1, PIPE_NOT_8BIT = 2 };
 
+// STEREO_PIPE_TRACE=1: the pipeline's events keep timestamps and every pipelined call prints, per work item and band, when
+// its upload, compute and download finished (ms after the call's first enqueue) - a diagnostic for the e2e numbers.
+static bool pipe_trace() {
+    static const bool on = getenv("STEREO_PIPE_TRACE") != nullptr;
+    return on;
+}
+
 static int ensure_pipe(stereo_ctx* ctx, int events) {
     if (!ctx->s_in) SB_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     if (!ctx->s_out) SB_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -393,7 +401,7 @@ static int ensure_pipe(stereo_ctx* ctx, int events) {
         if (!ev) { set_error("out of host memory"); return STEREO_ERR_ALLOC; }
         for (int i = 0; i < ctx->pipe_ev_cap; ++i) ev[i] = ctx->pipe_ev[i];
         for (int i = ctx->pipe_ev_cap; i < cap; ++i) {
-            cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            cudaError_t e = cudaEventCreateWithFlags(&ev[i], pipe_trace() ? cudaEventDefault : cudaEventDisableTiming);
             if (e != cudaSuccess) {
                 for (int k = ctx->pipe_ev_cap; k < i; ++k) cudaEventDestroy(ev[k]);
                 delete[] ev;
@@ -429,6 +437,32 @@ static int pipe_chunk_pairs(int n_pairs, int nb, int rows, int cols) {
     if (cp > PIPE_CPMAX) cp = PIPE_CPMAX;
     if (cp > n_pairs / 3) cp = n_pairs / 3;               // keep at least three items in flight
     return cp < 1 ? 1 : int(cp);
+}
+
+
+// Large images (4K): the first work item of a call starts with a short band and the last one ends with a short band, so
+// that the part of a call nothing overlaps - the first upload and the last download - is an eighth of an image, and the
+// items in between go as whole images (every launch sequence costs ~65 us of ramp-up, warm-up rows and tail whatever
+// its size: tools/e2e_sweep.py, STEREO_PIPE_TRACE).
+static bool pipe_ramped(const stereo_ctx* ctx, int rows, int cols) {
+    return ctx->pipe_bands == 0 && rows >= 1024 && (long long)rows * cols >= (4ll << 20);
+}
+
+// Row-band boundaries of work item w of a pipelined call: ascending, from 0 to rows.
+static void pipe_item_bounds(const stereo_ctx* ctx, int n_pairs, int n_items, int w, int rows, int cols, std::vector<int>& b) {
+    b.clear();
+    b.push_back(0);
+    if (pipe_ramped(ctx, rows, cols)) {
+        const int e = rows / 8;
+        if (w == 0) { b.push_back(e); b.push_back(3 * e); }
+        if (w == n_items - 1) { if (rows - 3 * e > b.back()) b.push_back(rows - 3 * e); b.push_back(rows - e); }
+        b.push_back(rows);
+        return;
+    }
+    const int nb = pipe_bands(ctx, n_pairs, rows);
+    const int band_rows = (rows + nb - 1) / nb;
+    for (int r = band_rows; r < rows; r += band_rows) b.push_back(r);
+    b.push_back(rows);
 }
 
 static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
@@ -481,55 +515,76 @@ static bool host_sample_is_8bit(const void* img, size_t step, int rows, int cols
 static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, int n_pairs, const HostPairIn* in,
                                      const HostDir* dirs, int n_dirs, int rows, int cols, int R, size_t disp_step, int elem) {
     if (ctx->force_path == STEREO_PATH_EXACT_F32 || ctx->force_path == STEREO_PATH_FAST_F32) return PIPE_NOT_APPLICABLE;
+    const auto t_call = std::chrono::steady_clock::now();       // (trace only)
+    double t_pack = 0.0, t_ring = 0.0;
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     if (type == PixType::F32)
         for (int i = 0; i < n_pairs; ++i)
             if (!host_sample_is_8bit(in[i].left, in[i].left_step, rows, cols) || !host_sample_is_8bit(in[i].right, in[i].right_step, rows, cols))
                 return PIPE_NOT_8BIT;
     // CV_32FC1 host images with enough host threads: converted to u8 on the HOST (checking that every pixel is 8-bit), so the
     // link carries 1 byte per pixel; otherwise the float rows are uploaded and converted / classified on the device.
+    // (Sending a share of the rows as floats next to the host conversion was measured and dropped: the copy engine's reads
+    // and the converting threads compete for the same host memory bandwidth - 4K x 4 pairs: 4.88 ms with none, 5.01 ms with a
+    // quarter, 5.57 ms with half of the rows as floats.)
     const bool pack = type == PixType::F32 && host_pack_enabled(ctx);
-    const PixType dtype = pack ? PixType::U8 : type;          // pixel type of the device-side input slots
-    const size_t hpx = type == PixType::F32 ? 4 : 1;          // host pixel bytes
-    const size_t px = dtype == PixType::F32 ? 4 : 1;
-    const size_t in_pitch = align256(cols * px), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
-    (void)hpx;
+    const bool any_f32 = type == PixType::F32 && !pack, any_pack = pack;
+    const size_t f_pitch = align256(size_t(cols) * 4), u8_pitch = align256(cols), d_pitch = align256(size_t(cols) * elem);
     // validate each direction on a full-image problem (pointers only need to be non-null here)
     Problem full{};
     full.cost = cost; full.rows = rows; full.cols = cols; full.row_begin = 0; full.row_end = rows;
     full.avail_begin = 0; full.avail_end = rows; full.R = R;
     full.ref = ImageView{in, u8_pitch, PixType::U8}; full.tgt = full.ref;
     full.disp = OutView{ctx, d_pitch, elem}; full.best = OutView{nullptr, 0, 4};
-    const int nb = pipe_bands(ctx, n_pairs, rows);
-    const int band_rows = (rows + nb - 1) / nb;
-    const int cp = pipe_chunk_pairs(n_pairs, nb, rows, cols);
+    const int nb_uniform = pipe_bands(ctx, n_pairs, rows);
+    const int cp = pipe_chunk_pairs(n_pairs, nb_uniform, rows, cols);
     const int n_items = (n_pairs + cp - 1) / cp;
+    // row bands of every work item (pipe_item_bounds): item w owns bounds[boff[w]] .. bounds[boff[w + 1] - 1]
+    std::vector<int> bounds, boff(n_items + 1, 0), tmpb;
+    for (int w = 0; w < n_items; ++w) {
+        pipe_item_bounds(ctx, n_pairs, n_items, w, rows, cols, tmpb);
+        bounds.insert(bounds.end(), tmpb.begin(), tmpb.end());
+        boff[w + 1] = int(bounds.size());
+    }
+    auto nbw = [&](int w) { return boff[w + 1] - boff[w] - 1; };                           // bands of item w
+    std::vector<int> uoff(n_items + 1, 0);                                                 // units (item, band) before item w
+    for (int w = 0; w < n_items; ++w) uoff[w + 1] = uoff[w] + nbw(w);
+    const int n_units = uoff[n_items];
     size_t scratch = 0;
+    int max_up = 0;                                       // most rows one unit uploads
     for (int d = 0; d < n_dirs; ++d) {
         full.dmin = dirs[d].dmin; full.dmax = dirs[d].dmax;
         int rc = validate(full, u8_pitch, u8_pitch);
         if (rc != STEREO_OK) return rc;
         if (!fast_supported(full)) return PIPE_NOT_APPLICABLE;
         // every band: the operand-row count depends on where the band starts relative to the FRPS-row stages
-        for (int b = 0; b < nb; ++b) {
-            Problem band = full; band.row_begin = b * band_rows; band.row_end = (b + 1) * band_rows < rows ? (b + 1) * band_rows : rows;
-            if (band.row_begin >= band.row_end) break;
-            const size_t need = size_t(n_dirs) * cp * fast_scratch_bytes(ctx, band);
-            scratch = need > scratch ? need : scratch;
+        for (int w = 0; w < n_items; ++w) {
+            int up = 0;
+            for (int b = 0; b < nbw(w); ++b) {
+                Problem band = full; band.row_begin = bounds[boff[w] + b]; band.row_end = bounds[boff[w] + b + 1];
+                const size_t need = size_t(n_dirs) * cp * fast_scratch_bytes(ctx, band);
+                scratch = need > scratch ? need : scratch;
+                const int up_hi = (b == nbw(w) - 1) ? rows : ((band.row_end + R + 16 < rows) ? band.row_end + R + 16 : rows);
+                max_up = up_hi - up > max_up ? up_hi - up : max_up;
+                up = up_hi;
+            }
         }
     }
     constexpr int NSTG = 4;                               // pinned staging ring of the host-packed uploads
-    int rc = ensure_pipe(ctx, 3 * n_items * nb + 4 + NSTG);
+    int rc = ensure_pipe(ctx, 3 * n_units + 4 + NSTG);
     if (rc != STEREO_OK) return rc;
     cudaStream_t s_in = ctx->s_in, s_cmp = ctx->stream, s_out = ctx->s_out;
+    // uploads go chunk by chunk (~a quarter of a large image): the first copy of a unit leaves while the host threads are
+    // still converting the rest of it
+    const int chunk_rows = cp > 1 || rows < 1024 ? max_up : ((rows + 3) / 4 < 128 ? 128 : (rows + 3) / 4);
+    const int stg_rows = chunk_rows < max_up ? chunk_rows : max_up;
     const size_t stg_pitch = (size_t(cols) + 63) & ~size_t(63);
-    const int stg_rows = band_rows + R + 16 < rows ? band_rows + R + 16 : rows;
     const size_t stg_slot = 2 * size_t(cp) * stg_rows * stg_pitch;
-    if (pack) { rc = ensure_pinned(ctx, NSTG * stg_slot); if (rc != STEREO_OK) return rc; }
+    if (any_pack) { rc = ensure_pinned(ctx, NSTG * stg_slot); if (rc != STEREO_OK) return rc; }
     int stg_used = 0;
 
     const int S = n_items < 3 ? n_items : 3;            // device slots (ring), one work item each
-    const size_t pair_bytes = 2 * align256(in_pitch * rows) + (dtype == PixType::F32 ? 2 * align256(u8_pitch * rows) : 0)
-                              + size_t(n_dirs) * align256(d_pitch * rows);
+    const size_t pair_bytes = 2 * align256(u8_pitch * rows) + (any_f32 ? 2 * align256(f_pitch * rows) : 0) + size_t(n_dirs) * align256(d_pitch * rows);
     const size_t slot_bytes = size_t(cp) * pair_bytes;
     if (size_t(S) * slot_bytes + 1024 > ctx->io.cap || scratch > ctx->arena.cap) {
         SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
@@ -537,98 +592,117 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
         if (scratch > ctx->arena.cap) { rc = ctx->arena.reserve(scratch); if (rc != STEREO_OK) return rc; }
     }
     ctx->io.reset();
-    struct Slot { char* l; char* r; uint8_t* l8; uint8_t* r8; char* out[2]; };
+    struct Slot { char* lf; char* rf; uint8_t* l8; uint8_t* r8; char* out[2]; };      // lf / rf: float rows awaiting conversion
     constexpr int CPMAX = PIPE_CPMAX;
     Slot slot[3][CPMAX] = {};
     for (int k = 0; k < S; ++k)
         for (int c = 0; c < cp; ++c) {
             Slot& sl = slot[k][c];
-            sl.l = static_cast<char*>(ctx->io.take(in_pitch * rows));
-            sl.r = static_cast<char*>(ctx->io.take(in_pitch * rows));
-            if (dtype == PixType::F32) {
-                sl.l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
-                sl.r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
-            } else {
-                sl.l8 = reinterpret_cast<uint8_t*>(sl.l);
-                sl.r8 = reinterpret_cast<uint8_t*>(sl.r);
+            sl.l8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+            sl.r8 = static_cast<uint8_t*>(ctx->io.take(u8_pitch * rows));
+            if (any_f32) {
+                sl.lf = static_cast<char*>(ctx->io.take(f_pitch * rows));
+                sl.rf = static_cast<char*>(ctx->io.take(f_pitch * rows));
             }
             for (int d = 0; d < n_dirs; ++d) sl.out[d] = static_cast<char*>(ctx->io.take(d_pitch * rows));
-            if (!sl.l || !sl.r || !sl.l8 || !sl.r8 || !sl.out[n_dirs - 1]) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
+            if (!sl.l8 || !sl.r8 || (any_f32 && (!sl.lf || !sl.rf)) || !sl.out[n_dirs - 1]) { set_error("io arena too small (internal)"); return STEREO_ERR_ALLOC; }
         }
-    auto ev = [&](int item, int band, int kind) { return ctx->pipe_ev[3 * (item * nb + band) + kind + 1]; };   // kind: 0 in, 1 cmp, 2 out
+    auto ev = [&](int item, int band, int kind) { return ctx->pipe_ev[3 * (uoff[item] + band) + kind + 1]; };   // kind: 0 in, 1 cmp, 2 out
 
     begin_call(ctx, s_cmp);
     // copy streams start after whatever the context's stream was doing with these buffers
     SB_CUDA(cudaEventRecord(ctx->pipe_ev[0], s_cmp));
     SB_CUDA(cudaStreamWaitEvent(s_in, ctx->pipe_ev[0], 0));
     SB_CUDA(cudaStreamWaitEvent(s_out, ctx->pipe_ev[0], 0));
-    if (dtype == PixType::F32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), s_cmp));
+    if (any_f32) SB_CUDA(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), s_cmp));
     ctx->last_path = STEREO_PATH_FAST_U8;
-    auto stg_ev = [&](int k) { return ctx->pipe_ev[3 * n_items * nb + 1 + k]; };
+    auto stg_ev = [&](int k) { return ctx->pipe_ev[3 * n_units + 1 + k]; };
+    struct FloatRows { int r0, n; };                      // float row ranges of the unit being uploaded (converted on the device)
+    std::vector<FloatRows> frows;
 
     for (int w = 0; w < n_items; ++w) {
         const Slot* sl = slot[w % S];
         const int i0 = w * cp, np = (n_pairs - i0 < cp) ? n_pairs - i0 : cp;     // pairs i0 .. i0+np-1 ride this item
         int uploaded = 0;
-        for (int b = 0; b < nb; ++b) {
-            const int rb = b * band_rows, re = (rb + band_rows < rows) ? rb + band_rows : rows;
-            if (rb >= re) {           // (rows not divisible: trailing empty band) keep the event chain intact
-                SB_CUDA(cudaEventRecord(ev(w, b, 0), s_in)); SB_CUDA(cudaEventRecord(ev(w, b, 1), s_cmp)); SB_CUDA(cudaEventRecord(ev(w, b, 2), s_out));
-                continue;
-            }
+        for (int b = 0; b < nbw(w); ++b) {
+            const int rb = bounds[boff[w] + b], re = bounds[boff[w] + b + 1];
             // ---- upload the rows this band adds: window halo R, the +1 row of the SSD flat-index wrap, and the
             //      operand rows the FRPS-row pipeline stages round up to
-            const int up_hi = (b == nb - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
-            const int nr = up_hi - uploaded;
-            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(w - S, nb - 1, 1), 0));   // slot inputs free again
-            if (nr > 0 && pack) {
-                // host threads convert this band's rows of every pair into a pinned staging slot, from where they are uploaded
-                const int k = stg_used % NSTG;
-                if (stg_used >= NSTG) SB_CUDA(cudaEventSynchronize(stg_ev(k)));      // the upload that last read this slot
-                ++stg_used;
-                uint8_t* stg = static_cast<uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
-                bool all8 = true;
-                for (int c = 0; c < np; ++c) {
-                    const HostPairIn& hp = in[i0 + c];
-                    uint8_t* sl_l = stg + size_t(2 * c) * stg_rows * stg_pitch;
-                    uint8_t* sl_r = stg + size_t(2 * c + 1) * stg_rows * stg_pitch;
-                    all8 = all8 && pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(static_cast<const char*>(hp.left) + size_t(uploaded) * hp.left_step),
-                                               hp.left_step, sl_l, stg_pitch, nr, cols);
-                    all8 = all8 && pack_f32_u8(*ctx->pool, reinterpret_cast<const float*>(static_cast<const char*>(hp.right) + size_t(uploaded) * hp.right_step),
-                                               hp.right_step, sl_r, stg_pitch, nr, cols);
-                    if (!all8) break;
-                    SB_CUDA(cudaMemcpy2DAsync(sl[c].l + size_t(uploaded) * in_pitch, in_pitch, sl_l, stg_pitch, cols, nr, cudaMemcpyHostToDevice, s_in));
-                    SB_CUDA(cudaMemcpy2DAsync(sl[c].r + size_t(uploaded) * in_pitch, in_pitch, sl_r, stg_pitch, cols, nr, cudaMemcpyHostToDevice, s_in));
+            const int up_hi = (b == nbw(w) - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
+            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_in, ev(w - S, nbw(w - S) - 1, 1), 0));   // slot inputs free again
+            frows.clear();
+            for (int r0 = uploaded; r0 < up_hi; r0 += chunk_rows) {
+                const int n = up_hi - r0 < chunk_rows ? up_hi - r0 : chunk_rows;
+                if (type == PixType::U8) {
+                    for (int c = 0; c < np; ++c) {
+                        const HostPairIn& hp = in[i0 + c];
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].l8 + size_t(r0) * u8_pitch, u8_pitch, static_cast<const char*>(hp.left) + size_t(r0) * hp.left_step,
+                                                  hp.left_step, cols, n, cudaMemcpyHostToDevice, s_in));
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].r8 + size_t(r0) * u8_pitch, u8_pitch, static_cast<const char*>(hp.right) + size_t(r0) * hp.right_step,
+                                                  hp.right_step, cols, n, cudaMemcpyHostToDevice, s_in));
+                    }
+                    continue;
                 }
-                if (!all8) {      // a pixel that is not 8-bit: give the call to the float kernels (nothing of it has reached the caller's maps
-                                  // that will not be overwritten)
-                    SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
-                    return PIPE_NOT_8BIT;
+                // float rows as they are (converted by classify_convert_kernel in front of the unit's kernels), or through the
+                // pinned staging ring as 8-bit pixels
+                const int nf = any_pack ? 0 : n;
+                if (nf > 0) {
+                    for (int c = 0; c < np; ++c) {
+                        const HostPairIn& hp = in[i0 + c];
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].lf + size_t(r0) * f_pitch, f_pitch, static_cast<const char*>(hp.left) + size_t(r0) * hp.left_step,
+                                                  hp.left_step, size_t(cols) * 4, nf, cudaMemcpyHostToDevice, s_in));
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].rf + size_t(r0) * f_pitch, f_pitch, static_cast<const char*>(hp.right) + size_t(r0) * hp.right_step,
+                                                  hp.right_step, size_t(cols) * 4, nf, cudaMemcpyHostToDevice, s_in));
+                    }
+                    frows.push_back(FloatRows{r0, nf});
                 }
-                SB_CUDA(cudaEventRecord(stg_ev(k), s_in));
-            } else if (nr > 0)
-                for (int c = 0; c < np; ++c) {
-                    const HostPairIn& hp = in[i0 + c];
-                    SB_CUDA(cudaMemcpy2DAsync(sl[c].l + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(hp.left) + size_t(uploaded) * hp.left_step,
-                                              hp.left_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
-                    SB_CUDA(cudaMemcpy2DAsync(sl[c].r + size_t(uploaded) * in_pitch, in_pitch, static_cast<const char*>(hp.right) + size_t(uploaded) * hp.right_step,
-                                              hp.right_step, cols * px, nr, cudaMemcpyHostToDevice, s_in));
+                const int p0 = r0 + nf, npk = n - nf;
+                if (npk > 0) {
+                    const int k = stg_used % NSTG;
+                    const auto t_r = std::chrono::steady_clock::now();
+                    if (stg_used >= NSTG) SB_CUDA(cudaEventSynchronize(stg_ev(k)));      // the upload that last read this slot
+                    t_ring += since(t_r);
+                    ++stg_used;
+                    uint8_t* stg = static_cast<uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
+                    PackJob jobs[2 * PIPE_CPMAX];
+                    for (int c = 0; c < np; ++c) {
+                        const HostPairIn& hp = in[i0 + c];
+                        jobs[2 * c] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.left) + size_t(p0) * hp.left_step), hp.left_step,
+                                              stg + size_t(2 * c) * stg_rows * stg_pitch, stg_pitch, npk, cols};
+                        jobs[2 * c + 1] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.right) + size_t(p0) * hp.right_step), hp.right_step,
+                                                  stg + size_t(2 * c + 1) * stg_rows * stg_pitch, stg_pitch, npk, cols};
+                    }
+                    const auto t_p = std::chrono::steady_clock::now();
+                    const bool all8 = pack_f32_u8_jobs(*ctx->pool, jobs, 2 * np);       // one dispatch of the pool per chunk
+                    t_pack += since(t_p);
+                    if (!all8) {
+                        // a pixel that is not 8-bit: give the call to the float kernels (nothing of it has reached the caller's
+                        // maps that will not be overwritten)
+                        SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
+                        return PIPE_NOT_8BIT;
+                    }
+                    for (int c = 0; c < np; ++c) {
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].l8 + size_t(p0) * u8_pitch, u8_pitch, jobs[2 * c].dst, stg_pitch, cols, npk, cudaMemcpyHostToDevice, s_in));
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].r8 + size_t(p0) * u8_pitch, u8_pitch, jobs[2 * c + 1].dst, stg_pitch, cols, npk, cudaMemcpyHostToDevice, s_in));
+                    }
+                    SB_CUDA(cudaEventRecord(stg_ev(k), s_in));
                 }
+            }
+            if (up_hi > uploaded) uploaded = up_hi;
             SB_CUDA(cudaEventRecord(ev(w, b, 0), s_in));
             // ---- compute
             SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w, b, 0), 0));
-            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w - S, nb - 1, 2), 0));  // slot outputs downloaded
-            if (dtype == PixType::F32 && nr > 0) {
-                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(nr, 8), 2);
+            if (b == 0 && w >= S) SB_CUDA(cudaStreamWaitEvent(s_cmp, ev(w - S, nbw(w - S) - 1, 2), 0));  // slot outputs downloaded
+            for (const FloatRows& fr : frows) {
+                dim3 cb(32, 8), cg(div_round_up(cols, 32), div_round_up(fr.n, 8), 2);
                 for (int c = 0; c < np; ++c) {
-                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].l + size_t(uploaded) * in_pitch), in_pitch,
-                                                                 sl[c].l8 + size_t(uploaded) * u8_pitch,
-                                                                 reinterpret_cast<const float*>(sl[c].r + size_t(uploaded) * in_pitch), in_pitch,
-                                                                 sl[c].r8 + size_t(uploaded) * u8_pitch, nr, cols, u8_pitch, ctx->d_flag);
+                    classify_convert_kernel<<<cg, cb, 0, s_cmp>>>(reinterpret_cast<const float*>(sl[c].lf + size_t(fr.r0) * f_pitch), f_pitch,
+                                                                 sl[c].l8 + size_t(fr.r0) * u8_pitch,
+                                                                 reinterpret_cast<const float*>(sl[c].rf + size_t(fr.r0) * f_pitch), f_pitch,
+                                                                 sl[c].r8 + size_t(fr.r0) * u8_pitch, fr.n, cols, u8_pitch, ctx->d_flag);
                     ctx->last_launches += 1;
                 }
             }
-            if (nr > 0) uploaded = up_hi;
             {
                 // direction-major: jobs with the same range sign are neighbours (they share offsets and pitches)
                 Problem pd[FMAXJOBS];
@@ -663,12 +737,26 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
             SB_CUDA(cudaEventRecord(ev(w, b, 2), s_out));
         }
     }
-    if (dtype == PixType::F32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
+    if (any_f32) SB_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s_cmp));
     end_call(ctx, s_cmp);
+    const double t_enq = since(t_call);
     SB_CUDA(cudaStreamSynchronize(s_cmp));
     SB_CUDA(cudaStreamSynchronize(s_out));
     SB_CUDA(cudaStreamSynchronize(s_in));
-    if (dtype == PixType::F32 && *ctx->h_flag != 0) return PIPE_NOT_8BIT;
+    if (pipe_trace()) {
+        fprintf(stderr, "[pipe] host: everything enqueued after %.3f ms (converting %.3f, waiting for a staging slot %.3f), streams idle after %.3f ms\n",
+                t_enq, t_pack, t_ring, since(t_call));
+        fprintf(stderr, "[pipe] %d pairs %dx%d, %d items, %d units, %s\n", n_pairs, rows, cols, n_items, n_units,
+                any_pack ? "host pack" : (type == PixType::F32 ? "float upload" : "u8"));
+        for (int w = 0; w < n_items; ++w)
+            for (int b = 0; b < nbw(w); ++b) {
+                float t[3] = {-1.f, -1.f, -1.f};
+                for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], ctx->pipe_ev[0], ev(w, b, k));
+                fprintf(stderr, "[pipe]   item %d rows %d..%d: in %.3f  compute %.3f  out %.3f ms\n", w, bounds[boff[w] + b], bounds[boff[w] + b + 1], t[0], t[1], t[2]);
+            }
+        (void)cudaGetLastError();
+    }
+    if (any_f32 && *ctx->h_flag != 0) return PIPE_NOT_8BIT;
     return STEREO_OK;
 }
 
@@ -915,9 +1003,33 @@ int stereo_host_pipeline_plan(int n_pairs, int rows, int cols, int bands_overrid
     stereo_ctx tmp;
     tmp.pipe_bands = bands_override;
     const int nb = pipe_bands(&tmp, n_pairs, rows);
-    *bands_per_pair = nb;
-    *pairs_per_item = pipe_chunk_pairs(n_pairs, nb, rows, cols);
+    const int cp = pipe_chunk_pairs(n_pairs, nb, rows, cols);
+    const int n_items = (n_pairs + cp - 1) / cp;
+    std::vector<int> b;
+    int most = 0;
+    for (int w = 0; w < n_items; w = (w == 0 && n_items > 2) ? n_items - 1 : w + 1) {      // first and last item hold the most bands
+        pipe_item_bounds(&tmp, n_pairs, n_items, w, rows, cols, b);
+        most = int(b.size()) - 1 > most ? int(b.size()) - 1 : most;
+    }
+    *bands_per_pair = most;
+    *pairs_per_item = cp;
     return STEREO_OK;
+}
+
+int stereo_host_pipeline_item_bands(int n_pairs, int rows, int cols, int bands_override, int item, int* bounds, int cap) {
+    if (n_pairs <= 0 || rows <= 0 || cols <= 0 || bands_override < 0 || item < 0 || !bounds || cap < 2) {
+        set_error("bad arguments"); return STEREO_ERR_INVALID_ARG;
+    }
+    stereo_ctx tmp;
+    tmp.pipe_bands = bands_override;
+    const int cp = pipe_chunk_pairs(n_pairs, pipe_bands(&tmp, n_pairs, rows), rows, cols);
+    const int n_items = (n_pairs + cp - 1) / cp;
+    if (item >= n_items) { set_error("item %d of %d", item, n_items); return STEREO_ERR_INVALID_ARG; }
+    std::vector<int> b;
+    pipe_item_bounds(&tmp, n_pairs, n_items, item, rows, cols, b);
+    if (int(b.size()) > cap) { set_error("%d boundaries, room for %d", int(b.size()), cap); return STEREO_ERR_INVALID_ARG; }
+    for (size_t i = 0; i < b.size(); ++i) bounds[i] = b[i];
+    return int(b.size());
 }
 
 // Pure host arithmetic (no device): the geometry of the hot-kernel launch a batch of `n_pairs` pair problems would get.

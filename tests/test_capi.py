@@ -99,9 +99,10 @@ def test_headline_hot_kernels_do_not_spill():
 
 
 def test_host_pipeline_plan():
-    """The cut of a host batch into pipeline items (pure host arithmetic): large single pairs go in ~512-row bands,
-    batches of large images in two bands, batches of small images several pairs per item (<= 4 = 8 directions per launch
-    sequence) with at least three items in flight."""
+    """The cut of a host batch into pipeline items (pure host arithmetic): 4K-sized images go unevenly - the first item of
+    a call begins and the last one ends with an eighth of the image, whole images in between -, other large images in
+    uniform bands, batches of small images several pairs per item (<= 4 = 8 directions per launch sequence) with at least
+    three items in flight."""
     lib = _capi.lib()
 
     def plan(n, rows, cols, override=0):
@@ -109,16 +110,30 @@ def test_host_pipeline_plan():
         assert lib.stereo_host_pipeline_plan(n, rows, cols, override, C.byref(b), C.byref(c)) == 0
         return b.value, c.value
 
-    assert plan(1, 2160, 3840) == (4, 1)
-    assert plan(2, 2160, 3840) == (4, 1)
-    assert plan(4, 2160, 3840) == (2, 1)
-    assert plan(1, 1080, 1920) == (2, 1)
+    def bands(n, rows, cols, item, override=0):
+        buf = (C.c_int * 64)()
+        k = lib.stereo_host_pipeline_item_bands(n, rows, cols, override, item, buf, 64)
+        assert k >= 2, _capi.last_error()
+        return list(buf[:k])
+
+    assert plan(1, 2160, 3840) == (5, 1)
+    assert plan(2, 2160, 3840) == (3, 1)
+    assert plan(4, 2160, 3840) == (3, 1)
+    assert bands(1, 2160, 3840, 0) == [0, 270, 810, 1350, 1890, 2160]
+    assert bands(4, 2160, 3840, 0) == [0, 270, 810, 2160]
+    assert bands(4, 2160, 3840, 1) == [0, 2160] == bands(4, 2160, 3840, 2)
+    assert bands(4, 2160, 3840, 3) == [0, 1350, 1890, 2160]
+    assert bands(2, 2160, 3840, 1, override=2) == [0, 1080, 2160]
+    assert plan(1, 1080, 1920) == (2, 1) and bands(1, 1080, 1920, 0) == [0, 540, 1080]
+    assert plan(4, 1080, 1920) == (2, 1)
     assert plan(1, 128, 128) == (1, 1)
-    assert plan(16, 720, 1280) == (1, 4)
+    assert plan(16, 720, 1280) == (1, 4) and bands(16, 720, 1280, 3) == [0, 720]
     assert plan(6, 720, 1280) == (1, 2)
     assert plan(512, 720, 1280) == (1, 4)
     assert plan(3, 2160, 3840, override=7) == (7, 1)
+    assert bands(1, 1001, 64, 0, override=3) == [0, 334, 668, 1001]
     assert lib.stereo_host_pipeline_plan(0, 10, 10, 0, None, None) != 0
+    assert lib.stereo_host_pipeline_item_bands(4, 2160, 3840, 0, 4, (C.c_int * 8)(), 8) < 0
 
 
 def test_docs_name_only_real_entry_points():

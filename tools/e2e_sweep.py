@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--cost", default="ssd")
     ap.add_argument("--kinds", nargs="+", default=["f32", "u8"])
+    ap.add_argument("--threads", type=int, nargs="+", default=[0], help="host packing threads (0: the library's default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rows, cols, nd, R = wl["rows"], wl["cols"], wl["ndisp"], wl["R"]
@@ -47,8 +48,9 @@ def main():
     for kind in args.kinds:
         src, px, fn = (hf, 4, lib.stereo_disparity_pair_batch_f32_host) if kind == "f32" else (hu, 1, lib.stereo_disparity_pair_batch_u8_host)
         for B in args.pairs:
-            for bands in args.bands:
+            for bands, threads in [(b, t) for b in args.bands for t in (args.threads if kind == "f32" else args.threads[:1])]:
                 ctx.set_pipe_bands(bands)
+                lib.stereo_ctx_set_host_threads(ctx.handle, threads)
 
                 def call():
                     rc = fn(ctx.handle, cost, B, src[0].data_ptr(), src[1].data_ptr(), cols * px, rows * cols * px, rows, cols, R,
@@ -62,7 +64,7 @@ def main():
                 for _ in range(args.steps):
                     call()
                 dt = (time.perf_counter() - t0) / args.steps
-                print(json.dumps({"workload": args.workload, "cost": args.cost, "kind": kind, "pairs_per_call": B, "bands": bands,
+                print(json.dumps({"workload": args.workload, "cost": args.cost, "kind": kind, "pairs_per_call": B, "bands": bands, "host_threads": lib.stereo_ctx_host_threads(ctx.handle),
                                   "ms_per_call": round(dt * 1e3, 3), "ms_per_pair": round(dt * 1e3 / B, 3),
                                   "Mpix_disp_per_s": round(B * 2 * rows * cols * nd / dt / 1e6, 1),
                                   "launches": ctx.last_launches}), flush=True)
