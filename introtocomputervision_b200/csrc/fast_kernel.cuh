@@ -258,6 +258,11 @@ struct RowShape {
 #ifndef SB_KEY2_LEA
 #define SB_KEY2_LEA 0
 #endif
+// Fused kernels: a diagonal takes its four candidates of a lane in two three-input minima (VIMNMX3: acc, the key held over
+// from the step before, this step's key) instead of four two-input ones.
+#ifndef SB_DIAG_MIN3
+#define SB_DIAG_MIN3 1
+#endif
 #ifndef SB_TAIL_BATCH
 #define SB_TAIL_BATCH 1
 #endif
@@ -428,6 +433,10 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
 #pragma unroll
         for (int m = 0; m < FM; ++m) acc[m] = NCC ? NCC_KEY_NONE : KEY_INVALID;      // running minima (SSD) / maxima (NCC)
     }
+    // SB_DIAG_MIN3: the keys of slots 3 and 1 wait one step - by then their diagonals sit in slots 2 and 0 and take them
+    // together with that step's key
+    constexpr bool DM3 = FUSED && SB_DIAG_MIN3 && FM == 4;
+    uint32_t held3 = NCC ? NCC_KEY_NONE : KEY_INVALID, held1 = held3;
     constexpr int LSF = 32 / HS;                                          // lanes per strip
     const uint32_t top_or = (FUSED && ll == LSF - 1) ? KEY_INVALID : 0u;  // the top lane of a strip opens a fresh diagonal every step
     // FUSED NCC.  Both maps order candidates by C * rs with rs = 1/sqrt(energy of the OTHER image's window): the own pixel
@@ -470,6 +479,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             }
         }
         uint32_t key[FM];
+        uint32_t key2[FM];       // (DM3: the partner keys of slots 1 and 3, held for the next step)
 #pragma unroll
         for (int m = 0; m < FM; ++m) {
             if (FSUM) {
@@ -503,7 +513,10 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                     else k2 = uint32_t(elv[k & 3]) + uint32_t(s[m]) * KEYMUL;
                     if (MODE == 3) k2 = k2 | einv[k & 3] | mmask[MODE == 3 ? m : 0];
                     if (MODE == 2 && (R > FFREE_MASK_R || OPF)) k2 |= lane_or;
-                    acc[m] = min(acc[m], k2);
+                    if (!DM3) acc[m] = min(acc[m], k2);
+                    else if (m == 2) acc[2] = min(min(acc[2], held3), k2);
+                    else if (m == 0) acc[0] = min(min(acc[0], held1), k2);
+                    else key2[m] = k2;
                 }
             } else {
                 const float rs = __int_as_float(e2v[k + m]);
@@ -526,7 +539,10 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                     uint32_t k2 = (uint32_t(__float_as_int(r2)) << NCC_KEY_SHIFT) + (lane_or2 + 4u * m);
                     if (MODE == 3) k2 = k2 & mmask[MODE == 3 ? m : 0];
                     if (MODE == 2) k2 = mmax < 0 ? NCC_KEY_NONE : k2;
-                    acc[m] = max(acc[m], k2);
+                    if (!DM3) acc[m] = max(acc[m], k2);
+                    else if (m == 2) acc[2] = max(max(acc[2], held3), k2);
+                    else if (m == 0) acc[0] = max(max(acc[0], held1), k2);
+                    else key2[m] = k2;
                 }
             }
         }
@@ -568,8 +584,13 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             else if (ll == 0) tl[k] = done;
             in = NCC ? (in & ~top_or) : (in | top_or);
             acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = in;
+            if (DM3) { held3 = key2[3]; held1 = key2[1]; }
         }
     }                                             // [pixel-loop-end]
+    if (DM3) {        // the last step's held keys: their diagonals now sit in slots 2 and 0
+        acc[2] = NCC ? max(acc[2], held3) : min(acc[2], held3);
+        acc[0] = NCC ? max(acc[0], held1) : min(acc[0], held1);
+    }
     if (FUSED) {
         // live diagonals: acc[m] <-> t = K + 4*ll + m <-> partner pixel x' = x2base + t; tail[t] <-> t < K
         __syncwarp();
