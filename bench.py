@@ -988,7 +988,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k_d256_w11", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=4, help="stereo pairs per GPU per step (a launch sequence carries up to 8 pairs = 16 directions)")
+    ap.add_argument("--pairs", type=int, default=4, help="stereo pairs per GPU per step (a launch sequence carries up to 16 pairs = 32 directions)")
     ap.add_argument("--ref-rows", type=int, default=4, help="CPU sample: image rows per host thread")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-suite", action="store_true", help="skip the suite of other configurations (N = 1 only)")

@@ -103,7 +103,7 @@ int stereo_ctx_last_path(const stereo_ctx* ctx);
  * verdict is left out (classification kernels + the kernels of the chosen family). */
 float stereo_ctx_last_kernel_ms(const stereo_ctx* ctx);
 /* Device time (ms) of the most recent call's HOT kernels only (the packed cost/WTA kernels; one launch
- * covers up to 16 directions of equally shaped problems), summed over the launches that were measured
+ * covers up to 32 directions of equally shaped problems), summed over the launches that were measured
  * (at most 16 per call); *launches_measured (nullable) receives how many that was.  <0 if the call used
  * no hot kernel.  This is the number the roofline report divides by. */
 float stereo_ctx_last_hot_kernel_ms(const stereo_ctx* ctx, int* launches_measured);
@@ -142,7 +142,7 @@ int stereo_ctx_host_threads(const stereo_ctx* ctx);
 int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
                             int* all_8bit);
 
-/* How the hot kernel of a batch of `n_pairs` (<= 4) equally shaped pair problems would be launched on a device with
+/* How the hot kernel of a batch of `n_pairs` (<= 16) equally shaped pair problems would be launched on a device with
  * `sm_count` SMs (pure host arithmetic, no device needed; tests pin the scheduling decisions with it).
  * schedule: 0 = linear split of the (tile, row) space, 1 = equal row segments per tile (fewer tiles than SMs),
  * 2 = row-band-major items strided over the CTAs (many tiles: neighbouring tiles walk the same rows together). */

@@ -86,7 +86,13 @@ constexpr int FWARPS = SB_FWARPS; // warps per CTA (K=24 pixels x 4 disparities 
 // merges of lanes whose partner pixel lies outside the image land at most one disparity range + a strip before the first
 // row or behind the last one.
 static inline size_t fused_part_pad_words(int G) { return size_t(G) * 128 + 512; }
-constexpr int FMAXJOBS = 16;    // directions (jobs) one launch sequence can carry (8 pairs; the parameter block stays below 4 KB)
+#ifndef SB_FMAXJOBS
+#define SB_FMAXJOBS 32
+#endif
+// directions (jobs) one launch sequence can carry: 16 pairs.  The parameter block (~5.6 KB) needs the large kernel parameters
+// of CUDA 12.1+ (sm_70+, up to 32764 bytes); 16 jobs (SB_FMAXJOBS=16) stay below the classic 4 KB.  720p/64 x 16 pairs:
+// 0.70 -> 0.67 ms per step with one launch sequence instead of two.
+constexpr int FMAXJOBS = SB_FMAXJOBS;
 constexpr int FMAXR = 7;        // largest window radius with 32-bit keys: 128*(2R+1)^2*255^2 < 2^31
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 constexpr int FFREE_MASK_R = 5;   // largest radius for which invalid candidates lose through the key alone
@@ -262,6 +268,9 @@ struct RowShape {
 // from the step before, this step's key) instead of four two-input ones.
 #ifndef SB_DIAG_MIN3
 #define SB_DIAG_MIN3 1
+#endif
+#ifndef SB_NCC_UNBIAS
+#define SB_NCC_UNBIAS 1
 #endif
 #ifndef SB_TAIL_BATCH
 #define SB_TAIL_BATCH 1
@@ -525,8 +534,12 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                 // (Sterbenz / common-ulp argument: 2^23*rs >= 2990 > magic/2 for R <= 5), i.e. ONE rounding (the per-pixel
                 // scales of fused launches may be twice as large: the addend then rounds, by at most half a key unit)
                 // OPF: `magic` arrives as 3 * 2^e (C may be negative): r lies in [2*2^e, 4*2^e)
-                const float cf = BIASED ? 0.f : (OPF ? __int_as_float(s[m]) : __int2float_rn(s[m]));
-                const float r = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, mg)) : __fmaf_rn(cf, rs, mg);
+                // fused pairs: both maps need C itself - one exact FADD (2^23 + C is a float, C < 2^23) shared by their two FFMAs
+                // instead of one addend FFMA per map
+                constexpr bool UNBIAS = BIASED && FUSED && SB_NCC_UNBIAS;
+                const float cf = UNBIAS ? __fadd_rn(__int_as_float(s[m]), -8388608.0f)
+                                        : (BIASED ? 0.f : (OPF ? __int_as_float(s[m]) : __int2float_rn(s[m])));
+                const float r = (BIASED && !UNBIAS) ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, mg)) : __fmaf_rn(cf, rs, mg);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
                 uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
                 if (MODE == 3) kv = kv & pmask[MODE == 3 ? k + m : 0] & mmask[MODE == 3 ? m : 0];
@@ -535,7 +548,7 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                     // the partner's key of the same cross term: its candidate is THIS pixel (rs_L[x] = elv), its scale the one of
                     // position k + m, its candidate index inside its group runs against this lane's (d' = -d)
                     const float rs2 = __int_as_float(elv[k & 3]), mg2 = pos_scale[FUSED && NCC ? k + m : 0];
-                    const float r2 = BIASED ? __fmaf_rn(__int_as_float(s[m]), rs2, __fmaf_rn(rs2, -8388608.0f, mg2)) : __fmaf_rn(cf, rs2, mg2);
+                    const float r2 = (BIASED && !UNBIAS) ? __fmaf_rn(__int_as_float(s[m]), rs2, __fmaf_rn(rs2, -8388608.0f, mg2)) : __fmaf_rn(cf, rs2, mg2);
                     uint32_t k2 = (uint32_t(__float_as_int(r2)) << NCC_KEY_SHIFT) + (lane_or2 + 4u * m);
                     if (MODE == 3) k2 = k2 & mmask[MODE == 3 ? m : 0];
                     if (MODE == 2) k2 = mmax < 0 ? NCC_KEY_NONE : k2;

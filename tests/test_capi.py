@@ -189,5 +189,5 @@ def test_launch_plan_pins_the_scheduling_decisions():
     for q in (plan(SSD, 0, 1, 128, 128, 6, 3), plan(SSD, 0, 2, 97, 3000, 2, 300), plan(NCC, 0, 3, 2000, 64, 0, 1)):
         assert 1 <= q.ctas <= 148 and q.stages >= 2 and q.smem_bytes <= 227 * 1024
     bad = _capi.LaunchPlan()
-    assert lib.stereo_launch_plan(SSD, 0, 9, 10, 10, 1, 1, 1, 148, C.byref(bad)) != 0     # more pairs than one launch carries
+    assert lib.stereo_launch_plan(SSD, 0, 17, 10, 10, 1, 1, 1, 148, C.byref(bad)) != 0    # more pairs than one launch carries
     assert lib.stereo_launch_plan(SSD, 0, 1, 10, 10, 9, 1, 1, 148, C.byref(bad)) != 0     # radius beyond the running-sum kernels

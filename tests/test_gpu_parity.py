@@ -144,9 +144,9 @@ def test_pair_equals_two_singles_and_batch_equals_pairs(ctx):
             assert np.array_equal(bl[i], dl) and np.array_equal(br[i], dr)
 
 
-@pytest.mark.parametrize("n,rng,R", [(5, 63, 4), (9, 40, 2), (6, 150, 5), (4, 127, 7), (17, 30, 1)])
+@pytest.mark.parametrize("n,rng,R", [(5, 63, 4), (9, 40, 2), (6, 150, 5), (4, 127, 7), (17, 30, 1), (33, 20, 3)])
 def test_device_batch_launch_chunks_vs_oracle(ctx, n, rng, R):
-    """Device batches share launch sequences (up to 16 directions each): chunk boundaries (8+1, 8+8+1 pairs),
+    """Device batches share launch sequences (up to 32 directions each): chunk boundaries (16+1, 16+16+1 pairs),
     2-strips-per-warp kernels (<= 64 candidates), one and two 128-disparity groups — all against the oracle."""
     import torch
     from introtocomputervision_b200 import _capi
