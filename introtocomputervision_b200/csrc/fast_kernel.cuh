@@ -272,6 +272,9 @@ struct RowShape {
 #ifndef SB_NCC_UNBIAS
 #define SB_NCC_UNBIAS 1
 #endif
+#ifndef SB_NCC_CHAIN
+#define SB_NCC_CHAIN 1
+#endif
 #ifndef SB_TAIL_BATCH
 #define SB_TAIL_BATCH 1
 #endif
@@ -324,6 +327,8 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
     using S = RowShape<R, K>;
     constexpr bool NCC = (COST == STEREO_COST_NCORR);
     constexpr bool BIASED = NCC && !OPF && (R <= NCC_BIAS_MAX_R);
+    // (one-strip fused kernels lose with it: 8 bytes spilled, 4K/256 pairs 2.33 -> 2.40 ms; unfused 3.04 -> 2.87, two-strip fused 0.60 -> 0.59)
+    constexpr bool NCC_CHAIN = NCC && SB_NCC_CHAIN && (!FUSED || HS == 2);
     constexpr uint32_t KEYMUL = OPF ? FKEY_MUL_F32 : uint32_t(2 << FKEY_BITS);
     int lpv[S::NC4];               // packed: s16x2 (new, old) of the reference image;  OPF: the entering row (float bits)
     int rqv[S::NQ4];               // packed: u8x4 of the target image;                 OPF: the entering row
@@ -541,7 +546,10 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
                                         : (BIASED ? 0.f : (OPF ? __int_as_float(s[m]) : __int2float_rn(s[m])));
                 const float r = (BIASED && !UNBIAS) ? __fmaf_rn(__int_as_float(s[m]), rs, __fmaf_rn(rs, -8388608.0f, mg)) : __fmaf_rn(cf, rs, mg);
                 // lane_or carries ((127 - 4*lane) << 2) | 3: reversed position of the lane's first candidate
-                uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (lane_or - 4u * m);
+                // CHAIN (rows without explicit masks): the candidate's own two position bits join in the maximum below (add-then-max
+                // is ONE instruction with the addend as an immediate; four distinct per-candidate constants would be four more
+                // live registers, or an extra add each)
+                uint32_t kv = (uint32_t(__float_as_int(r)) << NCC_KEY_SHIFT) + (NCC_CHAIN && MODE != 3 ? lane_or : lane_or - 4u * m);
                 if (MODE == 3) kv = kv & pmask[MODE == 3 ? k + m : 0] & mmask[MODE == 3 ? m : 0];
                 key[m] = kv;
                 if (FUSED) {
@@ -564,7 +572,13 @@ __device__ __forceinline__ void fast_row(int (&col)[FM][RowShape<R, K>::NC], con
             best = min(min(key[0], key[1]), min(key[2], key[3]));
             if (MODE == 2) best |= lane_or;
         } else {
-            best = max(max(key[0], key[1]), max(key[2], key[3]));
+            if (NCC_CHAIN && MODE != 3) {
+                best = key[0];
+#pragma unroll
+                for (int m = 1; m < FM; ++m) best = max(best, key[m] - 4u * m);
+            } else {
+                best = max(max(key[0], key[1]), max(key[2], key[3]));
+            }
             if (MODE == 2) best = mmax < 0 ? NCC_KEY_NONE : best;
         }
         if (HS == 1) {
