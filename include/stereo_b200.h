@@ -141,6 +141,10 @@ int stereo_ctx_host_threads(const stereo_ctx* ctx);
  * *all_8bit = 1 when every pixel is an integer in 0..255 (otherwise the u8 image is meaningless). */
 int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
                             int* all_8bit);
+/* Self-test of the worker pool behind the conversion (pure host code): `rounds` dispatches of 1..257 tasks on ONE pool of
+ * `threads` threads, with pauses long enough for the polling workers to fall asleep; STEREO_OK when every task of every
+ * dispatch ran exactly once (STEREO_ERR_UNSUPPORTED with the offending task in stereo_last_error() otherwise). */
+int stereo_host_pool_selftest(int threads, int rounds);
 
 /* How the hot kernel of a batch of `n_pairs` (<= 16) equally shaped pair problems would be launched on a device with
  * `sm_count` SMs (pure host arithmetic, no device needed; tests pin the scheduling decisions with it).

@@ -41,6 +41,7 @@ SIGNATURES = {
     "stereo_host_pipeline_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "stereo_host_pipeline_item_bands": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), _i]),
     "stereo_ctx_set_fuse_pairs": (_i, [_vp, _i]),
+    "stereo_host_pool_selftest": (_i, [_i, _i]),
     "stereo_ctx_set_host_threads": (_i, [_vp, _i]),
     "stereo_ctx_host_threads": (_i, [_vp]),
     "stereo_launch_plan": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -7,8 +7,10 @@
 #include "imgproc.cuh"
 #include "host_pack.hpp"
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -1077,6 +1079,21 @@ int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, siz
     }
     HostPool pool(threads);
     *all_8bit = pack_f32_u8(pool, src, src_step, dst, dst_step, rows, cols) ? 1 : 0;
+    return STEREO_OK;
+}
+
+int stereo_host_pool_selftest(int threads, int rounds) {
+    if (threads < 1 || threads > 256 || rounds < 1) { set_error("bad selftest arguments"); return STEREO_ERR_INVALID_ARG; }
+    HostPool pool(threads);
+    std::vector<std::atomic<int>> hits(257);
+    for (int r = 0; r < rounds; ++r) {
+        const int n_tasks = 1 + (r * 37) % 257;
+        for (int i = 0; i < n_tasks; ++i) hits[i].store(0, std::memory_order_relaxed);
+        pool.run(n_tasks, [&](int t) { hits[t].fetch_add(1, std::memory_order_relaxed); });
+        for (int i = 0; i < n_tasks; ++i)
+            if (hits[i].load() != 1) { set_error("round %d: task %d of %d ran %d times", r, i, n_tasks, hits[i].load()); return STEREO_ERR_UNSUPPORTED; }
+        if (r % 64 == 63) std::this_thread::sleep_for(std::chrono::microseconds(600));     // let the workers fall asleep now and then
+    }
     return STEREO_OK;
 }
 

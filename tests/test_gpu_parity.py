@@ -324,6 +324,39 @@ def test_host_batch_chunked_items_vs_oracle(ctx, n, kind):
                 assert float(np.mean(br[i] == oracle.ncorr_fast(Rf, Lf, R, 0, rng))) >= NCC_DISP_AGREE
 
 
+@pytest.mark.parametrize("n,kind", [(3, np.float32), (3, np.uint8), (1, np.float32), (2, np.uint8)])
+def test_host_batch_uneven_bands_of_large_images_vs_oracle(ctx, n, kind):
+    """4K-sized images (>= 1024 rows, >= 4 Mpix) are cut unevenly by the host pipeline: the call's first item begins and its
+    last item ends with an eighth of the image, whole images in between (one pair: five bands), uploads in quarter-image
+    chunks.  Every seam against the oracle, CV_32FC1 (host-converted) and uint8 inputs, plus a pixel that is not 8-bit
+    inside the LAST band of the last pair (the call must fall back to the float kernels and still be exact)."""
+    from introtocomputervision_b200 import _capi
+    import ctypes as C
+    rows, cols, R, rng = 1100, 3840, 3, 15
+    buf = (C.c_int * 16)()
+    k = _capi.lib().stereo_host_pipeline_item_bands(n, rows, cols, 0, 0, buf, 16)
+    assert list(buf[:k]) == ([0, 137, 411, 689, 963, 1100] if n == 1 else [0, 137, 411, 1100])
+    Ls, Rs = [], []
+    for i in range(n):
+        L, Rt, _ = synth.make_pair(rows, cols, 12, 8100 + 5 * i + n)
+        Ls.append(L), Rs.append(Rt)
+    Ls, Rs = np.stack(Ls).astype(kind), np.stack(Rs).astype(kind)
+
+    def check(bl, br):
+        for i in range(n):
+            Lf, Rf = Ls[i].astype(np.float32), Rs[i].astype(np.float32)
+            assert np.array_equal(bl[i], oracle.narrow_i8(oracle.ssd_fast(Lf, Rf, R, -rng, 0))), f"pair {i} L->R"
+            assert np.array_equal(br[i], oracle.narrow_i8(oracle.ssd_fast(Rf, Lf, R, 0, rng))), f"pair {i} R->L"
+
+    bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, R, rng, dtype=np.int8)
+    assert ctx.last_path == sb.PATH_FAST_U8
+    check(bl, br)
+    if kind == np.float32:
+        Ls[n - 1, rows - 20, 1717] += 0.5
+        bl, br = ctx.disparity_pair_batch(sb.COST_SSD, Ls, Rs, R, rng, dtype=np.int8)
+        check(bl, br)
+
+
 def test_host_batch_f32_non_8bit_pair_takes_float_kernels(ctx):
     # one noisy pair in a CV_32FC1 batch: the batch goes pair by pair, the noisy one on the float running-sum kernels
     n, rows, cols, R, rng = 5, 30, 110, 2, 17

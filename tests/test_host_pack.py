@@ -53,3 +53,12 @@ def test_host_pack(no_avx512):
         env["STEREO_NO_AVX512"] = "1"
     res = subprocess.run([sys.executable, "-c", CHILD % str(ROOT)], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0 and "pack ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("threads", [2, 5, 16])
+def test_host_pool_many_dispatches(threads):
+    """The polling worker pool: thousands of back-to-back dispatches on one pool (every task exactly once), including
+    dispatches that find the workers asleep."""
+    sys.path.insert(0, str(ROOT))
+    from introtocomputervision_b200 import _capi
+    assert _capi.lib().stereo_host_pool_selftest(threads, 3000) == 0, _capi.last_error()
