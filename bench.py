@@ -611,6 +611,18 @@ def run_ours(args, wl):
                     "def": "peak lane-ops / 8 ops per unit, the ceiling the north-star '>= 70 % of roofline' is stated against",
                     "hot_kernel": round(units_hot / t_hot / ceiling, 4),
                     "whole_step": round(value * 1e6 / world / ceiling, 4)}
+                if args.cost == "ssd":
+                    # measured ceiling of the kernel's own instruction mix (tools/microbench/mix.cu, profiles/r2w_microbench_mix.txt):
+                    # with every operand in registers and no memory, barriers or row code, the mix issues 0.716 inst/clk/SMSP at the
+                    # kernel's occupancy - the register file delivers ~1.65 operand reads per clock per SMSP to three-operand
+                    # integer instructions - i.e. 40.2 clocks per warp pixel step (256 units)
+                    mix_units_per_s = 256 / 40.2 * sms * 4 * peaks["sm_max_mhz"] * 1e6
+                    roof["instruction_mix_ceiling"] = {
+                        "inst_per_clk_per_smsp": 0.716, "clk_per_warp_pixel_step": 40.2, "value": round(mix_units_per_s / 1e6, 1), "unit": UNIT,
+                        "hot_kernel_frac": round(units_hot / t_hot / mix_units_per_s, 4),
+                        "def": "core mix of one pixel step (6 IDP.2A, 4 IADD3, 8 IMAD, 4 minima, REDUX, SHFL, 1.5 LDS.128 = 28.75 SASS instructions) "
+                               "issued from registers at 2 warps per scheduler on this GPU model; the kernel executes 37.5 instructions per step at 0.69 inst/clk",
+                        "source": "profiles/r2w_microbench_mix.txt"}
                 if unfused is not None:
                     ms_u, n_u, jobs_u = unfused
                     ach_u = OPS_PER_UNIT[args.cost] * jobs_u * rows * cols * nd / (ms_u * 1e-3)
