@@ -749,22 +749,27 @@ __device__ __forceinline__ void merge_ncc_block(const FastKernelParams& P, const
     const uint8_t* __restrict__ A = job.A; const size_t a_step = job.a_step;
     const uint8_t* __restrict__ B = job.B; const size_t b_step = job.b_step;
     void* best_out = job.best; const size_t best_step = job.best_step;
-    long long bestv[4]; int bestd[4];
+    // first maximum over the groups: a later group wins only with strictly more value bits (same pixel -> same key scale ->
+    // comparable); the winner's candidate index is decoded once per pixel
+    uint32_t bkey[4]; int bgrp[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { bestv[k] = -1; bestd[k] = 0; }
+    for (int k = 0; k < 4; ++k) { bkey[k] = NCC_KEY_NONE; bgrp[k] = 0; }
     auto take = [&](const int grp, const int4 kv) {
         const uint32_t keys[4] = {uint32_t(kv.x), uint32_t(kv.y), uint32_t(kv.z), uint32_t(kv.w)};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t key = keys[k];
-            if (key == NCC_KEY_NONE) continue;                          // no legal candidate in this group
-            const long long v = key >> NCC_KEY_SHIFT;                   // same strip row -> same magic -> comparable
-            if (v > bestv[k]) { bestv[k] = v; bestd[k] = job.dlo0 + g.dg * grp + (FGROUP - 1 - int((key >> 2) & (FGROUP - 1))); }
+            // (NCC_KEY_NONE = 0 never replaces anything; a legal key replaces NONE even when its value bits are 0)
+            if (key != NCC_KEY_NONE && (bkey[k] == NCC_KEY_NONE || (key >> NCC_KEY_SHIFT) > (bkey[k] >> NCC_KEY_SHIFT))) { bkey[k] = key; bgrp[k] = grp; }
         }
     };
 #pragma unroll
     for (int i = 0; i < MG_PRE; ++i) if (i < g.G) take(i, pre[i]);
     for (int grp = MG_PRE; grp < g.G; ++grp) take(grp, *reinterpret_cast<const int4*>(PART + (size_t(grp) * g.nrows + yy) * g.wpart + x4));
+    int bestd[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        bestd[k] = bkey[k] == NCC_KEY_NONE ? 0 : job.dlo0 + g.dg * bgrp[k] + (FGROUP - 1 - int((bkey[k] >> 2) & (FGROUP - 1)));
     const bool right_aligned = (job.dmin <= 0 && job.dmax <= 0);
     int disp[4], centre[4];
 #pragma unroll
