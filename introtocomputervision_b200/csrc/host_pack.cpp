@@ -90,6 +90,8 @@ struct HostPool::Impl {
     std::mutex mu;
     std::condition_variable cv_work;
     const std::function<void(int)>* fn = nullptr;
+    std::function<void(int)> job;       // the dispatch in flight (begin() .. end())
+    bool open = false, inline_only = false;
     int n_tasks = 0;
     std::atomic<int> next{0};
     std::atomic<int> generation{0};     // bumped by run() after fn / n_tasks / next / pending are in place
@@ -125,6 +127,7 @@ HostPool::HostPool(int threads) : impl_(new Impl), threads_(threads < 1 ? 1 : th
 }
 
 HostPool::~HostPool() {
+    end();
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
         impl_->stop.store(true);
@@ -135,45 +138,57 @@ HostPool::~HostPool() {
 }
 
 void HostPool::run(int n_tasks, const std::function<void(int)>& fn) {
-    if (n_tasks <= 0) return;
-    if (threads_ == 1 || n_tasks == 1) { for (int i = 0; i < n_tasks; ++i) fn(i); return; }
-    impl_->fn = &fn;
-    impl_->n_tasks = n_tasks;
+    begin(n_tasks, fn);
+    end();
+}
+
+// begin() publishes a dispatch and returns: the workers start on it while the caller does something else (the host
+// pipeline enqueues the previous chunk's copies and launches); end() lets the caller take whatever tasks are left and
+// returns when every task has finished.  One dispatch at a time; `fn` is copied.
+void HostPool::begin(int n_tasks, const std::function<void(int)>& fn) {
+    impl_->job = fn;
+    impl_->n_tasks = n_tasks < 0 ? 0 : n_tasks;
+    impl_->open = true;
+    if (threads_ == 1 || impl_->n_tasks <= 1) { impl_->inline_only = true; return; }      // end() runs it on the caller
+    impl_->inline_only = false;
+    impl_->fn = &impl_->job;
     impl_->next.store(0, std::memory_order_relaxed);
     impl_->pending.store(int(impl_->workers.size()), std::memory_order_relaxed);
     impl_->generation.fetch_add(1, std::memory_order_seq_cst);
     { std::lock_guard<std::mutex> lk(impl_->mu); }          // orders the bump against a worker that is about to sleep
     impl_->cv_work.notify_all();
-    for (int i; (i = impl_->next.fetch_add(1, std::memory_order_relaxed)) < n_tasks;) fn(i);       // the calling thread works too
-    // every worker has to pass through this generation (it reads fn / n_tasks) before the next run() may change them
+}
+
+void HostPool::end() {
+    if (!impl_->open) return;
+    impl_->open = false;
+    const int n_tasks = impl_->n_tasks;
+    if (impl_->inline_only) { for (int i = 0; i < n_tasks; ++i) impl_->job(i); return; }
+    for (int i; (i = impl_->next.fetch_add(1, std::memory_order_relaxed)) < n_tasks;) impl_->job(i);       // the calling thread works too
+    // every worker has to pass through this generation (it reads fn / n_tasks) before the next begin() may change them
     for (int polls = 0; impl_->pending.load(std::memory_order_acquire) != 0;) {
         cpu_relax();
         if ((++polls & 1023) == 0) std::this_thread::yield();
     }
 }
 
-bool pack_f32_u8_jobs(HostPool& pool, const PackJob* jobs, int n_jobs) {
-    // tasks of ~64K pixels: enough of them to balance, few enough to keep the dispatch cost invisible; the tasks of all
-    // images of one work item (left and right of every pair riding it) go out in ONE dispatch
-    constexpr int MAXJ = 16;
-    if (n_jobs > MAXJ) {
-        bool ok = true;
-        for (int j = 0; j < n_jobs; j += MAXJ) ok = pack_f32_u8_jobs(pool, jobs + j, n_jobs - j < MAXJ ? n_jobs - j : MAXJ) && ok;
-        return ok;
+// tasks of ~64K pixels: enough of them to balance, few enough to keep the dispatch cost invisible; the tasks of all images
+// of one upload chunk (left and right of every pair riding it) go out in ONE dispatch
+void PackAsync::begin(HostPool& pool, const PackJob* jobs, int n_jobs) {
+    n_ = n_jobs < 0 ? 0 : (n_jobs > MAXJ ? MAXJ : n_jobs);
+    first_[0] = 0;
+    for (int j = 0; j < n_; ++j) {
+        jobs_[j] = jobs[j];
+        rpt_[j] = (1 << 16) / (jobs[j].cols > 0 ? jobs[j].cols : 1);
+        if (rpt_[j] < 1) rpt_[j] = 1;
+        first_[j + 1] = first_[j] + (jobs[j].rows > 0 ? (jobs[j].rows + rpt_[j] - 1) / rpt_[j] : 0);
     }
-    int first[MAXJ + 1], rpt[MAXJ];
-    first[0] = 0;
-    for (int j = 0; j < n_jobs; ++j) {
-        rpt[j] = (1 << 16) / (jobs[j].cols > 0 ? jobs[j].cols : 1);
-        if (rpt[j] < 1) rpt[j] = 1;
-        first[j + 1] = first[j] + (jobs[j].rows > 0 ? (jobs[j].rows + rpt[j] - 1) / rpt[j] : 0);
-    }
-    std::atomic<int> bad{0};
-    pool.run(first[n_jobs], [&](int t) {
+    bad_.store(0, std::memory_order_relaxed);
+    pool.begin(first_[n_], [this](int t) {
         int j = 0;
-        while (t >= first[j + 1]) ++j;
-        const PackJob& J = jobs[j];
-        const int r0 = (t - first[j]) * rpt[j], r1 = r0 + rpt[j] < J.rows ? r0 + rpt[j] : J.rows;
+        while (t >= first_[j + 1]) ++j;
+        const PackJob& J = jobs_[j];
+        const int r0 = (t - first_[j]) * rpt_[j], r1 = r0 + rpt_[j] < J.rows ? r0 + rpt_[j] : J.rows;
         bool ok = true;
         for (int r = r0; r < r1; ++r) {
             const float* s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(J.src) + size_t(r) * J.src_step);
@@ -182,9 +197,23 @@ bool pack_f32_u8_jobs(HostPool& pool, const PackJob* jobs, int n_jobs) {
 #if defined(__x86_64__) && defined(__GNUC__)
         if (g_have_avx512) __builtin_ia32_sfence();       // the non-temporal stores are visible before the upload is enqueued
 #endif
-        if (!ok) bad.store(1, std::memory_order_relaxed);
+        if (!ok) bad_.store(1, std::memory_order_relaxed);
     });
-    return bad.load() == 0;
+}
+
+bool PackAsync::end(HostPool& pool) {
+    pool.end();
+    return bad_.load() == 0;
+}
+
+bool pack_f32_u8_jobs(HostPool& pool, const PackJob* jobs, int n_jobs) {
+    bool ok = true;
+    PackAsync pa;
+    for (int j = 0; j < n_jobs; j += PackAsync::MAXJ) {
+        pa.begin(pool, jobs + j, n_jobs - j < PackAsync::MAXJ ? n_jobs - j : PackAsync::MAXJ);
+        ok = pa.end(pool) && ok;
+    }
+    return ok;
 }
 
 bool pack_f32_u8(HostPool& pool, const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols) {

@@ -583,7 +583,6 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
     const size_t stg_pitch = (size_t(cols) + 63) & ~size_t(63);
     const size_t stg_slot = 2 * size_t(cp) * stg_rows * stg_pitch;
     if (any_pack) { rc = ensure_pinned(ctx, NSTG * stg_slot); if (rc != STEREO_OK) return rc; }
-    int stg_used = 0;
 
     const int S = n_items < 3 ? n_items : 3;            // device slots (ring), one work item each
     const size_t pair_bytes = 2 * align256(u8_pitch * rows) + (any_f32 ? 2 * align256(f_pitch * rows) : 0) + size_t(n_dirs) * align256(d_pitch * rows);
@@ -621,6 +620,44 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
     auto stg_ev = [&](int k) { return ctx->pipe_ev[3 * n_units + 1 + k]; };
     struct FloatRows { int r0, n; };                      // float row ranges of the unit being uploaded (converted on the device)
     std::vector<FloatRows> frows;
+    // host conversion runs one upload chunk ahead of the enqueueing thread: the chunks in the order the loops below meet them
+    struct PackChunk { int w, r0, n; };
+    std::vector<PackChunk> pchunks;
+    if (any_pack)
+        for (int w = 0; w < n_items; ++w) {
+            int up = 0;
+            for (int b = 0; b < nbw(w); ++b) {
+                const int re = bounds[boff[w] + b + 1];
+                const int up_hi = (b == nbw(w) - 1) ? rows : ((re + R + 16 < rows) ? re + R + 16 : rows);
+                for (int r0 = up; r0 < up_hi; r0 += chunk_rows) pchunks.push_back(PackChunk{w, r0, up_hi - r0 < chunk_rows ? up_hi - r0 : chunk_rows});
+                if (up_hi > up) up = up_hi;
+            }
+        }
+    // STEREO_PACK_AHEAD=0 (diagnostic): convert each chunk only when the loop reaches it, as before the look-ahead
+    static const bool pack_ahead = [] { const char* e = getenv("STEREO_PACK_AHEAD"); return !(e && atoi(e) == 0); }();
+    PackAsync pa;
+    struct PoolDrain { HostPool* p; ~PoolDrain() { if (p) p->end(); } } pool_drain{any_pack ? ctx->pool : nullptr};   // no conversion outlives `pa`
+    int pk = 0, pk_begun = 0;
+    auto pack_begin = [&](int idx) -> int {
+        const PackChunk& ch = pchunks[idx];
+        const int k = idx % NSTG;
+        const auto t_r = std::chrono::steady_clock::now();
+        if (idx >= NSTG) SB_CUDA(cudaEventSynchronize(stg_ev(k)));      // the upload that last read this staging slot
+        t_ring += since(t_r);
+        uint8_t* stg = static_cast<uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
+        const int i0 = ch.w * cp, np = (n_pairs - i0 < cp) ? n_pairs - i0 : cp;
+        PackJob jobs[2 * PIPE_CPMAX];
+        for (int c = 0; c < np; ++c) {
+            const HostPairIn& hp = in[i0 + c];
+            jobs[2 * c] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.left) + size_t(ch.r0) * hp.left_step), hp.left_step,
+                                  stg + size_t(2 * c) * stg_rows * stg_pitch, stg_pitch, ch.n, cols};
+            jobs[2 * c + 1] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.right) + size_t(ch.r0) * hp.right_step), hp.right_step,
+                                      stg + size_t(2 * c + 1) * stg_rows * stg_pitch, stg_pitch, ch.n, cols};
+        }
+        pa.begin(*ctx->pool, jobs, 2 * np);
+        pk_begun = idx + 1;
+        return STEREO_OK;
+    };
 
     for (int w = 0; w < n_items; ++w) {
         const Slot* sl = slot[w % S];
@@ -660,22 +697,15 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
                 }
                 const int p0 = r0 + nf, npk = n - nf;
                 if (npk > 0) {
-                    const int k = stg_used % NSTG;
-                    const auto t_r = std::chrono::steady_clock::now();
-                    if (stg_used >= NSTG) SB_CUDA(cudaEventSynchronize(stg_ev(k)));      // the upload that last read this slot
-                    t_ring += since(t_r);
-                    ++stg_used;
-                    uint8_t* stg = static_cast<uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
-                    PackJob jobs[2 * PIPE_CPMAX];
-                    for (int c = 0; c < np; ++c) {
-                        const HostPairIn& hp = in[i0 + c];
-                        jobs[2 * c] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.left) + size_t(p0) * hp.left_step), hp.left_step,
-                                              stg + size_t(2 * c) * stg_rows * stg_pitch, stg_pitch, npk, cols};
-                        jobs[2 * c + 1] = PackJob{reinterpret_cast<const float*>(static_cast<const char*>(hp.right) + size_t(p0) * hp.right_step), hp.right_step,
-                                                  stg + size_t(2 * c + 1) * stg_rows * stg_pitch, stg_pitch, npk, cols};
+                    // this chunk's conversion was started while the previous chunk's copies and launches were being enqueued
+                    // (the very first one starts here); the next chunk's starts before this one's copies are enqueued
+                    const int idx = pk++, k = idx % NSTG;
+                    if (idx >= int(pchunks.size()) || pchunks[idx].w != w || pchunks[idx].r0 != p0 || pchunks[idx].n != npk) {
+                        set_error("upload chunk list out of step (internal)"); return STEREO_ERR_INVALID_ARG;
                     }
+                    if (pk_begun <= idx) { rc = pack_begin(idx); if (rc != STEREO_OK) return rc; }
                     const auto t_p = std::chrono::steady_clock::now();
-                    const bool all8 = pack_f32_u8_jobs(*ctx->pool, jobs, 2 * np);       // one dispatch of the pool per chunk
+                    const bool all8 = pa.end(*ctx->pool);
                     t_pack += since(t_p);
                     if (!all8) {
                         // a pixel that is not 8-bit: give the call to the float kernels (nothing of it has reached the caller's
@@ -683,9 +713,13 @@ static int pairs_host_pipelined_body(stereo_ctx* ctx, int cost, PixType type, in
                         SB_CUDA(cudaStreamSynchronize(s_in)); SB_CUDA(cudaStreamSynchronize(s_cmp)); SB_CUDA(cudaStreamSynchronize(s_out));
                         return PIPE_NOT_8BIT;
                     }
+                    if (pack_ahead && idx + 1 < int(pchunks.size())) { rc = pack_begin(idx + 1); if (rc != STEREO_OK) return rc; }
+                    const uint8_t* stg = static_cast<const uint8_t*>(ctx->pinned) + size_t(k) * stg_slot;
                     for (int c = 0; c < np; ++c) {
-                        SB_CUDA(cudaMemcpy2DAsync(sl[c].l8 + size_t(p0) * u8_pitch, u8_pitch, jobs[2 * c].dst, stg_pitch, cols, npk, cudaMemcpyHostToDevice, s_in));
-                        SB_CUDA(cudaMemcpy2DAsync(sl[c].r8 + size_t(p0) * u8_pitch, u8_pitch, jobs[2 * c + 1].dst, stg_pitch, cols, npk, cudaMemcpyHostToDevice, s_in));
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].l8 + size_t(p0) * u8_pitch, u8_pitch, stg + size_t(2 * c) * stg_rows * stg_pitch, stg_pitch, cols, npk,
+                                                  cudaMemcpyHostToDevice, s_in));
+                        SB_CUDA(cudaMemcpy2DAsync(sl[c].r8 + size_t(p0) * u8_pitch, u8_pitch, stg + size_t(2 * c + 1) * stg_rows * stg_pitch, stg_pitch, cols, npk,
+                                                  cudaMemcpyHostToDevice, s_in));
                     }
                     SB_CUDA(cudaEventRecord(stg_ev(k), s_in));
                 }
