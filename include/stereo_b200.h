@@ -142,7 +142,7 @@ int stereo_ctx_host_threads(const stereo_ctx* ctx);
 int stereo_host_pack_f32_u8(const float* src, size_t src_step, uint8_t* dst, size_t dst_step, int rows, int cols, int threads,
                             int* all_8bit);
 /* Self-test of the worker pool behind the conversion (pure host code): `rounds` dispatches of 1..257 tasks on ONE pool of
- * `threads` threads, with pauses long enough for the polling workers to fall asleep; STEREO_OK when every task of every
+ * `threads` threads (blocking and begin / end form alternating), with pauses long enough for the polling workers to fall asleep; STEREO_OK when every task of every
  * dispatch ran exactly once (STEREO_ERR_UNSUPPORTED with the offending task in stereo_last_error() otherwise). */
 int stereo_host_pool_selftest(int threads, int rounds);
 

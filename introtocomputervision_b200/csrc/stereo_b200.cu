@@ -1123,7 +1123,15 @@ int stereo_host_pool_selftest(int threads, int rounds) {
     for (int r = 0; r < rounds; ++r) {
         const int n_tasks = 1 + (r * 37) % 257;
         for (int i = 0; i < n_tasks; ++i) hits[i].store(0, std::memory_order_relaxed);
-        pool.run(n_tasks, [&](int t) { hits[t].fetch_add(1, std::memory_order_relaxed); });
+        // odd rounds: the asynchronous form the host pipeline uses - the caller does something else between begin() and end()
+        if (r & 1) {
+            pool.begin(n_tasks, [&](int t) { hits[t].fetch_add(1, std::memory_order_relaxed); });
+            volatile int spin = 0;
+            for (int i = 0; i < (r % 7) * 300; ++i) spin = spin + i;
+            pool.end();
+        } else {
+            pool.run(n_tasks, [&](int t) { hits[t].fetch_add(1, std::memory_order_relaxed); });
+        }
         for (int i = 0; i < n_tasks; ++i)
             if (hits[i].load() != 1) { set_error("round %d: task %d of %d ran %d times", r, i, n_tasks, hits[i].load()); return STEREO_ERR_UNSUPPORTED; }
         if (r % 64 == 63) std::this_thread::sleep_for(std::chrono::microseconds(600));     // let the workers fall asleep now and then
